@@ -1,0 +1,161 @@
+/*
+ * szb200.h -- C ABI of libszb200.so: the B200-native replacement for the self-play hot path of
+ * DidItWork/Sigma-Zero (batched AlphaZero MCTS over many concurrent chess / Chess960 games).
+ *
+ * The reference has no FFI of its own: its boundary for this path is a Python call surface
+ * (SURVEY.md 8b).  Each entry point below names the reference call it replaces (file:line into the
+ * reference repository); the Python facade in sigma-zero_b200/ keeps the reference's names
+ * (mcts.MCTS0, mctsnode.Node, chess_tensor.ChessTensor, network.policyNN, sim.play_game) and calls
+ * these functions through ctypes.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types, opaque context, no torch / C++ types in any signature;
+ *   - every function returns 0 on success and a negative code on failure; szb_last_error(ctx) gives
+ *     the message;
+ *   - one context per GPU, used from one host thread; work is issued on the context's stream;
+ *   - I/O buffers belong to the caller and may be host (pageable or pinned) or device memory -- the
+ *     library copies with cudaMemcpyDefault on its stream and synchronises before returning when the
+ *     destination is host data;
+ *   - there is no CPU fallback: without a CUDA device every call fails with SZB_ERR_CUDA.
+ *
+ * Move indices are the reference's policy indices: plane*64 + row*8 + col in the mover's view,
+ * 0 <= index < 4672 (chess_tensor.py:221-306).  Planes are the reference's 119 input planes
+ * (chess_tensor.py:8-26,38-142), bit-packed: one uint64 per plane, bit (row*8+col).
+ */
+#ifndef SZB200_H
+#define SZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SZB_N_PLANES 119
+#define SZB_N_ACTIONS 4672
+#define SZB_MASK_WORDS 73
+#define SZB_MAX_MOVES 256          /* row stride of move-index outputs (>= 218) */
+
+enum {
+    SZB_OK = 0,
+    SZB_ERR_ARG = -1,              /* bad argument */
+    SZB_ERR_CUDA = -2,             /* CUDA runtime failure or no device */
+    SZB_ERR_ILLEGAL_MOVE = -3,     /* szb_games_push: at least one move was not legal (chess_tensor.py:91-92) */
+    SZB_ERR_ARENA = -4,            /* tree arena exhausted: raise szb_config.edges_per_node */
+    SZB_ERR_STATE = -5,            /* call made in the wrong state (no games, no weights, ...) */
+    SZB_ERR_UNSUPPORTED = -6
+};
+
+/* evaluator used by szb_search / szb_selfplay */
+enum {
+    SZB_EVAL_NET_BF16 = 0,         /* tcgen05/TMEM implicit-GEMM tower, bf16 in / fp32 accumulate */
+    SZB_EVAL_NET_FP32 = 1,         /* fp32 SIMT tower (parity mode, <= 1e-5 abs vs torch CPU fp32) */
+    SZB_EVAL_HASH = 2              /* integer-hash evaluator (exact-parity tests, tree-only benchmarks) */
+};
+
+typedef struct szb_ctx szb_ctx;
+
+typedef struct szb_config {
+    int32_t max_games;             /* capacity: concurrent games (trees) */
+    int32_t max_searches;          /* capacity: num_searches per move (train_RL.py:170) */
+    int32_t edges_per_node;        /* tree arena = max_games * (max_searches+1) * edges_per_node edges; 0 -> 48 */
+    int32_t reserved;
+} szb_config;
+
+/* A position crossing the ABI. */
+typedef struct szb_pos {
+    uint64_t pieces[12];           /* white P N B R Q K, black P N B R Q K; bit s = square s, a1 = 0, h8 = 63 */
+    uint8_t turn;                  /* 1 = white to move */
+    uint8_t castling_w;            /* files (bit f) of white rooks that may castle */
+    uint8_t castling_b;
+    int8_t ep_square;              /* -1 = none */
+    uint16_t halfmove_clock;
+    uint16_t ply;                  /* moves already played in this game object (len(board.move_stack)) */
+    uint8_t chess960;              /* castling written king-takes-rook (Board.from_chess960_pos) */
+    uint8_t outcome;               /* out: 0 running, 1 checkmate, 2 insufficient material, 3 stalemate,
+                                      4 seventy-five moves, 5 fivefold repetition (Board.outcome()) */
+    uint8_t rep_flags;             /* out: bit0 is_repetition(2), bit1 is_repetition(3) */
+    uint8_t n_legal;               /* out */
+    uint8_t pad[4];
+} szb_pos;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+const char *szb_version(void);
+int szb_create(int device_ordinal, const szb_config *cfg, szb_ctx **out);
+void szb_destroy(szb_ctx *ctx);
+const char *szb_last_error(const szb_ctx *ctx);
+/* the CUDA stream (cudaStream_t) all work of this context is ordered on */
+void *szb_stream(szb_ctx *ctx);
+int szb_synchronize(szb_ctx *ctx);
+
+/* ---- games: replaces ChessTensor.__init__/start_board/move_piece (chess_tensor.py:30-35,65-129) -- */
+/* start n_games games; start_id[g] = -1 -> chess.Board(), 0..959 -> Board.from_chess960_pos(id) */
+int szb_games_reset(szb_ctx *ctx, int32_t n_games, const int16_t *start_id);
+/* start n_games games from arbitrary positions (empty history) */
+int szb_games_set(szb_ctx *ctx, int32_t n_games, const szb_pos *positions);
+/* play move_index[i] in game game[i] (i < n; each game at most once per call).  status[i] (optional) is 0
+ * or SZB_ERR_ILLEGAL_MOVE; illegal moves leave their game untouched ("Invalid move", chess_tensor.py:91). */
+int szb_games_push(szb_ctx *ctx, int32_t n, const int32_t *game, const uint16_t *move_index, int32_t *status);
+/* current position of each listed game (game == NULL: games 0..n-1) */
+int szb_games_get(szb_ctx *ctx, int32_t n, const int32_t *game, szb_pos *out);
+/* replaces list(board.legal_moves) + actionsToTensor (chess_tensor.py:146,190-218): ascending policy
+ * indices of the legal moves, row stride SZB_MAX_MOVES, and their count */
+int szb_legal_moves(szb_ctx *ctx, int32_t n, const int32_t *game, uint16_t *index_out, uint16_t *count_out);
+/* replaces get_representation (chess_tensor.py:131-142) and actionsToTensor's mask: planes_out is
+ * uint64[n][119], mask_out (optional) uint64[n][73] with bit index = policy index */
+int szb_encode(szb_ctx *ctx, int32_t n, const int32_t *game, uint64_t *planes_out, uint64_t *mask_out);
+/* bit-packed planes -> float32 [n][119][8][8] (what mcts.py:73 feeds the network).  Both device pointers. */
+int szb_unpack_planes_f32(szb_ctx *ctx, int32_t n, const uint64_t *planes_dev, float *out_dev);
+
+/* ---- perft: bulk legal move generation + make-move (correctness config c1, movegen roofline) ---- */
+int szb_perft(szb_ctx *ctx, const szb_pos *pos, int32_t depth, uint64_t *nodes_out);
+/* timing hook for benchmarks: one breadth-first ply over the context's current frontier; see bench.py */
+int szb_perft_timed(szb_ctx *ctx, const szb_pos *pos, int32_t depth, uint64_t *nodes_out,
+                    float *ms_last_level, uint64_t *positions_last_level);
+
+/* ---- network: replaces policyNN.load_state_dict / forward (network.py:100-192, play.py:25-28) ---- */
+/* tensors of the fp32 state_dict by name (252 entries; *.num_batches_tracked may be omitted).
+ * data[i] are HOST pointers to contiguous fp32; the library folds BatchNorm (eval mode) into the
+ * convolutions and builds the fp32 and bf16 device packs. */
+int szb_net_load(szb_ctx *ctx, int32_t n_tensors, const char *const *names, const float *const *data,
+                 const int64_t *numel);
+/* policyNN.forward(x, inference=True): planes uint64[n][119] -> softmax policy float[n][4672], value float[n] */
+int szb_net_forward(szb_ctx *ctx, int32_t n, const uint64_t *planes, int32_t evaluator,
+                    float *policy_out, float *value_out);
+/* raw logits variant (inference=False) */
+int szb_net_forward_logits(szb_ctx *ctx, int32_t n, const uint64_t *planes, int32_t evaluator,
+                           float *logits_out, float *value_out);
+
+/* ---- search: replaces MCTS0.search (mcts.py:39-122) for every current game at once ---------------- */
+/* num_searches, c_puct = args['num_searches'], args['C']; learning as in mcts.py:91-96.
+ * visits_out (optional): uint32[n_games][4672], visit count of every root child at its policy index
+ *   (the reference returns count / sum(count), mcts.py:113-122);
+ * child_mask_out (optional): uint64[n_games][73], bit set for every root child (children with zero visits
+ *   are part of the reference's result dict);
+ * root_value_out (optional): float[n_games] network value of the root. */
+int szb_search(szb_ctx *ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
+               uint32_t *visits_out, uint64_t *child_mask_out, float *root_value_out);
+
+/* ---- self-play: replaces sim.play_game's ply loop (sim.py:46-76) ---------------------------------- */
+/* One ply for every unfinished game: search, pick a move (sample proportional to visits, sim.py:68, with a
+ * counter-based RNG keyed (seed, game, ply); or argmax with lowest index on ties when sample == 0), record
+ * (planes, visits, colour) and push the move.  moves_out (optional): int32[n_games] chosen policy index or -1
+ * for games already over.  n_active_out (optional): games still running afterwards. */
+int szb_selfplay_ply(szb_ctx *ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
+                     uint64_t seed, int32_t sample, int32_t *moves_out, int32_t *n_active_out);
+
+/* ---- counters (metrics) -------------------------------------------------------------- */
+typedef struct szb_stats {
+    uint64_t simulations;          /* iterations of mcts.py:49 executed */
+    uint64_t evaluations;          /* network / evaluator calls (non-terminal leaves) */
+    uint64_t terminal_visits;
+    uint64_t edges_allocated;      /* high-water mark of the edge arena in the last search */
+    uint64_t kernel_launches;      /* kernels of this library launched since creation */
+    uint64_t max_depth;
+} szb_stats;
+int szb_get_stats(szb_ctx *ctx, szb_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SZB200_H */

@@ -1,0 +1,78 @@
+"""ctypes binding of include/szb200.h.  Fails loudly when the CUDA library is missing: there is no fallback."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libszb200.so")
+
+N_PLANES, N_ACTIONS, MASK_WORDS, MAX_MOVES = 119, 4672, 73, 256
+EVAL_NET_BF16, EVAL_NET_FP32, EVAL_HASH = 0, 1, 2
+ERR_ILLEGAL_MOVE = -3
+
+
+class SzbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("szb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("max_games", ctypes.c_int32), ("max_searches", ctypes.c_int32),
+                ("edges_per_node", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class Pos(ctypes.Structure):
+    _fields_ = [("pieces", ctypes.c_uint64 * 12), ("turn", ctypes.c_uint8), ("castling_w", ctypes.c_uint8),
+                ("castling_b", ctypes.c_uint8), ("ep_square", ctypes.c_int8), ("halfmove_clock", ctypes.c_uint16),
+                ("ply", ctypes.c_uint16), ("chess960", ctypes.c_uint8), ("outcome", ctypes.c_uint8),
+                ("rep_flags", ctypes.c_uint8), ("n_legal", ctypes.c_uint8), ("pad", ctypes.c_uint8 * 4)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in
+                ("simulations", "evaluations", "terminal_visits", "edges_allocated", "kernel_launches", "max_depth")]
+
+
+_vp, _i32, _u64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float
+SIGNATURES = {
+    "szb_version": (ctypes.c_char_p, []),
+    "szb_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(Config), ctypes.POINTER(_vp)]),
+    "szb_destroy": (None, [_vp]),
+    "szb_last_error": (ctypes.c_char_p, [_vp]),
+    "szb_stream": (_vp, [_vp]),
+    "szb_synchronize": (ctypes.c_int, [_vp]),
+    "szb_games_reset": (ctypes.c_int, [_vp, _i32, _vp]),
+    "szb_games_set": (ctypes.c_int, [_vp, _i32, _vp]),
+    "szb_games_push": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "szb_games_get": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
+    "szb_legal_moves": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "szb_encode": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "szb_unpack_planes_f32": (ctypes.c_int, [_vp, _i32, _vp, _vp]),
+    "szb_perft": (ctypes.c_int, [_vp, ctypes.POINTER(Pos), _i32, ctypes.POINTER(_u64)]),
+    "szb_perft_timed": (ctypes.c_int, [_vp, ctypes.POINTER(Pos), _i32, ctypes.POINTER(_u64),
+                                       ctypes.POINTER(_f32), ctypes.POINTER(_u64)]),
+    "szb_net_load": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "szb_net_forward": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
+    "szb_net_forward_logits": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
+    "szb_search": (ctypes.c_int, [_vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "szb_selfplay_ply": (ctypes.c_int, [_vp, _i32, _f32, _i32, _i32, _u64, _i32, _vp, _vp]),
+    "szb_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
+}
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises if libszb200.so has not been built (python sigma-zero_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SzbError(-2, "libszb200.so is not built (%s); run `python __graft_entry__.py` or "
+                               "`python sigma-zero_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here == header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

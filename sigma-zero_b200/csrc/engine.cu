@@ -1,0 +1,852 @@
+// engine.cu -- games, flat SoA search tree, batched MCTS step kernels, perft, and the C ABI around them.
+//
+// One simulation step of mcts.py:49-109 for ALL games at once is four launches:
+//   k_select  : warp per tree, PUCT descent with shuffle arg-max           (mctsnode.py:23-37, mcts.py:54-55)
+//   k_expand  : thread per tree, make-move + legality + terminal + planes    (mcts.py:57-70, chess_tensor.py:88-172)
+//   evaluator : hash kernel or the network (net.cu)                         (mcts.py:72-75)
+//   k_finish  : warp per tree, mask/normalise/noise, child allocation, backup (mcts.py:77-109, mctsnode.py:39-63)
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include "engine.cuh"
+
+using namespace szb;
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+namespace szb {
+int fail(szb_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+int cuda_fail(szb_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, SZB_ERR_CUDA, "CUDA error %s (%d) at %s", cudaGetErrorString(e), (int)e, what);
+}
+void* ctx_stage(szb_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->stage_bytes) {
+        if (ctx->stage) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->stage); }
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        size_t want = std::max(bytes, (size_t)1 << 20);
+        if (cudaMalloc(&ctx->stage, want) != cudaSuccess) return nullptr;
+        ctx->stage_bytes = want;
+    }
+    return ctx->stage;
+}
+}  // namespace szb
+
+template <class T>
+static int dev_alloc(szb_ctx* ctx, T** out, size_t count) {
+    void* p = nullptr;
+    SZB_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    SZB_CUDA(ctx, cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), ctx->stream));
+    ctx->allocs.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_tables(Tables* sm, const Tables* g) {
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(g);
+    uint64_t* dst = reinterpret_cast<uint64_t*>(sm);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 8); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+__device__ __forceinline__ int state_slot(const Dev& d, int g, int node) { return node == 0 ? d.cur[g] : RING + node; }
+
+__device__ __forceinline__ void analyse(const Tables& T, Pos& p, uint16_t* mv, int& n) {
+    n = gen_legal(T, p, mv);
+    p.n_legal = (uint8_t)n;
+    p.outcome = outcome_of(T, p, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// games
+// ------------------------------------------------------------------------------------------------
+__global__ void k_games_init(Dev d, const Pos* start, int n) {
+    __shared__ Tables T;
+    load_tables(&T, d.tables);
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    Pos p = start[g];
+    uint16_t mv[MAX_MOVES];
+    int cnt;
+    finish_setup(T, p);
+    analyse(T, p, mv, cnt);
+    const int slot = p.ply & (RING - 1);
+    d.pool[(size_t)g * d.pool_stride + slot] = p;
+    d.cur[g] = slot;
+}
+
+__global__ void k_games_push(Dev d, int n, const int32_t* game, const uint16_t* index, int32_t* status) {
+    __shared__ Tables T;
+    load_tables(&T, d.tables);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = game ? game[i] : i;
+    if (g < 0 || g >= d.n_games) { status[i] = SZB_ERR_ARG; return; }
+    Pos* gp = d.pool + (size_t)g * d.pool_stride;
+    const Pos p = gp[d.cur[g]];
+    uint16_t mv[MAX_MOVES];
+    const uint16_t m = index[i] < N_ACTIONS ? index_to_move(p, index[i]) : MOVE_NONE;
+    bool ok = false;
+    if (m != MOVE_NONE) {
+        int cnt = gen_legal(T, p, mv);
+        for (int k = 0; k < cnt; k++) ok |= mv[k] == m;
+    }
+    if (!ok) { status[i] = SZB_ERR_ILLEGAL_MOVE; return; }
+    Pos q;
+    make_move(T, p, m, q);
+    q.prev = (uint32_t)d.cur[g];
+    set_repetition_flags(gp, q);
+    int cnt;
+    analyse(T, q, mv, cnt);
+    const int slot = q.ply & (RING - 1);
+    gp[slot] = q;
+    d.cur[g] = slot;
+    status[i] = 0;
+}
+
+__global__ void k_games_get(Dev d, int n, const int32_t* game, szb_pos* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = game ? game[i] : i;
+    szb_pos o;
+    memset(&o, 0, sizeof o);
+    if (g >= 0 && g < d.n_games) {
+        const Pos& p = d.pool[(size_t)g * d.pool_stride + d.cur[g]];
+        for (int t = 0; t < 6; t++) {
+            o.pieces[t] = p.bb[BB_P + t] & p.bb[BB_WHITE];
+            o.pieces[6 + t] = p.bb[BB_P + t] & p.bb[BB_BLACK];
+        }
+        o.turn = (p.flags & F_WHITE) ? 1 : 0;
+        o.castling_w = p.rights_w; o.castling_b = p.rights_b;
+        o.ep_square = p.ep; o.halfmove_clock = p.halfmove; o.ply = p.ply;
+        o.chess960 = (p.flags & F_960) ? 1 : 0;
+        o.outcome = p.outcome;
+        o.rep_flags = (uint8_t)(((p.flags & F_REP2) ? 1 : 0) | ((p.flags & F_REP3) ? 2 : 0));
+        o.n_legal = p.n_legal;
+    }
+    out[i] = o;
+}
+
+// legal indices (ascending) and/or planes + mask of the current positions
+__global__ void k_games_encode(Dev d, int n, const int32_t* game, uint16_t* index_out, uint16_t* count_out,
+                               uint64_t* planes_out, uint64_t* mask_out) {
+    __shared__ Tables T;
+    load_tables(&T, d.tables);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = game ? game[i] : i;
+    if (g < 0 || g >= d.n_games) { if (count_out) count_out[i] = 0; return; }
+    const Pos* gp = d.pool + (size_t)g * d.pool_stride;
+    const Pos p = gp[d.cur[g]];
+    uint16_t mv[MAX_MOVES];
+    const int cnt = gen_legal(T, p, mv);
+    uint64_t m[MASK_WORDS];
+    for (int w = 0; w < MASK_WORDS; w++) m[w] = 0;
+    for (int k = 0; k < cnt; k++) {
+        int idx = move_to_index(p, mv[k]);
+        m[idx >> 6] |= bit(idx & 63);
+    }
+    if (mask_out) for (int w = 0; w < MASK_WORDS; w++) mask_out[(size_t)i * MASK_WORDS + w] = m[w];
+    if (index_out) {
+        int k = 0;
+        for (int w = 0; w < MASK_WORDS; w++) {
+            uint64_t x = m[w];
+            while (x) { index_out[(size_t)i * SZB_MAX_MOVES + k++] = (uint16_t)(w * 64 + lsb(x)); x &= x - 1; }
+        }
+    }
+    if (count_out) count_out[i] = (uint16_t)cnt;
+    if (planes_out) pack_planes(gp, p, planes_out + (size_t)i * N_PLANES);
+}
+
+__global__ void k_unpack_planes_f32(int n, const uint64_t* planes, float* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // one output element
+    size_t total = (size_t)n * N_PLANES * 64;
+    if (i >= total) return;
+    size_t row = i >> 6;
+    out[i] = (float)((planes[row] >> (i & 63)) & 1ull);
+}
+
+// ------------------------------------------------------------------------------------------------
+// search step kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_search_begin(Dev d) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) *d.edge_top = 0ull;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    d.node_count[g] = 0;
+    d.node_edge0[r] = -1;
+    d.node_nchild[r] = 0;
+    d.node_pedge[r] = -1;
+    d.node_pnode[r] = 0;
+    const Pos& p = d.pool[(size_t)g * d.pool_stride + d.cur[g]];
+    d.node_term[r] = p.outcome != OUT_NONE;
+    d.node_tval[r] = p.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
+    d.root_n[g] = 1;
+    d.root_w[g] = 0.0;
+}
+
+// warp per tree
+__global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    int node = 0, depth = 0;
+    for (;;) {
+        const int n = d.node_nchild[r + node];
+        if (n == 0) {
+            if (lane == 0) { d.sel_node[g] = node; d.sel_edge[g] = -1; }
+            break;
+        }
+        const int e0 = d.node_edge0[r + node];
+        const int np = node == 0 ? d.root_n[g] : d.e_n[d.node_pedge[r + node]];
+        const float sq = sqrt_parent(np);
+        float best = -INFINITY;
+        int besti = 0x7FFFFFFF;
+        for (int i = lane; i < n; i += 32) {
+            const float s = puct_score(d.e_n[e0 + i], d.e_w[e0 + i], d.e_p[e0 + i], sq, c_puct);
+            if (s > best || besti == 0x7FFFFFFF) { best = s; besti = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_down_sync(0xFFFFFFFFu, best, off);
+            const int oi = __shfl_down_sync(0xFFFFFFFFu, besti, off);
+            if (oi != 0x7FFFFFFF && (besti == 0x7FFFFFFF || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+        }
+        besti = __shfl_sync(0xFFFFFFFFu, besti, 0);
+        const int e = e0 + besti;
+        const uint16_t c = d.e_child[e];
+        depth++;
+        if (c == NO_CHILD) {
+            if (lane == 0) { d.sel_node[g] = node; d.sel_edge[g] = e; }
+            break;
+        }
+        node = c;
+    }
+    if (lane == 0) atomicMax(&d.stats[3], (unsigned long long)depth);
+}
+
+// thread per tree
+__global__ void __launch_bounds__(32) k_expand(Dev d) {
+    __shared__ Tables T;
+    load_tables(&T, d.tables);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    Pos* gp = d.pool + (size_t)g * d.pool_stride;
+    const int e = d.sel_edge[g];
+    int node = d.sel_node[g];
+    uint16_t mv[MAX_MOVES];
+    int cnt = 0;
+    Pos q;
+    if (e >= 0) {
+        const int parent = node;
+        node = ++d.node_count[g];
+        const int pslot = state_slot(d, g, parent);
+        const Pos pp = gp[pslot];
+        const uint16_t m = index_to_move(pp, d.e_move[e]);
+        make_move(T, pp, m, q);
+        q.prev = (uint32_t)pslot;
+        set_repetition_flags(gp, q);
+        analyse(T, q, mv, cnt);
+        gp[RING + node] = q;
+        d.node_pedge[r + node] = e;
+        d.node_pnode[r + node] = (uint16_t)parent;
+        d.node_nchild[r + node] = 0;
+        d.node_edge0[r + node] = -1;
+        d.node_term[r + node] = q.outcome != OUT_NONE;
+        d.node_tval[r + node] = q.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
+        d.e_child[e] = (uint16_t)node;
+        d.sel_node[g] = node;
+    } else {
+        q = gp[state_slot(d, g, node)];
+        if (!d.node_term[r + node]) cnt = gen_legal(T, q, mv);
+    }
+    if (d.node_term[r + node]) {
+        d.leaf_value[g] = d.node_tval[r + node];
+        d.need_eval[g] = 0;
+        return;
+    }
+    uint64_t* mrow = d.mask + (size_t)g * MASK_STRIDE;
+    for (int w = 0; w < MASK_STRIDE; w++) mrow[w] = 0;
+    for (int k = 0; k < cnt; k++) {
+        const int idx = move_to_index(q, mv[k]);
+        mrow[idx >> 6] |= bit(idx & 63);
+    }
+    pack_planes(gp, q, d.planes + (size_t)g * PLANE_STRIDE);
+    d.need_eval[g] = 1;
+}
+
+// block per tree: policy[i] / value from the integer hash of the packed planes
+__global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
+    const int g = blockIdx.x;
+    if (!d.need_eval[g]) return;
+    __shared__ uint64_t h_sh;
+    if (threadIdx.x == 0) {
+        h_sh = he_fold(d.planes + (size_t)g * PLANE_STRIDE);
+        d.value[g] = he_value(h_sh);
+    }
+    __syncthreads();
+    const uint64_t h = h_sh;
+    float* pol = d.policy + (size_t)g * N_ACTIONS;
+    for (int i = threadIdx.x; i < N_ACTIONS; i += blockDim.x) pol[i] = he_policy(h, i);
+}
+
+// warp per tree
+__global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int node = d.sel_node[g];
+    float v;
+    if (d.need_eval[g]) {
+        const float* pol = d.policy + (size_t)g * N_ACTIONS;
+        const uint64_t* mk = d.mask + (size_t)g * MASK_STRIDE;
+        auto elem = [&](int e) -> float { return ((mk[e >> 6] >> (e & 63)) & 1ull) ? pol[e] : 0.0f; };
+        const float part = cascade_lane(elem, lane);
+        const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
+        int n_legal = 0;
+        for (int w = lane; w < MASK_WORDS; w += 32) n_legal += popc(mk[w]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) n_legal += __shfl_xor_sync(0xFFFFFFFFu, n_legal, off);
+        unsigned long long e0 = 0;
+        if (lane == 0) e0 = atomicAdd(d.edge_top, (unsigned long long)n_legal);
+        e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+        int count = 0;
+        if (e0 + (unsigned long long)n_legal > d.edge_cap) {
+            if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
+        } else {
+            for (int chunk = 0; chunk < N_ACTIONS / 32; chunk++) {
+                const uint32_t bits = (uint32_t)(mk[chunk >> 1] >> ((chunk & 1) * 32));
+                if (bits == 0) continue;
+                const int e = chunk * 32 + lane;
+                float pr = 0.0f;
+                bool has = (bits >> lane) & 1u;
+                if (has) { pr = f_div(pol[e], total); has = pr != 0.0f; }     // zero-prior children are dropped (mcts.py:87-89)
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
+                if (has) {
+                    const unsigned long long at = e0 + count + __popc(ballot & ((1u << lane) - 1));
+                    d.e_n[at] = 0;
+                    d.e_w[at] = 0.0;
+                    d.e_p[at] = learning ? noisy_prior(pr) : pr;
+                    d.e_move[at] = (uint16_t)e;
+                    d.e_child[at] = NO_CHILD;
+                }
+                count += __popc(ballot);
+            }
+        }
+        if (lane == 0) {
+            d.node_edge0[r + node] = (int32_t)e0;
+            d.node_nchild[r + node] = (uint16_t)count;
+        }
+        v = d.value[g];
+        if (node == 0 && lane == 0) d.root_val[g] = v;
+    } else {
+        v = d.leaf_value[g];
+    }
+    if (lane == 0) {
+        // backup (mctsnode.py:56-63): value_sum accumulates python doubles
+        double val = (double)v;
+        int nd = node;
+        for (;;) {
+            const int pe = d.node_pedge[r + nd];
+            if (pe < 0) break;
+            d.e_w[pe] += val;
+            d.e_n[pe] += 1;
+            val = -val;
+            nd = d.node_pnode[r + nd];
+        }
+        d.root_w[g] += val;
+        d.root_n[g] += 1;
+        atomicAdd(&d.stats[0], 1ull);
+        atomicAdd(&d.stats[d.need_eval[g] ? 1 : 2], 1ull);
+    }
+}
+
+__global__ void k_collect(Dev d, uint32_t* visits, uint64_t* child_mask, float* root_value) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    if (visits) for (int i = lane; i < N_ACTIONS; i += 32) visits[(size_t)g * N_ACTIONS + i] = 0;
+    if (child_mask) for (int i = lane; i < MASK_WORDS; i += 32) child_mask[(size_t)g * MASK_WORDS + i] = 0;
+    __syncwarp();
+    const int n = d.node_nchild[r], e0 = d.node_edge0[r];
+    for (int i = lane; i < n; i += 32) {
+        const int idx = d.e_move[e0 + i];
+        if (visits) visits[(size_t)g * N_ACTIONS + idx] = (uint32_t)d.e_n[e0 + i];
+        if (child_mask) atomicOr((unsigned long long*)&child_mask[(size_t)g * MASK_WORDS + (idx >> 6)], 1ull << (idx & 63));
+    }
+    if (root_value && lane == 0) root_value[g] = d.node_term[r] ? d.node_tval[r] : d.root_val[g];
+}
+
+// choose a move from the root visit counts (sim.py:68 sampling, or arg-max first-index as in eval.py:92-100)
+__global__ void k_pick(Dev d, uint64_t seed, int sample, int32_t* moves) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int n = d.node_nchild[r], e0 = d.node_edge0[r];
+    const Pos& p = d.pool[(size_t)g * d.pool_stride + d.cur[g]];
+    if (p.outcome != OUT_NONE || n == 0) { moves[g] = -1; return; }
+    long long total = 0;
+    for (int i = 0; i < n; i++) total += d.e_n[e0 + i];
+    int pick = 0;
+    if (sample && total > 0) {
+        const uint64_t rnd = mix64(mix64(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(g + 1))) + (uint64_t)p.ply);
+        const long long target = (long long)__umul64hi(rnd, (uint64_t)total);      // uniform in [0, total)
+        long long acc = 0;
+        for (int i = 0; i < n; i++) { acc += d.e_n[e0 + i]; if (acc > target) { pick = i; break; } }
+    } else {
+        int best = -1;
+        for (int i = 0; i < n; i++) if (d.e_n[e0 + i] > best) { best = d.e_n[e0 + i]; pick = i; }
+    }
+    moves[g] = d.e_move[e0 + pick];
+}
+
+__global__ void k_push_picked(Dev d, const int32_t* moves, int32_t* n_active) {
+    __shared__ Tables T;
+    load_tables(&T, d.tables);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.n_games) return;
+    if (moves[g] < 0) return;
+    Pos* gp = d.pool + (size_t)g * d.pool_stride;
+    const Pos p = gp[d.cur[g]];
+    const uint16_t m = index_to_move(p, moves[g]);
+    Pos q;
+    make_move(T, p, m, q);
+    q.prev = (uint32_t)d.cur[g];
+    set_repetition_flags(gp, q);
+    uint16_t mv[MAX_MOVES];
+    int cnt;
+    analyse(T, q, mv, cnt);
+    const int slot = q.ply & (RING - 1);
+    gp[slot] = q;
+    d.cur[g] = slot;
+    if (q.outcome == OUT_NONE) atomicAdd(n_active, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// perft: breadth-first expansion with bulk counting at the last ply
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_perft_count(const Tables* tables, const Pos* in, size_t n, unsigned long long* total) {
+    __shared__ Tables T;
+    load_tables(&T, tables);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (i < n) {
+        uint16_t mv[MAX_MOVES];
+        cnt = gen_legal(T, in[i], mv);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, off);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+}
+
+__global__ void __launch_bounds__(128) k_perft_expand(const Tables* tables, const Pos* in, size_t n, Pos* out, unsigned long long* top) {
+    __shared__ Tables T;
+    load_tables(&T, tables);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint16_t mv[MAX_MOVES];
+    int cnt = 0;
+    Pos p;
+    if (i < n) { p = in[i]; cnt = gen_legal(T, p, mv); }
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    unsigned long long base = 0;
+    if (lane == 31) base = atomicAdd(top, (unsigned long long)incl);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + (unsigned long long)(incl - cnt);
+    for (int k = 0; k < cnt; k++) {
+        Pos q;
+        make_move(T, p, mv[k], q);
+        q.prev = NO_PREV;
+        out[base + k] = q;
+    }
+}
+
+static uint64_t perft_rec(szb_ctx* ctx, const Pos* front, size_t n, int depth, int level, cudaError_t* err,
+                          float* ms_last, uint64_t* n_last) {
+    if (*err != cudaSuccess || n == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    unsigned long long total = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (depth == 1 && ms_last) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    cudaMemsetAsync(ctx->perft_counter, 0, sizeof(unsigned long long), st);
+    if (e0) cudaEventRecord(e0, st);
+    k_perft_count<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d.tables, front, n, ctx->perft_counter);
+    if (e0) cudaEventRecord(e1, st);
+    ctx->launches++;
+    cudaMemcpyAsync(&total, ctx->perft_counter, sizeof total, cudaMemcpyDeviceToHost, st);
+    *err = cudaStreamSynchronize(st);
+    if (*err != cudaSuccess) return 0;
+    if (e0) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (n >= *n_last) { *ms_last = ms; *n_last = n; }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (depth == 1) return total;
+    if (total > ctx->perft_cap) {
+        if (n == 1) { *err = cudaErrorMemoryAllocation; return 0; }
+        size_t h = n / 2;
+        return perft_rec(ctx, front, h, depth, level, err, ms_last, n_last) +
+               perft_rec(ctx, front + h, n - h, depth, level, err, ms_last, n_last);
+    }
+    while ((int)ctx->perft_levels.size() <= level + 1) ctx->perft_levels.push_back(nullptr);
+    if (!ctx->perft_levels[level + 1]) {
+        *err = cudaMalloc((void**)&ctx->perft_levels[level + 1], ctx->perft_cap * sizeof(Pos));
+        if (*err != cudaSuccess) return 0;
+    }
+    Pos* next = ctx->perft_levels[level + 1];
+    cudaMemsetAsync(ctx->perft_counter, 0, sizeof(unsigned long long), st);
+    k_perft_expand<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->d.tables, front, n, next, ctx->perft_counter);
+    ctx->launches++;
+    return perft_rec(ctx, next, (size_t)total, depth - 1, level + 1, err, ms_last, n_last);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static void pos_from_wire(const szb_pos& w, Pos& p) {
+    memset(&p, 0, sizeof p);
+    for (int t = 0; t < 6; t++) {
+        p.bb[BB_P + t] = w.pieces[t] | w.pieces[6 + t];
+        p.bb[BB_WHITE] |= w.pieces[t];
+        p.bb[BB_BLACK] |= w.pieces[6 + t];
+    }
+    p.flags = (uint8_t)((w.turn ? F_WHITE : 0) | (w.chess960 ? F_960 : 0));
+    p.rights_w = w.castling_w; p.rights_b = w.castling_b;
+    p.ep = w.ep_square;
+    p.halfmove = (uint8_t)std::min<int>(w.halfmove_clock, 250);
+    p.ply = w.ply;
+    p.prev = NO_PREV;
+}
+
+extern "C" {
+
+const char* szb_version(void) { return "szb200 0.1 (sm_100a)"; }
+
+const char* szb_last_error(const szb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void* szb_stream(szb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int szb_synchronize(szb_ctx* ctx) {
+    if (!ctx) return SZB_ERR_ARG;
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void szb_destroy(szb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    net_destroy(ctx);
+    for (void* p : ctx->allocs) cudaFree(p);
+    for (Pos* p : ctx->perft_levels) if (p) cudaFree(p);
+    if (ctx->perft_counter) cudaFree(ctx->perft_counter);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
+    if (!out || !cfg || cfg->max_games <= 0 || cfg->max_searches <= 0 || cfg->max_searches > 65000) return SZB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return SZB_ERR_CUDA;
+    szb_ctx* ctx = new szb_ctx();
+    ctx->device = device;
+    ctx->cfg = *cfg;
+    if (ctx->cfg.edges_per_node <= 0) ctx->cfg.edges_per_node = 48;
+    *out = ctx;        // returned even on failure so the caller can read the message, then destroy
+    SZB_CUDA(ctx, cudaSetDevice(device));
+    SZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    Dev& d = ctx->d;
+    const size_t G = (size_t)cfg->max_games;
+    d.nodes_per_game = cfg->max_searches + 1;
+    d.pool_stride = RING + d.nodes_per_game + 1;
+    d.n_games = 0;
+    const size_t NN = G * (size_t)d.nodes_per_game;
+    d.edge_cap = (unsigned long long)NN * (unsigned long long)ctx->cfg.edges_per_node;
+    build_tables(ctx->host_tables);
+    Tables* dt = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &dt, 1))) return rc;
+    SZB_CUDA(ctx, cudaMemcpyAsync(dt, &ctx->host_tables, sizeof(Tables), cudaMemcpyHostToDevice, ctx->stream));
+    d.tables = dt;
+#define A(field, count) if ((rc = dev_alloc(ctx, &d.field, (count)))) return rc
+    A(pool, G * (size_t)d.pool_stride);
+    A(cur, G);
+    A(node_edge0, NN); A(node_nchild, NN); A(node_pedge, NN); A(node_pnode, NN); A(node_term, NN); A(node_tval, NN);
+    A(node_count, G); A(root_n, G); A(root_w, G);
+    A(e_n, d.edge_cap); A(e_w, d.edge_cap); A(e_p, d.edge_cap); A(e_move, d.edge_cap); A(e_child, d.edge_cap);
+    A(edge_top, 1); A(error_flag, 1);
+    A(sel_node, G); A(sel_edge, G); A(need_eval, G); A(leaf_value, G);
+    A(planes, G * PLANE_STRIDE); A(mask, G * MASK_STRIDE);
+    A(policy, G * N_ACTIONS); A(value, G); A(root_val, G);
+    A(stats, 8);
+#undef A
+    if ((rc = dev_alloc(ctx, &ctx->d_moves, G + 1))) return rc;
+    SZB_CUDA(ctx, cudaMalloc((void**)&ctx->perft_counter, sizeof(unsigned long long)));
+    ctx->perft_cap = (size_t)4 << 20;      // positions per breadth-first level buffer (384 MiB)
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int games_upload(szb_ctx* ctx, int n, const std::vector<Pos>& start) {
+    Dev& d = ctx->d;
+    Pos* st = (Pos*)ctx_stage(ctx, sizeof(Pos) * (size_t)n);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    SZB_CUDA(ctx, cudaMemcpyAsync(st, start.data(), sizeof(Pos) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    d.n_games = n;
+    k_games_init<<<(n + 31) / 32, 32, 0, ctx->stream>>>(d, st, n);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int szb_games_reset(szb_ctx* ctx, int32_t n, const int16_t* start_id) {
+    if (!ctx || n <= 0 || n > ctx->cfg.max_games) return fail(ctx, SZB_ERR_ARG, "szb_games_reset: n_games out of range");
+    std::vector<Pos> start((size_t)n);
+    for (int g = 0; g < n; g++) {
+        int id = start_id ? start_id[g] : -1;
+        if (id > 959) return fail(ctx, SZB_ERR_ARG, "chess960 position index not 0 <= %d <= 959", id);
+        memset(&start[g], 0, sizeof(Pos));
+        start_position(ctx->host_tables, id, start[g]);
+    }
+    return games_upload(ctx, n, start);
+}
+
+int szb_games_set(szb_ctx* ctx, int32_t n, const szb_pos* positions) {
+    if (!ctx || !positions || n <= 0 || n > ctx->cfg.max_games) return fail(ctx, SZB_ERR_ARG, "szb_games_set: bad arguments");
+    std::vector<Pos> start((size_t)n);
+    for (int g = 0; g < n; g++) pos_from_wire(positions[g], start[g]);
+    return games_upload(ctx, n, start);
+}
+
+int szb_games_push(szb_ctx* ctx, int32_t n, const int32_t* game, const uint16_t* move_index, int32_t* status) {
+    if (!ctx || n <= 0 || !move_index) return fail(ctx, SZB_ERR_ARG, "szb_games_push: bad arguments");
+    if (ctx->d.n_games == 0) return fail(ctx, SZB_ERR_STATE, "no games");
+    const size_t bytes = (size_t)n * (4 + 2 + 4) + 64;
+    char* st = (char*)ctx_stage(ctx, bytes);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    int32_t* d_status = (int32_t*)st;
+    int32_t* d_game = (int32_t*)(st + 4 * (size_t)n);
+    uint16_t* d_idx = (uint16_t*)(st + 8 * (size_t)n);
+    if (game) SZB_CUDA(ctx, cudaMemcpyAsync(d_game, game, 4 * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(d_idx, move_index, 2 * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    k_games_push<<<(n + 31) / 32, 32, 0, ctx->stream>>>(ctx->d, n, game ? d_game : nullptr, d_idx, d_status);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    std::vector<int32_t> h((size_t)n);
+    SZB_CUDA(ctx, cudaMemcpyAsync(h.data(), d_status, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (status) SZB_CUDA(ctx, cudaMemcpy(status, h.data(), 4 * (size_t)n, cudaMemcpyDefault));
+    for (int i = 0; i < n; i++)
+        if (h[i] != 0) return fail(ctx, h[i], "Invalid move (entry %d)", i);
+    return 0;
+}
+
+int szb_games_get(szb_ctx* ctx, int32_t n, const int32_t* game, szb_pos* out) {
+    if (!ctx || n <= 0 || !out) return fail(ctx, SZB_ERR_ARG, "szb_games_get: bad arguments");
+    char* st = (char*)ctx_stage(ctx, (size_t)n * (sizeof(szb_pos) + 4));
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    szb_pos* d_out = (szb_pos*)st;
+    int32_t* d_game = (int32_t*)(st + sizeof(szb_pos) * (size_t)n);
+    if (game) SZB_CUDA(ctx, cudaMemcpyAsync(d_game, game, 4 * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    k_games_get<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->d, n, game ? d_game : nullptr, d_out);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    SZB_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(szb_pos) * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int encode_common(szb_ctx* ctx, int32_t n, const int32_t* game, uint16_t* index_out, uint16_t* count_out,
+                         uint64_t* planes_out, uint64_t* mask_out) {
+    if (!ctx || n <= 0) return fail(ctx, SZB_ERR_ARG, "bad arguments");
+    if (ctx->d.n_games == 0) return fail(ctx, SZB_ERR_STATE, "no games");
+    const size_t b_game = 4 * (size_t)n, b_idx = index_out ? 2 * (size_t)n * SZB_MAX_MOVES : 0, b_cnt = count_out ? 2 * (size_t)n : 0;
+    const size_t b_pl = planes_out ? 8 * (size_t)n * N_PLANES : 0, b_mk = mask_out ? 8 * (size_t)n * MASK_WORDS : 0;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char* st = (char*)ctx_stage(ctx, up(b_game) + up(b_idx) + up(b_cnt) + up(b_pl) + up(b_mk) + 256);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    int32_t* d_game = (int32_t*)st; st += up(b_game);
+    uint16_t* d_idx = (uint16_t*)st; st += up(b_idx);
+    uint16_t* d_cnt = (uint16_t*)st; st += up(b_cnt);
+    uint64_t* d_pl = (uint64_t*)st; st += up(b_pl);
+    uint64_t* d_mk = (uint64_t*)st;
+    if (game) SZB_CUDA(ctx, cudaMemcpyAsync(d_game, game, b_game, cudaMemcpyDefault, ctx->stream));
+    k_games_encode<<<(n + 31) / 32, 32, 0, ctx->stream>>>(ctx->d, n, game ? d_game : nullptr, index_out ? d_idx : nullptr,
+                                                        count_out ? d_cnt : nullptr, planes_out ? d_pl : nullptr,
+                                                        mask_out ? d_mk : nullptr);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    if (index_out) SZB_CUDA(ctx, cudaMemcpyAsync(index_out, d_idx, b_idx, cudaMemcpyDefault, ctx->stream));
+    if (count_out) SZB_CUDA(ctx, cudaMemcpyAsync(count_out, d_cnt, b_cnt, cudaMemcpyDefault, ctx->stream));
+    if (planes_out) SZB_CUDA(ctx, cudaMemcpyAsync(planes_out, d_pl, b_pl, cudaMemcpyDefault, ctx->stream));
+    if (mask_out) SZB_CUDA(ctx, cudaMemcpyAsync(mask_out, d_mk, b_mk, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int szb_legal_moves(szb_ctx* ctx, int32_t n, const int32_t* game, uint16_t* index_out, uint16_t* count_out) {
+    return encode_common(ctx, n, game, index_out, count_out, nullptr, nullptr);
+}
+
+int szb_encode(szb_ctx* ctx, int32_t n, const int32_t* game, uint64_t* planes_out, uint64_t* mask_out) {
+    return encode_common(ctx, n, game, nullptr, nullptr, planes_out, mask_out);
+}
+
+int szb_unpack_planes_f32(szb_ctx* ctx, int32_t n, const uint64_t* planes_dev, float* out_dev) {
+    if (!ctx || n <= 0 || !planes_dev || !out_dev) return fail(ctx, SZB_ERR_ARG, "bad arguments");
+    const size_t total = (size_t)n * N_PLANES * 64;
+    k_unpack_planes_f32<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(n, planes_dev, out_dev);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int szb_perft_timed(szb_ctx* ctx, const szb_pos* pos, int32_t depth, uint64_t* nodes_out, float* ms_last_level,
+                    uint64_t* positions_last_level) {
+    if (!ctx || !pos || !nodes_out || depth < 0) return fail(ctx, SZB_ERR_ARG, "szb_perft: bad arguments");
+    if (depth == 0) { *nodes_out = 1; return 0; }
+    Pos p;
+    pos_from_wire(*pos, p);
+    finish_setup(ctx->host_tables, p);
+    while (ctx->perft_levels.size() < 1) ctx->perft_levels.push_back(nullptr);
+    if (!ctx->perft_levels[0]) SZB_CUDA(ctx, cudaMalloc((void**)&ctx->perft_levels[0], ctx->perft_cap * sizeof(Pos)));
+    SZB_CUDA(ctx, cudaMemcpyAsync(ctx->perft_levels[0], &p, sizeof p, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t err = cudaSuccess;
+    float ms = 0;
+    uint64_t nl = 0;
+    uint64_t total = perft_rec(ctx, ctx->perft_levels[0], 1, depth, 0, &err, ms_last_level ? &ms : nullptr, &nl);
+    if (err != cudaSuccess) return cuda_fail(ctx, err, "perft");
+    *nodes_out = total;
+    if (ms_last_level) *ms_last_level = ms;
+    if (positions_last_level) *positions_last_level = nl;
+    return 0;
+}
+
+int szb_perft(szb_ctx* ctx, const szb_pos* pos, int32_t depth, uint64_t* nodes_out) {
+    return szb_perft_timed(ctx, pos, depth, nodes_out, nullptr, nullptr);
+}
+
+// ---- search ------------------------------------------------------------------------------------
+static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning, int evaluator) {
+    Dev& d = ctx->d;
+    const int G = d.n_games;
+    if (G == 0) return fail(ctx, SZB_ERR_STATE, "no games");
+    if (num_searches < 1 || num_searches > ctx->cfg.max_searches)
+        return fail(ctx, SZB_ERR_ARG, "num_searches %d outside [1, max_searches=%d]", num_searches, ctx->cfg.max_searches);
+    cudaStream_t st = ctx->stream;
+    SZB_CUDA(ctx, cudaMemsetAsync(d.error_flag, 0, sizeof(int32_t), st));
+    k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d);
+    ctx->launches++;
+    const int warp_blocks = (G * 32 + 127) / 128;
+    for (int s = 0; s < num_searches; s++) {
+        k_select<<<warp_blocks, 128, 0, st>>>(d, c_puct);
+        k_expand<<<(G + 31) / 32, 32, 0, st>>>(d);
+        ctx->launches += 2;
+        if (evaluator == SZB_EVAL_HASH) {
+            k_hash_eval<<<G, 128, 0, st>>>(d);
+            ctx->launches++;
+        } else {
+            int rc = net_evaluate_batch(ctx, evaluator, G);
+            if (rc) return rc;
+        }
+        k_finish<<<warp_blocks, 128, 0, st>>>(d, learning);
+        ctx->launches++;
+    }
+    SZB_CUDA(ctx, cudaGetLastError());
+    int32_t flag = 0;
+    unsigned long long top = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(&flag, d.error_flag, sizeof flag, cudaMemcpyDeviceToHost, st));
+    SZB_CUDA(ctx, cudaMemcpyAsync(&top, d.edge_top, sizeof top, cudaMemcpyDeviceToHost, st));
+    SZB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->edges_high_water = std::max<uint64_t>(ctx->edges_high_water, top);
+    if (flag) return fail(ctx, flag, "tree arena exhausted (%llu edges): raise szb_config.edges_per_node", d.edge_cap);
+    return 0;
+}
+
+int szb_search(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
+               uint32_t* visits_out, uint64_t* child_mask_out, float* root_value_out) {
+    if (!ctx) return SZB_ERR_ARG;
+    int rc = run_search(ctx, num_searches, c_puct, learning, evaluator);
+    if (rc) return rc;
+    Dev& d = ctx->d;
+    const size_t G = (size_t)d.n_games;
+    const size_t b_v = visits_out ? G * N_ACTIONS * 4 : 0, b_m = child_mask_out ? G * MASK_WORDS * 8 : 0, b_r = root_value_out ? G * 4 : 0;
+    if (b_v + b_m + b_r == 0) return 0;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char* st = (char*)ctx_stage(ctx, up(b_v) + up(b_m) + up(b_r) + 256);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    uint32_t* d_v = (uint32_t*)st; st += up(b_v);
+    uint64_t* d_m = (uint64_t*)st; st += up(b_m);
+    float* d_r = (float*)st;
+    k_collect<<<(unsigned)((G * 32 + 127) / 128), 128, 0, ctx->stream>>>(d, visits_out ? d_v : nullptr, child_mask_out ? d_m : nullptr,
+                                                                       root_value_out ? d_r : nullptr);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    if (visits_out) SZB_CUDA(ctx, cudaMemcpyAsync(visits_out, d_v, b_v, cudaMemcpyDefault, ctx->stream));
+    if (child_mask_out) SZB_CUDA(ctx, cudaMemcpyAsync(child_mask_out, d_m, b_m, cudaMemcpyDefault, ctx->stream));
+    if (root_value_out) SZB_CUDA(ctx, cudaMemcpyAsync(root_value_out, d_r, b_r, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
+                     uint64_t seed, int32_t sample, int32_t* moves_out, int32_t* n_active_out) {
+    if (!ctx) return SZB_ERR_ARG;
+    int rc = run_search(ctx, num_searches, c_puct, learning, evaluator);
+    if (rc) return rc;
+    Dev& d = ctx->d;
+    const int G = d.n_games;
+    int32_t* d_active = ctx->d_moves + ctx->cfg.max_games;
+    SZB_CUDA(ctx, cudaMemsetAsync(d_active, 0, sizeof(int32_t), ctx->stream));
+    k_pick<<<(G + 127) / 128, 128, 0, ctx->stream>>>(d, seed, sample, ctx->d_moves);
+    k_push_picked<<<(G + 31) / 32, 32, 0, ctx->stream>>>(d, ctx->d_moves, d_active);
+    ctx->launches += 2;
+    SZB_CUDA(ctx, cudaGetLastError());
+    if (moves_out) SZB_CUDA(ctx, cudaMemcpyAsync(moves_out, ctx->d_moves, 4 * (size_t)G, cudaMemcpyDefault, ctx->stream));
+    int32_t act = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(&act, d_active, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_active_out) *n_active_out = act;
+    return 0;
+}
+
+int szb_get_stats(szb_ctx* ctx, szb_stats* out) {
+    if (!ctx || !out) return SZB_ERR_ARG;
+    unsigned long long h[8];
+    SZB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d.stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->simulations = h[0];
+    out->evaluations = h[1];
+    out->terminal_visits = h[2];
+    out->max_depth = h[3];
+    out->edges_allocated = ctx->edges_high_water;
+    out->kernel_launches = ctx->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// engine.cuh -- context layout shared by engine.cu (games, tree, search, perft) and net.cu (network).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/szb200.h"
+#include "chess.cuh"
+#include "tree.cuh"
+
+namespace szb {
+
+constexpr int RING = 256;                  // real-game positions kept per game (repetition walk <= 150 plies)
+constexpr int PLANE_STRIDE = 120;          // uint64 per packed plane row (119 + 1 pad, 16-byte aligned rows)
+constexpr int MASK_STRIDE = 80;            // uint64 per legal-mask row (73 + pad)
+constexpr uint16_t NO_CHILD = 0xFFFF;
+
+struct Net;                                // net.cu
+
+// Device pointers of one context.  Passed to kernels by value.
+struct Dev {
+    // ---- games --------------------------------------------------------------------------------
+    Pos* pool;               // [max_games][pool_stride]: slots [0,RING) real game ring, RING+i = tree node i
+    int32_t* cur;            // [max_games] ring slot of the current position
+    const Tables* tables;
+    int pool_stride;
+    int n_games;
+    // ---- tree: visited nodes (one per simulation) -------------------------------------------------
+    int nodes_per_game;      // max_searches + 1
+    int32_t* node_edge0;     // first child edge (global index)
+    uint16_t* node_nchild;
+    int32_t* node_pedge;     // edge that leads here, -1 for the root
+    uint16_t* node_pnode;
+    uint8_t* node_term;      // terminal position
+    float* node_tval;        // its value: -1 mated, 0 draw
+    int32_t* node_count;     // [max_games] last node index in use
+    int32_t* root_n;         // [max_games] root.visit_count (starts at 1, mcts.py:46)
+    double* root_w;
+    // ---- tree: edges (one per child of every expanded node), structure of arrays ---------------
+    int32_t* e_n;            // child.visit_count
+    double* e_w;             // child.value_sum
+    float* e_p;              // child.prior
+    uint16_t* e_move;        // policy index of child.action_taken
+    uint16_t* e_child;       // visited-node index or NO_CHILD
+    unsigned long long edge_cap;
+    unsigned long long* edge_top;
+    int32_t* error_flag;
+    // ---- per simulation step ------------------------------------------------------------------
+    int32_t* sel_node;       // leaf (or, before expansion, its parent)
+    int32_t* sel_edge;       // edge to create a node for, -1 when the leaf already exists
+    uint8_t* need_eval;
+    float* leaf_value;
+    uint64_t* planes;        // [max_games][PLANE_STRIDE]
+    uint64_t* mask;          // [max_games][MASK_STRIDE]
+    float* policy;           // [max_games][4672] evaluator output ("softmax over everything")
+    float* value;            // [max_games]
+    float* root_val;         // [max_games] evaluator value of the root position
+    unsigned long long* stats;   // simulations, evaluations, terminal visits, max depth
+};
+
+}  // namespace szb
+
+struct szb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    szb_config cfg{};
+    szb::Dev d{};
+    szb::Tables host_tables;
+    std::vector<void*> allocs;
+    uint64_t launches = 0;
+    uint64_t edges_high_water = 0;
+    // perft scratch (lazy)
+    std::vector<szb::Pos*> perft_levels;
+    size_t perft_cap = 0;
+    unsigned long long* perft_counter = nullptr;
+    // staging (lazy, grown on demand)
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // network (net.cu)
+    szb::Net* net = nullptr;
+    // self-play records
+    int32_t* d_moves = nullptr;
+};
+
+namespace szb {
+int fail(szb_ctx* ctx, int code, const char* fmt, ...);
+int cuda_fail(szb_ctx* ctx, cudaError_t e, const char* what);
+void* ctx_stage(szb_ctx* ctx, size_t bytes);
+// net.cu: evaluate the rows of d.planes with need_eval set -> d.policy / d.value (softmax policy).
+int net_evaluate_batch(szb_ctx* ctx, int evaluator, int n);
+void net_destroy(szb_ctx* ctx);
+}  // namespace szb
+
+#define SZB_CUDA(ctx, call)                                             \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return szb::cuda_fail(ctx, _e, #call);   \
+    } while (0)

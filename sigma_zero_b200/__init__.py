@@ -1,0 +1,8 @@
+"""Import alias: the package directory is `sigma-zero_b200/` (not a valid Python identifier), so this stub
+makes it importable as `sigma_zero_b200` by pointing the package search path at it."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "sigma-zero_b200")
+__path__.insert(0, _real)
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

@@ -1,0 +1,117 @@
+"""GPU parity: batched MCTS (tree kernels + in-tree move generation + plane encoding) against the reference
+search.  With the integer-hash evaluator both sides see bit-identical "network" outputs, so visit counts and
+child sets must agree exactly (mcts.py:39-122 semantics incl. the zero-prior drop and the constant noise)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hash_eval, ref_path
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from sigma_zero_b200.engine import Engine
+    e = Engine(max_games=256, max_searches=800)
+    yield e
+    e.close()
+
+
+def _check(eng, games, n, C, learning, visits, child, tag=""):
+    from sigma_zero_b200.engine import child_indices
+    for g, og in enumerate(games):
+        _, root = ref_path.search(og, n, C, hash_eval.evaluator, learning=learning)
+        exp_idx = [c.index for c in root.children]
+        exp_n = [c.n for c in root.children]
+        got_idx = list(child_indices(child[g]))
+        assert got_idx == exp_idx, (tag, g)
+        assert visits[g, exp_idx].tolist() == exp_n, (tag, g)
+        assert int(visits[g].sum()) == sum(exp_n)
+
+
+def test_search_golden_visit_counts(eng, golden_dir):
+    """the 50 cases recorded from the UNMODIFIED reference MCTS0.search (tests/golden/search.npz)"""
+    from sigma_zero_b200.engine import EVAL_HASH, child_indices
+    z = np.load(os.path.join(golden_dir, "search.npz"))
+    off = np.concatenate([[0], np.cumsum(z["idx_len"])])
+    groups = {}
+    for i in range(len(z["sid"])):
+        groups.setdefault((int(z["n"][i]), float(z["C"][i]), bool(z["learning"][i])), []).append(i)
+    for (n, C, learning), members in groups.items():
+        specs = [(bool(z["c960"][i]), int(z["sid"][i]), str(z["moves"][i]).split()) for i in members]
+        util.setup_games(eng, specs)
+        visits, child, _ = eng.search(n, C, learning, EVAL_HASH)
+        for k, i in enumerate(members):
+            exp_idx = z["idx_flat"][off[i]:off[i + 1]].astype(np.int64)
+            assert np.array_equal(child_indices(child[k]), exp_idx), (i, n, C, learning)
+            assert np.array_equal(visits[k, exp_idx], z["visits_flat"][off[i]:off[i + 1]].astype(np.uint32)), i
+
+
+@pytest.mark.parametrize("learning", [False, True])
+def test_search_800_sims_vs_live_oracle(eng, learning):
+    """config-c2-shaped search (800 simulations, C=2) on a handful of games, vanilla and Chess960, mid-game"""
+    from sigma_zero_b200.engine import EVAL_HASH
+    rng = np.random.default_rng(9 + learning)
+    specs = []
+    for g in range(4):
+        c960 = g % 2 == 1
+        sid = int(rng.integers(960)) if c960 else 518
+        og = util.oracle_game(c960, sid)
+        moves = []
+        for _ in range(int(rng.integers(0, 40))):
+            legal = list(og.board.legal_moves)
+            if not legal or og.board.outcome() is not None:
+                break
+            m = legal[rng.integers(len(legal))]
+            moves.append(m.uci())
+            og.move_piece(m)
+        if og.board.outcome() is not None:
+            moves = moves[:-2]
+        specs.append((c960, sid, moves))
+    games = util.setup_games(eng, specs)
+    visits, child, _ = eng.search(800, 2.0, learning, EVAL_HASH)
+    _check(eng, games, 800, 2, learning, visits, child, "800")
+    st = eng.stats()
+    assert st["simulations"] >= 800 * len(specs)
+
+
+def test_selfplay_teacher_forced(eng):
+    """self-play plies on the GPU (search -> sample -> push); at every ply the oracle, fed the move the GPU
+    chose, must reproduce the position, and a fresh oracle search must reproduce the visit counts"""
+    from sigma_zero_b200.engine import EVAL_HASH
+    specs = [(False, 518, []), (True, 3, []), (True, 944, []), (False, 518, ["g2g4", "e7e5", "f2f3"])]
+    games = util.setup_games(eng, specs)
+    n = 48
+    for ply in range(12):
+        visits, child, _ = eng.search(n, 2.0, True, EVAL_HASH)
+        _check(eng, games, n, 2, True, visits, child, "ply%d" % ply)
+        moves, active = eng.selfplay_ply(n, 2.0, True, EVAL_HASH, seed=1234, sample=True)
+        for g, og in enumerate(games):
+            if og.board.outcome() is not None:
+                assert moves[g] == -1
+                continue
+            assert visits[g, moves[g]] > 0                  # sampled proportionally to visits => never an unvisited child
+            qp = {(m.from_square, m.to_square) for m in og.board.legal_moves if m.promotion == 5}
+            og.move_piece(ref_path.index_to_move(int(moves[g]), og.board.turn, qp))
+        planes, _ = eng.encode()
+        for g, og in enumerate(games):
+            assert np.array_equal(planes[g], hash_eval.pack_planes(og.get_representation()))
+
+
+def test_terminal_root_and_single_search(eng):
+    """search on a finished game returns no children (mcts.py:113-122 with an empty child list); num_searches=1
+    leaves every child at zero visits"""
+    from sigma_zero_b200 import _lib
+    from sigma_zero_b200.engine import EVAL_HASH
+    import chess
+    mate = chess.Board("7k/6Q1/6K1/8/8/8/8/8 b - - 0 1")
+    start = chess.Board()
+    eng.set_positions([util.wire_pos(mate, _lib), util.wire_pos(start, _lib)])
+    visits, child, _ = eng.search(10, 2.0, False, EVAL_HASH)
+    assert visits[0].sum() == 0 and child[0].sum() == 0
+    assert visits[1].sum() == 9
+    visits, child, _ = eng.search(1, 2.0, False, EVAL_HASH)
+    assert visits[1].sum() == 0 and child[1].sum() != 0
