@@ -1,12 +1,822 @@
-// net.cu -- placeholder until the network kernels land (next commit).
+// net.cu -- the policy/value network (network.py:89-192) as hand-written sm_100a kernels.
+//
+//   bf16 path : every convolution is an implicit GEMM on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor)
+//               stages activation windows and weight tiles in shared memory with 128-byte swizzle, one elected
+//               thread issues tcgen05.mma (128 x N x 16, bf16 in / fp32 accumulate in TMEM), four epilogue warps
+//               read the accumulator back with tcgen05.ld and fuse +bias(BN folded) [+residual] -> ReLU -> bf16.
+//               Warp-specialised persistent CTAs, 4-stage smem ring, double-buffered TMEM accumulator.
+//   fp32 path : SIMT FFMA implicit GEMM with the same folded weights (parity mode, <= 1e-5 abs vs torch CPU).
+//
+// Activations live in HBM as NHWC with a one-square zero halo: [B][10][10][C]; the nine taps of a 3x3
+// convolution are then plain shifted TMA boxes.  GEMM view: M = 64*B (board squares), N = C_out, K = taps*C_in.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <string>
 #include "engine.cuh"
+
 using namespace szb;
+
 namespace szb {
-int net_evaluate_batch(szb_ctx* ctx, int, int) { return fail(ctx, SZB_ERR_STATE, "network weights not loaded"); }
-void net_destroy(szb_ctx*) {}
+
+constexpr int HALO = 10;
+constexpr int C_TOWER = 256;
+constexpr int C_IN_PAD = 128;            // 119 input planes padded to 128 channels
+constexpr int N_BLOCKS = 19;
+constexpr int POLICY_PLANES = 73;
+constexpr int POLICY_PAD = 80;           // N of the last policy GEMM (multiple of 16)
+
+// ---- tcgen05 conv kernel geometry ---------------------------------------------------------------
+constexpr int TC_BLOCK_M = 128;          // two boards per tile
+constexpr int TC_BLOCK_K = 64;           // one 128-byte swizzle atom of bf16
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;       // 16 KiB
+constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr long long TC_TIMEOUT_CYCLES = 4000000000ll;          // ~2 s: a stuck pipeline flags an error instead of hanging the GPU
+
+struct ConvLayer {
+    int taps = 9, cin = 256, cout = 256, cout_pad = 256;
+    float* w32 = nullptr;                // [taps][cin][cout_pad]
+    float* bias = nullptr;               // [cout_pad]  (BatchNorm folded)
+    __nv_bfloat16* w16 = nullptr;        // [cout_pad][taps*cin]  K-major
+    CUtensorMap tm_w;
+};
+
+struct Net {
+    bool loaded = false;
+    int cap = 0;                         // boards the activation buffers hold (even)
+    ConvLayer stem, tower[2 * N_BLOCKS], p1, p2;
+    // value head (fp32 everywhere)
+    float* v_w = nullptr;                // [256] conv_v1 * bn scale
+    float v_b = 0.f;
+    float* fc1_w = nullptr;              // [256][64]
+    float* fc1_b = nullptr;              // [256]
+    float* fc2_w = nullptr;              // [256]
+    float fc2_b = 0.f;
+    // activations
+    __nv_bfloat16* in16 = nullptr;       // [cap][10][10][128]
+    __nv_bfloat16* act16[3] = {nullptr, nullptr, nullptr};     // [cap][10][10][256]
+    float* in32 = nullptr;
+    float* act32[3] = {nullptr, nullptr, nullptr};
+    float* logits = nullptr;             // [cap][4672]
+    CUtensorMap tm_in16, tm_act16[3];
+    int32_t* tc_error = nullptr;
+    int num_sms = 148;
+    std::vector<void*> allocs;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode(szb_ctx* ctx) {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    g_encode = (EncodeTiledFn)fn;
+    return 0;
 }
+
+// activations [B][10][10][C] bf16: box = 64 channels x 8 x 8 x 2 boards, 128B swizzle
+static int make_act_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, int boards) {
+    cuuint64_t dims[4] = {(cuuint64_t)channels, HALO, HALO, (cuuint64_t)boards};
+    cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * HALO, (cuuint64_t)channels * 2 * HALO * HALO};
+    cuuint32_t box[4] = {TC_BLOCK_K, 8, 8, 2};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+    return 0;
+}
+// weights [cout_pad][K] bf16: box = 64 k x cout_pad rows
+static int make_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int cout_pad) {
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {TC_BLOCK_K, (cuuint32_t)cout_pad};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return 0;
+}
+
+// =================================================================================================
+// PTX wrappers
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: returns false (and raises the flag) instead of spinning forever
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if (*abort_flag) return false;
+        if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; return false; }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1, layout type 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// =================================================================================================
+// tcgen05 implicit-GEMM convolution
+// =================================================================================================
+struct TcArgs {
+    int n_tiles;                 // ceil(B / 2)
+    int taps;                    // 9 or 1
+    int kchunks;                 // C_in / 64
+    const float* bias;           // [N]
+    const __nv_bfloat16* residual;   // halo NHWC [.][10][10][256] or null
+    __nv_bfloat16* out;          // halo NHWC (mode 0)
+    float* logits;               // [B][4672] (mode 1)
+    int n_boards;                // rows beyond this are not stored
+    int relu;
+    int32_t* error;
+};
+
+template <int N_TILE, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TcArgs a) {
+    constexpr int B_BYTES = N_TILE * TC_BLOCK_K * 2;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    constexpr int ACC_COLS = 256;                                // column stride between the two accumulator stages
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+    __shared__ float bias_sh[N_TILE];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    volatile int* abort_flag = &abort_sh;
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&bar_acc_full[s]), 1); mbar_init(smem_u32(&bar_acc_empty[s]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < N_TILE; i += blockDim.x) bias_sh[i] = a.bias[i];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    const int k_iters = a.taps * a.kchunks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x) {
+                for (int it = 0; it < k_iters; it++) {
+                    const int tap = it / a.kchunks, kc = it - tap * a.kchunks;
+                    const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
+                    if (!(ok = mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag))) break;
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    tma_load_4d(sa, &tm_a, full, kc * TC_BLOCK_K, kx, ky, tile * 2);
+                    tma_load_2d(sa + TC_A_BYTES, &tm_w, full, it * TC_BLOCK_K, 0);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x, local++) {
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                if (!(ok = mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int it = 0; it < k_iters; it++) {
+                    if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / 16; k++) {
+                        tc_mma_bf16(d_tmem, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it | k) != 0);
+                    }
+                    tc_commit(smem_u32(&bar_empty[stage]));        // frees the smem stage once these MMAs retire
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (ok) tc_commit(smem_u32(&bar_acc_full[acc]));
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> +bias [+residual] -> ReLU -> global =====
+        const int lane_group = warp & 3;                          // TMEM lanes this warp may read
+        int local = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x, local++) {
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            ok = mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase, abort_flag);
+            ok = __all_sync(0xFFFFFFFFu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            const int row = lane_group * 32 + lane;
+            const int m = tile * TC_BLOCK_M + row;
+            const int board = m >> 6, sq = m & 63;
+            const bool live = board < a.n_boards;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
+            const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + c0, v);
+                tmem_ld_wait();
+                if (MODE == 0) {
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + bias_sh[c0 + j];
+                    if (live) {
+                        if (a.residual) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + pix * C_TOWER + c0);
+                            uint4 r0 = rp[0], r1 = rp[1];
+                            const __nv_bfloat16* rb0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+                            const __nv_bfloat16* rb1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { f[j] += __bfloat162float(rb0[j]); f[8 + j] += __bfloat162float(rb1[j]); }
+                        }
+                        uint4 o[2];
+                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float x0 = f[2 * j], x1 = f[2 * j + 1];
+                            if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                            ob[j] = __floats2bfloat162_rn(x0, x1);
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(a.out + pix * C_TOWER + c0);
+                        op[0] = o[0];
+                        op[1] = o[1];
+                    }
+                } else {
+                    // policy logits, plane-major like torch.flatten(conv_p2(x)): index = plane*64 + row*8 + col
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const int c = c0 + j;
+                            if (c < POLICY_PLANES) a.logits[(size_t)board * N_ACTIONS + c * 64 + sq] = __uint_as_float(v[j]) + bias_sh[c];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+        }
+    }
+    // ===== teardown =====
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+    if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+}
+
+// =================================================================================================
+// fp32 SIMT convolution (parity path)
+// =================================================================================================
+struct F32Args {
+    const float* in;             // halo NHWC [B][10][10][cin]
+    const float* w;              // [taps][cin][cout_pad]
+    const float* bias;
+    const float* residual;       // halo NHWC [.][256] or null
+    float* out;                  // halo NHWC [.][256] (mode 0) / logits [B][4672] (mode 1)
+    int cin, cout_pad, taps, relu, mode;
+};
+
+// grid (B, cout_pad/64), 256 threads: thread = 4 squares x 4 output channels
+__global__ void __launch_bounds__(256) k_conv_f32(const F32Args a) {
+    __shared__ float in_s[HALO * HALO][33];
+    __shared__ __align__(16) float w_s[32][64];
+    const int b = blockIdx.x, co0 = blockIdx.y * 64;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int y = ty >> 1, x0 = (ty & 1) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    const float* inb = a.in + (size_t)b * HALO * HALO * a.cin;
+    for (int c0 = 0; c0 < a.cin; c0 += 32) {
+        __syncthreads();
+        for (int i = tid; i < HALO * HALO * 32; i += 256) {
+            const int pos = i >> 5, c = i & 31;
+            in_s[pos][c] = inb[(size_t)pos * a.cin + c0 + c];
+        }
+        for (int tap = 0; tap < a.taps; tap++) {
+            const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap % 3 : 1;
+            __syncthreads();
+            for (int i = tid; i < 32 * 64; i += 256) {
+                const int c = i >> 6, co = i & 63;
+                w_s[c][co] = a.w[((size_t)tap * a.cin + c0 + c) * a.cout_pad + co0 + co];
+            }
+            __syncthreads();
+            const int p0 = (y + ky) * HALO + x0 + kx;
+#pragma unroll 8
+            for (int c = 0; c < 32; c++) {
+                const float4 w = *reinterpret_cast<const float4*>(&w_s[c][tx * 4]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float v = in_s[p0 + i][c];
+                    acc[i][0] = fmaf(v, w.x, acc[i][0]);
+                    acc[i][1] = fmaf(v, w.y, acc[i][1]);
+                    acc[i][2] = fmaf(v, w.z, acc[i][2]);
+                    acc[i][3] = fmaf(v, w.w, acc[i][3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = x0 + i;
+        const size_t pix = ((size_t)b * HALO + y + 1) * HALO + x + 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int co = co0 + tx * 4 + j;
+            float v = acc[i][j] + a.bias[co];
+            if (a.mode == 0) {
+                if (a.residual) v += a.residual[pix * C_TOWER + co];
+                if (a.relu) v = fmaxf(v, 0.f);
+                a.out[pix * C_TOWER + co] = v;
+            } else if (co < POLICY_PLANES) {
+                a.out[(size_t)b * N_ACTIONS + co * 64 + y * 8 + x] = v;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// small fused kernels
+// =================================================================================================
+// bit-packed planes [B][stride] -> halo NHWC [B][10][10][128] (interior only; the halo stays zero)
+template <class T>
+__global__ void k_planes_to_nhwc(const uint64_t* planes, int stride, int n, T* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;        // (board, square, 8-channel group)
+    if (i >= (size_t)n * 64 * 16) return;
+    const int cg = (int)(i & 15), sq = (int)((i >> 4) & 63);
+    const size_t b = i >> 10;
+    const uint64_t* p = planes + b * stride;
+    T v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = cg * 8 + j;
+        const float f = c < N_PLANES ? (float)((p[c] >> sq) & 1ull) : 0.f;
+        if constexpr (sizeof(T) == 2) v[j] = __float2bfloat16(f); else v[j] = f;
+    }
+    T* o = out + (((size_t)b * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1) * C_IN_PAD + cg * 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j] = v[j];
+}
+
+// value head (network.py:156-174): conv1x1 256->1 (+BN, ReLU) -> fc 64->256 (ReLU) -> fc 256->1 -> tanh.  Block per board.
+template <class T>
+__global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v_w, float v_b, const float* fc1_w, const float* fc1_b,
+                                                    const float* fc2_w, float fc2_b, float* value, int n) {
+    __shared__ float plane[64];
+    __shared__ float red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int sq = tid >> 2, part = tid & 3;
+    const T* row = act + (((size_t)b * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1) * C_TOWER + part * 64;
+    float s = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 64; c++) {
+        float x;
+        if constexpr (sizeof(T) == 2) x = __bfloat162float(row[c]); else x = row[c];
+        s = fmaf(x, v_w[part * 64 + c], s);
+    }
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
+    if (part == 0) plane[sq] = fmaxf(s + v_b, 0.f);
+    __syncthreads();
+    float h = fc1_b[tid];
+#pragma unroll 8
+    for (int k = 0; k < 64; k++) h = fmaf(plane[k], fc1_w[tid * 64 + k], h);
+    h = fmaxf(h, 0.f) * fc2_w[tid];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, off);
+    if ((tid & 31) == 0) red[tid >> 5] = h;
+    __syncthreads();
+    if (tid == 0) {
+        float t = fc2_b;
+        for (int w = 0; w < 8; w++) t += red[w];
+        value[b] = tanhf(t);
+    }
+}
+
+// nn.Softmax(dim=1) over the 4672 logits of every board (network.py:190).  Block per board, fixed reduction order.
+__global__ void __launch_bounds__(256) k_softmax(const float* logits, float* policy, int n) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* l = logits + (size_t)b * N_ACTIONS;
+    float* p = policy + (size_t)b * N_ACTIONS;
+    float mx = -INFINITY;
+    for (int i = tid; i < N_ACTIONS; i += 256) mx = fmaxf(mx, l[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]); bcast = m; }
+    __syncthreads();
+    mx = bcast;
+    float e[(N_ACTIONS + 255) / 256];
+    float s = 0.f;
+    int k = 0;
+    for (int i = tid; i < N_ACTIONS; i += 256, k++) { e[k] = expf(l[i] - mx); s += e[k]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; w++) t += red[w]; bcast = t; }
+    __syncthreads();
+    const float tot = bcast;
+    k = 0;
+    for (int i = tid; i < N_ACTIONS; i += 256, k++) p[i] = __fdiv_rn(e[k], tot);
+}
+
+// =================================================================================================
+// host: weights
+// =================================================================================================
+static uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+template <class T>
+static int net_alloc(szb_ctx* ctx, Net* net, T** out, size_t count, bool zero = true) {
+    void* p = nullptr;
+    SZB_CUDA(ctx, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) SZB_CUDA(ctx, cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), ctx->stream));
+    net->allocs.push_back(p);
+    *out = (T*)p;
+    return 0;
+}
+
+struct BN { const float *g, *b, *m, *v; };
+
+// conv weight [cout][cin_src][kh][kw] (+ optional BN, + optional conv bias) -> folded device packs
+static int upload_conv(szb_ctx* ctx, Net* net, ConvLayer& L, const float* w, int cout, int cin_src, int cin, int taps, int cout_pad,
+                       const BN* bn, const float* conv_bias) {
+    L.taps = taps; L.cin = cin; L.cout = cout; L.cout_pad = cout_pad;
+    const int K = taps * cin;
+    std::vector<float> w32((size_t)taps * cin * cout_pad, 0.f), bias((size_t)cout_pad, 0.f);
+    std::vector<uint16_t> w16((size_t)cout_pad * K, 0);
+    for (int co = 0; co < cout; co++) {
+        double scale = 1.0, shift = conv_bias ? conv_bias[co] : 0.0;
+        if (bn) {
+            scale = (double)bn->g[co] / std::sqrt((double)bn->v[co] + 1e-5);
+            shift = (double)bn->b[co] - (double)bn->m[co] * scale;
+        }
+        bias[co] = (float)shift;
+        for (int ci = 0; ci < cin_src; ci++)
+            for (int t = 0; t < taps; t++) {
+                const float f = (float)((double)w[((size_t)co * cin_src + ci) * taps + t] * scale);
+                w32[((size_t)t * cin + ci) * cout_pad + co] = f;
+                w16[(size_t)co * K + (size_t)t * cin + ci] = f2bf(f);
+            }
+    }
+    int rc;
+    if ((rc = net_alloc(ctx, net, &L.w32, w32.size(), false))) return rc;
+    if ((rc = net_alloc(ctx, net, &L.bias, bias.size(), false))) return rc;
+    if ((rc = net_alloc(ctx, net, &L.w16, w16.size(), false))) return rc;
+    SZB_CUDA(ctx, cudaMemcpyAsync(L.w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(L.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(L.w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // host vectors die at scope exit
+    return make_w_map(ctx, &L.tm_w, L.w16, K, cout_pad);
+}
+
+void net_destroy(szb_ctx* ctx) {
+    if (!ctx->net) return;
+    for (void* p : ctx->net->allocs) cudaFree(p);
+    delete ctx->net;
+    ctx->net = nullptr;
+}
+
+static int net_alloc_activations(szb_ctx* ctx, Net* net) {
+    int rc;
+    const size_t cap = (size_t)net->cap;
+    if ((rc = net_alloc(ctx, net, &net->in16, cap * HALO * HALO * C_IN_PAD))) return rc;
+    if ((rc = net_alloc(ctx, net, &net->in32, cap * HALO * HALO * C_IN_PAD))) return rc;
+    for (int i = 0; i < 3; i++) {
+        if ((rc = net_alloc(ctx, net, &net->act16[i], cap * HALO * HALO * C_TOWER))) return rc;
+        if ((rc = net_alloc(ctx, net, &net->act32[i], cap * HALO * HALO * C_TOWER))) return rc;
+        if ((rc = make_act_map(ctx, &net->tm_act16[i], net->act16[i], C_TOWER, net->cap))) return rc;
+    }
+    if ((rc = make_act_map(ctx, &net->tm_in16, net->in16, C_IN_PAD, net->cap))) return rc;
+    if ((rc = net_alloc(ctx, net, &net->logits, cap * N_ACTIONS))) return rc;
+    if ((rc = net_alloc(ctx, net, &net->tc_error, 1))) return rc;
+    return 0;
+}
+
+// =================================================================================================
+// host: forward
+// =================================================================================================
+template <int N_TILE, int MODE>
+static int launch_tc(szb_ctx* ctx, Net* net, const CUtensorMap& tm_a, const ConvLayer& L, const __nv_bfloat16* residual,
+                     __nv_bfloat16* out, float* logits, int n, int relu) {
+    static bool attr_set = false;
+    constexpr int smem = TC_STAGES * (TC_A_BYTES + N_TILE * TC_BLOCK_K * 2) + 1024;
+    if (!attr_set) {
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_conv_tc<N_TILE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    TcArgs a;
+    a.n_tiles = (n + 1) / 2;
+    a.taps = L.taps;
+    a.kchunks = L.cin / TC_BLOCK_K;
+    a.bias = L.bias;
+    a.residual = residual;
+    a.out = out;
+    a.logits = logits;
+    a.n_boards = n;
+    a.relu = relu;
+    a.error = net->tc_error;
+    const int grid = std::min(a.n_tiles, net->num_sms);
+    k_conv_tc<N_TILE, MODE><<<grid, TC_THREADS, smem, ctx->stream>>>(tm_a, L.tm_w, a);
+    ctx->launches++;
+    return 0;
+}
+
+static void launch_f32(szb_ctx* ctx, const float* in, const ConvLayer& L, const float* residual, float* out, int n, int relu, int mode) {
+    F32Args a;
+    a.in = in; a.w = L.w32; a.bias = L.bias; a.residual = residual; a.out = out;
+    a.cin = L.cin; a.cout_pad = L.cout_pad; a.taps = L.taps; a.relu = relu; a.mode = mode;
+    k_conv_f32<<<dim3(n, L.cout_pad / 64), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+}
+
+// planes (device, row stride `stride` uint64) -> net->logits + value_out (device)
+static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t* planes, int stride, float* value_out) {
+    Net* net = ctx->net;
+    if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
+    if (n > net->cap) return fail(ctx, SZB_ERR_ARG, "batch %d exceeds capacity %d", n, net->cap);
+    cudaStream_t st = ctx->stream;
+    const unsigned up_blocks = (unsigned)(((size_t)n * 64 * 16 + 255) / 256);
+    if (evaluator == SZB_EVAL_NET_BF16) {
+        k_planes_to_nhwc<__nv_bfloat16><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in16);
+        ctx->launches++;
+        int rc;
+        if ((rc = launch_tc<256, 0>(ctx, net, net->tm_in16, net->stem, nullptr, net->act16[0], nullptr, n, 1))) return rc;
+        int x = 0;
+        for (int blk = 0; blk < N_BLOCKS; blk++) {
+            const int y = (x + 1) % 3, o = (x + 2) % 3;
+            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->tower[2 * blk], nullptr, net->act16[y], nullptr, n, 1))) return rc;
+            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[y], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1))) return rc;
+            x = o;
+        }
+        const int y = (x + 1) % 3;
+        if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->p1, nullptr, net->act16[y], nullptr, n, 1))) return rc;
+        if ((rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0))) return rc;
+        k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
+        ctx->launches++;
+    } else if (evaluator == SZB_EVAL_NET_FP32) {
+        k_planes_to_nhwc<float><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in32);
+        ctx->launches++;
+        launch_f32(ctx, net->in32, net->stem, nullptr, net->act32[0], n, 1, 0);
+        int x = 0;
+        for (int blk = 0; blk < N_BLOCKS; blk++) {
+            const int y = (x + 1) % 3, o = (x + 2) % 3;
+            launch_f32(ctx, net->act32[x], net->tower[2 * blk], nullptr, net->act32[y], n, 1, 0);
+            launch_f32(ctx, net->act32[y], net->tower[2 * blk + 1], net->act32[x], net->act32[o], n, 1, 0);
+            x = o;
+        }
+        const int y = (x + 1) % 3;
+        launch_f32(ctx, net->act32[x], net->p1, nullptr, net->act32[y], n, 1, 0);
+        launch_f32(ctx, net->act32[y], net->p2, nullptr, net->logits, n, 0, 1);
+        k_value_head<float><<<n, 256, 0, st>>>(net->act32[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
+        ctx->launches++;
+    } else {
+        return fail(ctx, SZB_ERR_ARG, "unknown evaluator %d", evaluator);
+    }
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int net_evaluate_batch(szb_ctx* ctx, int evaluator, int n) {
+    int rc = net_forward_device(ctx, evaluator, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value);
+    if (rc) return rc;
+    k_softmax<<<n, 256, 0, ctx->stream>>>(ctx->net->logits, ctx->d.policy, n);
+    ctx->launches++;
+    return 0;
+}
+
+static int check_tc_error(szb_ctx* ctx) {
+    int32_t flag = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->net->tc_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) return fail(ctx, SZB_ERR_CUDA, "tcgen05 convolution pipeline timed out (mbarrier wait exceeded its bound)");
+    return 0;
+}
+
+}  // namespace szb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
 extern "C" {
-int szb_net_load(szb_ctx* ctx, int32_t, const char* const*, const float* const*, const int64_t*) { return fail(ctx, SZB_ERR_UNSUPPORTED, "not built yet"); }
-int szb_net_forward(szb_ctx* ctx, int32_t, const uint64_t*, int32_t, float*, float*) { return fail(ctx, SZB_ERR_STATE, "network weights not loaded"); }
-int szb_net_forward_logits(szb_ctx* ctx, int32_t, const uint64_t*, int32_t, float*, float*) { return fail(ctx, SZB_ERR_STATE, "network weights not loaded"); }
+
+int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
+    if (!ctx || n_tensors <= 0 || !names || !data || !numel) return fail(ctx, SZB_ERR_ARG, "szb_net_load: bad arguments");
+    int rc;
+    if ((rc = get_encode(ctx))) return rc;
+    std::map<std::string, std::pair<const float*, int64_t>> sd;
+    for (int i = 0; i < n_tensors; i++) sd[names[i]] = {data[i], numel[i]};
+    auto get = [&](const std::string& k, int64_t want, const float** out) -> int {
+        auto it = sd.find(k);
+        if (it == sd.end()) return fail(ctx, SZB_ERR_ARG, "state_dict is missing '%s'", k.c_str());
+        if (it->second.second != want) return fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.second, (long long)want);
+        *out = it->second.first;
+        return 0;
+    };
+    auto get_bn = [&](const std::string& p, int c, BN* bn) -> int {
+        int r;
+        if ((r = get(p + ".weight", c, &bn->g))) return r;
+        if ((r = get(p + ".bias", c, &bn->b))) return r;
+        if ((r = get(p + ".running_mean", c, &bn->m))) return r;
+        return get(p + ".running_var", c, &bn->v);
+    };
+    net_destroy(ctx);
+    Net* net = new Net();
+    ctx->net = net;
+    cudaDeviceProp prop;
+    SZB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    net->num_sms = prop.multiProcessorCount;
+    net->cap = (ctx->cfg.max_games + 1) & ~1;
+
+    const float* w;
+    BN bn;
+    // stem: conv1 [256,119,3,3] + norm_layer
+    if ((rc = get("conv1.weight", 256LL * 119 * 9, &w)) || (rc = get_bn("norm_layer", 256, &bn))) return rc;
+    if ((rc = upload_conv(ctx, net, net->stem, w, 256, 119, C_IN_PAD, 9, 256, &bn, nullptr))) return rc;
+    for (int b = 0; b < N_BLOCKS; b++) {
+        for (int j = 0; j < 2; j++) {
+            const std::string p = "resnet_blocks." + std::to_string(b);
+            if ((rc = get(p + ".conv" + std::to_string(j + 1) + ".weight", 256LL * 256 * 9, &w))) return rc;
+            if ((rc = get_bn(p + ".bn" + std::to_string(j + 1), 256, &bn))) return rc;
+            if ((rc = upload_conv(ctx, net, net->tower[2 * b + j], w, 256, 256, 256, 9, 256, &bn, nullptr))) return rc;
+        }
+    }
+    if ((rc = get("conv_p1.weight", 256LL * 256, &w)) || (rc = get_bn("p_norm1", 256, &bn))) return rc;
+    if ((rc = upload_conv(ctx, net, net->p1, w, 256, 256, 256, 1, 256, &bn, nullptr))) return rc;
+    const float* pb;
+    if ((rc = get("conv_p2.weight", 73LL * 256, &w)) || (rc = get("conv_p2.bias", 73, &pb))) return rc;
+    // the fp32 kernel wants cout_pad % 64 == 0, the tcgen05 kernel reads POLICY_PAD rows: pad to 128 and map the first 80
+    if ((rc = upload_conv(ctx, net, net->p2, w, 73, 256, 256, 1, 128, nullptr, pb))) return rc;
+    if ((rc = make_w_map(ctx, &net->p2.tm_w, net->p2.w16, 256, POLICY_PAD))) return rc;
+    // value head
+    const float *vw, *f1w, *f1b, *f2w, *f2b;
+    if ((rc = get("conv_v1.weight", 256, &vw)) || (rc = get_bn("v_norm", 1, &bn))) return rc;
+    if ((rc = get("fc_v1.weight", 256LL * 64, &f1w)) || (rc = get("fc_v1.bias", 256, &f1b))) return rc;
+    if ((rc = get("fc_v2.weight", 256, &f2w)) || (rc = get("fc_v2.bias", 1, &f2b))) return rc;
+    {
+        const double scale = (double)bn.g[0] / std::sqrt((double)bn.v[0] + 1e-5);
+        std::vector<float> vws(256);
+        for (int c = 0; c < 256; c++) vws[c] = (float)((double)vw[c] * scale);
+        net->v_b = (float)((double)bn.b[0] - (double)bn.m[0] * scale);
+        net->fc2_b = f2b[0];
+        if ((rc = net_alloc(ctx, net, &net->v_w, 256, false)) || (rc = net_alloc(ctx, net, &net->fc1_w, 256 * 64, false)) ||
+            (rc = net_alloc(ctx, net, &net->fc1_b, 256, false)) || (rc = net_alloc(ctx, net, &net->fc2_w, 256, false)))
+            return rc;
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->v_w, vws.data(), 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_w, f1w, 256 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_b, f1b, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc2_w, f2w, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if ((rc = net_alloc_activations(ctx, net))) return rc;
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    net->loaded = true;
+    return 0;
 }
+
+static int net_forward_common(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* policy_out, float* value_out, bool softmax) {
+    if (!ctx || n <= 0 || !planes) return fail(ctx, SZB_ERR_ARG, "szb_net_forward: bad arguments");
+    if (!ctx->net || !ctx->net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
+    Net* net = ctx->net;
+    // process in chunks of the activation capacity; staging: planes + value (+ policy)
+    const int cap = net->cap;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t b_pl = up((size_t)cap * N_PLANES * 8), b_v = up((size_t)cap * 4), b_p = up((size_t)cap * N_ACTIONS * 4);
+    char* st = (char*)ctx_stage(ctx, b_pl + b_v + b_p);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    uint64_t* d_pl = (uint64_t*)st;
+    float* d_v = (float*)(st + b_pl);
+    float* d_p = (float*)(st + b_pl + b_v);
+    for (int lo = 0; lo < n; lo += cap) {
+        const int m = std::min(cap, n - lo);
+        SZB_CUDA(ctx, cudaMemcpyAsync(d_pl, planes + (size_t)lo * N_PLANES, (size_t)m * N_PLANES * 8, cudaMemcpyDefault, ctx->stream));
+        int rc = net_forward_device(ctx, evaluator, m, d_pl, N_PLANES, d_v);
+        if (rc) return rc;
+        const float* src = net->logits;
+        if (softmax) {
+            k_softmax<<<m, 256, 0, ctx->stream>>>(net->logits, d_p, m);
+            ctx->launches++;
+            src = d_p;
+        }
+        if (policy_out) SZB_CUDA(ctx, cudaMemcpyAsync(policy_out + (size_t)lo * N_ACTIONS, src, (size_t)m * N_ACTIONS * 4, cudaMemcpyDefault, ctx->stream));
+        if (value_out) SZB_CUDA(ctx, cudaMemcpyAsync(value_out + lo, d_v, (size_t)m * 4, cudaMemcpyDefault, ctx->stream));
+        SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    SZB_CUDA(ctx, cudaGetLastError());
+    if (evaluator == SZB_EVAL_NET_BF16) return check_tc_error(ctx);
+    return 0;
+}
+
+int szb_net_forward(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* policy_out, float* value_out) {
+    return net_forward_common(ctx, n, planes, evaluator, policy_out, value_out, true);
+}
+
+int szb_net_forward_logits(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* logits_out, float* value_out) {
+    return net_forward_common(ctx, n, planes, evaluator, logits_out, value_out, false);
+}
+
+}  // extern "C"
