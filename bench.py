@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement: MCTS simulations/s (and self-play moves/s) at 800 simulations per move
+over >= 1024 concurrent chess games per B200, beside the reference's CPU path on the same box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+A "step" is one pass of the hot path over one batch: one self-play ply for every game of the batch =
+`num_searches` MCTS simulations per game (select -> move generation / encoding -> network -> expand / backup),
+then a move sampled from the visit counts and pushed (szb_selfplay_ply; reference: sim.py:46-76).
+
+  value   : whole-job simulations/s with the games resident in HBM (device-timed, CUDA events on the library's
+            stream, max over ranks);
+  e2e     : the same metric through the host-buffer API: every step uploads the batch's positions from pinned
+            host memory (szb_games_set), searches, and reads the visit counts + child masks back to pinned host
+            memory (szb_search) -- the call the MCTS0.search facade makes;
+  roofline: the dominant kernel (one 3x3 256->256 tcgen05 tower convolution) timed live with CUDA events inside
+            the timed region, against the measured bf16 peak of MEASURED_PEAKS.json;
+  cpu_baseline / --impl reference: the restated reference search (oracle/ref_path.py: the reference's Python
+            control flow + torch CPU fp32 network, batch 1, all host threads) on a bounded sample of the workload.
+
+oracle/ is used here only as that CPU baseline; the measured product path is libszb200.so (no fallback).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mcts_simulations_per_sec"
+UNIT = "simulations/s"
+FLOP_PER_EVAL = 2914845184                    # 2 x MACs of one policyNN forward
+FLOP_TOWER_CONV_PER_BOARD = 2 * 64 * 256 * 2304   # one 3x3 256->256 layer on one board
+WORKLOADS = {
+    # BASELINE.json configs[2] / configs[3]
+    "c2": dict(games=1024, sims=800, chess960=False,
+               name="c2: 1024 concurrent vanilla-chess games x 800 sims/move, bf16 network, C=2, learning=True"),
+    "c3": dict(games=4096, sims=800, chess960=True,
+               name="c3: 4096 concurrent Chess960 games x 800 sims/move, bf16 network, C=2, learning=True"),
+}
+C_PUCT = 2.0
+SEED = 0
+MAX_PREFIX = 40                                # S2 "random-played" start positions: U{0..40} random legal plies
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="B200_PROFILING.md fallback")
+
+
+def traffic_per_launch(games):
+    """dram read+write bytes of one tower-conv launch from the committed ncu --set full capture, if it matches"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+        e = d.get("k_conv_tc_256_0", {})
+        return e.get("dram_bytes_per_launch") if int(e.get("boards", -1)) == int(games) else None
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload: S2 random-played start positions (same generator for both arms: ascending policy-index order)
+# ---------------------------------------------------------------------------------------------------
+def prefix_rng(g):
+    return np.random.default_rng([SEED, int(g)])
+
+
+def start_id_of(g, chess960):
+    return (SEED + int(g)) % 960 if chess960 else -1
+
+
+def play_prefixes_gpu(eng, game_ids, chess960):
+    """random legal plies through the engine (szb_legal_moves / szb_games_push); returns plies played per game"""
+    n = len(game_ids)
+    eng.reset([start_id_of(g, chess960) for g in game_ids])
+    rngs = [prefix_rng(g) for g in game_ids]
+    want = np.array([int(r.integers(0, MAX_PREFIX + 1)) for r in rngs])
+    played = np.zeros(n, dtype=np.int64)
+    for ply in range(MAX_PREFIX):
+        idx, cnt = eng.legal_moves()
+        who, mv = [], []
+        for g in range(n):
+            if ply < want[g] and cnt[g] > 0:
+                k = int(rngs[g].integers(0, int(cnt[g])))
+                who.append(g)
+                mv.append(int(idx[g, k]))
+        if not who:
+            break
+        eng.push(who, mv)
+        played[who] += 1
+    return played
+
+
+def oracle_prefix_game(g, chess960):
+    """the same prefix for one game through the oracle (reference arm / cpu baseline)"""
+    from oracle import ref_path
+    sid = start_id_of(g, chess960)
+    game = ref_path.RefGame(chess960=chess960, start_id=sid if chess960 else None)
+    rng = prefix_rng(g)
+    want = int(rng.integers(0, MAX_PREFIX + 1))
+    for _ in range(want):
+        b = game.board
+        pairs = sorted((ref_path.move_to_index(m, b.turn), m) for m in b.legal_moves)
+        if not pairs:
+            break
+        k = int(rng.integers(0, len(pairs)))
+        game.move_piece(pairs[k][1])
+    return game
+
+
+def seeded_model():
+    """policyNN default init under torch.manual_seed(0), eval mode (the real weights are a git-LFS pointer in the
+    reference); a user-supplied supervised_model_best.pt (> 1 KB) is used instead when present"""
+    import torch
+    from sigma_zero_b200.network import policyNN
+    torch.manual_seed(0)
+    model = policyNN({}).eval()
+    for cand in (os.path.join(ROOT, "supervised_model_best.pt"), "supervised_model_best.pt"):
+        if os.path.exists(cand) and os.path.getsize(cand) > 1024:
+            model.load_state_dict(torch.load(cand, map_location="cpu"))
+            return model, "file:" + cand
+    return model, "random-init torch.manual_seed(0)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc = device, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference (oracle) timing
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(chess960, sims_per_step, steps, warmup, game=0):
+    """restated reference search on the host: one game, one move decision of `sims_per_step` simulations per step
+    (batch-1 torch CPU fp32 forward per simulation, mcts.py:72-75).  Returns (sims/s, seconds per step, threads)."""
+    import torch
+    from oracle import ref_path
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = ref_path.build_policy_nn().eval()
+    ev = ref_path.torch_evaluator(model)
+    g = oracle_prefix_game(game, chess960)
+    if g.board.outcome() is not None:
+        g = oracle_prefix_game(game + 1, chess960)
+    for _ in range(warmup):
+        ref_path.search(g, max(8, sims_per_step // 8), C_PUCT, ev, learning=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ref_path.search(g, sims_per_step, C_PUCT, ev, learning=True)
+    dt = time.perf_counter() - t0
+    return sims_per_step * steps / dt, dt / steps, threads
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sims = args.ref_sims
+    rate, sec_step, threads = cpu_reference_run(wl["chess960"], sims, args.steps, args.warmup)
+    sample = "1 game (workload game 0, random-played prefix) x 1 move decision x %d of the %d simulations per step" % (sims, wl["sims"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "games": wl["games"], "num_searches": wl["sims"], "C": C_PUCT,
+                   "note": "reference CPU path: python control flow + torch CPU fp32 batch-1 network over the oracle chess stand-in"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from sigma_zero_b200 import _lib
+    from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    G, S = wl["games"], wl["sims"]
+    eng = Engine(max_games=G, max_searches=S, device=local)
+    model, weights = seeded_model()
+
+    # weights: rank 0's flat fp32 buffer broadcast over NCCL (the only collective of the path), then szb_net_load
+    bcast_ms = None
+    if world > 1:
+        from sigma_zero_b200.train_RL import flatten_state_dict, unflatten_into
+        keys, flat = flatten_state_dict(model.state_dict())
+        flat = flat.to(dev)
+        dist.broadcast(flat, src=0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(flat, src=0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+        unflatten_into(model, keys, flat.cpu())
+    eng.load_state_dict(model.state_dict())
+
+    # weak scaling: every rank owns its own block of G games (global game ids rank*G .. rank*G+G-1)
+    game_ids = list(range(rank * G, rank * G + G))
+    play_prefixes_gpu(eng, game_ids, wl["chess960"])
+
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident run (value) ---------------------------------------------------------------
+    for w in range(args.warmup):
+        eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)
+    eng.set_profiling(True)
+    st0 = eng.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    sims_done = moves_done = 0
+    for k in range(args.steps):
+        moves, _ = eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)
+        live = int((moves >= 0).sum())
+        sims_done += live * S
+        moves_done += live
+    e1.record(ext)
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    st1 = eng.stats()
+    pt = eng.phase_times()
+    eng.set_profiling(False)
+    total_sims = sum_over_ranks(sims_done)
+    total_moves = sum_over_ranks(moves_done)
+    launches = int(sum_over_ranks(st1["kernel_launches"] - st0["kernel_launches"]))
+    evals = int(sum_over_ranks(st1["evaluations"] - st0["evaluations"]))
+    value = total_sims / (ms * 1e-3)
+
+    # ---- end-to-end run through host buffers (e2e) --------------------------------------------------
+    pos_bytes = G * 112
+    pin_pos = torch.empty(pos_bytes, dtype=torch.uint8, pin_memory=True)
+    pin_vis = torch.empty((G, 4672), dtype=torch.int32, pin_memory=True)
+    pin_child = torch.empty((G, 73), dtype=torch.int64, pin_memory=True)
+    cur = eng.positions()
+    import ctypes
+    ctypes.memmove(pin_pos.data_ptr(), ctypes.addressof(cur), pos_bytes)
+    np_pos = pin_pos.numpy()
+    np_vis = pin_vis.numpy().view(np.uint32)
+    np_child = pin_child.numpy().view(np.uint64)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        eng.set_positions_buffer(np_pos, G)                                   # H2D: G x szb_pos
+        eng.search(S, C_PUCT, True, EVAL_NET_BF16, out=(np_vis, np_child, None))    # D2H: visits + child masks
+        return int(np_vis.sum(dtype=np.int64))
+
+    e2e_step()                                                                # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(ext)
+    visit_sum = 0
+    for k in range(e2e_steps):
+        visit_sum += e2e_step()
+    f1.record(ext)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), wall_ms))                # host-side copies count: take the longer clock
+    live_games = int((np_vis.sum(axis=1) > 0).sum())
+    e2e_value = sum_over_ranks(live_games * S * e2e_steps) / (e2e_ms * 1e-3)
+    assert visit_sum == live_games * (S - 1) * e2e_steps, "visit counts must sum to num_searches-1 per live game"
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------
+    pk = peaks()
+    roof = None
+    if pt["conv_launches"] > 0:
+        conv_ms = pt["conv_ms"] / pt["conv_launches"]
+        achieved = FLOP_TOWER_CONV_PER_BOARD * pt["conv_boards"] / (conv_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_conv_tc<256,0> (3x3 256->256 tower convolution, tcgen05 implicit GEMM)",
+                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                "frac_of_burst": achieved / pk["bf16_burst"], "peak_kind": "sustained, " + pk["source"],
+                "traffic": traffic_per_launch(pt["conv_boards"]), "ms_per_launch": conv_ms, "launches_timed": pt["conv_launches"],
+                "flop_per_launch": FLOP_TOWER_CONV_PER_BOARD * pt["conv_boards"]}
+    steps_total = max(1, pt["steps"])
+    phases = {k: pt[k] / steps_total for k in ("select_ms", "expand_ms", "eval_ms", "finish_ms")}
+    net_tflops = (FLOP_PER_EVAL * G) / (phases["eval_ms"] * 1e-3) / 1e12 if phases["eval_ms"] > 0 else None
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n = args.cpu_sims
+        rate, sec, threads = cpu_reference_run(wl["chess960"], n, 1, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "1 game (workload game 0) x 1 move decision x %d simulations, torch CPU fp32 batch-1 network (%.1f s)" % (n, sec)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["name"], "games_per_gpu": G, "num_searches": S, "C": C_PUCT, "learning": True,
+                       "chess960": wl["chess960"], "positions": "S2 random-played: U{0..40} random legal plies from the start, seed 0",
+                       "weights": weights, "parallelism": "games sharded, %d x network replica" % world,
+                       "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
+                             % (G * 100 * 256 * 2 // 2 ** 20)},
+            "moves_per_sec": total_moves / (ms * 1e-3), "evals_per_sec": evals / (ms * 1e-3),
+            "network_tflops_in_step": net_tflops, "phase_ms_per_simulation_step": phases,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pos_bytes,
+                    "d2h_bytes_per_step": G * 4672 * 4 + G * 73 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "szb_games_set(host positions) + szb_search(host visit/child buffers), pinned memory"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "weights_broadcast_ms": bcast_ms, "lib": _lib.LIB_PATH.replace(ROOT + os.sep, ""),
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--games", type=int, default=None, help="override games per GPU (parity / debugging; not a bench line)")
+    ap.add_argument("--sims", type=int, default=None, help="override simulations per move (debugging)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-sims", type=int, default=200, help="--impl reference: simulations per step (bounded sample)")
+    ap.add_argument("--cpu-sims", type=int, default=400, help="cpu_baseline: simulations in the bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.games:
+        wl["games"] = args.games
+        wl["name"] += " [games overridden: %d]" % args.games
+    if args.sims:
+        wl["sims"] = args.sims
+        wl["name"] += " [sims overridden: %d]" % args.sims
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -136,6 +136,23 @@ int szb_net_forward_logits(szb_ctx *ctx, int32_t n, const uint64_t *planes, int3
 int szb_search(szb_ctx *ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
                uint32_t *visits_out, uint64_t *child_mask_out, float *root_value_out);
 
+/* compact form of the last search's result: for every game the root children in ascending policy-index order
+ * (row stride SZB_MAX_MOVES), their visit counts and their number -- the (move, visit_count) pairs of
+ * mcts.py:113-116.  Valid until the next search. */
+int szb_root_children(szb_ctx *ctx, uint16_t *index_out, uint32_t *visits_out, uint16_t *count_out);
+
+/* read-only export of one game's search tree (backs the mctsnode.Node view, mctsnode.py:8-18).
+ * Nodes are the visited nodes in creation order (node 0 = root); node_* arrays have max_nodes entries,
+ * edge_* arrays max_edges entries; each node's children are edges [node_first[i], node_first[i]+node_count[i]).
+ * edge_child is the visited-node index behind an edge or -1.  n_nodes_out / n_edges_out receive the totals
+ * (SZB_ERR_ARG if a capacity is too small). */
+int szb_tree_export(szb_ctx *ctx, int32_t game, int32_t max_nodes, int32_t max_edges,
+                    int32_t *node_first, int32_t *node_count, int32_t *node_parent, int32_t *node_parent_edge,
+                    uint8_t *node_terminal, float *node_terminal_value,
+                    int32_t *edge_visits, double *edge_value_sum, float *edge_prior, uint16_t *edge_move,
+                    int32_t *edge_child, int32_t *root_visits_out, double *root_value_sum_out,
+                    int32_t *n_nodes_out, int32_t *n_edges_out);
+
 /* ---- self-play: replaces sim.play_game's ply loop (sim.py:46-76) ---------------------------------- */
 /* One ply for every unfinished game: search, pick a move (sample proportional to visits, sim.py:68, with a
  * counter-based RNG keyed (seed, game, ply); or argmax with lowest index on ties when sample == 0), record
@@ -154,6 +171,29 @@ typedef struct szb_stats {
     uint64_t max_depth;
 } szb_stats;
 int szb_get_stats(szb_ctx *ctx, szb_stats *out);
+
+/* ---- measurement hooks (bench.py; CUDA events recorded on the context's stream) ------------------ */
+/* per-phase device time of the simulation steps of searches run while profiling is on */
+typedef struct szb_phase_times {
+    float select_ms, expand_ms, eval_ms, finish_ms;   /* totals over `steps` simulation steps */
+    int32_t steps;
+    int32_t reserved;
+    uint64_t select_edges;     /* children scanned by PUCT selection (16 B each: N 4 + W 8 + P 4) */
+    uint64_t select_levels;    /* tree levels descended (16 B node header each) */
+    uint64_t backup_levels;    /* edges updated by backup (24 B read-modify-write each) */
+    uint64_t edges_written;    /* children created by expansion (20 B each) */
+    float conv_ms;             /* total device time of the timed tower convolution launches (one 3x3 256->256
+                                  tcgen05 layer with residual per bf16 forward), CUDA events on the context's stream */
+    int32_t conv_launches;     /* how many launches conv_ms covers */
+    int32_t conv_boards;       /* boards per timed launch (the GEMM's M / 64) */
+    int32_t reserved2;
+} szb_phase_times;
+int szb_set_profiling(szb_ctx *ctx, int32_t on);
+int szb_get_phase_times(szb_ctx *ctx, szb_phase_times *out);
+/* average duration (ms) of one launch of a kernel run `iters` times back to back on n boards:
+ * which = 0: one 3x3 256->256 tower convolution (tcgen05, with residual) ; 1: whole bf16 forward ;
+ * 2: whole fp32 forward ; 3: one 3x3 256->256 fp32 SIMT convolution */
+int szb_time_kernel(szb_ctx *ctx, int32_t which, int32_t n, int32_t iters, float *ms_avg_out);
 
 #ifdef __cplusplus
 }

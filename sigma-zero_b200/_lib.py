@@ -33,6 +33,15 @@ class Stats(ctypes.Structure):
                 ("simulations", "evaluations", "terminal_visits", "edges_allocated", "kernel_launches", "max_depth")]
 
 
+class PhaseTimes(ctypes.Structure):
+    _fields_ = [("select_ms", ctypes.c_float), ("expand_ms", ctypes.c_float), ("eval_ms", ctypes.c_float),
+                ("finish_ms", ctypes.c_float), ("steps", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("select_edges", ctypes.c_uint64), ("select_levels", ctypes.c_uint64),
+                ("backup_levels", ctypes.c_uint64), ("edges_written", ctypes.c_uint64),
+                ("conv_ms", ctypes.c_float), ("conv_launches", ctypes.c_int32), ("conv_boards", ctypes.c_int32),
+                ("reserved2", ctypes.c_int32)]
+
+
 _vp, _i32, _u64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float
 SIGNATURES = {
     "szb_version": (ctypes.c_char_p, []),
@@ -55,8 +64,14 @@ SIGNATURES = {
     "szb_net_forward": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "szb_net_forward_logits": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "szb_search": (ctypes.c_int, [_vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "szb_root_children": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "szb_tree_export": (ctypes.c_int, [_vp, _i32, _i32, _i32] + [_vp] * 11 + [ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_double),
+                                                                          ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "szb_selfplay_ply": (ctypes.c_int, [_vp, _i32, _f32, _i32, _i32, _u64, _i32, _vp, _vp]),
     "szb_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
+    "szb_set_profiling": (ctypes.c_int, [_vp, _i32]),
+    "szb_get_phase_times": (ctypes.c_int, [_vp, ctypes.POINTER(PhaseTimes)]),
+    "szb_time_kernel": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(_f32)]),
 }
 
 _lib = None

@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
     if (g >= d.n_games) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     int node = 0, depth = 0;
+    unsigned long long scanned = 0;
     for (;;) {
         const int n = d.node_nchild[r + node];
         if (n == 0) {
@@ -230,13 +231,18 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
         const int e = e0 + besti;
         const uint16_t c = d.e_child[e];
         depth++;
+        scanned += (unsigned long long)n;
         if (c == NO_CHILD) {
             if (lane == 0) { d.sel_node[g] = node; d.sel_edge[g] = e; }
             break;
         }
         node = c;
     }
-    if (lane == 0) atomicMax(&d.stats[3], (unsigned long long)depth);
+    if (lane == 0) {
+        atomicMax(&d.stats[3], (unsigned long long)depth);
+        atomicAdd(&d.stats[4], scanned);
+        atomicAdd(&d.stats[5], (unsigned long long)depth);
+    }
 }
 
 // thread per tree
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
         // backup (mctsnode.py:56-63): value_sum accumulates python doubles
         double val = (double)v;
         int nd = node;
+        unsigned long long levels = 0;
         for (;;) {
             const int pe = d.node_pedge[r + nd];
             if (pe < 0) break;
@@ -369,7 +376,10 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
             d.e_n[pe] += 1;
             val = -val;
             nd = d.node_pnode[r + nd];
+            levels++;
         }
+        atomicAdd(&d.stats[6], levels);
+        if (d.need_eval[g]) atomicAdd(&d.stats[7], (unsigned long long)d.node_nchild[r + node]);
         d.root_w[g] += val;
         d.root_n[g] += 1;
         atomicAdd(&d.stats[0], 1ull);
@@ -392,6 +402,55 @@ __global__ void k_collect(Dev d, uint32_t* visits, uint64_t* child_mask, float* 
         if (child_mask) atomicOr((unsigned long long*)&child_mask[(size_t)g * MASK_WORDS + (idx >> 6)], 1ull << (idx & 63));
     }
     if (root_value && lane == 0) root_value[g] = d.node_term[r] ? d.node_tval[r] : d.root_val[g];
+}
+
+// compact root children: index / visits / count per game
+__global__ void k_root_children(Dev d, uint16_t* index, uint32_t* visits, uint16_t* count) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= d.n_games) return;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int n = d.node_nchild[r], e0 = d.node_edge0[r];
+    for (int i = lane; i < SZB_MAX_MOVES; i += 32) {
+        index[(size_t)g * SZB_MAX_MOVES + i] = i < n ? d.e_move[e0 + i] : 0;
+        visits[(size_t)g * SZB_MAX_MOVES + i] = i < n ? (uint32_t)d.e_n[e0 + i] : 0u;
+    }
+    if (lane == 0) count[g] = (uint16_t)n;
+}
+
+// gather one game's tree into contiguous arrays (inspection path; one warp)
+__global__ void k_tree_export(Dev d, int g, int max_nodes, int max_edges, int32_t* node_first, int32_t* node_count,
+                              int32_t* node_parent, int32_t* node_pedge, uint8_t* node_term, float* node_tval,
+                              int32_t* e_n, double* e_w, float* e_p, uint16_t* e_move, int32_t* e_child, int32_t* totals) {
+    const int lane = threadIdx.x;
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int n_nodes = d.node_count[g] + 1;
+    int off = 0;
+    bool overflow = n_nodes > max_nodes;
+    for (int i = 0; i < n_nodes && !overflow; i++) {
+        const int n = d.node_nchild[r + i], e0 = d.node_edge0[r + i];
+        if (off + n > max_edges) { overflow = true; break; }
+        if (lane == 0) {
+            node_first[i] = off; node_count[i] = n;
+            node_parent[i] = i == 0 ? -1 : (int)d.node_pnode[r + i];
+            node_pedge[i] = -1;                       // patched below once the parent's range is known
+            node_term[i] = d.node_term[r + i]; node_tval[i] = d.node_tval[r + i];
+        }
+        for (int k = lane; k < n; k += 32) {
+            e_n[off + k] = d.e_n[e0 + k]; e_w[off + k] = d.e_w[e0 + k]; e_p[off + k] = d.e_p[e0 + k];
+            e_move[off + k] = d.e_move[e0 + k];
+            const uint16_t c = d.e_child[e0 + k];
+            e_child[off + k] = c == NO_CHILD ? -1 : (int)c;
+        }
+        off += n;
+    }
+    __syncwarp();
+    if (!overflow)
+        for (int i = 1 + lane; i < n_nodes; i += 32) {
+            const int pn = d.node_pnode[r + i];
+            node_pedge[i] = node_first[pn] + (d.node_pedge[r + i] - d.node_edge0[r + pn]);
+        }
+    if (lane == 0) { totals[0] = overflow ? -1 : n_nodes; totals[1] = off; totals[2] = d.root_n[g]; }
 }
 
 // choose a move from the root visit counts (sim.py:68 sampling, or arg-max first-index as in eval.py:92-100)
@@ -560,6 +619,8 @@ void szb_destroy(szb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     net_destroy(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->conv_events) cudaEventDestroy(e);
     for (Pos* p : ctx->perft_levels) if (p) cudaFree(p);
     if (ctx->perft_counter) cudaFree(ctx->perft_counter);
     if (ctx->stage) cudaFree(ctx->stage);
@@ -763,9 +824,21 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d);
     ctx->launches++;
     const int warp_blocks = (G * 32 + 127) / 128;
+    const bool prof = ctx->profiling;
+    if (prof) {
+        while ((int)ctx->prof_events.size() < 5 * num_searches) {
+            cudaEvent_t e;
+            SZB_CUDA(ctx, cudaEventCreate(&e));
+            ctx->prof_events.push_back(e);
+        }
+    }
     for (int s = 0; s < num_searches; s++) {
+        cudaEvent_t* ev = prof ? &ctx->prof_events[5 * (size_t)s] : nullptr;
+        if (prof) cudaEventRecord(ev[0], st);
         k_select<<<warp_blocks, 128, 0, st>>>(d, c_puct);
+        if (prof) cudaEventRecord(ev[1], st);
         k_expand<<<(G + 31) / 32, 32, 0, st>>>(d);
+        if (prof) cudaEventRecord(ev[2], st);
         ctx->launches += 2;
         if (evaluator == SZB_EVAL_HASH) {
             k_hash_eval<<<G, 128, 0, st>>>(d);
@@ -774,7 +847,9 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             int rc = net_evaluate_batch(ctx, evaluator, G);
             if (rc) return rc;
         }
+        if (prof) cudaEventRecord(ev[3], st);
         k_finish<<<warp_blocks, 128, 0, st>>>(d, learning);
+        if (prof) cudaEventRecord(ev[4], st);
         ctx->launches++;
     }
     SZB_CUDA(ctx, cudaGetLastError());
@@ -785,6 +860,19 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     SZB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->edges_high_water = std::max<uint64_t>(ctx->edges_high_water, top);
     if (flag) return fail(ctx, flag, "tree arena exhausted (%llu edges): raise szb_config.edges_per_node", d.edge_cap);
+    if (prof) {
+        for (int s = 0; s < num_searches; s++) {
+            cudaEvent_t* ev = &ctx->prof_events[5 * (size_t)s];
+            for (int k = 0; k < 4; k++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+                ctx->phase_ms[k] += ms;
+            }
+        }
+        ctx->phase_steps += num_searches;
+        net_collect_conv_times(ctx);
+    }
+    if (evaluator == SZB_EVAL_NET_BF16) return net_check_error(ctx);
     return 0;
 }
 
@@ -814,6 +902,66 @@ int szb_search(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learnin
     return 0;
 }
 
+int szb_root_children(szb_ctx* ctx, uint16_t* index_out, uint32_t* visits_out, uint16_t* count_out) {
+    if (!ctx || !index_out || !visits_out || !count_out) return fail(ctx, SZB_ERR_ARG, "szb_root_children: bad arguments");
+    Dev& d = ctx->d;
+    const size_t G = (size_t)d.n_games;
+    if (G == 0) return fail(ctx, SZB_ERR_STATE, "no games");
+    const size_t b_i = G * SZB_MAX_MOVES * 2, b_v = G * SZB_MAX_MOVES * 4, b_c = (G * 2 + 255) & ~(size_t)255;
+    char* st = (char*)ctx_stage(ctx, b_i + b_v + b_c);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    uint32_t* d_v = (uint32_t*)st;
+    uint16_t* d_i = (uint16_t*)(st + b_v);
+    uint16_t* d_c = (uint16_t*)(st + b_v + b_i);
+    k_root_children<<<(unsigned)((G * 32 + 127) / 128), 128, 0, ctx->stream>>>(d, d_i, d_v, d_c);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    SZB_CUDA(ctx, cudaMemcpyAsync(index_out, d_i, b_i, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(visits_out, d_v, b_v, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(count_out, d_c, G * 2, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int szb_tree_export(szb_ctx* ctx, int32_t game, int32_t max_nodes, int32_t max_edges, int32_t* node_first, int32_t* node_count,
+                    int32_t* node_parent, int32_t* node_parent_edge, uint8_t* node_terminal, float* node_terminal_value,
+                    int32_t* edge_visits, double* edge_value_sum, float* edge_prior, uint16_t* edge_move, int32_t* edge_child,
+                    int32_t* root_visits_out, double* root_value_sum_out, int32_t* n_nodes_out, int32_t* n_edges_out) {
+    if (!ctx || game < 0 || game >= ctx->d.n_games || max_nodes <= 0 || max_edges <= 0) return fail(ctx, SZB_ERR_ARG, "szb_tree_export: bad arguments");
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t mn = (size_t)max_nodes, me = (size_t)max_edges;
+    const size_t o_nf = 0, o_nc = o_nf + up(mn * 4), o_np = o_nc + up(mn * 4), o_ne = o_np + up(mn * 4), o_nt = o_ne + up(mn * 4),
+                 o_nv = o_nt + up(mn), o_ew = o_nv + up(mn * 4), o_en = o_ew + up(me * 8), o_ep = o_en + up(me * 4),
+                 o_ec = o_ep + up(me * 4), o_em = o_ec + up(me * 4), o_tot = o_em + up(me * 2), total = o_tot + 256;
+    char* st = (char*)ctx_stage(ctx, total);
+    if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
+    k_tree_export<<<1, 32, 0, ctx->stream>>>(ctx->d, game, max_nodes, max_edges, (int32_t*)(st + o_nf), (int32_t*)(st + o_nc),
+                                            (int32_t*)(st + o_np), (int32_t*)(st + o_ne), (uint8_t*)(st + o_nt), (float*)(st + o_nv),
+                                            (int32_t*)(st + o_en), (double*)(st + o_ew), (float*)(st + o_ep), (uint16_t*)(st + o_em),
+                                            (int32_t*)(st + o_ec), (int32_t*)(st + o_tot));
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    int32_t tot[3];
+    double rw = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(tot, st + o_tot, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(&rw, ctx->d.root_w + game, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (tot[0] < 0) return fail(ctx, SZB_ERR_ARG, "szb_tree_export: capacity too small");
+    const size_t nn = (size_t)tot[0], ne = (size_t)tot[1];
+    struct { void* dst; size_t off, bytes; } cp[] = {
+        {node_first, o_nf, nn * 4}, {node_count, o_nc, nn * 4}, {node_parent, o_np, nn * 4}, {node_parent_edge, o_ne, nn * 4},
+        {node_terminal, o_nt, nn}, {node_terminal_value, o_nv, nn * 4}, {edge_visits, o_en, ne * 4}, {edge_value_sum, o_ew, ne * 8},
+        {edge_prior, o_ep, ne * 4}, {edge_move, o_em, ne * 2}, {edge_child, o_ec, ne * 4}};
+    for (auto& c : cp)
+        if (c.dst && c.bytes) SZB_CUDA(ctx, cudaMemcpyAsync(c.dst, st + c.off, c.bytes, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (root_visits_out) *root_visits_out = tot[2];
+    if (root_value_sum_out) *root_value_sum_out = rw;
+    if (n_nodes_out) *n_nodes_out = (int32_t)nn;
+    if (n_edges_out) *n_edges_out = (int32_t)ne;
+    return 0;
+}
+
 int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
                      uint64_t seed, int32_t sample, int32_t* moves_out, int32_t* n_active_out) {
     if (!ctx) return SZB_ERR_ARG;
@@ -832,6 +980,32 @@ int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t l
     SZB_CUDA(ctx, cudaMemcpyAsync(&act, d_active, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_active_out) *n_active_out = act;
+    return 0;
+}
+
+int szb_set_profiling(szb_ctx* ctx, int32_t on) {
+    if (!ctx) return SZB_ERR_ARG;
+    ctx->profiling = on != 0;
+    for (int k = 0; k < 4; k++) ctx->phase_ms[k] = 0;
+    ctx->phase_steps = 0;
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->conv_events_used = 0;
+    ctx->conv_ms = 0; ctx->conv_launches = 0;
+    SZB_CUDA(ctx, cudaMemsetAsync(ctx->d.stats + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
+    if (!ctx || !out) return SZB_ERR_ARG;
+    unsigned long long h[8];
+    SZB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d.stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->select_ms = ctx->phase_ms[0]; out->expand_ms = ctx->phase_ms[1];
+    out->eval_ms = ctx->phase_ms[2]; out->finish_ms = ctx->phase_ms[3];
+    out->steps = ctx->phase_steps; out->reserved = 0;
+    out->select_edges = h[4]; out->select_levels = h[5]; out->backup_levels = h[6]; out->edges_written = h[7];
+    net_collect_conv_times(ctx);
+    out->conv_ms = ctx->conv_ms; out->conv_launches = ctx->conv_launches; out->conv_boards = ctx->conv_boards; out->reserved2 = 0;
     return 0;
 }
 

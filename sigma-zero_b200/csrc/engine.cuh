@@ -55,7 +55,8 @@ struct Dev {
     float* policy;           // [max_games][4672] evaluator output ("softmax over everything")
     float* value;            // [max_games]
     float* root_val;         // [max_games] evaluator value of the root position
-    unsigned long long* stats;   // simulations, evaluations, terminal visits, max depth
+    unsigned long long* stats;   // 0 simulations, 1 evaluations, 2 terminal visits, 3 max depth,
+                                 // 4 select edges, 5 select levels, 6 backup levels, 7 edges written
 };
 
 }  // namespace szb
@@ -81,6 +82,15 @@ struct szb_ctx {
     szb::Net* net = nullptr;
     // self-play records
     int32_t* d_moves = nullptr;
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    float phase_ms[4] = {0, 0, 0, 0};
+    int phase_steps = 0;
+    std::vector<cudaEvent_t> conv_events;      // pairs around the timed tower convolution (net.cu)
+    size_t conv_events_used = 0;
+    float conv_ms = 0;
+    int conv_launches = 0, conv_boards = 0;
 };
 
 namespace szb {
@@ -90,6 +100,9 @@ void* ctx_stage(szb_ctx* ctx, size_t bytes);
 // net.cu: evaluate the rows of d.planes with need_eval set -> d.policy / d.value (softmax policy).
 int net_evaluate_batch(szb_ctx* ctx, int evaluator, int n);
 void net_destroy(szb_ctx* ctx);
+int net_check_error(szb_ctx* ctx);
+// net.cu: fold the recorded conv event pairs into ctx->conv_ms (call after the stream is synchronised)
+void net_collect_conv_times(szb_ctx* ctx);
 }  // namespace szb
 
 #define SZB_CUDA(ctx, call)                                             \

@@ -634,6 +634,31 @@ static void launch_f32(szb_ctx* ctx, const float* in, const ConvLayer& L, const 
     ctx->launches++;
 }
 
+// next unused (start, stop) event pair for the conv timing hook; null if events cannot be created
+static cudaEvent_t* conv_event_pair(szb_ctx* ctx) {
+    if (ctx->conv_events_used + 2 > ctx->conv_events.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess) return nullptr;
+        if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return nullptr; }
+        ctx->conv_events.push_back(a);
+        ctx->conv_events.push_back(b);
+    }
+    cudaEvent_t* p = &ctx->conv_events[ctx->conv_events_used];
+    ctx->conv_events_used += 2;
+    return p;
+}
+
+void net_collect_conv_times(szb_ctx* ctx) {
+    for (size_t i = 0; i + 1 < ctx->conv_events_used; i += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->conv_events[i], ctx->conv_events[i + 1]) == cudaSuccess) {
+            ctx->conv_ms += ms;
+            ctx->conv_launches++;
+        }
+    }
+    ctx->conv_events_used = 0;
+}
+
 // planes (device, row stride `stride` uint64) -> net->logits + value_out (device)
 static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t* planes, int stride, float* value_out) {
     Net* net = ctx->net;
@@ -650,7 +675,11 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t
         for (int blk = 0; blk < N_BLOCKS; blk++) {
             const int y = (x + 1) % 3, o = (x + 2) % 3;
             if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->tower[2 * blk], nullptr, net->act16[y], nullptr, n, 1))) return rc;
+            // measurement hook: while profiling, bracket ONE tower layer (block 9, second conv, with residual) per forward
+            cudaEvent_t* cev = (ctx->profiling && blk == 9) ? conv_event_pair(ctx) : nullptr;
+            if (cev) cudaEventRecord(cev[0], st);
             if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[y], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1))) return rc;
+            if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; }
             x = o;
         }
         const int y = (x + 1) % 3;
@@ -689,7 +718,7 @@ int net_evaluate_batch(szb_ctx* ctx, int evaluator, int n) {
     return 0;
 }
 
-static int check_tc_error(szb_ctx* ctx) {
+int net_check_error(szb_ctx* ctx) {
     int32_t flag = 0;
     SZB_CUDA(ctx, cudaMemcpyAsync(&flag, ctx->net->tc_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -807,8 +836,41 @@ static int net_forward_common(szb_ctx* ctx, int32_t n, const uint64_t* planes, i
         SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     SZB_CUDA(ctx, cudaGetLastError());
-    if (evaluator == SZB_EVAL_NET_BF16) return check_tc_error(ctx);
+    if (evaluator == SZB_EVAL_NET_BF16) return net_check_error(ctx);
     return 0;
+}
+
+int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float* ms_avg_out) {
+    if (!ctx || !ms_avg_out || n <= 0 || iters <= 0) return fail(ctx, SZB_ERR_ARG, "szb_time_kernel: bad arguments");
+    Net* net = ctx->net;
+    if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
+    if (n > net->cap) return fail(ctx, SZB_ERR_ARG, "batch %d exceeds capacity %d", n, net->cap);
+    cudaEvent_t e0, e1;
+    SZB_CUDA(ctx, cudaEventCreate(&e0));
+    SZB_CUDA(ctx, cudaEventCreate(&e1));
+    int rc = 0;
+    for (int pass = 0; pass < 2 && !rc; pass++) {          // pass 0 warms up
+        const int reps = pass == 0 ? 3 : iters;
+        SZB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        for (int i = 0; i < reps && !rc; i++) {
+            switch (which) {
+            case 0: rc = launch_tc<256, 0>(ctx, net, net->tm_act16[i & 1], net->tower[1], net->act16[2], net->act16[(i + 1) & 1], nullptr, n, 1); break;
+            case 1: rc = net_forward_device(ctx, SZB_EVAL_NET_BF16, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
+            case 2: rc = net_forward_device(ctx, SZB_EVAL_NET_FP32, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
+            case 3: launch_f32(ctx, net->act32[i & 1], net->tower[1], net->act32[2], net->act32[(i + 1) & 1], n, 1, 0); break;
+            default: rc = fail(ctx, SZB_ERR_ARG, "unknown kernel selector %d", which);
+            }
+        }
+        SZB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    float ms = 0;
+    if (!rc) { cudaEventElapsedTime(&ms, e0, e1); *ms_avg_out = ms / iters; }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    SZB_CUDA(ctx, cudaGetLastError());
+    return net_check_error(ctx);
 }
 
 int szb_net_forward(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* policy_out, float* value_out) {

@@ -66,6 +66,12 @@ class Engine:
         self._check(self.lib.szb_games_set(self._h, len(positions), ctypes.cast(arr, ctypes.c_void_p)))
         self.n_games = len(positions)
 
+    def set_positions_buffer(self, buf, n):
+        """buf: contiguous host array holding n szb_pos structs (112 bytes each), e.g. a view of pinned memory"""
+        assert buf.nbytes >= n * ctypes.sizeof(_lib.Pos)
+        self._check(self.lib.szb_games_set(self._h, int(n), _ptr(buf)))
+        self.n_games = int(n)
+
     def push(self, games, move_indices, raise_on_illegal=True):
         games = None if games is None else np.ascontiguousarray(games, dtype=np.int32)
         idx = np.ascontiguousarray(move_indices, dtype=np.uint16)
@@ -144,14 +150,44 @@ class Engine:
 
     # ---- search ------------------------------------------------------------------------------
     def search(self, num_searches, c_puct=2.0, learning=False, evaluator=EVAL_NET_BF16,
-               want_visits=True, want_children=True, want_value=False):
+               want_visits=True, want_children=True, want_value=False, out=None):
+        """out: optional (visits uint32[G,4672], child_mask uint64[G,73], root_value float32[G]) host arrays to fill
+        (e.g. views of pinned memory); entries may be None."""
         G = self.n_games
-        visits = np.zeros((G, N_ACTIONS), dtype=np.uint32) if want_visits else None
-        child = np.zeros((G, MASK_WORDS), dtype=np.uint64) if want_children else None
-        val = np.zeros(G, dtype=np.float32) if want_value else None
+        if out is not None:
+            visits, child, val = out
+        else:
+            visits = np.zeros((G, N_ACTIONS), dtype=np.uint32) if want_visits else None
+            child = np.zeros((G, MASK_WORDS), dtype=np.uint64) if want_children else None
+            val = np.zeros(G, dtype=np.float32) if want_value else None
         self._check(self.lib.szb_search(self._h, int(num_searches), float(c_puct), int(bool(learning)), int(evaluator),
                                         _ptr(visits), _ptr(child), _ptr(val)))
         return visits, child, val
+
+    def root_children(self):
+        """(index uint16[G,256], visits uint32[G,256], count uint16[G]) of the last search"""
+        G = self.n_games
+        idx = np.zeros((G, MAX_MOVES), dtype=np.uint16)
+        vis = np.zeros((G, MAX_MOVES), dtype=np.uint32)
+        cnt = np.zeros(G, dtype=np.uint16)
+        self._check(self.lib.szb_root_children(self._h, _ptr(idx), _ptr(vis), _ptr(cnt)))
+        return idx, vis, cnt
+
+    def tree_export(self, game=0):
+        """dict of numpy arrays describing one game's search tree (see szb_tree_export)"""
+        mn = self.max_searches + 1
+        me = mn * 218
+        a = dict(node_first=np.zeros(mn, np.int32), node_count=np.zeros(mn, np.int32), node_parent=np.zeros(mn, np.int32),
+                 node_parent_edge=np.zeros(mn, np.int32), node_terminal=np.zeros(mn, np.uint8),
+                 node_terminal_value=np.zeros(mn, np.float32), edge_visits=np.zeros(me, np.int32),
+                 edge_value_sum=np.zeros(me, np.float64), edge_prior=np.zeros(me, np.float32),
+                 edge_move=np.zeros(me, np.uint16), edge_child=np.zeros(me, np.int32))
+        rn, rw, nn, ne = ctypes.c_int32(), ctypes.c_double(), ctypes.c_int32(), ctypes.c_int32()
+        self._check(self.lib.szb_tree_export(self._h, int(game), mn, me, *[_ptr(v) for v in a.values()],
+                                             ctypes.byref(rn), ctypes.byref(rw), ctypes.byref(nn), ctypes.byref(ne)))
+        out = {k: (v[:nn.value] if k.startswith("node_") else v[:ne.value]) for k, v in a.items()}
+        out["root_visits"], out["root_value_sum"] = rn.value, rw.value
+        return out
 
     def selfplay_ply(self, num_searches, c_puct=2.0, learning=True, evaluator=EVAL_NET_BF16, seed=0, sample=True):
         moves = np.zeros(self.n_games, dtype=np.int32)
@@ -160,6 +196,19 @@ class Engine:
                                               int(evaluator), int(seed), int(bool(sample)), _ptr(moves),
                                               ctypes.cast(ctypes.byref(active), ctypes.c_void_p)))
         return moves, active.value
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.szb_set_profiling(self._h, int(bool(on))))
+
+    def phase_times(self):
+        t = _lib.PhaseTimes()
+        self._check(self.lib.szb_get_phase_times(self._h, ctypes.byref(t)))
+        return {n: getattr(t, n) for n, _ in _lib.PhaseTimes._fields_ if n != "reserved"}
+
+    def time_kernel(self, which, n, iters=20):
+        ms = ctypes.c_float()
+        self._check(self.lib.szb_time_kernel(self._h, int(which), int(n), int(iters), ctypes.byref(ms)))
+        return ms.value
 
     def stats(self):
         s = _lib.Stats()

@@ -1,0 +1,87 @@
+"""Drop-in for the reference's sim.py.  `play_game` keeps the reference signature (one game);
+`generate_training_data` plays all `num_games` games concurrently on the GPU -- that batch is the product's
+hot path (szb_selfplay_ply: search for every game, sample a move proportional to visits, push it)."""
+import os
+
+import numpy as np
+import torch
+
+from . import chess_compat as chess
+from . import runtime
+from .chess_tensor import index_move
+
+
+def _empty_history():
+    return {'states': [], 'actions': [], 'rewards': [], 'colours': []}
+
+
+def selfplay_batch(model, args, num_games, c960=False, seed=None, start_ids=None, max_plies=None, learning=True,
+                   sample=True, record=True):
+    """Plays num_games games in lock step.  Returns one history dict per game (sim.py:38-43 schema) plus counters."""
+    n_search = int(args['num_searches'])
+    eng = runtime.get_engine(min_games=num_games, min_searches=n_search)
+    runtime.sync_weights(eng, model)
+    eng.owner = None
+    rng = np.random.default_rng(seed)
+    if start_ids is None:
+        start_ids = rng.integers(0, 960, size=num_games) if c960 else np.full(num_games, -1)
+    eng.reset(start_ids)
+    seed64 = int(rng.integers(0, 2 ** 62)) if seed is None else int(seed)
+    games = [_empty_history() for _ in range(num_games)]
+    evaluator = runtime.evaluator_of(model)
+    plies = 0
+    active = num_games
+    while active > 0 and (max_plies is None or plies < max_plies):
+        if record:
+            planes, _ = eng.encode(want_mask=False)
+            pos = eng.positions()
+        moves, active = eng.selfplay_ply(n_search, float(args['C']), learning, evaluator, seed=seed64, sample=sample)
+        if record:
+            idx, vis, cnt = eng.root_children()
+            states = runtime.unpack_planes(planes)
+            for g in range(num_games):
+                if moves[g] < 0:
+                    continue
+                white = bool(pos[g].turn)
+                k = int(cnt[g])
+                total = int(vis[g, :k].sum())
+                pawns = pos[g].pieces[0 if white else 6]
+                probs = {}
+                for i, c in zip(idx[g, :k], vis[g, :k]):
+                    m = index_move(int(i), white)
+                    if m.promotion is None and (pawns >> m.from_square) & 1 and m.to_square // 8 in (0, 7):
+                        m = chess.make_move(m.from_square, m.to_square, chess.QUEEN)
+                    probs[m] = int(c) / total
+                h = games[g]
+                h['states'].append(torch.from_numpy(states[g]))
+                h['actions'].append(probs)
+                h['colours'].append(white)
+        plies += 1
+    final = eng.positions()
+    for g, h in enumerate(games):
+        o = final[g].outcome
+        result = "*" if o == 0 else ("1/2-1/2" if o != 1 else ("0-1" if final[g].turn else "1-0"))
+        reward = 1 if result == "1-0" else (-1 if result == "0-1" else 0)
+        h['rewards'] = [reward if i % 2 == 0 else -reward for i in range(len(h['actions']))]
+        h['result'] = result
+    return games, {"plies": plies, "simulations": plies * n_search * num_games}
+
+
+def play_game(model, args, c960=False):
+    """One self-play game (reference signature, sim.py:31-99)."""
+    games, _ = selfplay_batch(model, args, 1, c960=c960)
+    h = games[0]
+    print("Result", h.pop('result'))
+    return h
+
+
+def generate_training_data(model, num_games=1, args=None, return_dict=None, c960=False):
+    """num_games self-play games, concatenated like sim.py:102-123 -- but played concurrently on the GPU."""
+    games, _ = selfplay_batch(model, args, num_games, c960=c960)
+    out = _empty_history()
+    for h in games:
+        for key in out:
+            out[key] += h[key]
+    if return_dict is not None:
+        return_dict[os.getpid()] = out
+    return out
