@@ -37,7 +37,6 @@ if ROOT not in sys.path:
 METRIC = "mcts_simulations_per_sec"
 UNIT = "simulations/s"
 FLOP_PER_EVAL = 2914845184                    # 2 x MACs of one policyNN forward
-FLOP_TOWER_CONV_PER_BOARD = 2 * 64 * 256 * 2304   # one 3x3 256->256 layer on one board
 WORKLOADS = {
     # BASELINE.json configs[2] / configs[3]
     "c2": dict(games=1024, sims=800, chess960=False,
@@ -59,17 +58,19 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="B200_PROFILING.md fallback")
 
 
-def traffic_per_launch(games):
-    """dram read+write bytes of one tower-conv launch from the committed ncu --set full capture, if it matches"""
+def traffic_per_launch(kind, boards):
+    """dram read+write bytes of one launch of the timed kernel from the committed ncu --set full capture
+    (profiles/traffic.json), if a capture of that kernel at that batch exists"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     try:
-        d = json.load(open(p))
-        e = d.get("k_conv_tc_256_0", {})
-        return e.get("dram_bytes_per_launch") if int(e.get("boards", -1)) == int(games) else None
+        for e in json.load(open(p)).get("captures", []):
+            if int(e["conv_kind"]) == int(kind) and int(e["boards"]) == int(boards):
+                return e["dram_bytes_per_launch"]
     except Exception:
-        return None
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -360,12 +361,15 @@ def run_ours(args, wl):
     roof = None
     if pt["conv_launches"] > 0:
         conv_ms = pt["conv_ms"] / pt["conv_launches"]
-        achieved = FLOP_TOWER_CONV_PER_BOARD * pt["conv_boards"] / (conv_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_conv_tc<256,0> (3x3 256->256 tower convolution, tcgen05 implicit GEMM)",
+        achieved = pt["conv_flop"] / (conv_ms * 1e-3) / 1e12
+        kernel = {2: "k_tower_tc2: stem + 38 tower 3x3 convolutions + policy 1x1 in one persistent CTA-pair launch (tcgen05 cta_group::2 implicit GEMM)",
+                  1: "k_tower_tc2 on one 3x3 256->256 tower convolution (CTA-pair tcgen05 implicit GEMM)",
+                  0: "k_conv_tc<256,0> on one 3x3 256->256 tower convolution (single-CTA tcgen05 implicit GEMM)"}[pt["conv_kind"]]
+        roof = {"bound": "tensor", "kernel": kernel,
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "frac_of_burst": achieved / pk["bf16_burst"], "peak_kind": "sustained, " + pk["source"],
-                "traffic": traffic_per_launch(pt["conv_boards"]), "ms_per_launch": conv_ms, "launches_timed": pt["conv_launches"],
-                "flop_per_launch": FLOP_TOWER_CONV_PER_BOARD * pt["conv_boards"]}
+                "traffic": traffic_per_launch(pt["conv_kind"], pt["conv_boards"]), "ms_per_launch": conv_ms,
+                "launches_timed": pt["conv_launches"], "flop_per_launch": pt["conv_flop"], "boards_per_launch": pt["conv_boards"]}
     steps_total = max(1, pt["steps"])
     phases = {k: pt[k] / steps_total for k in ("select_ms", "expand_ms", "eval_ms", "finish_ms")}
     net_tflops = (FLOP_PER_EVAL * G) / (phases["eval_ms"] * 1e-3) / 1e12 if phases["eval_ms"] > 0 else None

@@ -182,17 +182,19 @@ typedef struct szb_phase_times {
     uint64_t select_levels;    /* tree levels descended (16 B node header each) */
     uint64_t backup_levels;    /* edges updated by backup (24 B read-modify-write each) */
     uint64_t edges_written;    /* children created by expansion (20 B each) */
-    float conv_ms;             /* total device time of the timed tower convolution launches (one 3x3 256->256
-                                  tcgen05 layer with residual per bf16 forward), CUDA events on the context's stream */
-    int32_t conv_launches;     /* how many launches conv_ms covers */
+    float conv_ms;             /* total device time of the timed network launches, CUDA events on the context's stream */
+    int32_t conv_launches;     /* how many launches conv_ms covers (one per bf16 forward) */
     int32_t conv_boards;       /* boards per timed launch (the GEMM's M / 64) */
-    int32_t reserved2;
+    int32_t conv_kind;         /* what is timed: 2 = k_tower_tc2, the whole tower (stem + 38 convolutions + policy 1x1) in one
+                                  launch; 1 = k_tower_tc2 on one 3x3 256->256 layer; 0 = k_conv_tc<256,0> on one such layer */
+    uint64_t conv_flop;        /* algorithmic FLOP (2 x MAC, no padding credit) of one timed launch */
 } szb_phase_times;
 int szb_set_profiling(szb_ctx *ctx, int32_t on);
 int szb_get_phase_times(szb_ctx *ctx, szb_phase_times *out);
 /* average duration (ms) of one launch of a kernel run `iters` times back to back on n boards:
- * which = 0: one 3x3 256->256 tower convolution (tcgen05, with residual) ; 1: whole bf16 forward ;
- * 2: whole fp32 forward ; 3: one 3x3 256->256 fp32 SIMT convolution */
+ * which = 0: one 3x3 256->256 tower convolution (single-CTA tcgen05 kernel, with residual) ; 1: whole bf16 forward ;
+ * 2: whole fp32 forward ; 3: one 3x3 256->256 fp32 SIMT convolution ; 4: one 3x3 256->256 tower convolution
+ * (CTA-pair kernel) ; 5: the whole tower in one CTA-pair launch */
 int szb_time_kernel(szb_ctx *ctx, int32_t which, int32_t n, int32_t iters, float *ms_avg_out);
 
 #ifdef __cplusplus

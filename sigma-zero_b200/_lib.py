@@ -39,7 +39,7 @@ class PhaseTimes(ctypes.Structure):
                 ("select_edges", ctypes.c_uint64), ("select_levels", ctypes.c_uint64),
                 ("backup_levels", ctypes.c_uint64), ("edges_written", ctypes.c_uint64),
                 ("conv_ms", ctypes.c_float), ("conv_launches", ctypes.c_int32), ("conv_boards", ctypes.c_int32),
-                ("reserved2", ctypes.c_int32)]
+                ("conv_kind", ctypes.c_int32), ("conv_flop", ctypes.c_uint64)]
 
 
 _vp, _i32, _u64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float

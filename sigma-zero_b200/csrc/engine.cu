@@ -1005,7 +1005,7 @@ int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
     out->steps = ctx->phase_steps; out->reserved = 0;
     out->select_edges = h[4]; out->select_levels = h[5]; out->backup_levels = h[6]; out->edges_written = h[7];
     net_collect_conv_times(ctx);
-    out->conv_ms = ctx->conv_ms; out->conv_launches = ctx->conv_launches; out->conv_boards = ctx->conv_boards; out->reserved2 = 0;
+    out->conv_ms = ctx->conv_ms; out->conv_launches = ctx->conv_launches; out->conv_boards = ctx->conv_boards; out->conv_kind = ctx->net_tower_mode; out->conv_flop = ctx->conv_flop;
     return 0;
 }
 

@@ -91,6 +91,8 @@ struct szb_ctx {
     size_t conv_events_used = 0;
     float conv_ms = 0;
     int conv_launches = 0, conv_boards = 0;
+    uint64_t conv_flop = 0;                    // algorithmic FLOP of one timed launch
+    int net_tower_mode = 2;                    // which bf16 tower kernel runs (net.cu: Net::tower_mode)
 };
 
 namespace szb {

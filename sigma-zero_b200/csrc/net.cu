@@ -11,6 +11,7 @@
 // convolution are then plain shifted TMA boxes.  GEMM view: M = 64*B (board squares), N = C_out, K = taps*C_in.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <map>
@@ -27,6 +28,9 @@ constexpr int C_IN_PAD = 128;            // 119 input planes padded to 128 chann
 constexpr int N_BLOCKS = 19;
 constexpr int POLICY_PLANES = 73;
 constexpr int POLICY_PAD = 80;           // N of the last policy GEMM (multiple of 16)
+// algorithmic FLOP (2 x MAC, no credit for channel padding) per board: one 3x3 256->256 layer; stem + 38 tower layers + policy 1x1
+constexpr uint64_t FLOP_TOWER_LAYER = 2ull * 64 * 256 * 2304;
+constexpr uint64_t FLOP_TOWER_ALL = 2ull * 64 * 256 * (119 * 9 + 38 * 2304 + 256);
 
 // ---- tcgen05 conv kernel geometry ---------------------------------------------------------------
 constexpr int TC_BLOCK_M = 128;          // two boards per tile
@@ -43,6 +47,9 @@ struct ConvLayer {
     __nv_bfloat16* w16 = nullptr;        // [cout_pad][taps*cin]  K-major
     CUtensorMap tm_w;
 };
+
+struct TowerMaps;
+struct TowerArgs;
 
 struct Net {
     bool loaded = false;
@@ -63,6 +70,14 @@ struct Net {
     float* logits = nullptr;             // [cap][4672]
     CUtensorMap tm_in16, tm_act16[3];
     int32_t* tc_error = nullptr;
+    // CTA-pair tower kernel (k_tower_tc2): all 40 N=256 layers in one weight / bias buffer + per-item completion counters
+    __nv_bfloat16* w16_all = nullptr;    // [MAX_TOWER_LAYERS * 256][2304]
+    float* bias_all = nullptr;           // [MAX_TOWER_LAYERS][256]
+    int32_t* ready = nullptr;            // [MAX_TOWER_LAYERS][ceil(cap / 4)]
+    struct TowerMaps* tower_maps = nullptr;   // host copies, passed by value at launch
+    struct TowerArgs* tower_args = nullptr;
+    int final_x = 0, final_y = 0;        // activation buffers holding the tower output / the policy-head hidden layer
+    int tower_mode = 2;                  // 0: single-CTA kernel per layer, 1: pair kernel per layer, 2: pair kernel, one launch
     int num_sms = 148;
     std::vector<void*> allocs;
 };
@@ -357,6 +372,296 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 }
 
 // =================================================================================================
+// tower kernel: CTA-pair (cta_group::2) implicit GEMM over a RANGE OF LAYERS in one persistent launch
+// =================================================================================================
+// The single-CTA kernel above is shared-memory-bandwidth bound (ncu, profiles/r01a_*): per 64-wide K step it
+// writes 48 KiB by TMA and reads 48 KiB by UTCHMMA in the 512 cycles the MMAs need -> 192 B/cycle against the
+// 128 B/cycle the SM has -> tensor pipe 68 % busy.  Here two CTAs of a cluster form one 256 x 256 tile
+// (4 boards x 256 channels): each CTA stages its own 128 rows of A and HALF of the weight tile, the leader
+// issues tcgen05.mma.cta_group::2, and both SMs read the two weight halves -> 64 KiB per 512 cycles.
+//
+// The launch is persistent over (layer, tile) work items in layer-major order, statically dealt round-robin to
+// the CTA pairs.  A 3x3 convolution of a board needs only that board of the previous layer, so item (l, t)
+// depends on item (l-1, t) alone: the producer acquires a per-item completion counter before its first
+// activation load, the epilogue warps release it after their last store.  Items are taken in increasing order
+// by every pair, so the wait chain always ends at the first layer: no deadlock, no grid-wide barrier, no wave
+// quantisation between layers (10240 items over 74 pairs instead of 40 launches of 3.46 waves).
+constexpr int T2_STAGES = 6;
+constexpr int T2_A_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's 128 rows (two boards) of A
+constexpr int T2_B_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's half (128 output channels) of the weight tile
+constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
+constexpr int T2_SMEM = T2_STAGES * T2_STAGE_BYTES + 1024;
+constexpr int MAX_TOWER_LAYERS = 40;                      // stem + 38 tower convolutions + policy 1x1
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the pair's even CTA
+constexpr int READY_PER_ITEM = 8;                         // 4 epilogue warps x 2 CTAs
+
+struct TowerLayer {
+    uint8_t a_map;       // 0: input planes (128 ch), 1..3: activation buffer 0..2
+    uint8_t taps;        // 9 or 1
+    uint8_t kchunks;     // C_in / 64
+    uint8_t res;         // activation buffer of the residual, 255 = none
+    uint8_t out;         // activation buffer written
+    uint8_t relu;
+    uint8_t pad[2];
+};
+
+struct alignas(64) TowerMaps {
+    CUtensorMap a[4];    // input planes, activation buffers 0..2: box 64 ch x 8 x 8 x 2 boards
+    CUtensorMap w;       // all layers' folded weights [MAX_TOWER_LAYERS * 256][2304]: box 64 k x 128 rows
+};
+
+struct TowerArgs {
+    int n_pair_tiles;    // ceil(boards / 4)
+    int n_boards;
+    int layer_begin, layer_end;
+    int32_t* ready;      // [MAX_TOWER_LAYERS][n_pair_tiles] completion counters, zeroed before the launch
+    const float* bias;   // [MAX_TOWER_LAYERS][256]
+    __nv_bfloat16* act[3];
+    int32_t* error;
+    TowerLayer L[MAX_TOWER_LAYERS];
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-CTA TMA loads: data lands in THIS CTA's shared memory, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// MMA completion -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ TowerArgs a) {
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr int ACC_COLS = 256;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[T2_STAGES], bar_empty[T2_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+    __shared__ float bias_sh[2][C_TOWER];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_items = (a.layer_end - a.layer_begin) * a.n_pair_tiles;
+    volatile int* abort_flag = &abort_sh;
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < T2_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&bar_acc_full[s]), 1); mbar_init(smem_u32(&bar_acc_empty[s]), READY_PER_ITEM); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                           // both CTAs' barriers and TMEM exist from here on
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===== TMA producer (one thread in each CTA) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int item = pair; item < n_items && ok; item += n_pairs) {
+                const int l = a.layer_begin + item / a.n_pair_tiles, t = item % a.n_pair_tiles;
+                const TowerLayer L = a.L[l];
+                if (l > a.layer_begin) {
+                    // item (l-1, t) must be complete: all 8 epilogue warps of whichever pair ran it have stored and released
+                    const int32_t* flag = a.ready + (size_t)(l - 1) * a.n_pair_tiles + t;
+                    if (ld_acquire_gpu(flag) < READY_PER_ITEM) {
+                        const long long t0 = clock64();
+                        while (ld_acquire_gpu(flag) < READY_PER_ITEM) {
+                            if (*abort_flag) { ok = false; break; }
+                            if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; ok = false; break; }
+                        }
+                        if (!ok) break;
+                    }
+                    asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores -> this thread's TMA reads
+                }
+                const CUtensorMap* tm_a = &maps.a[L.a_map];
+                const int k_iters = L.taps * L.kchunks;
+                const int board0 = (t * 2 + (int)rank) * 2;
+                const int wrow = l * C_TOWER + (int)rank * 128;
+                for (int it = 0; it < k_iters; it++) {
+                    const int tap = it / L.kchunks, kc = it - tap * L.kchunks;
+                    const int ky = L.taps == 9 ? tap / 3 : 1, kx = L.taps == 9 ? tap - (tap / 3) * 3 : 1;
+                    if (!(ok = mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag))) break;
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(full, 2 * T2_STAGE_BYTES);       // both CTAs' bytes land on the leader's barrier
+                    tma2_load_4d(sa, tm_a, full, kc * TC_BLOCK_K, kx, ky, board0);
+                    tma2_load_2d(sa + T2_A_BYTES, &maps.w, full, it * TC_BLOCK_K, wrow);
+                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local = 0;
+            bool ok = true;
+            for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
+                const TowerLayer L = a.L[a.layer_begin + item / a.n_pair_tiles];
+                const int k_iters = L.taps * L.kchunks;
+                const int acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                if (!(ok = mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int it = 0; it < k_iters; it++) {
+                    if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
+                    const uint32_t sb = sa + T2_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / 16; k++) {
+                        tc2_mma_bf16(d_tmem, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it | k) != 0);
+                    }
+                    tc2_commit(smem_u32(&bar_empty[stage]));
+                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (ok) tc2_commit(smem_u32(&bar_acc_full[acc]));
+            }
+        }
+    } else {
+        // ===== epilogue (4 warps in each CTA): TMEM -> +bias [+residual] -> ReLU -> bf16 NHWC store =====
+        const int lane_group = warp & 3;
+        const int etid = threadIdx.x - 64;                         // 0..127
+        int local = 0;
+        bool ok = true;
+        for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
+            const int l = a.layer_begin + item / a.n_pair_tiles, t = item % a.n_pair_tiles;
+            const TowerLayer L = a.L[l];
+            const int acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            bias_sh[acc][etid] = a.bias[l * C_TOWER + etid];
+            bias_sh[acc][etid + 128] = a.bias[l * C_TOWER + etid + 128];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            ok = mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase, abort_flag);
+            ok = __all_sync(0xFFFFFFFFu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            const int row = lane_group * 32 + lane;
+            const int m = (t * 2 + (int)rank) * TC_BLOCK_M + row;
+            const int board = m >> 6, sq = m & 63;
+            const bool live = board < a.n_boards;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
+            const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
+            const __nv_bfloat16* resp = (L.res != 255 && live) ? a.act[L.res] + pix * C_TOWER : nullptr;
+            __nv_bfloat16* outp = a.act[L.out] + pix * C_TOWER;
+            uint4 rnext[4];
+            if (resp) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) rnext[q] = reinterpret_cast<const uint4*>(resp)[q];
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < C_TOWER; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c0, v);
+                uint4 rcur[4];
+                if (resp) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) rcur[q] = rnext[q];
+                    if (c0 + 32 < C_TOWER) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) rnext[q] = reinterpret_cast<const uint4*>(resp + c0 + 32)[q];
+                    }
+                }
+                tmem_ld_wait();
+                if (live) {
+                    uint4 o[4];
+                    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(rcur);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        float x0 = __uint_as_float(v[2 * j]) + bias_sh[acc][c0 + 2 * j];
+                        float x1 = __uint_as_float(v[2 * j + 1]) + bias_sh[acc][c0 + 2 * j + 1];
+                        if (resp) {
+                            const float2 r = __bfloat1622float2(rb[j]);
+                            x0 += r.x;
+                            x1 += r.y;
+                        }
+                        if (L.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        ob[j] = __floats2bfloat162_rn(x0, x1);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(outp + c0);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) op[q] = o[q];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_leader(smem_u32(&bar_acc_empty[acc]));            // accumulator stage free again (leader's barrier)
+                __threadfence();
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(a.ready + (size_t)l * a.n_pair_tiles + t), "r"(1) : "memory");
+            }
+        }
+    }
+    // ===== teardown =====
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+    if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+}
+
+// =================================================================================================
 // fp32 SIMT convolution (parity path)
 // =================================================================================================
 struct F32Args {
@@ -577,6 +882,8 @@ static int upload_conv(szb_ctx* ctx, Net* net, ConvLayer& L, const float* w, int
 void net_destroy(szb_ctx* ctx) {
     if (!ctx->net) return;
     for (void* p : ctx->net->allocs) cudaFree(p);
+    delete ctx->net->tower_maps;
+    delete ctx->net->tower_args;
     delete ctx->net;
     ctx->net = nullptr;
 }
@@ -597,9 +904,92 @@ static int net_alloc_activations(szb_ctx* ctx, Net* net) {
     return 0;
 }
 
+// combined weight / bias buffers, layer table and tensor maps of the CTA-pair tower kernel
+static int net_setup_tower(szb_ctx* ctx, Net* net) {
+    int rc;
+    constexpr int KMAX = 9 * C_TOWER;
+    if ((rc = net_alloc(ctx, net, &net->w16_all, (size_t)MAX_TOWER_LAYERS * C_TOWER * KMAX))) return rc;
+    if ((rc = net_alloc(ctx, net, &net->bias_all, (size_t)MAX_TOWER_LAYERS * C_TOWER))) return rc;
+    if ((rc = net_alloc(ctx, net, &net->ready, (size_t)MAX_TOWER_LAYERS * ((net->cap + 3) / 4)))) return rc;
+    delete net->tower_maps;
+    delete net->tower_args;
+    net->tower_maps = new TowerMaps();
+    net->tower_args = new TowerArgs();
+    TowerArgs& a = *net->tower_args;
+    memset(&a, 0, sizeof a);
+    auto put = [&](int l, const ConvLayer& L) -> int {
+        const int K = L.taps * L.cin;
+        SZB_CUDA(ctx, cudaMemcpy2DAsync(net->w16_all + (size_t)l * C_TOWER * KMAX, (size_t)KMAX * 2, L.w16, (size_t)K * 2, (size_t)K * 2,
+                                        C_TOWER, cudaMemcpyDeviceToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->bias_all + (size_t)l * C_TOWER, L.bias, C_TOWER * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    };
+    auto layer = [&](int l, int a_map, int taps, int kchunks, int res, int out) {
+        TowerLayer& T = a.L[l];
+        T.a_map = (uint8_t)a_map; T.taps = (uint8_t)taps; T.kchunks = (uint8_t)kchunks;
+        T.res = (uint8_t)res; T.out = (uint8_t)out; T.relu = 1;
+    };
+    if ((rc = put(0, net->stem))) return rc;
+    layer(0, 0, 9, C_IN_PAD / TC_BLOCK_K, 255, 0);
+    int x = 0;
+    for (int blk = 0; blk < N_BLOCKS; blk++) {
+        const int y = (x + 1) % 3, o = (x + 2) % 3;
+        if ((rc = put(1 + 2 * blk, net->tower[2 * blk])) || (rc = put(2 + 2 * blk, net->tower[2 * blk + 1]))) return rc;
+        layer(1 + 2 * blk, 1 + x, 9, C_TOWER / TC_BLOCK_K, 255, y);
+        layer(2 + 2 * blk, 1 + y, 9, C_TOWER / TC_BLOCK_K, x, o);
+        x = o;
+    }
+    const int y = (x + 1) % 3;
+    if ((rc = put(MAX_TOWER_LAYERS - 1, net->p1))) return rc;
+    layer(MAX_TOWER_LAYERS - 1, 1 + x, 1, C_TOWER / TC_BLOCK_K, 255, y);
+    net->final_x = x;
+    net->final_y = y;
+    a.ready = net->ready;
+    a.bias = net->bias_all;
+    for (int i = 0; i < 3; i++) a.act[i] = net->act16[i];
+    a.error = net->tc_error;
+    net->tower_maps->a[0] = net->tm_in16;
+    for (int i = 0; i < 3; i++) net->tower_maps->a[1 + i] = net->tm_act16[i];
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)KMAX, (cuuint64_t)MAX_TOWER_LAYERS * C_TOWER};
+        cuuint64_t strides[1] = {(cuuint64_t)KMAX * 2};
+        cuuint32_t box[2] = {TC_BLOCK_K, 128};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode(&net->tower_maps->w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, net->w16_all, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(tower weights) failed: %d", (int)r);
+    }
+    const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
+    if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
+    ctx->net_tower_mode = net->tower_mode;
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // =================================================================================================
 // host: forward
 // =================================================================================================
+// layers [layer_begin, layer_end) of the tower for n boards in one persistent CTA-pair launch
+static int launch_tower(szb_ctx* ctx, Net* net, int n, int layer_begin, int layer_end) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+        attr_set = true;
+    }
+    TowerArgs a = *net->tower_args;
+    a.n_pair_tiles = (n + 3) / 4;
+    a.n_boards = n;
+    a.layer_begin = layer_begin;
+    a.layer_end = layer_end;
+    if (layer_end - layer_begin > 1)
+        SZB_CUDA(ctx, cudaMemsetAsync(net->ready, 0, sizeof(int32_t) * (size_t)MAX_TOWER_LAYERS * a.n_pair_tiles, ctx->stream));
+    const int grid = 2 * std::min(a.n_pair_tiles, net->num_sms / 2);
+    k_tower_tc2<<<grid, TC_THREADS, T2_SMEM, ctx->stream>>>(*net->tower_maps, a);
+    ctx->launches++;
+    return 0;
+}
+
 template <int N_TILE, int MODE>
 static int launch_tc(szb_ctx* ctx, Net* net, const CUtensorMap& tm_a, const ConvLayer& L, const __nv_bfloat16* residual,
                      __nv_bfloat16* out, float* logits, int n, int relu) {
@@ -670,20 +1060,38 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t
         k_planes_to_nhwc<__nv_bfloat16><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in16);
         ctx->launches++;
         int rc;
-        if ((rc = launch_tc<256, 0>(ctx, net, net->tm_in16, net->stem, nullptr, net->act16[0], nullptr, n, 1))) return rc;
-        int x = 0;
-        for (int blk = 0; blk < N_BLOCKS; blk++) {
-            const int y = (x + 1) % 3, o = (x + 2) % 3;
-            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->tower[2 * blk], nullptr, net->act16[y], nullptr, n, 1))) return rc;
-            // measurement hook: while profiling, bracket ONE tower layer (block 9, second conv, with residual) per forward
-            cudaEvent_t* cev = (ctx->profiling && blk == 9) ? conv_event_pair(ctx) : nullptr;
+        int x, y;
+        if (net->tower_mode == 0) {
+            // single-CTA kernel, one launch per layer (kept as the A/B reference of the pair kernel)
+            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_in16, net->stem, nullptr, net->act16[0], nullptr, n, 1))) return rc;
+            x = 0;
+            for (int blk = 0; blk < N_BLOCKS; blk++) {
+                const int yy = (x + 1) % 3, o = (x + 2) % 3;
+                if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->tower[2 * blk], nullptr, net->act16[yy], nullptr, n, 1))) return rc;
+                cudaEvent_t* cev = (ctx->profiling && blk == 9) ? conv_event_pair(ctx) : nullptr;
+                if (cev) cudaEventRecord(cev[0], st);
+                if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[yy], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1))) return rc;
+                if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_LAYER * (uint64_t)n; }
+                x = o;
+            }
+            y = (x + 1) % 3;
+            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->p1, nullptr, net->act16[y], nullptr, n, 1))) return rc;
+        } else if (net->tower_mode == 1) {
+            for (int l = 0; l < MAX_TOWER_LAYERS; l++) {
+                cudaEvent_t* cev = (ctx->profiling && l == 20) ? conv_event_pair(ctx) : nullptr;
+                if (cev) cudaEventRecord(cev[0], st);
+                if ((rc = launch_tower(ctx, net, n, l, l + 1))) return rc;
+                if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_LAYER * (uint64_t)n; }
+            }
+            x = net->final_x; y = net->final_y;
+        } else {
+            // stem + 38 tower convolutions + policy 1x1 in ONE persistent launch; measurement hook brackets exactly that launch
+            cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
             if (cev) cudaEventRecord(cev[0], st);
-            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[y], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1))) return rc;
-            if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; }
-            x = o;
+            if ((rc = launch_tower(ctx, net, n, 0, MAX_TOWER_LAYERS))) return rc;
+            if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_ALL * (uint64_t)n; }
+            x = net->final_x; y = net->final_y;
         }
-        const int y = (x + 1) % 3;
-        if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->p1, nullptr, net->act16[y], nullptr, n, 1))) return rc;
         if ((rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0))) return rc;
         k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
         ctx->launches++;
@@ -802,6 +1210,7 @@ int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, cons
         SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     if ((rc = net_alloc_activations(ctx, net))) return rc;
+    if ((rc = net_setup_tower(ctx, net))) return rc;
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     net->loaded = true;
     return 0;
@@ -858,6 +1267,8 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
             case 1: rc = net_forward_device(ctx, SZB_EVAL_NET_BF16, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
             case 2: rc = net_forward_device(ctx, SZB_EVAL_NET_FP32, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
             case 3: launch_f32(ctx, net->act32[i & 1], net->tower[1], net->act32[2], net->act32[(i + 1) & 1], n, 1, 0); break;
+            case 4: rc = launch_tower(ctx, net, n, 20, 21); break;                       // one tower layer, CTA-pair kernel
+            case 5: rc = launch_tower(ctx, net, n, 0, MAX_TOWER_LAYERS); break;          // whole tower, one launch
             default: rc = fail(ctx, SZB_ERR_ARG, "unknown kernel selector %d", which);
             }
         }

@@ -128,3 +128,28 @@ def test_batch_invariance(setup, evaluator):
     assert np.array_equal(pol_b[7:14], pol_a) and np.array_equal(val_b[14:], val_a[:5])
     pol_c, val_c = eng.net_forward(packed[2:3], evaluator)
     assert np.array_equal(pol_c[0], pol_a[2]) and val_c[0] == val_a[2]
+
+
+def test_tower_kernel_variants_bit_identical(monkeypatch):
+    """the three bf16 tower implementations (single-CTA per layer, CTA-pair per layer, CTA-pair one persistent launch
+    with per-item dependency counters) run the same MMAs in the same K order: their outputs must be bit-identical,
+    at a batch that spans several waves of the persistent kernel and is not a multiple of the 4-board pair tile"""
+    from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
+    torch.manual_seed(2)
+    model = ref_path.build_policy_nn().eval()
+    _randomise_bn(model, 11)
+    x = _positions(9, seed=21)
+    packed = np.stack([hash_eval.pack_planes(p) for p in x])
+    n = 4 * 74 * 2 + 3                      # > 2 items per CTA pair per layer, ragged last tile
+    big = packed[np.arange(n) % len(packed)]
+    outs = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("SZB_TOWER_MODE", mode)
+        eng = Engine(max_games=n, max_searches=4)
+        eng.load_state_dict(model.state_dict())
+        outs.append(eng.net_forward(big, EVAL_NET_BF16, logits=True))
+        eng.close()
+    for l, v in outs[1:]:
+        assert np.array_equal(l, outs[0][0]) and np.array_equal(v, outs[0][1])
+    # and the batch really is periodic: every copy of a position gives the same logits
+    assert np.array_equal(outs[2][0][:len(packed)], outs[2][0][len(packed):2 * len(packed)])

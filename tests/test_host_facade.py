@@ -1,0 +1,136 @@
+"""Host-side logic of the drop-in facade (no GPU): the closed-form move <-> index codec against the golden
+vectors recorded from the UNMODIFIED reference codec, plane packing, game sharding, the flat weight buffer and
+its broadcast over a world_size-2 gloo group, and bench.py's reference-arm JSON contract."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+
+def test_facade_codec_known_answers():
+    from sigma_zero_b200 import chess_compat as cc
+    from sigma_zero_b200.chess_tensor import index_move, move_index
+    kat = [("e2e4", 1, 116), ("e7e5", 0, 115), ("g1f3", 1, 4094), ("g8f6", 0, 3641), ("e1g1", 1, 1020),
+           ("e1h1", 1, 1084), ("a7a8q", 1, 8), ("a7a8n", 1, 4104), ("b7a8r", 1, 4617), ("h2h1b", 0, 4296),
+           ("g2h1n", 0, 4233)]
+    for u, w, idx in kat:
+        m = cc.Move.from_uci(u)
+        assert move_index(m, bool(w)) == idx, u
+        back = index_move(idx, bool(w), {u: True} if u.endswith("q") else None)
+        assert back.uci() == u, (u, back.uci())
+
+
+def test_facade_codec_golden(golden_dir):
+    """every legal move of 333 positions reached by the reference: facade index == reference index, and decode inverts"""
+    from sigma_zero_b200 import chess_compat as cc
+    from sigma_zero_b200.chess_tensor import actionsToTensor, index_move, move_index, tensorToAction
+    z = np.load(os.path.join(golden_dir, "codec.npz"))
+    off = np.concatenate([[0], np.cumsum(z["idx_len"])])
+    for i in range(0, len(z["sid"]), 3):
+        ucis = str(z["uci"][i]).split()
+        want = z["idx_flat"][off[i]:off[i + 1]].astype(int).tolist()
+        white = (len(str(z["moves"][i]).split()) % 2) == 0
+        moves = [cc.Move.from_uci(u) for u in ucis]
+        got = sorted(move_index(m, white) for m in moves)
+        assert got == sorted(want), i
+        mask, qp = actionsToTensor(moves, white)
+        assert mask.sum().item() == len(moves) and set(mask.nonzero().flatten().tolist()) == set(want)
+        decoded = tensorToAction(mask, white, qp)
+        assert sorted(m.uci() for m in decoded) == sorted(ucis), i
+        for m in moves:
+            assert index_move(move_index(m, white), white, qp).uci() == m.uci()
+
+
+def test_plane_packing_roundtrip(golden_dir):
+    from sigma_zero_b200 import runtime
+    z = np.load(os.path.join(golden_dir, "codec.npz"))
+    words = z["planes"][:16]
+    planes = runtime.unpack_planes(words)
+    assert planes.shape == (16, 119, 8, 8) and planes.dtype == bool
+    assert np.array_equal(runtime.pack_planes(planes), words)
+    # bit (row*8+col) of word k is planes[k,row,col]
+    k, r, c = 5, 7, 4
+    assert bool((int(words[0, k]) >> (r * 8 + c)) & 1) == bool(planes[0, k, r, c])
+
+
+def test_shards_cover_all_games():
+    from sigma_zero_b200.train_RL import shard_of
+    for n in (1, 7, 500, 1024):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard_of(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_state_dict_layout_and_flat_buffer():
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.train_RL import flatten_state_dict, unflatten_into
+    torch.manual_seed(3)
+    a = policyNN({})
+    sd = a.state_dict()
+    assert len(sd) == 252 and sum(v.numel() for k, v in sd.items() if not k.endswith("num_batches_tracked")) == 22809420 + 2 * (256 * 40 + 1)
+    keys, flat = flatten_state_dict(sd)
+    b = policyNN({})
+    unflatten_into(b, keys, flat)
+    for k in keys:
+        assert torch.equal(a.state_dict()[k], b.state_dict()[k]), k
+    with pytest.raises(RuntimeError):
+        policyNN({}).train()(torch.zeros(1, 119, 8, 8))      # inference-only: never a silent torch fallback
+
+
+def _bcast_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.train_RL import broadcast_weights, flatten_state_dict, shard_of
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                    # ranks start with DIFFERENT weights
+    m = policyNN({})
+    nbytes = broadcast_weights(m, src=0)
+    _, flat = flatten_state_dict(m.state_dict())
+    digest = torch.tensor([float(flat.double().sum()), float(flat.abs().double().sum())], dtype=torch.float64)
+    gathered = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, digest)
+    lo, hi = shard_of(500, rank, world)
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([hi - lo]))
+    if rank == 0:
+        out.put((nbytes, [g.tolist() for g in gathered], [int(s) for s in sizes]))
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    nbytes, digests, sizes = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert nbytes == (22809420 + 2 * (256 * 40 + 1)) * 4        # parameters + BN running statistics, fp32
+    assert digests[0] == digests[1]                              # rank 1 now holds rank 0's weights
+    assert sum(sizes) == 500
+
+
+def test_bench_reference_arm_contract():
+    out = subprocess.run([sys.executable, os.path.join(util.ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--ref-sims", "8"], capture_output=True, text=True, timeout=600, cwd=util.ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "mcts_simulations_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    for k in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config"):
+        assert k in line
