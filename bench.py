@@ -296,7 +296,6 @@ def run_ours(args, wl):
     # ---- device-resident run (value) ---------------------------------------------------------------
     for w in range(args.warmup):
         eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)
-    eng.set_profiling(True)
     st0 = eng.stats()
     sampler = ClockSampler(local)
     barrier()
@@ -314,6 +313,10 @@ def run_ours(args, wl):
     clocks = sampler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     st1 = eng.stats()
+    # measurement pass (not part of `value`): one more step with the library's profiling on, which serialises the two
+    # cohorts on the context's stream and brackets every phase and the network's tower launch with CUDA events
+    eng.set_profiling(True)
+    eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)
     pt = eng.phase_times()
     eng.set_profiling(False)
     total_sims = sum_over_ranks(sims_done)
@@ -390,10 +393,12 @@ def run_ours(args, wl):
             "config": {"workload": wl["name"], "games_per_gpu": G, "num_searches": S, "C": C_PUCT, "learning": True,
                        "chess960": wl["chess960"], "positions": "S2 random-played: U{0..40} random legal plies from the start, seed 0",
                        "weights": weights, "parallelism": "games sharded, %d x network replica" % world,
+                       "pipelining": "2 cohorts of %d games on two streams (tree kernels of one run under the other's network kernel)" % (G // 2),
                        "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
                              % (G * 100 * 256 * 2 // 2 ** 20)},
             "moves_per_sec": total_moves / (ms * 1e-3), "evals_per_sec": evals / (ms * 1e-3),
             "network_tflops_in_step": net_tflops, "phase_ms_per_simulation_step": phases,
+            "phase_note": "phases and roofline come from one extra profiled step (single cohort, CUDA events on the library stream) run right after the timed region",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pos_bytes,
                     "d2h_bytes_per_step": G * 4672 * 4 + G * 73 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "szb_games_set(host positions) + szb_search(host visit/child buffers), pinned memory"},

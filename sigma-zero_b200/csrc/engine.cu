@@ -7,6 +7,7 @@
 //   k_finish  : warp per tree, mask/normalise/noise, child allocation, backup (mcts.py:77-109, mctsnode.py:39-63)
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include "engine.cuh"
@@ -200,9 +201,9 @@ __global__ void k_search_begin(Dev d) {
 
 // warp per tree
 __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (g >= d.n_games) return;
+    if (g >= d.g_end) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     int node = 0, depth = 0;
     unsigned long long scanned = 0;
@@ -249,8 +250,8 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
 __global__ void __launch_bounds__(32) k_expand(Dev d) {
     __shared__ Tables T;
     load_tables(&T, d.tables);
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= d.n_games) return;
+    const int g = d.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= d.g_end) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     Pos* gp = d.pool + (size_t)g * d.pool_stride;
     const int e = d.sel_edge[g];
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(32) k_expand(Dev d) {
 
 // block per tree: policy[i] / value from the integer hash of the packed planes
 __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
-    const int g = blockIdx.x;
+    const int g = d.g_begin + blockIdx.x;
     if (!d.need_eval[g]) return;
     __shared__ uint64_t h_sh;
     if (threadIdx.x == 0) {
@@ -313,9 +314,9 @@ __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
 
 // warp per tree
 __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (g >= d.n_games) return;
+    if (g >= d.g_end) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     const int node = d.sel_node[g];
     float v;
@@ -624,6 +625,11 @@ void szb_destroy(szb_ctx* ctx) {
     for (Pos* p : ctx->perft_levels) if (p) cudaFree(p);
     if (ctx->perft_counter) cudaFree(ctx->perft_counter);
     if (ctx->stage) cudaFree(ctx->stage);
+    for (int c = 0; c < 2; c++) {
+        if (ctx->cohort_stream[c]) cudaStreamDestroy(ctx->cohort_stream[c]);
+        if (ctx->ev_join[c]) cudaEventDestroy(ctx->ev_join[c]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -640,6 +646,15 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     *out = ctx;        // returned even on failure so the caller can read the message, then destroy
     SZB_CUDA(ctx, cudaSetDevice(device));
     SZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->work = ctx->stream;
+    for (int c = 0; c < 2; c++) {
+        SZB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->cohort_stream[c], cudaStreamNonBlocking));
+        SZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join[c], cudaEventDisableTiming));
+    }
+    SZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    ctx->cohorts = cfg->cohorts;
+    if (ctx->cohorts < 0 || ctx->cohorts > 2) return fail(ctx, SZB_ERR_ARG, "szb_config.cohorts must be 0 (automatic), 1 or 2");
+    if (const char* e = getenv("SZB_COHORTS")) { if (e[0] == '1' || e[0] == '2') ctx->cohorts = e[0] - '0'; }   // measurement aid
     Dev& d = ctx->d;
     const size_t G = (size_t)cfg->max_games;
     d.nodes_per_game = cfg->max_searches + 1;
@@ -821,9 +836,10 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         return fail(ctx, SZB_ERR_ARG, "num_searches %d outside [1, max_searches=%d]", num_searches, ctx->cfg.max_searches);
     cudaStream_t st = ctx->stream;
     SZB_CUDA(ctx, cudaMemsetAsync(d.error_flag, 0, sizeof(int32_t), st));
+    d.g_begin = 0;
+    d.g_end = G;
     k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d);
     ctx->launches++;
-    const int warp_blocks = (G * 32 + 127) / 128;
     const bool prof = ctx->profiling;
     if (prof) {
         while ((int)ctx->prof_events.size() < 5 * num_searches) {
@@ -832,26 +848,55 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             ctx->prof_events.push_back(e);
         }
     }
-    for (int s = 0; s < num_searches; s++) {
-        cudaEvent_t* ev = prof ? &ctx->prof_events[5 * (size_t)s] : nullptr;
-        if (prof) cudaEventRecord(ev[0], st);
-        k_select<<<warp_blocks, 128, 0, st>>>(d, c_puct);
-        if (prof) cudaEventRecord(ev[1], st);
-        k_expand<<<(G + 31) / 32, 32, 0, st>>>(d);
-        if (prof) cudaEventRecord(ev[2], st);
-        ctx->launches += 2;
-        if (evaluator == SZB_EVAL_HASH) {
-            k_hash_eval<<<G, 128, 0, st>>>(d);
-            ctx->launches++;
-        } else {
-            int rc = net_evaluate_batch(ctx, evaluator, G);
-            if (rc) return rc;
-        }
-        if (prof) cudaEventRecord(ev[3], st);
-        k_finish<<<warp_blocks, 128, 0, st>>>(d, learning);
-        if (prof) cudaEventRecord(ev[4], st);
-        ctx->launches++;
+    // Cohorts: the games are split into two halves that step independently on two streams, so that one half's tree
+    // kernels (select / expand / finish: latency-bound, a few hundred resident warps) run under the other half's
+    // tensor-bound network kernel.  Games never interact, so results do not depend on the split.  Profiling keeps one
+    // cohort on the context's stream so that per-phase and per-kernel durations mean what they say.
+    int n_cohorts = ctx->cohorts ? ctx->cohorts : (G >= 256 ? 2 : 1);
+    if (prof || G < 8) n_cohorts = 1;
+    int bounds[3] = {0, G, G};
+    if (n_cohorts == 2) bounds[1] = ((G / 2 + 3) / 4) * 4;        // network tiles are 4 boards wide
+    if (n_cohorts == 2) {
+        SZB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        for (int c = 0; c < 2; c++) SZB_CUDA(ctx, cudaStreamWaitEvent(ctx->cohort_stream[c], ctx->ev_fork, 0));
     }
+    int rc = 0;
+    for (int s = 0; s < num_searches && !rc; s++) {
+        for (int c = 0; c < n_cohorts && !rc; c++) {
+            Dev dc = d;
+            dc.g_begin = bounds[c];
+            dc.g_end = bounds[c + 1];
+            const int n = dc.g_end - dc.g_begin;
+            cudaStream_t cs = n_cohorts == 2 ? ctx->cohort_stream[c] : st;
+            ctx->work = cs;
+            const int warp_blocks = (n * 32 + 127) / 128;
+            cudaEvent_t* ev = prof ? &ctx->prof_events[5 * (size_t)s] : nullptr;
+            if (prof) cudaEventRecord(ev[0], cs);
+            k_select<<<warp_blocks, 128, 0, cs>>>(dc, c_puct);
+            if (prof) cudaEventRecord(ev[1], cs);
+            k_expand<<<(n + 31) / 32, 32, 0, cs>>>(dc);
+            if (prof) cudaEventRecord(ev[2], cs);
+            ctx->launches += 2;
+            if (evaluator == SZB_EVAL_HASH) {
+                k_hash_eval<<<n, 128, 0, cs>>>(dc);
+                ctx->launches++;
+            } else {
+                rc = net_evaluate_batch(ctx, evaluator, dc.g_begin, n);
+            }
+            if (prof) cudaEventRecord(ev[3], cs);
+            k_finish<<<warp_blocks, 128, 0, cs>>>(dc, learning);
+            if (prof) cudaEventRecord(ev[4], cs);
+            ctx->launches++;
+        }
+    }
+    ctx->work = st;
+    if (n_cohorts == 2) {
+        for (int c = 0; c < 2; c++) {
+            SZB_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], ctx->cohort_stream[c]));
+            SZB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+        }
+    }
+    if (rc) { cudaStreamSynchronize(st); return rc; }
     SZB_CUDA(ctx, cudaGetLastError());
     int32_t flag = 0;
     unsigned long long top = 0;

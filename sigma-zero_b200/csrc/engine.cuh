@@ -25,6 +25,7 @@ struct Dev {
     const Tables* tables;
     int pool_stride;
     int n_games;
+    int g_begin, g_end;      // game range the step kernels of this launch work on (a cohort of the search batch)
     // ---- tree: visited nodes (one per simulation) -------------------------------------------------
     int nodes_per_game;      // max_searches + 1
     int32_t* node_edge0;     // first child edge (global index)
@@ -64,6 +65,10 @@ struct Dev {
 struct szb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t work = nullptr;               // stream the launch helpers use: `stream`, or a cohort stream inside a search
+    cudaStream_t cohort_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int cohorts = 0;                           // 0 = automatic
     std::string err;
     szb_config cfg{};
     szb::Dev d{};
@@ -99,8 +104,8 @@ namespace szb {
 int fail(szb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(szb_ctx* ctx, cudaError_t e, const char* what);
 void* ctx_stage(szb_ctx* ctx, size_t bytes);
-// net.cu: evaluate the rows of d.planes with need_eval set -> d.policy / d.value (softmax policy).
-int net_evaluate_batch(szb_ctx* ctx, int evaluator, int n);
+// net.cu: evaluate games [g0, g0 + n) of d.planes -> d.policy / d.value (softmax policy) on ctx->work.
+int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n);
 void net_destroy(szb_ctx* ctx);
 int net_check_error(szb_ctx* ctx);
 // net.cu: fold the recorded conv event pairs into ctx->conv_ms (call after the stream is synchronised)

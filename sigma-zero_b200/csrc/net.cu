@@ -58,7 +58,7 @@ struct Net {
     // value head (fp32 everywhere)
     float* v_w = nullptr;                // [256] conv_v1 * bn scale
     float v_b = 0.f;
-    float* fc1_w = nullptr;              // [256][64]
+    float* fc1_w = nullptr;              // [64][256] (fc_v1.weight transposed)
     float* fc1_b = nullptr;              // [256]
     float* fc2_w = nullptr;              // [256]
     float fc2_b = 0.f;
@@ -209,7 +209,8 @@ struct TcArgs {
     const __nv_bfloat16* residual;   // halo NHWC [.][10][10][256] or null
     __nv_bfloat16* out;          // halo NHWC (mode 0)
     float* logits;               // [B][4672] (mode 1)
-    int n_boards;                // rows beyond this are not stored
+    int n_boards;                // boards beyond board0 + n_boards are not stored
+    int board0;                  // first board of this launch inside the activation buffers (cohort offset, even)
     int relu;
     int32_t* error;
 };
@@ -263,7 +264,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     mbar_expect_tx(full, STAGE_BYTES);
-                    tma_load_4d(sa, &tm_a, full, kc * TC_BLOCK_K, kx, ky, tile * 2);
+                    tma_load_4d(sa, &tm_a, full, kc * TC_BLOCK_K, kx, ky, a.board0 + tile * 2);
                     tma_load_2d(sa + TC_A_BYTES, &tm_w, full, it * TC_BLOCK_K, 0);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -311,8 +312,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             tc_fence_after();
             const int row = lane_group * 32 + lane;
             const int m = tile * TC_BLOCK_M + row;
-            const int board = m >> 6, sq = m & 63;
-            const bool live = board < a.n_boards;
+            const int board = a.board0 + (m >> 6), sq = m & 63;
+            const bool live = board < a.board0 + a.n_boards;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
             const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
 #pragma unroll 1
@@ -413,6 +414,7 @@ struct alignas(64) TowerMaps {
 struct TowerArgs {
     int n_pair_tiles;    // ceil(boards / 4)
     int n_boards;
+    int board0;          // first board of this launch inside the activation buffers (cohort offset, multiple of 4)
     int layer_begin, layer_end;
     int32_t* ready;      // [MAX_TOWER_LAYERS][n_pair_tiles] completion counters, zeroed before the launch
     const float* bias;   // [MAX_TOWER_LAYERS][256]
@@ -530,7 +532,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 }
                 const CUtensorMap* tm_a = &maps.a[L.a_map];
                 const int k_iters = L.taps * L.kchunks;
-                const int board0 = (t * 2 + (int)rank) * 2;
+                const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
                 const int wrow = l * C_TOWER + (int)rank * 128;
                 for (int it = 0; it < k_iters; it++) {
                     const int tap = it / L.kchunks, kc = it - tap * L.kchunks;
@@ -595,8 +597,8 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             tc_fence_after();
             const int row = lane_group * 32 + lane;
             const int m = (t * 2 + (int)rank) * TC_BLOCK_M + row;
-            const int board = m >> 6, sq = m & 63;
-            const bool live = board < a.n_boards;
+            const int board = a.board0 + (m >> 6), sq = m & 63;
+            const bool live = board < a.board0 + a.n_boards;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
             const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
             const __nv_bfloat16* resp = (L.res != 255 && live) ? a.act[L.res] + pix * C_TOWER : nullptr;
@@ -758,20 +760,37 @@ __global__ void k_planes_to_nhwc(const uint64_t* planes, int stride, int n, T* o
 }
 
 // value head (network.py:156-174): conv1x1 256->1 (+BN, ReLU) -> fc 64->256 (ReLU) -> fc 256->1 -> tanh.  Block per board.
+// fc1_wT is fc_v1.weight transposed to [64][256] so that the 256 threads read consecutive floats.
 template <class T>
-__global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v_w, float v_b, const float* fc1_w, const float* fc1_b,
+__global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v_w, float v_b, const float* fc1_wT, const float* fc1_b,
                                                     const float* fc2_w, float fc2_b, float* value, int n) {
     __shared__ float plane[64];
     __shared__ float red[8];
+    __shared__ float vw_sh[C_TOWER];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int sq = tid >> 2, part = tid & 3;
+    vw_sh[tid] = v_w[tid];
+    __syncthreads();
     const T* row = act + (((size_t)b * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1) * C_TOWER + part * 64;
+    const float* vw = vw_sh + part * 64;
     float s = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < 64; c++) {
-        float x;
-        if constexpr (sizeof(T) == 2) x = __bfloat162float(row[c]); else x = row[c];
-        s = fmaf(x, v_w[part * 64 + c], s);
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint4 u = reinterpret_cast<const uint4*>(row)[q];
+            const __nv_bfloat16* h8 = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+            for (int j = 0; j < 8; j++) s = fmaf(__bfloat162float(h8[j]), vw[q * 8 + j], s);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const float4 u = reinterpret_cast<const float4*>(row)[q];
+            s = fmaf(u.x, vw[q * 4], s);
+            s = fmaf(u.y, vw[q * 4 + 1], s);
+            s = fmaf(u.z, vw[q * 4 + 2], s);
+            s = fmaf(u.w, vw[q * 4 + 3], s);
+        }
     }
     s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
     s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
@@ -779,7 +798,7 @@ __global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v
     __syncthreads();
     float h = fc1_b[tid];
 #pragma unroll 8
-    for (int k = 0; k < 64; k++) h = fmaf(plane[k], fc1_w[tid * 64 + k], h);
+    for (int k = 0; k < 64; k++) h = fmaf(plane[k], fc1_wT[k * 256 + tid], h);
     h = fmaxf(h, 0.f) * fc2_w[tid];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, off);
@@ -971,7 +990,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
 // host: forward
 // =================================================================================================
 // layers [layer_begin, layer_end) of the tower for n boards in one persistent CTA-pair launch
-static int launch_tower(szb_ctx* ctx, Net* net, int n, int layer_begin, int layer_end) {
+static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, int layer_end) {
     static bool attr_set = false;
     if (!attr_set) {
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
@@ -980,19 +999,21 @@ static int launch_tower(szb_ctx* ctx, Net* net, int n, int layer_begin, int laye
     TowerArgs a = *net->tower_args;
     a.n_pair_tiles = (n + 3) / 4;
     a.n_boards = n;
+    a.board0 = b0;
     a.layer_begin = layer_begin;
     a.layer_end = layer_end;
+    a.ready = net->ready + (size_t)MAX_TOWER_LAYERS * (b0 / 4);      // cohorts (disjoint board ranges) get disjoint counter regions
     if (layer_end - layer_begin > 1)
-        SZB_CUDA(ctx, cudaMemsetAsync(net->ready, 0, sizeof(int32_t) * (size_t)MAX_TOWER_LAYERS * a.n_pair_tiles, ctx->stream));
+        SZB_CUDA(ctx, cudaMemsetAsync(a.ready, 0, sizeof(int32_t) * (size_t)MAX_TOWER_LAYERS * a.n_pair_tiles, ctx->work));
     const int grid = 2 * std::min(a.n_pair_tiles, net->num_sms / 2);
-    k_tower_tc2<<<grid, TC_THREADS, T2_SMEM, ctx->stream>>>(*net->tower_maps, a);
+    k_tower_tc2<<<grid, TC_THREADS, T2_SMEM, ctx->work>>>(*net->tower_maps, a);
     ctx->launches++;
     return 0;
 }
 
 template <int N_TILE, int MODE>
 static int launch_tc(szb_ctx* ctx, Net* net, const CUtensorMap& tm_a, const ConvLayer& L, const __nv_bfloat16* residual,
-                     __nv_bfloat16* out, float* logits, int n, int relu) {
+                     __nv_bfloat16* out, float* logits, int n, int relu, int b0 = 0) {
     static bool attr_set = false;
     constexpr int smem = TC_STAGES * (TC_A_BYTES + N_TILE * TC_BLOCK_K * 2) + 1024;
     if (!attr_set) {
@@ -1008,10 +1029,11 @@ static int launch_tc(szb_ctx* ctx, Net* net, const CUtensorMap& tm_a, const Conv
     a.out = out;
     a.logits = logits;
     a.n_boards = n;
+    a.board0 = b0;
     a.relu = relu;
     a.error = net->tc_error;
     const int grid = std::min(a.n_tiles, net->num_sms);
-    k_conv_tc<N_TILE, MODE><<<grid, TC_THREADS, smem, ctx->stream>>>(tm_a, L.tm_w, a);
+    k_conv_tc<N_TILE, MODE><<<grid, TC_THREADS, smem, ctx->work>>>(tm_a, L.tm_w, a);
     ctx->launches++;
     return 0;
 }
@@ -1020,7 +1042,7 @@ static void launch_f32(szb_ctx* ctx, const float* in, const ConvLayer& L, const 
     F32Args a;
     a.in = in; a.w = L.w32; a.bias = L.bias; a.residual = residual; a.out = out;
     a.cin = L.cin; a.cout_pad = L.cout_pad; a.taps = L.taps; a.relu = relu; a.mode = mode;
-    k_conv_f32<<<dim3(n, L.cout_pad / 64), 256, 0, ctx->stream>>>(a);
+    k_conv_f32<<<dim3(n, L.cout_pad / 64), 256, 0, ctx->work>>>(a);
     ctx->launches++;
 }
 
@@ -1049,38 +1071,41 @@ void net_collect_conv_times(szb_ctx* ctx) {
     ctx->conv_events_used = 0;
 }
 
-// planes (device, row stride `stride` uint64) -> net->logits + value_out (device)
-static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t* planes, int stride, float* value_out) {
+// planes (device, row stride `stride` uint64; row 0 = board b0) -> net->logits[b0..] + value_out[0..n) (device).
+// b0 is the first board inside the activation buffers (a multiple of 4): cohorts of one search use disjoint ranges.
+// All launches go to ctx->work.
+static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out) {
     Net* net = ctx->net;
     if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
-    if (n > net->cap) return fail(ctx, SZB_ERR_ARG, "batch %d exceeds capacity %d", n, net->cap);
-    cudaStream_t st = ctx->stream;
+    if (b0 + n > net->cap || (b0 & 3)) return fail(ctx, SZB_ERR_ARG, "batch [%d, %d) outside capacity %d", b0, b0 + n, net->cap);
+    cudaStream_t st = ctx->work;
     const unsigned up_blocks = (unsigned)(((size_t)n * 64 * 16 + 255) / 256);
+    const size_t in_off = (size_t)b0 * HALO * HALO * C_IN_PAD, act_off = (size_t)b0 * HALO * HALO * C_TOWER;
     if (evaluator == SZB_EVAL_NET_BF16) {
-        k_planes_to_nhwc<__nv_bfloat16><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in16);
+        k_planes_to_nhwc<__nv_bfloat16><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in16 + in_off);
         ctx->launches++;
         int rc;
         int x, y;
         if (net->tower_mode == 0) {
             // single-CTA kernel, one launch per layer (kept as the A/B reference of the pair kernel)
-            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_in16, net->stem, nullptr, net->act16[0], nullptr, n, 1))) return rc;
+            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_in16, net->stem, nullptr, net->act16[0], nullptr, n, 1, b0))) return rc;
             x = 0;
             for (int blk = 0; blk < N_BLOCKS; blk++) {
                 const int yy = (x + 1) % 3, o = (x + 2) % 3;
-                if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->tower[2 * blk], nullptr, net->act16[yy], nullptr, n, 1))) return rc;
+                if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->tower[2 * blk], nullptr, net->act16[yy], nullptr, n, 1, b0))) return rc;
                 cudaEvent_t* cev = (ctx->profiling && blk == 9) ? conv_event_pair(ctx) : nullptr;
                 if (cev) cudaEventRecord(cev[0], st);
-                if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[yy], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1))) return rc;
+                if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[yy], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1, b0))) return rc;
                 if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_LAYER * (uint64_t)n; }
                 x = o;
             }
             y = (x + 1) % 3;
-            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->p1, nullptr, net->act16[y], nullptr, n, 1))) return rc;
+            if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->p1, nullptr, net->act16[y], nullptr, n, 1, b0))) return rc;
         } else if (net->tower_mode == 1) {
             for (int l = 0; l < MAX_TOWER_LAYERS; l++) {
                 cudaEvent_t* cev = (ctx->profiling && l == 20) ? conv_event_pair(ctx) : nullptr;
                 if (cev) cudaEventRecord(cev[0], st);
-                if ((rc = launch_tower(ctx, net, n, l, l + 1))) return rc;
+                if ((rc = launch_tower(ctx, net, b0, n, l, l + 1))) return rc;
                 if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_LAYER * (uint64_t)n; }
             }
             x = net->final_x; y = net->final_y;
@@ -1088,28 +1113,30 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t
             // stem + 38 tower convolutions + policy 1x1 in ONE persistent launch; measurement hook brackets exactly that launch
             cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
             if (cev) cudaEventRecord(cev[0], st);
-            if ((rc = launch_tower(ctx, net, n, 0, MAX_TOWER_LAYERS))) return rc;
+            if ((rc = launch_tower(ctx, net, b0, n, 0, MAX_TOWER_LAYERS))) return rc;
             if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_ALL * (uint64_t)n; }
             x = net->final_x; y = net->final_y;
         }
-        if ((rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0))) return rc;
-        k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
+        if ((rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0, b0))) return rc;
+        k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x] + act_off, net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w,
+                                                       net->fc2_b, value_out, n);
         ctx->launches++;
     } else if (evaluator == SZB_EVAL_NET_FP32) {
-        k_planes_to_nhwc<float><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in32);
+        float* a32[3] = {net->act32[0] + act_off, net->act32[1] + act_off, net->act32[2] + act_off};
+        k_planes_to_nhwc<float><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in32 + in_off);
         ctx->launches++;
-        launch_f32(ctx, net->in32, net->stem, nullptr, net->act32[0], n, 1, 0);
+        launch_f32(ctx, net->in32 + in_off, net->stem, nullptr, a32[0], n, 1, 0);
         int x = 0;
         for (int blk = 0; blk < N_BLOCKS; blk++) {
             const int y = (x + 1) % 3, o = (x + 2) % 3;
-            launch_f32(ctx, net->act32[x], net->tower[2 * blk], nullptr, net->act32[y], n, 1, 0);
-            launch_f32(ctx, net->act32[y], net->tower[2 * blk + 1], net->act32[x], net->act32[o], n, 1, 0);
+            launch_f32(ctx, a32[x], net->tower[2 * blk], nullptr, a32[y], n, 1, 0);
+            launch_f32(ctx, a32[y], net->tower[2 * blk + 1], a32[x], a32[o], n, 1, 0);
             x = o;
         }
         const int y = (x + 1) % 3;
-        launch_f32(ctx, net->act32[x], net->p1, nullptr, net->act32[y], n, 1, 0);
-        launch_f32(ctx, net->act32[y], net->p2, nullptr, net->logits, n, 0, 1);
-        k_value_head<float><<<n, 256, 0, st>>>(net->act32[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
+        launch_f32(ctx, a32[x], net->p1, nullptr, a32[y], n, 1, 0);
+        launch_f32(ctx, a32[y], net->p2, nullptr, net->logits + (size_t)b0 * N_ACTIONS, n, 0, 1);
+        k_value_head<float><<<n, 256, 0, st>>>(a32[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
         ctx->launches++;
     } else {
         return fail(ctx, SZB_ERR_ARG, "unknown evaluator %d", evaluator);
@@ -1118,10 +1145,11 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int n, const uint64_t
     return 0;
 }
 
-int net_evaluate_batch(szb_ctx* ctx, int evaluator, int n) {
-    int rc = net_forward_device(ctx, evaluator, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value);
+// evaluate games [g0, g0 + n) of the search batch (g0 a multiple of 4): d.planes -> d.policy (softmax) / d.value, on ctx->work
+int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n) {
+    int rc = net_forward_device(ctx, evaluator, g0, n, ctx->d.planes + (size_t)g0 * PLANE_STRIDE, PLANE_STRIDE, ctx->d.value + g0);
     if (rc) return rc;
-    k_softmax<<<n, 256, 0, ctx->stream>>>(ctx->net->logits, ctx->d.policy, n);
+    k_softmax<<<n, 256, 0, ctx->work>>>(ctx->net->logits + (size_t)g0 * N_ACTIONS, ctx->d.policy + (size_t)g0 * N_ACTIONS, n);
     ctx->launches++;
     return 0;
 }
@@ -1204,7 +1232,10 @@ int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, cons
             (rc = net_alloc(ctx, net, &net->fc1_b, 256, false)) || (rc = net_alloc(ctx, net, &net->fc2_w, 256, false)))
             return rc;
         SZB_CUDA(ctx, cudaMemcpyAsync(net->v_w, vws.data(), 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_w, f1w, 256 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<float> f1t(256 * 64);                       // [64][256]: coalesced reads in k_value_head
+        for (int o = 0; o < 256; o++)
+            for (int k = 0; k < 64; k++) f1t[k * 256 + o] = f1w[o * 64 + k];
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_w, f1t.data(), 256 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
         SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_b, f1b, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
         SZB_CUDA(ctx, cudaMemcpyAsync(net->fc2_w, f2w, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
         SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1232,11 +1263,11 @@ static int net_forward_common(szb_ctx* ctx, int32_t n, const uint64_t* planes, i
     for (int lo = 0; lo < n; lo += cap) {
         const int m = std::min(cap, n - lo);
         SZB_CUDA(ctx, cudaMemcpyAsync(d_pl, planes + (size_t)lo * N_PLANES, (size_t)m * N_PLANES * 8, cudaMemcpyDefault, ctx->stream));
-        int rc = net_forward_device(ctx, evaluator, m, d_pl, N_PLANES, d_v);
+        int rc = net_forward_device(ctx, evaluator, 0, m, d_pl, N_PLANES, d_v);
         if (rc) return rc;
         const float* src = net->logits;
         if (softmax) {
-            k_softmax<<<m, 256, 0, ctx->stream>>>(net->logits, d_p, m);
+            k_softmax<<<m, 256, 0, ctx->work>>>(net->logits, d_p, m);
             ctx->launches++;
             src = d_p;
         }
@@ -1264,11 +1295,11 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
         for (int i = 0; i < reps && !rc; i++) {
             switch (which) {
             case 0: rc = launch_tc<256, 0>(ctx, net, net->tm_act16[i & 1], net->tower[1], net->act16[2], net->act16[(i + 1) & 1], nullptr, n, 1); break;
-            case 1: rc = net_forward_device(ctx, SZB_EVAL_NET_BF16, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
-            case 2: rc = net_forward_device(ctx, SZB_EVAL_NET_FP32, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
+            case 1: rc = net_forward_device(ctx, SZB_EVAL_NET_BF16, 0, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
+            case 2: rc = net_forward_device(ctx, SZB_EVAL_NET_FP32, 0, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
             case 3: launch_f32(ctx, net->act32[i & 1], net->tower[1], net->act32[2], net->act32[(i + 1) & 1], n, 1, 0); break;
-            case 4: rc = launch_tower(ctx, net, n, 20, 21); break;                       // one tower layer, CTA-pair kernel
-            case 5: rc = launch_tower(ctx, net, n, 0, MAX_TOWER_LAYERS); break;          // whole tower, one launch
+            case 4: rc = launch_tower(ctx, net, 0, n, 20, 21); break;                       // one tower layer, CTA-pair kernel
+            case 5: rc = launch_tower(ctx, net, 0, n, 0, MAX_TOWER_LAYERS); break;          // whole tower, one launch
             default: rc = fail(ctx, SZB_ERR_ARG, "unknown kernel selector %d", which);
             }
         }

@@ -15,10 +15,10 @@ def _ptr(a):
 
 
 class Engine:
-    def __init__(self, max_games=1024, max_searches=800, device=0, edges_per_node=0):
+    def __init__(self, max_games=1024, max_searches=800, device=0, edges_per_node=0, cohorts=0):
         self.lib = _lib.load()
         self.max_games, self.max_searches = int(max_games), int(max_searches)
-        cfg = _lib.Config(self.max_games, self.max_searches, int(edges_per_node), 0)
+        cfg = _lib.Config(self.max_games, self.max_searches, int(edges_per_node), int(cohorts))
         h = ctypes.c_void_p()
         rc = self.lib.szb_create(int(device), ctypes.byref(cfg), ctypes.byref(h))
         self._h = h

@@ -1,0 +1,142 @@
+"""GPU parity through the drop-in facade (the reference's own call surface): MCTS0.search / Node / ChessTensor /
+policyNN / sim.play_game running on libszb200, against the restated reference search fed with THE SAME network
+outputs (the GPU's fp32 forward) -- the north-star's "given identical network outputs in fp32 mode, MCTS visit
+counts and selected moves are bit-exact"."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hash_eval, ref_path
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+OPENING = ["e2e4", "c7c5", "g1f3", "d7d6", "d2d4", "c5d4", "f3d4", "g8f6", "b1c3", "a7a6"]
+
+
+@pytest.fixture(scope="module")
+def fp32_model():
+    from sigma_zero_b200.network import policyNN
+    torch.manual_seed(5)
+    return policyNN({"precision": "fp32"}).eval()
+
+
+@pytest.fixture(scope="module")
+def evaluator(fp32_model):
+    """oracle-side evaluator: the GPU's own fp32 forward for the planes the oracle produces (identical network outputs)"""
+    from sigma_zero_b200.engine import EVAL_NET_FP32, Engine
+    eng = Engine(max_games=2, max_searches=4)
+    eng.load_state_dict(fp32_model.state_dict())
+
+    def ev(planes):
+        pol, val = eng.net_forward(hash_eval.pack_planes(planes)[None], EVAL_NET_FP32)
+        return pol[0], val[0]
+
+    yield ev
+    eng.close()
+
+
+@pytest.mark.parametrize("learning", [False, True])
+def test_mcts0_search_matches_reference_with_identical_network_outputs(fp32_model, evaluator, learning):
+    from sigma_zero_b200 import chess_compat as cc
+    from sigma_zero_b200.chess_tensor import ChessTensor
+    from sigma_zero_b200.mcts import MCTS0
+    args = {"C": 2, "num_searches": 60}
+    game = ChessTensor()
+    for u in OPENING:
+        game.move_piece(cc.Move.from_uci(u))
+    mcts = MCTS0(game, args, fp32_model)
+    probs = mcts.search(game.board, verbose=False, learning=learning)
+    og = util.oracle_game(False, -1, OPENING)
+    ref_probs, ref_root = ref_path.search(og, args["num_searches"], args["C"], evaluator, learning=learning)
+    assert [m.uci() for m in probs] == [m.uci() for m in ref_probs]            # same children, ascending move index
+    assert list(probs.values()) == list(ref_probs.values())                      # same visit fractions, exactly
+    assert max(probs, key=probs.get).uci() == max(ref_probs, key=ref_probs.get).uci()   # same selected move
+    # Node view of the device tree (mctsnode.py fields)
+    root = mcts.tree()
+    assert root.visit_count == 1 + args["num_searches"] and root.visit_count == ref_root.n
+    assert [c.visit_count for c in root.children] == [c.n for c in ref_root.children]
+    assert [c.value_sum for c in root.children] == [c.w for c in ref_root.children]
+    assert [np.float32(c.prior) for c in root.children] == [np.float32(c.prior) for c in ref_root.children]
+    assert root.select().action_taken.uci() == ref_path._select(ref_root, args["C"]).move.uci()
+    with pytest.raises(RuntimeError):
+        root.expand([])
+
+
+def test_chess_tensor_facade_matches_oracle_game():
+    from sigma_zero_b200 import chess_compat as cc
+    from sigma_zero_b200.chess_tensor import ChessTensor
+    game = ChessTensor()
+    og = util.oracle_game(False, -1)
+    for u in OPENING + ["c1g5", "e7e6", "d1d2", "f8e7", "e1c1"]:         # includes castling (vanilla: e1c1)
+        assert sorted(m.uci() for m in game.get_moves()) == sorted(m.uci() for m in og.board.legal_moves)
+        game.move_piece(cc.Move.from_uci(u))
+        og.move_piece(util.chess.Move.from_uci(u))
+        assert np.array_equal(game.get_representation().numpy(), og.get_representation())
+        assert game.get_value_and_terminated() == og.value_and_terminated()
+        assert game.board.turn == og.board.turn and game.board.halfmove_clock == og.board.halfmove_clock
+        for colour in (True, False):
+            assert game.board.has_kingside_castling_rights(colour) == og.board.has_kingside_castling_rights(colour)
+            assert game.board.has_queenside_castling_rights(colour) == og.board.has_queenside_castling_rights(colour)
+    # the absolute-orientation stacks the reference keeps (chess_tensor.py:123-129): un-flip the player's view
+    view = og.get_representation()
+    if og.board.turn:
+        assert np.array_equal(game.representation.numpy(), view[:, ::-1, :])
+    else:
+        assert np.array_equal(game.black_representation.numpy(), view[:, :, ::-1])
+    with pytest.raises(ValueError, match="Invalid move"):
+        game.move_piece(cc.Move.from_uci("a1a8"))
+
+
+def test_policynn_facade_forward_matches_torch(fp32_model):
+    ref = ref_path.build_policy_nn().eval()
+    ref.load_state_dict(fp32_model.state_dict())                 # same 252-key layout (network.py / play.py:25-28)
+    x = torch.from_numpy(np.stack([util.oracle_game(False, -1, OPENING[:k]).get_representation() for k in (0, 3, 10)])).float()
+    p, v = fp32_model(x, inference=True)
+    with torch.no_grad():
+        rp, rv = ref(x, inference=True)
+    assert p.shape == (3, 4672) and v.shape == (3, 1)
+    assert (p - rp).abs().max().item() <= 1e-5 and (v - rv).abs().max().item() <= 1e-5
+
+
+def test_play_game_facade_schema():
+    """sim.play_game drop-in (bf16 network, 8 searches/move): the reference's history schema, consistent rewards"""
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.sim import generate_training_data, selfplay_batch
+    torch.manual_seed(0)
+    model = policyNN({}).eval()
+    args = {"C": 2, "num_searches": 8, "num_selfPlay_iterations": 6, "chess960": True}
+    games, counters = selfplay_batch(model, args, 6, c960=True, seed=3, max_plies=12)
+    assert len(games) == 6 and counters["plies"] == 12
+    for h in games:
+        n = len(h["actions"])
+        assert n == len(h["states"]) == len(h["colours"]) == len(h["rewards"]) == 12
+        assert h["states"][0].shape == (119, 8, 8) and h["states"][0].dtype == torch.bool
+        assert h["colours"][0] is True and h["colours"][1] is False
+        for probs in h["actions"]:
+            assert abs(sum(probs.values()) - 1.0) < 1e-9
+        assert h["result"] == "*" and set(h["rewards"]) == {0}
+    merged = {}
+    out = generate_training_data(model, num_games=2, args={"C": 2, "num_searches": 4}, return_dict=merged, c960=False)
+    assert len(merged) == 1 and set(out) == {"states", "actions", "rewards", "colours"}
+    assert len(out["states"]) == len(out["actions"]) == len(out["rewards"]) == len(out["colours"]) > 0
+
+
+def test_bf16_visit_counts_track_the_fp32_search():
+    """config c2's check: the bf16 tcgen05 network drives the same search as the fp32 parity network up to rounding.
+    Visit distributions are compared per game (total-variation distance) -- exact equality is not expected."""
+    from sigma_zero_b200.engine import EVAL_NET_BF16, EVAL_NET_FP32, Engine
+    torch.manual_seed(0)
+    model = ref_path.build_policy_nn().eval()
+    eng = Engine(max_games=32, max_searches=200)
+    eng.load_state_dict(model.state_dict())
+    specs = [(g % 2 == 1, 518 if g % 2 == 0 else (37 * g) % 960, OPENING[: (g % 6)] if g % 2 == 0 else []) for g in range(32)]
+    util.setup_games(eng, specs)
+    v16, _, _ = eng.search(200, 2.0, False, EVAL_NET_BF16)
+    v32, _, _ = eng.search(200, 2.0, False, EVAL_NET_FP32)
+    assert (v16.sum(1) == 199).all() and (v32.sum(1) == 199).all()
+    tv = 0.5 * np.abs(v16.astype(np.float64) - v32).sum(1) / 199.0
+    same_top = float((v16.argmax(1) == v32.argmax(1)).mean())
+    print("bf16 vs fp32 search: mean TV %.4f  max TV %.4f  same top move %.2f" % (tv.mean(), tv.max(), same_top))
+    assert tv.mean() < 0.15 and same_top >= 0.6
+    eng.close()
