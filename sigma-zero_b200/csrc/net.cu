@@ -28,9 +28,9 @@ constexpr int C_IN_PAD = 128;            // 119 input planes padded to 128 chann
 constexpr int N_BLOCKS = 19;
 constexpr int POLICY_PLANES = 73;
 constexpr int POLICY_PAD = 80;           // N of the last policy GEMM (multiple of 16)
-// algorithmic FLOP (2 x MAC, no credit for channel padding) per board: one 3x3 256->256 layer; stem + 38 tower layers + policy 1x1
+// algorithmic FLOP (2 x MAC, no credit for channel padding) per board: one 3x3 256->256 layer; stem + 38 tower layers + policy 1x1 + policy out
 constexpr uint64_t FLOP_TOWER_LAYER = 2ull * 64 * 256 * 2304;
-constexpr uint64_t FLOP_TOWER_ALL = 2ull * 64 * 256 * (119 * 9 + 38 * 2304 + 256);
+constexpr uint64_t FLOP_TOWER_ALL = 2ull * 64 * (256 * (119 * 9 + 38 * 2304 + 256) + 73 * 256);
 
 // ---- tcgen05 conv kernel geometry ---------------------------------------------------------------
 constexpr int TC_BLOCK_M = 128;          // two boards per tile
@@ -392,7 +392,8 @@ constexpr int T2_A_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's 128 rows
 constexpr int T2_B_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's half (128 output channels) of the weight tile
 constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
 constexpr int T2_SMEM = T2_STAGES * T2_STAGE_BYTES + 1024;
-constexpr int MAX_TOWER_LAYERS = 40;                      // stem + 38 tower convolutions + policy 1x1
+constexpr int MAX_TOWER_LAYERS = 41;                      // stem + 38 tower convolutions + policy 1x1 + policy output (256 -> 73)
+constexpr int POLICY_LAYER = MAX_TOWER_LAYERS - 1;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the pair's even CTA
 constexpr int READY_PER_ITEM = 8;                         // 4 epilogue warps x 2 CTAs
 
@@ -403,12 +404,14 @@ struct TowerLayer {
     uint8_t res;         // activation buffer of the residual, 255 = none
     uint8_t out;         // activation buffer written
     uint8_t relu;
-    uint8_t pad[2];
+    uint8_t mode;        // 0: bf16 NHWC activations, 1: fp32 policy logits [board][4672] (plane-major)
+    uint8_t n_half;      // output channels per CTA of the pair: 128 (N = 256) or 64 (N = 128, the 73 policy planes padded)
 };
 
 struct alignas(64) TowerMaps {
     CUtensorMap a[4];    // input planes, activation buffers 0..2: box 64 ch x 8 x 8 x 2 boards
     CUtensorMap w;       // all layers' folded weights [MAX_TOWER_LAYERS * 256][2304]: box 64 k x 128 rows
+    CUtensorMap w64;     // same buffer, box 64 k x 64 rows (policy output layer)
 };
 
 struct TowerArgs {
@@ -419,6 +422,7 @@ struct TowerArgs {
     int32_t* ready;      // [MAX_TOWER_LAYERS][n_pair_tiles] completion counters, zeroed before the launch
     const float* bias;   // [MAX_TOWER_LAYERS][256]
     __nv_bfloat16* act[3];
+    float* logits;       // [boards][4672]
     int32_t* error;
     TowerLayer L[MAX_TOWER_LAYERS];
 };
@@ -477,7 +481,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ TowerArgs a) {
-    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);      // M = 256, N per layer
     constexpr int ACC_COLS = 256;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -533,16 +537,18 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 const CUtensorMap* tm_a = &maps.a[L.a_map];
                 const int k_iters = L.taps * L.kchunks;
                 const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
-                const int wrow = l * C_TOWER + (int)rank * 128;
+                const int wrow = l * C_TOWER + (int)rank * L.n_half;
+                const CUtensorMap* tm_w = L.n_half == 128 ? &maps.w : &maps.w64;
+                const uint32_t stage_tx = 2u * (T2_A_BYTES + (uint32_t)L.n_half * TC_BLOCK_K * 2);
                 for (int it = 0; it < k_iters; it++) {
                     const int tap = it / L.kchunks, kc = it - tap * L.kchunks;
                     const int ky = L.taps == 9 ? tap / 3 : 1, kx = L.taps == 9 ? tap - (tap / 3) * 3 : 1;
                     if (!(ok = mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag))) break;
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
-                    if (rank == 0) mbar_expect_tx(full, 2 * T2_STAGE_BYTES);       // both CTAs' bytes land on the leader's barrier
+                    if (rank == 0) mbar_expect_tx(full, stage_tx);                  // both CTAs' bytes land on the leader's barrier
                     tma2_load_4d(sa, tm_a, full, kc * TC_BLOCK_K, kx, ky, board0);
-                    tma2_load_2d(sa + T2_A_BYTES, &maps.w, full, it * TC_BLOCK_K, wrow);
+                    tma2_load_2d(sa + T2_A_BYTES, tm_w, full, it * TC_BLOCK_K, wrow);
                     if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -557,6 +563,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
                 const TowerLayer L = a.L[a.layer_begin + item / a.n_pair_tiles];
                 const int k_iters = L.taps * L.kchunks;
+                const uint32_t idesc = IDESC_BASE | ((uint32_t)(2 * L.n_half >> 3) << 17);
                 const int acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 if (!(ok = mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
@@ -569,7 +576,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     const uint32_t sb = sa + T2_A_BYTES;
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / 16; k++) {
-                        tc2_mma_bf16(d_tmem, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it | k) != 0);
+                        tc2_mma_bf16(d_tmem, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (it | k) != 0);
                     }
                     tc2_commit(smem_u32(&bar_empty[stage]));
                     if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
@@ -601,6 +608,25 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             const bool live = board < a.board0 + a.n_boards;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
             const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
+            if (L.mode == 1) {
+                // policy logits, plane-major like torch.flatten(conv_p2(x)): index = plane * 64 + row * 8 + col
+                float* lg = a.logits + (size_t)board * N_ACTIONS + sq;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 96; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (c0 + j < POLICY_PLANES) lg[(c0 + j) * 64] = __uint_as_float(v[j]) + bias_sh[acc][c0 + j];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(smem_u32(&bar_acc_empty[acc]));      // last layer: nothing waits on its counter
+                continue;
+            }
             const __nv_bfloat16* resp = (L.res != 255 && live) ? a.act[L.res] + pix * C_TOWER : nullptr;
             __nv_bfloat16* outp = a.act[L.out] + pix * C_TOWER;
             uint4 rnext[4];
@@ -946,7 +972,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     auto layer = [&](int l, int a_map, int taps, int kchunks, int res, int out) {
         TowerLayer& T = a.L[l];
         T.a_map = (uint8_t)a_map; T.taps = (uint8_t)taps; T.kchunks = (uint8_t)kchunks;
-        T.res = (uint8_t)res; T.out = (uint8_t)out; T.relu = 1;
+        T.res = (uint8_t)res; T.out = (uint8_t)out; T.relu = 1; T.mode = 0; T.n_half = 128;
     };
     if ((rc = put(0, net->stem))) return rc;
     layer(0, 0, 9, C_IN_PAD / TC_BLOCK_K, 255, 0);
@@ -959,8 +985,15 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
         x = o;
     }
     const int y = (x + 1) % 3;
-    if ((rc = put(MAX_TOWER_LAYERS - 1, net->p1))) return rc;
-    layer(MAX_TOWER_LAYERS - 1, 1 + x, 1, C_TOWER / TC_BLOCK_K, 255, y);
+    if ((rc = put(POLICY_LAYER - 1, net->p1))) return rc;
+    layer(POLICY_LAYER - 1, 1 + x, 1, C_TOWER / TC_BLOCK_K, 255, y);
+    // policy output 256 -> 73 (+ conv bias): N = 128 (two halves of 64 rows, the 73 planes zero-padded), fp32 logits epilogue
+    SZB_CUDA(ctx, cudaMemcpy2DAsync(net->w16_all + (size_t)POLICY_LAYER * C_TOWER * KMAX, (size_t)KMAX * 2, net->p2.w16, (size_t)C_TOWER * 2,
+                                    (size_t)C_TOWER * 2, 128, cudaMemcpyDeviceToDevice, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(net->bias_all + (size_t)POLICY_LAYER * C_TOWER, net->p2.bias, 128 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    layer(POLICY_LAYER, 1 + y, 1, C_TOWER / TC_BLOCK_K, 255, 0);
+    a.L[POLICY_LAYER].relu = 0; a.L[POLICY_LAYER].mode = 1; a.L[POLICY_LAYER].n_half = 64;
+    a.logits = net->logits;
     net->final_x = x;
     net->final_y = y;
     a.ready = net->ready;
@@ -978,6 +1011,11 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(tower weights) failed: %d", (int)r);
+        box[1] = 64;
+        r = g_encode(&net->tower_maps->w64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, net->w16_all, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(policy weights) failed: %d", (int)r);
     }
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
@@ -1102,7 +1140,7 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
             y = (x + 1) % 3;
             if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[x], net->p1, nullptr, net->act16[y], nullptr, n, 1, b0))) return rc;
         } else if (net->tower_mode == 1) {
-            for (int l = 0; l < MAX_TOWER_LAYERS; l++) {
+            for (int l = 0; l < POLICY_LAYER; l++) {
                 cudaEvent_t* cev = (ctx->profiling && l == 20) ? conv_event_pair(ctx) : nullptr;
                 if (cev) cudaEventRecord(cev[0], st);
                 if ((rc = launch_tower(ctx, net, b0, n, l, l + 1))) return rc;
@@ -1110,14 +1148,15 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
             }
             x = net->final_x; y = net->final_y;
         } else {
-            // stem + 38 tower convolutions + policy 1x1 in ONE persistent launch; measurement hook brackets exactly that launch
+            // stem + 38 tower convolutions + both policy 1x1 layers in ONE persistent launch; the measurement hook brackets exactly that launch
             cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
             if (cev) cudaEventRecord(cev[0], st);
             if ((rc = launch_tower(ctx, net, b0, n, 0, MAX_TOWER_LAYERS))) return rc;
             if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_ALL * (uint64_t)n; }
             x = net->final_x; y = net->final_y;
         }
-        if ((rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0, b0))) return rc;
+        // (the one-launch tower ends with the policy output layer; the per-layer modes use the single-CTA kernel for it)
+        if (net->tower_mode != 2 && (rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0, b0))) return rc;
         k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x] + act_off, net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w,
                                                        net->fc2_b, value_out, n);
         ctx->launches++;
