@@ -108,6 +108,18 @@ static int make_act_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels,
     if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
     return 0;
 }
+// activations [B][10][10][C] bf16 seen as (c, x, board, y): box = 64 channels x 10 x 2 boards x 10 -> shared memory rows
+// [y][board][x], the resident halo chunk of k_tower_tc2 (strides need not ascend: probed, scripts/desc_probe.cu)
+static int make_halo_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, int boards) {
+    cuuint64_t dims[4] = {(cuuint64_t)channels, HALO, (cuuint64_t)boards, HALO};
+    cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * HALO * HALO, (cuuint64_t)channels * 2 * HALO};
+    cuuint32_t box[4] = {TC_BLOCK_K, HALO, 2, HALO};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(halo activations) failed: %d", (int)r);
+    return 0;
+}
 // weights [cout_pad][K] bf16: box = 64 k x cout_pad rows
 static int make_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int cout_pad) {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)cout_pad};
@@ -155,6 +167,15 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
         if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; return false; }
     }
 }
+// all 32 lanes wait; the result is warp-uniform
+__device__ __forceinline__ bool warp_mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+    return __all_sync(0xFFFFFFFFu, mbar_wait(bar, parity, abort_flag));
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -179,11 +200,11 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
         : "memory");
 }
 // K-major, 128-byte swizzle: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1, layout type 2
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -258,14 +279,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
             bool ok = true;
             for (int tile = blockIdx.x; tile < a.n_tiles && ok; tile += gridDim.x) {
                 for (int it = 0; it < k_iters; it++) {
-                    const int tap = it / a.kchunks, kc = it - tap * a.kchunks;
+                    const int kc = it / a.taps, tap = it - kc * a.taps;          // K chunk outer, tap inner: the order k_tower_tc2 accumulates in
                     const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
                     if (!(ok = mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag))) break;
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     mbar_expect_tx(full, STAGE_BYTES);
                     tma_load_4d(sa, &tm_a, full, kc * TC_BLOCK_K, kx, ky, a.board0 + tile * 2);
-                    tma_load_2d(sa + TC_A_BYTES, &tm_w, full, it * TC_BLOCK_K, 0);
+                    tma_load_2d(sa + TC_A_BYTES, &tm_w, full, (tap * a.kchunks + kc) * TC_BLOCK_K, 0);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -387,11 +408,21 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUte
 // activation load, the epilogue warps release it after their last store.  Items are taken in increasing order
 // by every pair, so the wait chain always ends at the first layer: no deadlock, no grid-wide barrier, no wave
 // quantisation between layers (10240 items over 74 pairs instead of 40 launches of 3.46 waves).
-constexpr int T2_STAGES = 6;
-constexpr int T2_A_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's 128 rows (two boards) of A
-constexpr int T2_B_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's half (128 output channels) of the weight tile
-constexpr int T2_STAGE_BYTES = T2_A_BYTES + T2_B_BYTES;
-constexpr int T2_SMEM = T2_STAGES * T2_STAGE_BYTES + 1024;
+// Shared memory of one CTA: a ring of T2_A_CHUNKS activation chunks and a ring of T2_B_STAGES weight stages.
+// An activation chunk is ONE 64-channel slice of this CTA's two boards INCLUDING the halo, 200 pixel rows of 128 bytes
+// in the order [y 0..9][board 0..1][x 0..9] (one TMA box through a tensor map with dims (c, x, board, y)).  All nine
+// taps of a 3x3 convolution read it in place: the A descriptor of tap (ky, kx) starts (ky * 20 + kx) rows into the
+// chunk and strides 10 rows (1280 B) between 8-row groups, so MMA row m = (oy * 2 + board) * 8 + ox reads halo pixel
+// (oy + ky, ox + kx).  tcgen05.mma applies the 128-byte swizzle to absolute shared-memory address bits, exactly like
+// TMA, so starts and strides that are not multiples of 1024 B are fine (probed on hardware: scripts/desc_probe.cu).
+// => an activation byte is loaded from L2 once per layer instead of once per tap.
+constexpr int T2_A_CHUNKS = 4;
+constexpr int T2_A_ROWS = 2 * HALO * HALO;                // 200
+constexpr int T2_A_CHUNK_BYTES = T2_A_ROWS * 128;         // 25600 = 25 * 1024
+constexpr int T2_A_SBO = HALO * 128;                      // 1280: one halo row of one board
+constexpr int T2_B_STAGES = 7;
+constexpr int T2_B_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's half (128 output channels) of a 64-wide weight tile
+constexpr int T2_SMEM = T2_A_CHUNKS * T2_A_CHUNK_BYTES + T2_B_STAGES * T2_B_BYTES + 1024;
 constexpr int MAX_TOWER_LAYERS = 41;                      // stem + 38 tower convolutions + policy 1x1 + policy output (256 -> 73)
 constexpr int POLICY_LAYER = MAX_TOWER_LAYERS - 1;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the pair's even CTA
@@ -409,7 +440,7 @@ struct TowerLayer {
 };
 
 struct alignas(64) TowerMaps {
-    CUtensorMap a[4];    // input planes, activation buffers 0..2: box 64 ch x 8 x 8 x 2 boards
+    CUtensorMap a[4];    // input planes, activation buffers 0..2 with dims (c, x, board, y): box 64 ch x 10 x 2 boards x 10
     CUtensorMap w;       // all layers' folded weights [MAX_TOWER_LAYERS * 256][2304]: box 64 k x 128 rows
     CUtensorMap w64;     // same buffer, box 64 k x 64 rows (policy output layer)
 };
@@ -459,6 +490,18 @@ __device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, ui
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, with the two shared-memory descriptors given as (lo, hi) halves
+__device__ __forceinline__ void tc2_mma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                   uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
 }
@@ -485,12 +528,14 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
     constexpr int ACC_COLS = 256;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[T2_STAGES], bar_empty[T2_STAGES], bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_a_full[T2_A_CHUNKS], bar_a_empty[T2_A_CHUNKS], bar_b_full[T2_B_STAGES], bar_b_empty[T2_B_STAGES],
+        bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
     __shared__ float bias_sh[2][C_TOWER];
 
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = smem_a + T2_A_CHUNKS * T2_A_CHUNK_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -499,7 +544,8 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
 
     if (threadIdx.x == 0) {
         abort_sh = 0;
-        for (int s = 0; s < T2_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < T2_A_CHUNKS; s++) { mbar_init(smem_u32(&bar_a_full[s]), 1); mbar_init(smem_u32(&bar_a_empty[s]), 1); }
+        for (int s = 0; s < T2_B_STAGES; s++) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
         for (int s = 0; s < 2; s++) { mbar_init(smem_u32(&bar_acc_full[s]), 1); mbar_init(smem_u32(&bar_acc_empty[s]), READY_PER_ITEM); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -513,75 +559,116 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp == 0) {
-        // ===== TMA producer (one thread in each CTA) =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+        // ===== TMA producer (warp 0 of each CTA, convergent; one elected lane issues) =====
+        {
+            const uint32_t bar_af0 = smem_u32(&bar_a_full[0]), bar_ae0 = smem_u32(&bar_a_empty[0]);
+            const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
+            uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0;
             bool ok = true;
             for (int item = pair; item < n_items && ok; item += n_pairs) {
                 const int l = a.layer_begin + item / a.n_pair_tiles, t = item % a.n_pair_tiles;
                 const TowerLayer L = a.L[l];
                 if (l > a.layer_begin) {
-                    // item (l-1, t) must be complete: all 8 epilogue warps of whichever pair ran it have stored and released
+                    // item (l-1, t) must be complete: all 8 epilogue warps of whichever pair ran it have stored and released.
+                    // Every lane acquires (one transaction) so that whichever lane is elected below has done so.
                     const int32_t* flag = a.ready + (size_t)(l - 1) * a.n_pair_tiles + t;
-                    if (ld_acquire_gpu(flag) < READY_PER_ITEM) {
+                    if (!__all_sync(0xFFFFFFFFu, ld_acquire_gpu(flag) >= READY_PER_ITEM)) {
                         const long long t0 = clock64();
-                        while (ld_acquire_gpu(flag) < READY_PER_ITEM) {
-                            if (*abort_flag) { ok = false; break; }
-                            if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; ok = false; break; }
+                        for (;;) {
+                            if (__all_sync(0xFFFFFFFFu, ld_acquire_gpu(flag) >= READY_PER_ITEM)) break;
+                            bool give_up = *abort_flag != 0;
+                            if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; give_up = true; }
+                            if (__any_sync(0xFFFFFFFFu, give_up)) { ok = false; break; }
                         }
                         if (!ok) break;
                     }
                     asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores -> this thread's TMA reads
                 }
                 const CUtensorMap* tm_a = &maps.a[L.a_map];
-                const int k_iters = L.taps * L.kchunks;
                 const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
                 const int wrow = l * C_TOWER + (int)rank * L.n_half;
                 const CUtensorMap* tm_w = L.n_half == 128 ? &maps.w : &maps.w64;
-                const uint32_t stage_tx = 2u * (T2_A_BYTES + (uint32_t)L.n_half * TC_BLOCK_K * 2);
-                for (int it = 0; it < k_iters; it++) {
-                    const int tap = it / L.kchunks, kc = it - tap * L.kchunks;
-                    const int ky = L.taps == 9 ? tap / 3 : 1, kx = L.taps == 9 ? tap - (tap / 3) * 3 : 1;
-                    if (!(ok = mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag))) break;
-                    const uint32_t full = smem_u32(&bar_full[stage]);
-                    const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
-                    if (rank == 0) mbar_expect_tx(full, stage_tx);                  // both CTAs' bytes land on the leader's barrier
-                    tma2_load_4d(sa, tm_a, full, kc * TC_BLOCK_K, kx, ky, board0);
-                    tma2_load_2d(sa + T2_A_BYTES, tm_w, full, it * TC_BLOCK_K, wrow);
-                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                const uint32_t b_tx = 2u * (uint32_t)L.n_half * TC_BLOCK_K * 2;
+                for (int kc = 0; kc < L.kchunks && ok; kc++) {
+                    // one 64-channel slice of both boards' halo tiles: read by all taps of this K chunk
+                    if (!(ok = warp_mbar_wait(bar_ae0 + ac * 8, a_phase ^ 1, abort_flag))) break;
+                    if (elect_one()) {
+                        const uint32_t a_full = bar_af0 + ac * 8;
+                        if (rank == 0) mbar_expect_tx(a_full, 2u * T2_A_CHUNK_BYTES);     // both CTAs' bytes land on the leader's barrier
+                        tma2_load_4d(smem_a + ac * T2_A_CHUNK_BYTES, tm_a, a_full, kc * TC_BLOCK_K, 0, board0, 0);
+                    }
+                    __syncwarp();
+                    if (++ac == T2_A_CHUNKS) { ac = 0; a_phase ^= 1; }
+                    int kcol = kc * TC_BLOCK_K;                                           // weight column of (tap 0, kc); taps are C_in apart
+                    for (int tap = 0; tap < L.taps; tap++, kcol += L.kchunks * TC_BLOCK_K) {
+                        if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
+                        if (elect_one()) {
+                            const uint32_t b_full = bar_bf0 + bs * 8;
+                            if (rank == 0) mbar_expect_tx(b_full, b_tx);
+                            tma2_load_2d(smem_b + bs * T2_B_BYTES, tm_w, b_full, kcol, wrow);
+                        }
+                        __syncwarp();
+                        if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
-        if (lane == 0 && rank == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+        // One thread feeds the tensor cores of both SMs; its instruction stream is the limit once loads are ahead (ncu: no
+        // barrier stalls, ~1100 cycles of issue per 512 cycles of MMA with naive descriptor code).  So: descriptors are
+        // kept as (lo, hi) halves with constant hi and an incrementally advanced lo, barrier addresses are computed once,
+        // the 3x3 tap loop has no division.
+        // The whole warp runs the loop convergently (so the compiler keeps descriptors and barrier addresses in uniform
+        // registers instead of broadcasting them per MMA); one elected lane issues.
+        if (rank == 0) {
+            constexpr uint32_t A_HI = (uint32_t)(T2_A_SBO >> 4) | (1u << 14) | (2u << 29);      // SBO, version 1, SWIZZLE_128B
+            constexpr uint32_t B_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t LO_FLAGS = 1u << 16;                                              // LBO field (unused for swizzled K-major) = 1
+            const uint32_t a_lo0 = ((smem_a >> 4) & 0x3FFFu) | LO_FLAGS, b_lo0 = ((smem_b >> 4) & 0x3FFFu) | LO_FLAGS;
+            const uint32_t bar_af0 = smem_u32(&bar_a_full[0]), bar_ae0 = smem_u32(&bar_a_empty[0]);
+            const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
+            const uint32_t bar_cf0 = smem_u32(&bar_acc_full[0]), bar_ce0 = smem_u32(&bar_acc_empty[0]);
+            uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0;
             int local = 0;
             bool ok = true;
             for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
                 const TowerLayer L = a.L[a.layer_begin + item / a.n_pair_tiles];
-                const int k_iters = L.taps * L.kchunks;
                 const uint32_t idesc = IDESC_BASE | ((uint32_t)(2 * L.n_half >> 3) << 17);
-                const int acc = local & 1;
+                const uint32_t acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
-                if (!(ok = mbar_wait(smem_u32(&bar_acc_empty[acc]), acc_phase ^ 1, abort_flag))) break;
+                if (!(ok = warp_mbar_wait(bar_ce0 + acc * 8, acc_phase ^ 1, abort_flag))) break;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-                for (int it = 0; it < k_iters; it++) {
-                    if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
-                    tc_fence_after();
-                    const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
-                    const uint32_t sb = sa + T2_A_BYTES;
-#pragma unroll
-                    for (int k = 0; k < TC_BLOCK_K / 16; k++) {
-                        tc2_mma_bf16(d_tmem, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), idesc, (it | k) != 0);
+                const int t0 = L.taps == 9 ? 0 : 1, t1 = L.taps == 9 ? 3 : 2;                     // 1x1 convolution = centre tap
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < L.kchunks && ok; kc++) {
+                    if (!(ok = warp_mbar_wait(bar_af0 + ac * 8, a_phase, abort_flag))) break;
+                    const uint32_t chunk_lo = a_lo0 + ac * (T2_A_CHUNK_BYTES >> 4);
+                    for (int ky = t0; ky < t1 && ok; ky++) {
+                        uint32_t a_lo = chunk_lo + (uint32_t)(ky * 2 * HALO + t0) * (128 >> 4);   // halo pixel (ky, board 0, kx = t0)
+                        for (int kx = t0; kx < t1; kx++, a_lo += 128 >> 4) {
+                            if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + bs * (T2_B_BYTES >> 4);
+                            if (elect_one()) {
+                                tc2_mma_bf16_split(d_tmem, a_lo, A_HI, b_lo, B_HI, idesc, accumulate);
+                                tc2_mma_bf16_split(d_tmem, a_lo + 2, A_HI, b_lo + 2, B_HI, idesc, 1u);
+                                tc2_mma_bf16_split(d_tmem, a_lo + 4, A_HI, b_lo + 4, B_HI, idesc, 1u);
+                                tc2_mma_bf16_split(d_tmem, a_lo + 6, A_HI, b_lo + 6, B_HI, idesc, 1u);
+                                tc2_commit(bar_be0 + bs * 8);
+                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
+                        }
                     }
-                    tc2_commit(smem_u32(&bar_empty[stage]));
-                    if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+                    if (ok && elect_one()) tc2_commit(bar_ae0 + ac * 8);                          // chunk free once its last tap's MMAs retire
+                    __syncwarp();
+                    if (++ac == T2_A_CHUNKS) { ac = 0; a_phase ^= 1; }
                 }
-                if (ok) tc2_commit(smem_u32(&bar_acc_full[acc]));
+                if (ok && elect_one()) tc2_commit(bar_cf0 + acc * 8);
+                __syncwarp();
             }
         }
     } else {
@@ -602,9 +689,10 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             ok = __all_sync(0xFFFFFFFFu, ok);
             if (!ok) break;
             tc_fence_after();
+            // accumulator row (TMEM lane) = (oy * 2 + board-in-CTA) * 8 + ox
             const int row = lane_group * 32 + lane;
-            const int m = (t * 2 + (int)rank) * TC_BLOCK_M + row;
-            const int board = a.board0 + (m >> 6), sq = m & 63;
+            const int board = a.board0 + (t * 2 + (int)rank) * 2 + ((row >> 3) & 1);
+            const int sq = (row >> 4) * 8 + (row & 7);
             const bool live = board < a.board0 + a.n_boards;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
             const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
@@ -1000,8 +1088,9 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     a.bias = net->bias_all;
     for (int i = 0; i < 3; i++) a.act[i] = net->act16[i];
     a.error = net->tc_error;
-    net->tower_maps->a[0] = net->tm_in16;
-    for (int i = 0; i < 3; i++) net->tower_maps->a[1 + i] = net->tm_act16[i];
+    if ((rc = make_halo_map(ctx, &net->tower_maps->a[0], net->in16, C_IN_PAD, net->cap))) return rc;
+    for (int i = 0; i < 3; i++)
+        if ((rc = make_halo_map(ctx, &net->tower_maps->a[1 + i], net->act16[i], C_TOWER, net->cap))) return rc;
     {
         cuuint64_t dims[2] = {(cuuint64_t)KMAX, (cuuint64_t)MAX_TOWER_LAYERS * C_TOWER};
         cuuint64_t strides[1] = {(cuuint64_t)KMAX * 2};
