@@ -841,19 +841,24 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d);
     ctx->launches++;
     const bool prof = ctx->profiling;
+    const char* trace_path = getenv("SZB_TRACE");            // debugging aid: per-cohort phase timestamps of this search as CSV
+    const bool trace = prof && trace_path && trace_path[0];
     if (prof) {
-        while ((int)ctx->prof_events.size() < 5 * num_searches) {
+        while ((int)ctx->prof_events.size() < 5 * num_searches * (trace ? 2 : 1)) {
             cudaEvent_t e;
             SZB_CUDA(ctx, cudaEventCreate(&e));
             ctx->prof_events.push_back(e);
         }
     }
-    // Cohorts: the games are split into two halves that step independently on two streams, so that one half's tree
+    // Cohorts: the games can be split into two halves that step independently on two streams, so that one half's tree
     // kernels (select / expand / finish: latency-bound, a few hundred resident warps) run under the other half's
-    // tensor-bound network kernel.  Games never interact, so results do not depend on the split.  Profiling keeps one
-    // cohort on the context's stream so that per-phase and per-kernel durations mean what they say.
-    int n_cohorts = ctx->cohorts ? ctx->cohorts : (G >= 256 ? 2 : 1);
-    if (prof || G < 8) n_cohorts = 1;
+    // tensor-bound network kernel.  Games never interact, so results do not depend on the split.  Measured (trace,
+    // scripts/trace_cohorts.py): the overlap works, but a 512-board tower launch is ~10 % less efficient per board than a
+    // 1024-board one (only 1.7 items per CTA pair between an item and the one it depends on), which cancels the gain at
+    // 1024 games -- so the automatic setting splits only batches of >= 2048 games.  Profiling keeps one cohort on the
+    // context's stream so that per-phase and per-kernel durations mean what they say.
+    int n_cohorts = ctx->cohorts ? ctx->cohorts : (G >= 2048 ? 2 : 1);
+    if ((prof && !trace) || G < 8) n_cohorts = 1;
     int bounds[3] = {0, G, G};
     if (n_cohorts == 2) bounds[1] = ((G / 2 + 3) / 4) * 4;        // network tiles are 4 boards wide
     if (n_cohorts == 2) {
@@ -870,7 +875,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             cudaStream_t cs = n_cohorts == 2 ? ctx->cohort_stream[c] : st;
             ctx->work = cs;
             const int warp_blocks = (n * 32 + 127) / 128;
-            cudaEvent_t* ev = prof ? &ctx->prof_events[5 * (size_t)s] : nullptr;
+            cudaEvent_t* ev = prof ? &ctx->prof_events[5 * ((size_t)s * (trace ? 2 : 1) + (trace ? c : 0))] : nullptr;
             if (prof) cudaEventRecord(ev[0], cs);
             k_select<<<warp_blocks, 128, 0, cs>>>(dc, c_puct);
             if (prof) cudaEventRecord(ev[1], cs);
@@ -905,6 +910,24 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     SZB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->edges_high_water = std::max<uint64_t>(ctx->edges_high_water, top);
     if (flag) return fail(ctx, flag, "tree arena exhausted (%llu edges): raise szb_config.edges_per_node", d.edge_cap);
+    if (trace) {
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "step,cohort,select_start_ms,expand_start_ms,eval_start_ms,finish_start_ms,finish_end_ms\n");
+            for (int s = 0; s < num_searches; s++)
+                for (int c = 0; c < n_cohorts; c++) {
+                    cudaEvent_t* ev = &ctx->prof_events[5 * ((size_t)s * 2 + c)];
+                    fprintf(f, "%d,%d", s, c);
+                    for (int k = 0; k < 5; k++) {
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, ctx->prof_events[0], ev[k]);
+                        fprintf(f, ",%.4f", ms);
+                    }
+                    fprintf(f, "\n");
+                }
+            fclose(f);
+        }
+        return 0;
+    }
     if (prof) {
         for (int s = 0; s < num_searches; s++) {
             cudaEvent_t* ev = &ctx->prof_events[5 * (size_t)s];
