@@ -720,7 +720,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             uint4 rnext[4];
             if (resp) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) rnext[q] = reinterpret_cast<const uint4*>(resp)[q];
+                for (int q = 0; q < 4; q++) rnext[q] = __ldcg(reinterpret_cast<const uint4*>(resp) + q);      // written by another SM: bypass L1
             }
 #pragma unroll 1
             for (int c0 = 0; c0 < C_TOWER; c0 += 32) {
@@ -732,7 +732,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     for (int q = 0; q < 4; q++) rcur[q] = rnext[q];
                     if (c0 + 32 < C_TOWER) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) rnext[q] = reinterpret_cast<const uint4*>(resp + c0 + 32)[q];
+                        for (int q = 0; q < 4; q++) rnext[q] = __ldcg(reinterpret_cast<const uint4*>(resp + c0 + 32) + q);
                     }
                 }
                 tmem_ld_wait();
