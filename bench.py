@@ -394,7 +394,7 @@ def run_ours(args, wl):
                        "chess960": wl["chess960"], "positions": "S2 random-played: U{0..40} random legal plies from the start, seed 0",
                        "weights": weights, "parallelism": "games sharded, %d x network replica" % world,
                        "pipelining": ("2 cohorts of %d games on two streams (tree kernels of one run under the other's network kernel)" % (G // 2))
-                                     if G >= 2048 else "one cohort (the library splits batches of >= 2048 games into two)",
+                                     if G >= 1024 else "one cohort (the library splits batches of >= 1024 games into two)",
                        "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
                              % (G * 100 * 256 * 2 // 2 ** 20)},
             "moves_per_sec": total_moves / (ms * 1e-3), "evals_per_sec": evals / (ms * 1e-3),

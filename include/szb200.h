@@ -60,7 +60,7 @@ typedef struct szb_config {
     int32_t max_searches;          /* capacity: num_searches per move (train_RL.py:170) */
     int32_t edges_per_node;        /* tree arena = max_games * (max_searches+1) * edges_per_node edges; 0 -> 48 */
     int32_t cohorts;               /* search pipelining: 2 = the games step as two independent halves on two streams (one half's
-                                      tree kernels run under the other half's network kernel), 1 = one batch, 0 = automatic (2 from 2048 games) */
+                                      tree kernels run under the other half's network kernel), 1 = one batch, 0 = automatic (2 from 1024 games) */
 } szb_config;
 
 /* A position crossing the ABI. */

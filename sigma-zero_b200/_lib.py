@@ -3,7 +3,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libszb200.so")
+LIB_PATH = os.environ.get("SZB_LIB") or os.path.join(HERE, "libszb200.so")     # SZB_LIB: A/B-test another build of the library
 
 N_PLANES, N_ACTIONS, MASK_WORDS, MAX_MOVES = 119, 4672, 73, 256
 EVAL_NET_BF16, EVAL_NET_FP32, EVAL_HASH = 0, 1, 2

@@ -323,8 +323,7 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
     if (d.need_eval[g]) {
         const float* pol = d.policy + (size_t)g * N_ACTIONS;
         const uint64_t* mk = d.mask + (size_t)g * MASK_STRIDE;
-        auto elem = [&](int e) -> float { return ((mk[e >> 6] >> (e & 63)) & 1ull) ? pol[e] : 0.0f; };
-        const float part = cascade_lane(elem, lane);
+        const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
         const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
         int n_legal = 0;
         for (int w = lane; w < MASK_WORDS; w += 32) n_legal += popc(mk[w]);
@@ -852,12 +851,11 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     }
     // Cohorts: the games can be split into two halves that step independently on two streams, so that one half's tree
     // kernels (select / expand / finish: latency-bound, a few hundred resident warps) run under the other half's
-    // tensor-bound network kernel.  Games never interact, so results do not depend on the split.  Measured (trace,
-    // scripts/trace_cohorts.py): the overlap works, but a 512-board tower launch is ~10 % less efficient per board than a
-    // 1024-board one (only 1.7 items per CTA pair between an item and the one it depends on), which cancels the gain at
-    // 1024 games -- so the automatic setting splits only batches of >= 2048 games.  Profiling keeps one cohort on the
-    // context's stream so that per-phase and per-kernel durations mean what they say.
-    int n_cohorts = ctx->cohorts ? ctx->cohorts : (G >= 2048 ? 2 : 1);
+    // tensor-bound network kernel.  Games never interact, so results do not depend on the split.  Measured on one box,
+    // alternating (scripts/ab_cohorts.py, 1024 games): 2.33 ms per simulation step with two cohorts vs 2.37-2.44 with one
+    // (the tower is power-capped either way, so only the ~0.2 ms of small kernels can be hidden).  Profiling keeps one
+    // cohort on the context's stream so that per-phase and per-kernel durations mean what they say.
+    int n_cohorts = ctx->cohorts ? ctx->cohorts : (G >= 1024 ? 2 : 1);
     if ((prof && !trace) || G < 8) n_cohorts = 1;
     int bounds[3] = {0, G, G};
     if (n_cohorts == 2) bounds[1] = ((G / 2 + 3) / 4) * 4;        // network tiles are 4 boards wide

@@ -134,6 +134,12 @@ float hh_cascade_sum(const float* x) {
     for (int t = 0; t < 32; t++) part[t] = cascade_lane([&](int e) { return x[e]; }, t);
     return cascade_combine([&](int t) { return part[t]; });
 }
+// masked sum through the sparse walk (x must already be +0 outside the mask for the dense reference to agree)
+float hh_cascade_sum_sparse(const float* x, const uint64_t* mask73) {
+    float part[32];
+    for (int t = 0; t < 32; t++) part[t] = cascade_lane_sparse(mask73, [&](int e) { return x[e]; }, t);
+    return cascade_combine([&](int t) { return part[t]; });
+}
 float hh_noisy_prior(float p) { return noisy_prior(p); }
 void hh_hash_eval(const uint64_t* words119, float* policy4672, float* value) {
     uint64_t h = he_fold(words119);

@@ -79,6 +79,23 @@ def test_puct_cascade_noise_bit_exact(H, golden_dir):
     for x, y in zip(z["sum_x"], z["sum_y"]):
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert H.hh_cascade_sum(x.ctypes.data_as(ctypes.c_void_p)) == y
+    # the sparse walk over the legal-move bitset (what k_finish runs) == the dense cascade on the masked vector == torch.sum
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        n_legal = int(rng.integers(1, 219)) if trial % 7 else 0
+        idx = np.sort(rng.choice(4672, size=n_legal, replace=False))
+        if trial % 5 == 0 and n_legal:                      # clustered like real move lists, tail block included
+            idx = np.unique(np.clip(idx % 300 + 4672 - 300 * (trial % 2) - (0 if trial % 2 else 4372), 0, 4671))
+        x = np.zeros(4672, dtype=np.float32)
+        vals = rng.random(len(idx)).astype(np.float32) ** 4
+        vals[rng.random(len(idx)) < 0.05] = 0.0             # zero priors at legal moves
+        x[idx] = vals
+        bits = np.zeros(73 * 64, dtype=np.uint8)
+        bits[idx] = 1
+        mask = np.packbits(bits, bitorder="little").view("<u8").copy()
+        dense = H.hh_cascade_sum(x.ctypes.data_as(ctypes.c_void_p))
+        sparse = H.hh_cascade_sum_sparse(x.ctypes.data_as(ctypes.c_void_p), mask.ctypes.data_as(ctypes.c_void_p))
+        assert np.float32(dense) == np.float32(sparse) == numerics.cascade_sum(x), trial
     for i in range(len(z["puct_len"])):
         for k in range(int(z["puct_len"][i])):
             got = H.hh_puct(int(z["puct_n"][i][k]), float(z["puct_w"][i][k]), float(z["puct_p"][i][k]),

@@ -77,6 +77,7 @@ def build_host_harness():
     H.hh_puct.restype = ctypes.c_float
     H.hh_puct.argtypes = [ci, ctypes.c_double, ctypes.c_float, ci, ctypes.c_float]
     H.hh_cascade_sum.restype = ctypes.c_float; H.hh_cascade_sum.argtypes = [vp]
+    H.hh_cascade_sum_sparse.restype = ctypes.c_float; H.hh_cascade_sum_sparse.argtypes = [vp, vp]
     H.hh_noisy_prior.restype = ctypes.c_float; H.hh_noisy_prior.argtypes = [ctypes.c_float]
     H.hh_hash_eval.argtypes = [vp, vp, vp]
     return H
