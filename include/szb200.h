@@ -156,11 +156,15 @@ int szb_tree_export(szb_ctx *ctx, int32_t game, int32_t max_nodes, int32_t max_e
 
 /* ---- self-play: replaces sim.play_game's ply loop (sim.py:46-76) ---------------------------------- */
 /* One ply for every unfinished game: search, pick a move (sample proportional to visits, sim.py:68, with a
- * counter-based RNG keyed (seed, game, ply); or argmax with lowest index on ties when sample == 0), record
+ * counter-based RNG keyed (seed, global game id, ply); or argmax with lowest index on ties when sample == 0), record
  * (planes, visits, colour) and push the move.  moves_out (optional): int32[n_games] chosen policy index or -1
  * for games already over.  n_active_out (optional): games still running afterwards. */
 int szb_selfplay_ply(szb_ctx *ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
                      uint64_t seed, int32_t sample, int32_t *moves_out, int32_t *n_active_out);
+
+/* Global id of this context's game 0 (default 0).  The move-sampling RNG is keyed (seed, global game id, ply), so a game's
+ * moves do not depend on which rank / shard plays it (train_RL.py:219-239 fans games out to workers). */
+int szb_set_game_id_base(szb_ctx *ctx, uint64_t base);
 
 /* ---- counters (metrics) -------------------------------------------------------------- */
 typedef struct szb_stats {

@@ -68,6 +68,7 @@ SIGNATURES = {
     "szb_tree_export": (ctypes.c_int, [_vp, _i32, _i32, _i32] + [_vp] * 11 + [ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_double),
                                                                           ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "szb_selfplay_ply": (ctypes.c_int, [_vp, _i32, _f32, _i32, _i32, _u64, _i32, _vp, _vp]),
+    "szb_set_game_id_base": (ctypes.c_int, [_vp, _u64]),
     "szb_get_stats": (ctypes.c_int, [_vp, ctypes.POINTER(Stats)]),
     "szb_set_profiling": (ctypes.c_int, [_vp, _i32]),
     "szb_get_phase_times": (ctypes.c_int, [_vp, ctypes.POINTER(PhaseTimes)]),

@@ -454,7 +454,7 @@ __global__ void k_tree_export(Dev d, int g, int max_nodes, int max_edges, int32_
 }
 
 // choose a move from the root visit counts (sim.py:68 sampling, or arg-max first-index as in eval.py:92-100)
-__global__ void k_pick(Dev d, uint64_t seed, int sample, int32_t* moves) {
+__global__ void k_pick(Dev d, uint64_t seed, uint64_t game_id_base, int sample, int32_t* moves) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= d.n_games) return;
     const size_t r = (size_t)g * d.nodes_per_game;
@@ -465,7 +465,7 @@ __global__ void k_pick(Dev d, uint64_t seed, int sample, int32_t* moves) {
     for (int i = 0; i < n; i++) total += d.e_n[e0 + i];
     int pick = 0;
     if (sample && total > 0) {
-        const uint64_t rnd = mix64(mix64(seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(g + 1))) + (uint64_t)p.ply);
+        const uint64_t rnd = mix64(mix64(seed ^ (0x9E3779B97F4A7C15ull * (game_id_base + (uint64_t)g + 1))) + (uint64_t)p.ply);
         const long long target = (long long)__umul64hi(rnd, (uint64_t)total);      // uniform in [0, total)
         long long acc = 0;
         for (int i = 0; i < n; i++) { acc += d.e_n[e0 + i]; if (acc > target) { pick = i; break; } }
@@ -1037,7 +1037,7 @@ int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t l
     const int G = d.n_games;
     int32_t* d_active = ctx->d_moves + ctx->cfg.max_games;
     SZB_CUDA(ctx, cudaMemsetAsync(d_active, 0, sizeof(int32_t), ctx->stream));
-    k_pick<<<(G + 127) / 128, 128, 0, ctx->stream>>>(d, seed, sample, ctx->d_moves);
+    k_pick<<<(G + 127) / 128, 128, 0, ctx->stream>>>(d, seed, ctx->game_id_base, sample, ctx->d_moves);
     k_push_picked<<<(G + 31) / 32, 32, 0, ctx->stream>>>(d, ctx->d_moves, d_active);
     ctx->launches += 2;
     SZB_CUDA(ctx, cudaGetLastError());
@@ -1046,6 +1046,12 @@ int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t l
     SZB_CUDA(ctx, cudaMemcpyAsync(&act, d_active, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_active_out) *n_active_out = act;
+    return 0;
+}
+
+int szb_set_game_id_base(szb_ctx* ctx, uint64_t base) {
+    if (!ctx) return SZB_ERR_ARG;
+    ctx->game_id_base = base;
     return 0;
 }
 

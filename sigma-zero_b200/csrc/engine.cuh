@@ -87,6 +87,7 @@ struct szb_ctx {
     szb::Net* net = nullptr;
     // self-play records
     int32_t* d_moves = nullptr;
+    uint64_t game_id_base = 0;                 // global id of game 0 of this context (move-sampling RNG key; sharding)
     // profiling
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;

@@ -197,6 +197,10 @@ class Engine:
                                               ctypes.cast(ctypes.byref(active), ctypes.c_void_p)))
         return moves, active.value
 
+    def set_game_id_base(self, base):
+        """global id of game 0 (keys the move-sampling RNG so that shards of one job play the same games)"""
+        self._check(self.lib.szb_set_game_id_base(self._h, int(base)))
+
     def set_profiling(self, on=True):
         self._check(self.lib.szb_set_profiling(self._h, int(bool(on))))
 

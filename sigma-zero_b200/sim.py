@@ -16,17 +16,24 @@ def _empty_history():
 
 
 def selfplay_batch(model, args, num_games, c960=False, seed=None, start_ids=None, max_plies=None, learning=True,
-                   sample=True, record=True):
-    """Plays num_games games in lock step.  Returns one history dict per game (sim.py:38-43 schema) plus counters."""
+                   sample=True, record=True, game_id_base=0):
+    """Plays num_games games in lock step.  Returns one history dict per game (sim.py:38-43 schema) plus counters.
+
+    With a `seed`, everything random about a game -- its Chess960 start position (the reference draws random.randint(0,
+    959), chess_tensor.py:69) and the moves sampled from the visit counts (sim.py:68) -- is a function of (seed, global game
+    id = game_id_base + index) only, so a job sharded over ranks plays exactly the games a single process would."""
     n_search = int(args['num_searches'])
     eng = runtime.get_engine(min_games=num_games, min_searches=n_search)
     runtime.sync_weights(eng, model)
     eng.owner = None
-    rng = np.random.default_rng(seed)
+    if seed is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 62))
     if start_ids is None:
-        start_ids = rng.integers(0, 960, size=num_games) if c960 else np.full(num_games, -1)
+        start_ids = ([int(np.random.default_rng([int(seed), int(game_id_base) + g]).integers(0, 960)) for g in range(num_games)]
+                     if c960 else np.full(num_games, -1))
     eng.reset(start_ids)
-    seed64 = int(rng.integers(0, 2 ** 62)) if seed is None else int(seed)
+    eng.set_game_id_base(game_id_base)
+    seed64 = int(seed)
     games = [_empty_history() for _ in range(num_games)]
     evaluator = runtime.evaluator_of(model)
     plies = 0

@@ -64,5 +64,5 @@ def selfplay_iteration(model, args, seed=0, max_plies=None):
         broadcast_weights(model, 0, dev)
     lo, hi = shard_of(int(args['num_selfPlay_iterations']), rank, world)
     games, counters = selfplay_batch(model, args, hi - lo, c960=bool(args.get('chess960', False)),
-                                     seed=seed * 1000003 + lo, max_plies=max_plies)
+                                     seed=seed, max_plies=max_plies, game_id_base=lo)
     return games, counters

@@ -140,3 +140,28 @@ def test_bf16_visit_counts_track_the_fp32_search():
     print("bf16 vs fp32 search: mean TV %.4f  max TV %.4f  same top move %.2f" % (tv.mean(), tv.max(), same_top))
     assert tv.mean() < 0.15 and same_top >= 0.6
     eng.close()
+
+
+def test_sharded_selfplay_plays_the_same_games():
+    """a job split over ranks (train_RL.shard_of blocks, game_id_base = first global id) must produce, game for
+    game, what one process produces -- start positions, sampled moves, visit distributions.  Two 'ranks' are emulated one
+    after the other on this GPU."""
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.sim import selfplay_batch
+    from sigma_zero_b200.train_RL import shard_of
+    torch.manual_seed(0)
+    model = policyNN({}).eval()
+    args = {"C": 2, "num_searches": 12}
+    whole, _ = selfplay_batch(model, args, 10, c960=True, seed=7, max_plies=6)
+    parts = []
+    for rank in range(2):
+        lo, hi = shard_of(10, rank, 2)
+        games, _ = selfplay_batch(model, args, hi - lo, c960=True, seed=7, max_plies=6, game_id_base=lo)
+        parts += games
+    assert len(parts) == len(whole) == 10
+    for a, b in zip(whole, parts):
+        assert len(a["actions"]) == len(b["actions"]) == 6
+        for pa, pb in zip(a["actions"], b["actions"]):
+            assert [m.uci() for m in pa] == [m.uci() for m in pb] and list(pa.values()) == list(pb.values())
+        for sa, sb in zip(a["states"], b["states"]):
+            assert torch.equal(sa, sb)
