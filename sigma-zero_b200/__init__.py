@@ -9,6 +9,7 @@ The reference's module names are mirrored one to one:
     sigma_zero_b200.network.policyNN      <- network.py:89-192
     sigma_zero_b200.sim                   <- sim.py (play_game, generate_training_data)
     sigma_zero_b200.train_RL              <- train_RL.py:156-244 (self-play fan-out + args only)
+    sigma_zero_b200.arena                 <- test_update.py:26-83 (new-vs-current promotion match; a "next" row)
 
 `install_dropin()` additionally registers those modules under the reference's flat names (`mcts`,
 `mctsnode`, `chess_tensor`, `network`, `sim`) so reference-style scripts run unchanged.

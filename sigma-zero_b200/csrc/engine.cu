@@ -199,28 +199,33 @@ __global__ void k_search_begin(Dev d) {
     d.root_w[g] = 0.0;
 }
 
-// warp per tree
+// warp per tree.  Two dependent memory round trips per level: (child count, first edge) of the node, then the four edge
+// arrays of its children read side by side; the parent's visit count and the chosen child's node index travel down in
+// registers (the winning lane already holds them) instead of being re-read through node_pedge / e_child.
 __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
     const int g = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (g >= d.g_end) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     int node = 0, depth = 0;
+    int np = d.root_n[g];                                  // visit count of the node being expanded (root: mcts.py:46)
     unsigned long long scanned = 0;
     for (;;) {
         const int n = d.node_nchild[r + node];
+        const int e0 = d.node_edge0[r + node];
         if (n == 0) {
             if (lane == 0) { d.sel_node[g] = node; d.sel_edge[g] = -1; }
             break;
         }
-        const int e0 = d.node_edge0[r + node];
-        const int np = node == 0 ? d.root_n[g] : d.e_n[d.node_pedge[r + node]];
         const float sq = sqrt_parent(np);
         float best = -INFINITY;
-        int besti = 0x7FFFFFFF;
+        int besti = 0x7FFFFFFF, best_n = 0;
+        uint16_t best_child = NO_CHILD;
         for (int i = lane; i < n; i += 32) {
-            const float s = puct_score(d.e_n[e0 + i], d.e_w[e0 + i], d.e_p[e0 + i], sq, c_puct);
-            if (s > best || besti == 0x7FFFFFFF) { best = s; besti = i; }
+            const int cn = d.e_n[e0 + i];
+            const uint16_t cc = d.e_child[e0 + i];
+            const float s = puct_score(cn, d.e_w[e0 + i], d.e_p[e0 + i], sq, c_puct);
+            if (s > best || besti == 0x7FFFFFFF) { best = s; besti = i; best_n = cn; best_child = cc; }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -229,8 +234,10 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
             if (oi != 0x7FFFFFFF && (besti == 0x7FFFFFFF || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
         }
         besti = __shfl_sync(0xFFFFFFFFu, besti, 0);
+        // child i was scored by lane i % 32, which still holds its visit count and node index
+        np = __shfl_sync(0xFFFFFFFFu, best_n, besti & 31);
+        const uint16_t c = (uint16_t)__shfl_sync(0xFFFFFFFFu, (int)best_child, besti & 31);
         const int e = e0 + besti;
-        const uint16_t c = d.e_child[e];
         depth++;
         scanned += (unsigned long long)n;
         if (c == NO_CHILD) {

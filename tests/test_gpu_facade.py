@@ -165,3 +165,34 @@ def test_sharded_selfplay_plays_the_same_games():
             assert [m.uci() for m in pa] == [m.uci() for m in pb] and list(pa.values()) == list(pb.values())
         for sa, sb in zip(a["states"], b["states"]):
             assert torch.equal(sa, sb)
+
+
+def test_arena_match_between_two_networks():
+    """SURVEY 8f rank 2 (test_update.py): two networks, every game concurrently, arg-max moves, learning=False.  The moves of
+    the first ply are checked against a stand-alone search of the same positions with the same weights."""
+    from sigma_zero_b200.arena import play_match, update_model
+    from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
+    from sigma_zero_b200.network import policyNN
+    torch.manual_seed(1)
+    a = policyNN({}).eval()
+    torch.manual_seed(2)
+    b = policyNN({}).eval()
+    args = {"C": 2, "num_searches": 24}
+    out = play_match(a, b, 6, args, c960=True, seed=3, max_plies=5)
+    assert out["plies"] == 5 and len(out["results"]) == 6 and out["a_is_white"] == [True, False] * 3
+    assert all(r == "*" for r in out["results"]) and out["score_a"] == 0.0
+    again = play_match(a, b, 6, args, c960=True, seed=3, max_plies=5)
+    assert again == out                                             # deterministic
+    assert update_model(b, a, matches=1, args=args, max_plies=4) is False      # nothing finished in 4 plies -> no promotion
+    # first ply of a vanilla game: network a is White in game 0, network b in game 1 -- each move must be the first arg-max
+    # of a stand-alone search of the start position with that network's weights
+    one = play_match(a, b, 2, args, c960=False, max_plies=1)
+    assert one["plies"] == 1
+    for g, model in enumerate((a, b)):
+        eng = Engine(max_games=1, max_searches=24, cohorts=1)
+        eng.load_state_dict(model.state_dict())
+        eng.reset([-1])
+        eng.search(24, 2.0, False, EVAL_NET_BF16, want_visits=False, want_children=False)
+        idx, vis, cnt = eng.root_children()
+        assert one["moves"][g] == [int(idx[0, int(np.argmax(vis[0, :cnt[0]]))])]
+        eng.close()

@@ -134,3 +134,40 @@ def test_bench_reference_arm_contract():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     for k in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config"):
         assert k in line
+
+
+def test_record_format_roundtrip(tmp_path, golden_dir):
+    """packed self-play records: states, sparse visit distributions and outcomes survive pack -> save -> load -> unpack"""
+    from sigma_zero_b200 import chess_compat as cc, records, runtime
+    from sigma_zero_b200.chess_tensor import actionsToTensor
+    z = np.load(os.path.join(golden_dir, "codec.npz"))
+    games = []
+    for g in range(3):
+        h = {"states": [], "actions": [], "rewards": [], "colours": []}
+        for k in range(4):
+            i = 7 * g + k
+            white = (len(str(z["moves"][i]).split()) % 2) == 0
+            ucis = str(z["uci"][i]).split()
+            if not ucis:
+                continue
+            p = np.random.default_rng(i).random(len(ucis))
+            p /= p.sum()
+            h["states"].append(torch.from_numpy(runtime.unpack_planes(z["planes"][i])))
+            h["actions"].append({cc.Move.from_uci(u): float(x) for u, x in zip(ucis, p)})
+            h["colours"].append(white)
+            h["rewards"].append((-1) ** k)
+        games.append(h)
+    rec = records.pack_records(games)
+    n = sum(len(h["actions"]) for h in games)
+    assert rec["states"].shape == (n, 119) and rec["pi_off"][-1] == len(rec["pi_index"]) and len(rec["z"]) == n
+    records.save(str(tmp_path / "r.npz"), rec)
+    back = records.load(str(tmp_path / "r.npz"))
+    planes = records.unpack_states(back)
+    dense = records.dense_policy(back)
+    i = 0
+    for g, h in enumerate(games):
+        for s, a, r, c in zip(h["states"], h["actions"], h["rewards"], h["colours"]):
+            assert np.array_equal(planes[i], s.numpy()) and back["z"][i] == r and back["colour"][i] == c and back["game"][i] == g
+            want, _ = actionsToTensor(a, c)                      # the reference's own dense soft target (train_RL.py:43-45)
+            assert np.allclose(dense[i], want.numpy(), atol=1e-7)
+            i += 1
