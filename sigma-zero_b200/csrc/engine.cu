@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
         node = c;
     }
     if (lane == 0) {
-        atomicMax(&d.stats[3], (unsigned long long)depth);
-        atomicAdd(&d.stats[4], scanned);
-        atomicAdd(&d.stats[5], (unsigned long long)depth);
+        unsigned long long* gs = d.gstats + (size_t)g * 8;
+        if ((unsigned long long)depth > gs[3]) gs[3] = (unsigned long long)depth;
+        gs[4] += scanned;
+        gs[5] += (unsigned long long)depth;
     }
 }
 
@@ -321,24 +322,38 @@ __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
 
 // warp per tree
 __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
+    __shared__ int want_sh[4];
+    __shared__ unsigned long long base_sh;
     const int g = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (g >= d.g_end) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const bool active = g < d.g_end;
+    const bool eval = active && d.need_eval[g];
+    // children to allocate: one bump of the shared edge arena per BLOCK (four trees), not one same-address atomic per tree
+    int n_legal = 0;
+    if (eval) {
+        const uint64_t* mk = d.mask + (size_t)g * MASK_STRIDE;
+        for (int w = lane; w < MASK_WORDS; w += 32) n_legal += popc(mk[w]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) n_legal += __shfl_xor_sync(0xFFFFFFFFu, n_legal, off);
+    }
+    if (lane == 0) want_sh[wib] = n_legal;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tot = want_sh[0] + want_sh[1] + want_sh[2] + want_sh[3];
+        base_sh = tot ? atomicAdd(d.edge_top, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (!active) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     const int node = d.sel_node[g];
     float v;
-    if (d.need_eval[g]) {
+    if (eval) {
         const float* pol = d.policy + (size_t)g * N_ACTIONS;
         const uint64_t* mk = d.mask + (size_t)g * MASK_STRIDE;
         const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
         const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
-        int n_legal = 0;
-        for (int w = lane; w < MASK_WORDS; w += 32) n_legal += popc(mk[w]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) n_legal += __shfl_xor_sync(0xFFFFFFFFu, n_legal, off);
-        unsigned long long e0 = 0;
-        if (lane == 0) e0 = atomicAdd(d.edge_top, (unsigned long long)n_legal);
-        e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+        unsigned long long e0 = base_sh;
+        for (int k = 0; k < wib; k++) e0 += (unsigned long long)want_sh[k];
         int count = 0;
         if (e0 + (unsigned long long)n_legal > d.edge_cap) {
             if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
@@ -385,12 +400,37 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
             nd = d.node_pnode[r + nd];
             levels++;
         }
-        atomicAdd(&d.stats[6], levels);
-        if (d.need_eval[g]) atomicAdd(&d.stats[7], (unsigned long long)d.node_nchild[r + node]);
+        unsigned long long* gs = d.gstats + (size_t)g * 8;
+        gs[6] += levels;
+        if (d.need_eval[g]) gs[7] += (unsigned long long)d.node_nchild[r + node];
         d.root_w[g] += val;
         d.root_n[g] += 1;
-        atomicAdd(&d.stats[0], 1ull);
-        atomicAdd(&d.stats[d.need_eval[g] ? 1 : 2], 1ull);
+        gs[0] += 1ull;
+        gs[d.need_eval[g] ? 1 : 2] += 1ull;
+    }
+}
+
+// per-game counter rows -> totals (sum, except max depth); rows are cleared.  One block.
+__global__ void __launch_bounds__(256) k_fold_stats(Dev d, int n_games) {
+    __shared__ unsigned long long part[256][8];
+    unsigned long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int g = threadIdx.x; g < n_games; g += 256) {
+        unsigned long long* gs = d.gstats + (size_t)g * 8;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned long long v = gs[k];
+            acc[k] = k == 3 ? (v > acc[k] ? v : acc[k]) : acc[k] + v;
+            gs[k] = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) part[threadIdx.x][k] = acc[k];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int k = threadIdx.x;
+        unsigned long long t = 0;
+        for (int i = 0; i < 256; i++) t = k == 3 ? (part[i][k] > t ? part[i][k] : t) : t + part[i][k];
+        if (k == 3) { if (t > d.stats[3]) d.stats[3] = t; } else d.stats[k] += t;
     }
 }
 
@@ -684,7 +724,7 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     A(sel_node, G); A(sel_edge, G); A(need_eval, G); A(leaf_value, G);
     A(planes, G * PLANE_STRIDE); A(mask, G * MASK_STRIDE);
     A(policy, G * N_ACTIONS); A(value, G); A(root_val, G);
-    A(stats, 8);
+    A(stats, 8); A(gstats, G * 8);
 #undef A
     if ((rc = dev_alloc(ctx, &ctx->d_moves, G + 1))) return rc;
     SZB_CUDA(ctx, cudaMalloc((void**)&ctx->perft_counter, sizeof(unsigned long long)));
@@ -1070,6 +1110,7 @@ int szb_set_profiling(szb_ctx* ctx, int32_t on) {
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->conv_events_used = 0;
     ctx->conv_ms = 0; ctx->conv_launches = 0;
+    k_fold_stats<<<1, 256, 0, ctx->stream>>>(ctx->d, ctx->cfg.max_games);
     SZB_CUDA(ctx, cudaMemsetAsync(ctx->d.stats + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
     return 0;
 }
@@ -1077,6 +1118,7 @@ int szb_set_profiling(szb_ctx* ctx, int32_t on) {
 int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
     if (!ctx || !out) return SZB_ERR_ARG;
     unsigned long long h[8];
+    k_fold_stats<<<1, 256, 0, ctx->stream>>>(ctx->d, ctx->cfg.max_games);
     SZB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d.stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     out->select_ms = ctx->phase_ms[0]; out->expand_ms = ctx->phase_ms[1];
@@ -1091,6 +1133,7 @@ int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
 int szb_get_stats(szb_ctx* ctx, szb_stats* out) {
     if (!ctx || !out) return SZB_ERR_ARG;
     unsigned long long h[8];
+    k_fold_stats<<<1, 256, 0, ctx->stream>>>(ctx->d, ctx->cfg.max_games);
     SZB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d.stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     out->simulations = h[0];

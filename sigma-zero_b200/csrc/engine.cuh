@@ -56,8 +56,10 @@ struct Dev {
     float* policy;           // [max_games][4672] evaluator output ("softmax over everything")
     float* value;            // [max_games]
     float* root_val;         // [max_games] evaluator value of the root position
-    unsigned long long* stats;   // 0 simulations, 1 evaluations, 2 terminal visits, 3 max depth,
+    unsigned long long* stats;   // totals: 0 simulations, 1 evaluations, 2 terminal visits, 3 max depth,
                                  // 4 select edges, 5 select levels, 6 backup levels, 7 edges written
+    unsigned long long* gstats;  // [max_games][8] the same counters per game: the step kernels bump their own game's row
+                                 // (no same-address atomics on the hot path), k_fold_stats folds the rows into `stats`
 };
 
 }  // namespace szb
