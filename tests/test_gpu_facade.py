@@ -196,3 +196,18 @@ def test_arena_match_between_two_networks():
         idx, vis, cnt = eng.root_children()
         assert one["moves"][g] == [int(idx[0, int(np.argmax(vis[0, :cnt[0]]))])]
         eng.close()
+
+
+def test_playtensor_single_game_api():
+    """one game, model replies with the arg-max move of its search"""
+    from sigma_zero_b200.play import PlayTensor
+    torch.manual_seed(4)
+    p = PlayTensor(num_searches=16)
+    assert p.check_if_end() is None
+    p.move("e2e4")
+    reply = p.model_move()
+    assert p.board.turn is True and len(p.board.move_stack) == 2 and reply.uci() == p.board.move_stack[-1].uci()
+    with pytest.raises(ValueError, match="Invalid move"):
+        p.move("e2e4")
+    p.start_new_game()
+    assert len(p.board.move_stack) == 0

@@ -115,3 +115,27 @@ def test_terminal_root_and_single_search(eng):
     assert visits[1].sum() == 9
     visits, child, _ = eng.search(1, 2.0, False, EVAL_HASH)
     assert visits[1].sum() == 0 and child[1].sum() != 0
+
+
+def test_cohort_split_does_not_change_results():
+    """the two-cohort pipeline (two game halves stepping on two streams) must give exactly the visit counts of the single
+    batch -- with the hash evaluator (exact) and with the bf16 network (batch-invariant kernels)"""
+    import torch
+    from sigma_zero_b200.engine import EVAL_HASH, EVAL_NET_BF16, Engine
+    torch.manual_seed(0)
+    sd = ref_path.build_policy_nn().eval().state_dict()
+    n = 30                                                  # split 16 / 14: ragged second cohort, 4-board tile boundary inside
+    out = {}
+    for c in (1, 2):
+        e = Engine(max_games=n, max_searches=40, cohorts=c)
+        e.load_state_dict(sd)
+        e.reset([(-1 if g % 3 else (53 * g) % 960) for g in range(n)])
+        for ply in range(3):                                # a few plies so that positions differ between games
+            idx, cnt = e.legal_moves()
+            e.push(list(range(n)), [int(idx[g, (7 * g + ply) % cnt[g]]) for g in range(n)])
+        vh, ch, _ = e.search(40, 2.0, True, EVAL_HASH)
+        vn, cn, _ = e.search(40, 2.0, True, EVAL_NET_BF16)
+        out[c] = (vh, ch, vn, cn)
+        e.close()
+    for a, b in zip(out[1], out[2]):
+        assert np.array_equal(a, b)
