@@ -1,14 +1,17 @@
 // net.cu -- the policy/value network (network.py:89-192) as hand-written sm_100a kernels.
 //
-//   bf16 path : every convolution is an implicit GEMM on the 5th-gen tensor cores: TMA (cp.async.bulk.tensor)
-//               stages activation windows and weight tiles in shared memory with 128-byte swizzle, one elected
-//               thread issues tcgen05.mma (128 x N x 16, bf16 in / fp32 accumulate in TMEM), four epilogue warps
-//               read the accumulator back with tcgen05.ld and fuse +bias(BN folded) [+residual] -> ReLU -> bf16.
-//               Warp-specialised persistent CTAs, 4-stage smem ring, double-buffered TMEM accumulator.
+//   bf16 path : every convolution is an implicit GEMM on the 5th-gen tensor cores (GEMM view: M = 64*B board squares,
+//               N = C_out, K = taps*C_in; bf16 in, fp32 accumulate in TMEM, epilogue +bias(BN folded) [+residual] -> ReLU
+//               -> bf16 fused after tcgen05.ld).
+//               k_tower_tc2  (the product path): ONE persistent launch over all 41 layers; CTA pairs with
+//                            tcgen05.mma.cta_group::2 (256 x 256 x 16), weight tiles split between the two CTAs, a whole
+//                            halo tile of activations resident in shared memory per 64-channel K chunk (all nine taps read
+//                            it in place through shifted descriptors), per-item dependency counters between layers.
+//               k_conv_tc    (first version, kept for A/B and the bit-identity test): single CTA, 128 x N x 16, one launch per
+//                            layer, one TMA box per tap.
 //   fp32 path : SIMT FFMA implicit GEMM with the same folded weights (parity mode, <= 1e-5 abs vs torch CPU).
 //
-// Activations live in HBM as NHWC with a one-square zero halo: [B][10][10][C]; the nine taps of a 3x3
-// convolution are then plain shifted TMA boxes.  GEMM view: M = 64*B (board squares), N = C_out, K = taps*C_in.
+// Activations live in HBM as NHWC bf16 with a one-square zero halo: [B][10][10][C]; a tap is a shifted window of it.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
