@@ -1,9 +1,12 @@
 """Drop-in for the reference's network.py: policyNN with the same 252-key state_dict (so
 `model.load_state_dict(torch.load("supervised_model_best.pt", map_location="cpu"))` works, play.py:25-28)
-whose forward runs on the hand-written sm_100a kernels of libszb200 (szb_net_forward), not on torch ops.
+whose inference forward -- the one the self-play hot path uses, model.eval() as in train_RL.py:213 -- runs on the
+hand-written sm_100a kernels of libszb200 (szb_net_forward), not on torch ops, and has no fallback.
 
-The torch modules below are parameter containers only (state_dict / load_state_dict / .to()).  `precision`
-selects the kernel family: "bf16" = tcgen05/TMEM implicit-GEMM tower, "fp32" = SIMT parity path."""
+`precision` selects the kernel family: "bf16" = tcgen05/TMEM implicit-GEMM tower, "fp32" = SIMT parity path.
+
+In model.train() mode the same modules are evaluated by torch with autograd (batch-statistics BatchNorm), which is what
+the reference's fine-tuning step does (train_RL.py:77-154; SURVEY.md 8f rank 1, a "next" row outside the hot path)."""
 import torch
 import torch.nn as nn
 
@@ -21,8 +24,11 @@ class BasicBlock(nn.Module):
         self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
 
-    def forward(self, x):  # pragma: no cover - parameters only
-        raise RuntimeError("BasicBlock is a parameter container; policyNN.forward runs the CUDA kernels")
+    def forward(self, x):
+        """torch path (training only; network.py:66-83)"""
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + x)
 
 
 class policyNN(nn.Module):
@@ -43,12 +49,29 @@ class policyNN(nn.Module):
         self.fc_v2 = nn.Linear(256, 1)
         self.resnet_blocks = nn.Sequential(*[BasicBlock(256, 256) for _ in range(19)])
 
-    @torch.no_grad()
+    def forward_torch(self, x, inference=False):
+        """the reference's forward (network.py:176-192) on torch ops with autograd: the TRAINING path"""
+        x = torch.relu(self.norm_layer(self.conv1(x)))
+        x = self.resnet_blocks(x)
+        p = torch.relu(self.p_norm1(self.conv_p1(x)))
+        p = torch.flatten(self.conv_p2(p), start_dim=1)
+        v = torch.relu(self.v_norm(self.conv_v1(x)))
+        v = torch.relu(self.fc_v1(torch.flatten(v, start_dim=1)))
+        v = torch.tanh(self.fc_v2(v))
+        if inference:
+            p = torch.softmax(p, dim=1)
+        return p, v
+
     def forward(self, x, inference=False):
-        """x: [B,119,8,8] 0/1 planes (any dtype/device) -> (policy [B,4672], value [B,1]) on x's device.
-        BatchNorm runs in eval mode (running statistics), as in the reference's self-play (train_RL.py:213)."""
+        """x: [B,119,8,8] 0/1 planes -> (policy [B,4672], value [B,1]) on x's device.
+        model.eval(): the CUDA kernels (BatchNorm folded with its running statistics, as in the reference's self-play,
+        train_RL.py:213); no gradient, no fallback.  model.train(): torch ops with autograd (fine-tuning)."""
         if self.training:
-            raise RuntimeError("the CUDA forward is inference-only (model.eval()); training is outside the self-play hot path")
+            return self.forward_torch(x, inference)
+        with torch.no_grad():
+            return self._forward_cuda(x, inference)
+
+    def _forward_cuda(self, x, inference):
         eng = runtime.get_engine(min_games=int(x.shape[0]))
         runtime.sync_weights(eng, self)
         packed = runtime.pack_planes(x.detach().cpu().numpy())

@@ -1,11 +1,14 @@
-"""Self-play fan-out of the reference's train_RL.py (args + launcher only, train_RL.py:156-244).
+"""Self-play fan-out of the reference's train_RL.py (args + launcher, train_RL.py:156-244) and, as a "next" row
+(SURVEY.md 8f rank 1), its fine-tuning step on the self-play records (train_RL.py:77-154) in torch.
 
 The reference spawns `num_process` CPU workers that each play `num_games // num_process` games one after another
 and merges their pickled dicts.  Here every rank (one process per GPU, torch.distributed over NCCL) plays its
 shard of the games concurrently on its GPU; the only collective is the broadcast of the flat fp32 weight buffer
 from the trainer rank at the start of an iteration.  `num_selfPlay_iterations` -- which the reference's args
 carry but never read -- is defined as the number of self-play games per outer iteration.
-Training itself (chessDataset / train / test) is outside the self-play hot path."""
+Training (train_on_records / rl_iteration below) is outside the self-play hot path: it runs the reference's own torch
+recipe -- loss = MSE(v, z) + CE(logits, pi) (:103-113), Adam lr 1e-4 wd 1e-4 (:187), StepLR(500, 0.95) (:199) -- on the
+packed record format of records.py; the weights it produces reach the CUDA engine through runtime.sync_weights."""
 import os
 
 import torch
@@ -66,3 +69,64 @@ def selfplay_iteration(model, args, seed=0, max_plies=None):
     games, counters = selfplay_batch(model, args, hi - lo, c960=bool(args.get('chess960', False)),
                                      seed=seed, max_plies=max_plies, game_id_base=lo)
     return games, counters
+
+
+def make_optimiser(model, lr=1e-4, weight_decay=1e-4):
+    """the reference's optimiser and schedule (train_RL.py:187,199)"""
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    return opt, torch.optim.lr_scheduler.StepLR(opt, step_size=500, gamma=0.95)
+
+
+def train_on_records(model, rec, epochs=1, batch_size=64, optimiser=None, lr_scheduler=None, device=None, seed=0, log=None):
+    """Fine-tunes `model` on packed self-play records (records.pack_records): per batch
+    loss = mse_loss(v, z) + cross_entropy(logits, pi) with pi the soft visit-fraction target (train_RL.py:103-113).
+    Returns the per-batch (mse, ce) losses.  The model is left in eval() mode, ready for the next self-play iteration."""
+    import numpy as np
+    from . import records
+    if optimiser is None:
+        optimiser, lr_scheduler = make_optimiser(model)
+    device = torch.device(device) if device is not None else next(model.parameters()).device
+    model.to(device).train()
+    n = len(rec["z"])
+    rng = np.random.default_rng(seed)
+    history = []
+    for epoch in range(epochs):
+        order = rng.permutation(n)
+        for lo in range(0, n, batch_size):
+            rows = order[lo:lo + batch_size]
+            if len(rows) < 2:
+                continue                                     # BatchNorm needs more than one sample in training mode
+            x = torch.from_numpy(records.unpack_states(rec, rows)).to(device=device, dtype=torch.float32)
+            pi = torch.from_numpy(records.dense_policy(rec, rows)).to(device)
+            z = torch.from_numpy(rec["z"][rows].astype(np.float32)).to(device)
+            p, v = model(x)
+            mse = torch.nn.functional.mse_loss(v.squeeze(-1), z)
+            ce = torch.nn.functional.cross_entropy(p, pi)
+            optimiser.zero_grad()
+            (mse + ce).backward()
+            optimiser.step()
+            if lr_scheduler is not None:
+                lr_scheduler.step()
+            history.append((float(mse.detach()), float(ce.detach())))
+            if log is not None:
+                log({"MSE Loss": history[-1][0], "CE Loss": history[-1][1]}, len(history))
+    model.eval()
+    return history
+
+
+def rl_iteration(model, args, seed=0, max_plies=None, epochs=None, optimiser=None, lr_scheduler=None, train_device=None):
+    """One outer iteration of train_RL.main (:205-264): sharded self-play with the current weights (rank 0's are broadcast),
+    records gathered on every rank, the same fine-tuning step everywhere (identical data + identical seed => identical
+    weights, so the next iteration's broadcast is a formality).  Returns (records, loss history)."""
+    import torch.distributed as dist
+    from . import records
+    games, _ = selfplay_iteration(model, args, seed=seed, max_plies=max_plies)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, games)
+        games = [g for part in parts for g in part]
+    rec = records.pack_records(games)
+    hist = train_on_records(model, rec, epochs=int(args.get('num_epochs', 1)) if epochs is None else epochs,
+                            batch_size=int(args.get('batch_size', 64)), optimiser=optimiser, lr_scheduler=lr_scheduler,
+                            device=train_device, seed=seed)
+    return rec, hist

@@ -211,3 +211,31 @@ def test_playtensor_single_game_api():
         p.move("e2e4")
     p.start_new_game()
     assert len(p.board.move_stack) == 0
+
+
+def test_selfplay_train_selfplay_loop():
+    """the reference's outer loop in miniature (train_RL.py:205-264): self-play on the CUDA engine -> packed records -> the
+    reference's fine-tuning step in torch on the GPU -> the engine picks the new weights up for the next self-play"""
+    from sigma_zero_b200 import records
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.sim import selfplay_batch
+    from sigma_zero_b200.train_RL import train_on_records
+    torch.manual_seed(0)
+    model = policyNN({}).eval()
+    args = {"C": 2, "num_searches": 16}
+    games, _ = selfplay_batch(model, args, 8, c960=False, seed=1, max_plies=4)
+    for g in games:                                         # unfinished games carry zero rewards: give the value head something to fit
+        g["rewards"] = [1 if i % 2 == 0 else -1 for i in range(len(g["rewards"]))]
+    rec = records.pack_records(games)
+    assert rec["states"].shape == (32, 119)
+    x = torch.from_numpy(records.unpack_states(rec, [0, 5])).float()
+    before_p, before_v = model(x, inference=True)            # CUDA kernels, old weights
+    hist = train_on_records(model, rec, epochs=3, batch_size=16, device="cuda")
+    assert len(hist) == 6 and all(np.isfinite(h).all() for h in hist) and sum(hist[-1]) < sum(hist[0])
+    after_p, after_v = model(x, inference=True)              # CUDA kernels again: weights re-sent because they changed
+    assert not torch.equal(before_p, after_p) and not torch.equal(before_v, after_v)
+    with torch.no_grad():
+        ref_p, ref_v = model.forward_torch(x.cuda(), inference=True)        # same weights through torch (eval-mode BN)
+    assert (after_p - ref_p.cpu()).abs().max().item() <= 2e-2 and (after_v - ref_v.cpu()).abs().max().item() <= 2e-2
+    games2, _ = selfplay_batch(model, args, 8, c960=False, seed=1, max_plies=2)
+    assert len(games2) == 8 and all(len(g["actions"]) == 2 for g in games2)

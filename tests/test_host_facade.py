@@ -82,8 +82,10 @@ def test_state_dict_layout_and_flat_buffer():
     unflatten_into(b, keys, flat)
     for k in keys:
         assert torch.equal(a.state_dict()[k], b.state_dict()[k]), k
-    with pytest.raises(RuntimeError):
-        policyNN({}).train()(torch.zeros(1, 119, 8, 8))      # inference-only: never a silent torch fallback
+    if not torch.cuda.is_available():
+        from sigma_zero_b200.engine import SzbError
+        with pytest.raises(SzbError):                        # the self-play (eval) forward never falls back to torch
+            policyNN({}).eval()(torch.zeros(1, 119, 8, 8))
 
 
 def _bcast_worker(rank, world, port, out):
@@ -171,3 +173,35 @@ def test_record_format_roundtrip(tmp_path, golden_dir):
             want, _ = actionsToTensor(a, c)                      # the reference's own dense soft target (train_RL.py:43-45)
             assert np.allclose(dense[i], want.numpy(), atol=1e-7)
             i += 1
+
+
+def test_training_path_matches_reference_architecture_and_learns():
+    """the torch training forward of the facade's policyNN (model.train()) is the reference architecture:
+    same outputs as the restated reference network for the same state_dict; a few fine-tuning steps on packed records reduce
+    the reference's loss (train_RL.py:103-113)"""
+    from oracle import ref_path
+    from sigma_zero_b200 import records, runtime
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.train_RL import make_optimiser, train_on_records
+    torch.manual_seed(0)
+    model = policyNN({})
+    ref = ref_path.build_policy_nn()
+    ref.load_state_dict(model.state_dict())
+    z = np.load(os.path.join(util.GOLDEN if hasattr(util, "GOLDEN") else os.path.join(util.ROOT, "tests", "golden"), "codec.npz"))
+    planes = runtime.unpack_planes(z["planes"][:6])
+    x = torch.from_numpy(planes).float()
+    model.eval(); ref.eval()
+    with torch.no_grad():
+        p0, v0 = model.forward_torch(x, inference=True)
+        p1, v1 = ref(x, inference=True)
+    assert torch.equal(p0, p1) and torch.equal(v0, v1)
+    # records: 6 positions, a peaked target on one legal move each, alternating outcomes
+    rec = {"states": z["planes"][:6].astype(np.uint64), "pi_index": np.array([116, 115, 4094, 3641, 116, 115], dtype=np.uint16),
+           "pi_prob": np.ones(6, dtype=np.float32), "pi_off": np.arange(7, dtype=np.int64),
+           "z": np.array([1, -1, 1, -1, 0, 0], dtype=np.int8), "colour": np.array([1, 0, 1, 0, 1, 0], dtype=bool),
+           "game": np.zeros(6, dtype=np.int32)}
+    before = [t.clone() for t in model.parameters()]
+    opt, sched = make_optimiser(model, lr=1e-3)
+    hist = train_on_records(model, rec, epochs=6, batch_size=6, optimiser=opt, lr_scheduler=sched, device="cpu")
+    assert len(hist) == 6 and sum(hist[-1]) < sum(hist[0])
+    assert not model.training and any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
