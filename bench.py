@@ -422,8 +422,8 @@ def main():
     ap.add_argument("--games", type=int, default=None, help="override games per GPU (parity / debugging; not a bench line)")
     ap.add_argument("--sims", type=int, default=None, help="override simulations per move (debugging)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--ref-sims", type=int, default=200, help="--impl reference: simulations per step (bounded sample)")
-    ap.add_argument("--cpu-sims", type=int, default=400, help="cpu_baseline: simulations in the bounded sample")
+    ap.add_argument("--ref-sims", type=int, default=800, help="--impl reference: simulations per step (bounded sample)")
+    ap.add_argument("--cpu-sims", type=int, default=2000, help="cpu_baseline: simulations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

@@ -14,6 +14,7 @@
 // Activations live in HBM as NHWC bf16 with a one-square zero halo: [B][10][10][C]; a tap is a shifted window of it.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -81,6 +82,8 @@ struct Net {
     struct TowerArgs* tower_args = nullptr;
     int final_x = 0, final_y = 0;        // activation buffers holding the tower output / the policy-head hidden layer
     int tower_mode = 2;                  // 0: single-CTA kernel per layer, 1: pair kernel per layer, 2: pair kernel, one launch
+    int tower_nsplit = 0;                // 0: automatic (launch_tower), else forced 1 / 2 / 4
+    int last_nsplit = 1;                 // what the last multi-layer launch used (trace aid)
     int num_sms = 148;
     std::vector<void*> allocs;
 };
@@ -154,6 +157,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
@@ -445,7 +459,9 @@ struct TowerLayer {
 struct alignas(64) TowerMaps {
     CUtensorMap a[4];    // input planes, activation buffers 0..2 with dims (c, x, board, y): box 64 ch x 10 x 2 boards x 10
     CUtensorMap w;       // all layers' folded weights [MAX_TOWER_LAYERS * 256][2304]: box 64 k x 128 rows
-    CUtensorMap w64;     // same buffer, box 64 k x 64 rows (policy output layer)
+    CUtensorMap w64;     // same buffer, box 64 k x 64 rows (policy output layer; N-split launches)
+    CUtensorMap w32;     // box 64 k x 32 rows
+    CUtensorMap w16;     // box 64 k x 16 rows
 };
 
 struct TowerArgs {
@@ -453,11 +469,13 @@ struct TowerArgs {
     int n_boards;
     int board0;          // first board of this launch inside the activation buffers (cohort offset, multiple of 4)
     int layer_begin, layer_end;
+    int nsplit;          // 1, 2 or 4: a (layer, tile) is cut into nsplit work items of N / nsplit output channels each (small batches)
     int32_t* ready;      // [MAX_TOWER_LAYERS][n_pair_tiles] completion counters, zeroed before the launch
     const float* bias;   // [MAX_TOWER_LAYERS][256]
     __nv_bfloat16* act[3];
     float* logits;       // [boards][4672]
     int32_t* error;
+    unsigned long long* trace;   // measurement aid (SZB_TOWER_TRACE): [item][4] %globaltimer stamps of the leader CTA, or null
     TowerLayer L[MAX_TOWER_LAYERS];
 };
 
@@ -519,10 +537,51 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// descriptor high words of k_tower_tc2's operands: SBO, version 1, SWIZZLE_128B
+constexpr uint32_t T2_A_HI = (uint32_t)(T2_A_SBO >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t T2_B_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+
+// small-batch MMA issue of one K chunk of a 3x3 layer: nine taps in weight stages of TPS taps (4 + 4 + 1 or 2 + 2 + 2 + 2 + 1),
+// each tap four K = 16 MMAs; straight-line, all descriptor offsets immediates.  Called warp-convergently by the leader's MMA warp.
+template <int TPS>
+__device__ __forceinline__ bool mma_chunk_3x3(uint32_t d_tmem, uint32_t chunk_lo, uint32_t b_lo0, uint32_t bar_bf0, uint32_t bar_be0,
+                                              uint32_t& bs, uint32_t& b_phase, uint32_t idesc, uint32_t accumulate, volatile int* abort_flag) {
+    constexpr uint32_t TILE_LO = (uint32_t)((128 / TPS) * TC_BLOCK_K * 2) >> 4;      // one tap's weight tile: 128 / TPS rows per CTA
+#pragma unroll
+    for (int s0 = 0; s0 < 9; s0 += TPS) {
+        if (!warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag)) return false;
+        tc_fence_after();
+        const uint32_t b_base = b_lo0 + bs * (T2_B_BYTES >> 4);
+        if (elect_one()) {
+#pragma unroll
+            for (int u = 0; u < TPS; u++) {
+                const int tap = s0 + u;
+                if (tap < 9) {
+                    const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * HALO + tap % 3) * (128 >> 4);     // halo pixel (ky, board 0, kx)
+                    const uint32_t b_lo = b_base + u * TILE_LO;
+                    tc2_mma_bf16_split(d_tmem, a_lo, T2_A_HI, b_lo, T2_B_HI, idesc, tap == 0 ? accumulate : 1u);
+                    tc2_mma_bf16_split(d_tmem, a_lo + 2, T2_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                    tc2_mma_bf16_split(d_tmem, a_lo + 4, T2_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                    tc2_mma_bf16_split(d_tmem, a_lo + 6, T2_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                }
+            }
+            tc2_commit(bar_be0 + bs * 8);
+        }
+        __syncwarp();
+        if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
+    }
+    return true;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
@@ -542,7 +601,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int n_items = (a.layer_end - a.layer_begin) * a.n_pair_tiles;
+    const int n_items = (a.layer_end - a.layer_begin) * a.n_pair_tiles * a.nsplit;
     volatile int* abort_flag = &abort_sh;
 
     if (threadIdx.x == 0) {
@@ -563,30 +622,37 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
 
     if (warp == 0) {
         // ===== TMA producer (warp 0 of each CTA, convergent; one elected lane issues) =====
-        {
-            const uint32_t bar_af0 = smem_u32(&bar_a_full[0]), bar_ae0 = smem_u32(&bar_a_empty[0]);
-            const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
-            uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0;
-            bool ok = true;
+        // One blocking in-order stream (a polled two-stream variant was measured: the 32-lane mbarrier polling competes with
+        // the MMAs for shared-memory cycles, +5 % tower time at 1024 boards).
+        const uint32_t bar_af0 = smem_u32(&bar_a_full[0]), bar_ae0 = smem_u32(&bar_a_empty[0]);
+        const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
+        const int need = READY_PER_ITEM * a.nsplit;
+        uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0;
+        bool ok = true;
+        // tile (l-1, t) must be complete: all 8 epilogue warps of every pair that ran one of its nsplit items have stored and
+        // released.  Every lane acquires (one transaction) so that whichever lane is elected afterwards has done so.
+        auto wait_dependency = [&](int l, int t) -> bool {
+            const int32_t* flag = a.ready + (size_t)(l - 1) * a.n_pair_tiles + t;
+            if (!__all_sync(0xFFFFFFFFu, ld_acquire_gpu(flag) >= need)) {
+                const long long t0 = clock64();
+                for (;;) {
+                    if (__all_sync(0xFFFFFFFFu, ld_acquire_gpu(flag) >= need)) break;
+                    bool give_up = *abort_flag != 0;
+                    if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; give_up = true; }
+                    if (__any_sync(0xFFFFFFFFu, give_up)) return false;
+                }
+            }
+            asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores -> this thread's TMA reads
+            return true;
+        };
+        if (a.nsplit == 1) {
+            // large batches: per K chunk the activation chunk, then its weight tiles (one per stage) -- in steady state the rings
+            // keep the loads ~7 taps ahead of the MMAs
             for (int item = pair; item < n_items && ok; item += n_pairs) {
                 const int l = a.layer_begin + item / a.n_pair_tiles, t = item % a.n_pair_tiles;
                 const TowerLayer L = a.L[l];
-                if (l > a.layer_begin) {
-                    // item (l-1, t) must be complete: all 8 epilogue warps of whichever pair ran it have stored and released.
-                    // Every lane acquires (one transaction) so that whichever lane is elected below has done so.
-                    const int32_t* flag = a.ready + (size_t)(l - 1) * a.n_pair_tiles + t;
-                    if (!__all_sync(0xFFFFFFFFu, ld_acquire_gpu(flag) >= READY_PER_ITEM)) {
-                        const long long t0 = clock64();
-                        for (;;) {
-                            if (__all_sync(0xFFFFFFFFu, ld_acquire_gpu(flag) >= READY_PER_ITEM)) break;
-                            bool give_up = *abort_flag != 0;
-                            if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; give_up = true; }
-                            if (__any_sync(0xFFFFFFFFu, give_up)) { ok = false; break; }
-                        }
-                        if (!ok) break;
-                    }
-                    asm volatile("fence.proxy.async.global;" ::: "memory");     // generic-proxy stores -> this thread's TMA reads
-                }
+                if (l > a.layer_begin && !(ok = wait_dependency(l, t))) break;
+                if (a.trace && rank == 0 && lane == 0) a.trace[(size_t)item * 4 + 0] = global_ns();      // dependency resolved
                 const CUtensorMap* tm_a = &maps.a[L.a_map];
                 const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
                 const int wrow = l * C_TOWER + (int)rank * L.n_half;
@@ -615,6 +681,60 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     }
                 }
             }
+        } else {
+            // small batches (at most one item per pair and layer; every item really waits for its dependency).  An item's weight
+            // tiles are only 128 / nsplit rows per CTA, so a 16 KiB stage takes `tps` consecutive tiles (one barrier, several
+            // boxes): with one small tile per stage the 7-stage ring covers ~0.5 us of MMAs, less than one L2 -> SM latency, and
+            // the item runs at TMA latency (traced: 9 us per 3x3 layer for 2.4 us of MMAs).  The first stages are issued BEFORE
+            // the dependency wait (weights do not depend on the previous layer), then all activation chunks at once, then the
+            // remaining weight stages.
+            for (int item = pair; item < n_items && ok; item += n_pairs) {
+                const int ti = item / a.nsplit, q = item - ti * a.nsplit;
+                const int l = a.layer_begin + ti / a.n_pair_tiles, t = ti % a.n_pair_tiles;
+                const TowerLayer L = a.L[l];
+                const CUtensorMap* tm_a = &maps.a[L.a_map];
+                const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
+                const int nh = L.n_half / a.nsplit;                               // weight rows per CTA of this item
+                const int tps = L.taps == 9 ? a.nsplit : 1;                       // weight tiles per stage (3x3 layers: 128 / nh)
+                const int wrow = l * C_TOWER + q * 2 * nh + (int)rank * nh;
+                const CUtensorMap* tm_w = nh == 64 ? &maps.w64 : nh == 32 ? &maps.w32 : &maps.w16;
+                const uint32_t tile_bytes = (uint32_t)nh * TC_BLOCK_K * 2;
+                const int n_b = L.taps * L.kchunks;
+                int jb = 0, kc_b = 0, tap_b = 0;
+                // next stage of weight tiles in MMA order (K chunk outer, tap inner; stages do not straddle K chunks, so the MMA
+                // warp's per-chunk code is straight-line); weight column of (tap, kc): taps are C_in apart
+                auto issue_b_stage = [&]() -> bool {
+                    if (!warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag)) return false;
+                    const int cnt = min(tps, L.taps - tap_b);
+                    if (elect_one()) {
+                        const uint32_t b_full = bar_bf0 + bs * 8;
+                        if (rank == 0) mbar_expect_tx(b_full, 2u * tile_bytes * (uint32_t)cnt);
+                        for (int u = 0; u < cnt; u++)
+                            tma2_load_2d(smem_b + bs * T2_B_BYTES + u * tile_bytes, tm_w, b_full, ((tap_b + u) * L.kchunks + kc_b) * TC_BLOCK_K, wrow);
+                    }
+                    __syncwarp();
+                    if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
+                    tap_b += cnt;
+                    if (tap_b == L.taps) { tap_b = 0; kc_b++; }
+                    jb += cnt;
+                    return true;
+                };
+                for (int k = 0; k < T2_B_STAGES && jb < n_b && ok; k++) ok = issue_b_stage();
+                if (!ok) break;
+                if (l > a.layer_begin && !(ok = wait_dependency(l, t))) break;
+                if (a.trace && rank == 0 && lane == 0) a.trace[(size_t)item * 4 + 0] = global_ns();      // dependency resolved
+                for (int kc = 0; kc < L.kchunks && ok; kc++) {
+                    if (!(ok = warp_mbar_wait(bar_ae0 + ac * 8, a_phase ^ 1, abort_flag))) break;
+                    if (elect_one()) {
+                        const uint32_t a_full = bar_af0 + ac * 8;
+                        if (rank == 0) mbar_expect_tx(a_full, 2u * T2_A_CHUNK_BYTES);
+                        tma2_load_4d(smem_a + ac * T2_A_CHUNK_BYTES, tm_a, a_full, kc * TC_BLOCK_K, 0, board0, 0);
+                    }
+                    __syncwarp();
+                    if (++ac == T2_A_CHUNKS) { ac = 0; a_phase ^= 1; }
+                }
+                while (jb < n_b && ok) ok = issue_b_stage();
+            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (leader CTA only) =====
@@ -625,8 +745,6 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         // The whole warp runs the loop convergently (so the compiler keeps descriptors and barrier addresses in uniform
         // registers instead of broadcasting them per MMA); one elected lane issues.
         if (rank == 0) {
-            constexpr uint32_t A_HI = (uint32_t)(T2_A_SBO >> 4) | (1u << 14) | (2u << 29);      // SBO, version 1, SWIZZLE_128B
-            constexpr uint32_t B_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
             constexpr uint32_t LO_FLAGS = 1u << 16;                                              // LBO field (unused for swizzled K-major) = 1
             const uint32_t a_lo0 = ((smem_a >> 4) & 0x3FFFu) | LO_FLAGS, b_lo0 = ((smem_b >> 4) & 0x3FFFu) | LO_FLAGS;
             const uint32_t bar_af0 = smem_u32(&bar_a_full[0]), bar_ae0 = smem_u32(&bar_a_empty[0]);
@@ -636,37 +754,44 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             int local = 0;
             bool ok = true;
             for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
-                const TowerLayer L = a.L[a.layer_begin + item / a.n_pair_tiles];
-                const uint32_t idesc = IDESC_BASE | ((uint32_t)(2 * L.n_half >> 3) << 17);
+                const TowerLayer L = a.L[a.layer_begin + item / (a.n_pair_tiles * a.nsplit)];
+                const uint32_t idesc = IDESC_BASE | ((uint32_t)(2 * L.n_half / a.nsplit >> 3) << 17);
                 const uint32_t acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 if (!(ok = warp_mbar_wait(bar_ce0 + acc * 8, acc_phase ^ 1, abort_flag))) break;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-                const int t0 = L.taps == 9 ? 0 : 1, t1 = L.taps == 9 ? 3 : 2;                     // 1x1 convolution = centre tap
                 uint32_t accumulate = 0;
+                // One MMA costs this warp ~100 cycles of instructions in a generic tap loop (traced: 210 ns per tap of four MMAs
+                // whatever N) -- as long as the four N = 256 MMAs of a tap themselves (512 cycles), and far longer than the
+                // N <= 128 MMAs of small-batch items -- so the nine taps of a K chunk are straight-line code (mma_chunk_3x3).
                 for (int kc = 0; kc < L.kchunks && ok; kc++) {
                     if (!(ok = warp_mbar_wait(bar_af0 + ac * 8, a_phase, abort_flag))) break;
+                    if (a.trace && kc == 0 && lane == 0) a.trace[(size_t)item * 4 + 1] = global_ns();     // first activation chunk in shared memory
                     const uint32_t chunk_lo = a_lo0 + ac * (T2_A_CHUNK_BYTES >> 4);
-                    for (int ky = t0; ky < t1 && ok; ky++) {
-                        uint32_t a_lo = chunk_lo + (uint32_t)(ky * 2 * HALO + t0) * (128 >> 4);   // halo pixel (ky, board 0, kx = t0)
-                        for (int kx = t0; kx < t1; kx++, a_lo += 128 >> 4) {
-                            if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
-                            tc_fence_after();
-                            const uint32_t b_lo = b_lo0 + bs * (T2_B_BYTES >> 4);
-                            if (elect_one()) {
-                                tc2_mma_bf16_split(d_tmem, a_lo, A_HI, b_lo, B_HI, idesc, accumulate);
-                                tc2_mma_bf16_split(d_tmem, a_lo + 2, A_HI, b_lo + 2, B_HI, idesc, 1u);
-                                tc2_mma_bf16_split(d_tmem, a_lo + 4, A_HI, b_lo + 4, B_HI, idesc, 1u);
-                                tc2_mma_bf16_split(d_tmem, a_lo + 6, A_HI, b_lo + 6, B_HI, idesc, 1u);
-                                tc2_commit(bar_be0 + bs * 8);
-                            }
-                            __syncwarp();
-                            accumulate = 1;
-                            if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
+                    if (L.taps == 9) {
+                        // a weight stage holds nsplit consecutive taps of 128 / nsplit rows per CTA (see the producer)
+                        ok = a.nsplit == 1   ? mma_chunk_3x3<1>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                             : a.nsplit == 2 ? mma_chunk_3x3<2>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                                             : mma_chunk_3x3<4>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag);
+                    } else {
+                        // 1x1 convolution = centre tap, one weight tile per stage
+                        if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                        tc_fence_after();
+                        const uint32_t a_lo = chunk_lo + (uint32_t)(2 * HALO + 1) * (128 >> 4);
+                        const uint32_t b_lo = b_lo0 + bs * (T2_B_BYTES >> 4);
+                        if (elect_one()) {
+                            tc2_mma_bf16_split(d_tmem, a_lo, T2_A_HI, b_lo, T2_B_HI, idesc, accumulate);
+                            tc2_mma_bf16_split(d_tmem, a_lo + 2, T2_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                            tc2_mma_bf16_split(d_tmem, a_lo + 4, T2_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                            tc2_mma_bf16_split(d_tmem, a_lo + 6, T2_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                            tc2_commit(bar_be0 + bs * 8);
                         }
+                        __syncwarp();
+                        if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
                     }
-                    if (ok && elect_one()) tc2_commit(bar_ae0 + ac * 8);                          // chunk free once its last tap's MMAs retire
+                    accumulate = 1;
+                    if (ok && elect_one()) tc2_commit(bar_ae0 + ac * 8);                              // chunk free once its last tap's MMAs retire
                     __syncwarp();
                     if (++ac == T2_A_CHUNKS) { ac = 0; a_phase ^= 1; }
                 }
@@ -681,17 +806,15 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         int local = 0;
         bool ok = true;
         for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
-            const int l = a.layer_begin + item / a.n_pair_tiles, t = item % a.n_pair_tiles;
+            const int ti = item / a.nsplit, q = item - ti * a.nsplit;
+            const int l = a.layer_begin + ti / a.n_pair_tiles, t = ti % a.n_pair_tiles;
             const TowerLayer L = a.L[l];
+            const int n_item = 2 * L.n_half / a.nsplit, cb = q * n_item;      // this item's output channels: [cb, cb + n_item)
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             bias_sh[acc][etid] = a.bias[l * C_TOWER + etid];
             bias_sh[acc][etid + 128] = a.bias[l * C_TOWER + etid + 128];
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            ok = mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase, abort_flag);
-            ok = __all_sync(0xFFFFFFFFu, ok);
-            if (!ok) break;
-            tc_fence_after();
             // accumulator row (TMEM lane) = (oy * 2 + board-in-CTA) * 8 + ox
             const int row = lane_group * 32 + lane;
             const int board = a.board0 + (t * 2 + (int)rank) * 2 + ((row >> 3) & 1);
@@ -699,18 +822,39 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             const bool live = board < a.board0 + a.n_boards;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + acc * ACC_COLS;
             const size_t pix = ((size_t)board * HALO + (sq >> 3) + 1) * HALO + (sq & 7) + 1;
+            // The residual (output of layer l - 2) starts its way from L2 before the accumulator wait -- but only once this warp
+            // has itself acquired the completion counter of tile (l-1, t), which implies (l-2, t): before the accumulator
+            // barrier nothing else orders this warp after the other pairs' stores.  One poll; if the tile is not complete
+            // yet the loads are issued after the wait as before.
+            const __nv_bfloat16* resp = (L.mode == 0 && L.res != 255 && live) ? a.act[L.res] + pix * C_TOWER + cb : nullptr;
+            uint4 rnext[4];
+            const bool early = l == a.layer_begin || ld_acquire_gpu(a.ready + (size_t)(l - 1) * a.n_pair_tiles + t) >= READY_PER_ITEM * a.nsplit;
+            if (resp && early) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) rnext[u] = __ldcg(reinterpret_cast<const uint4*>(resp) + u);      // written by another SM: bypass L1
+            }
+            ok = mbar_wait(smem_u32(&bar_acc_full[acc]), acc_phase, abort_flag);
+            ok = __all_sync(0xFFFFFFFFu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            if (resp && !early) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) rnext[u] = __ldcg(reinterpret_cast<const uint4*>(resp) + u);
+            }
+            const bool tracer = a.trace && rank == 0 && warp == 2 && lane == 0;
+            if (tracer) a.trace[(size_t)item * 4 + 2] = global_ns();                    // accumulator complete
             if (L.mode == 1) {
                 // policy logits, plane-major like torch.flatten(conv_p2(x)): index = plane * 64 + row * 8 + col
                 float* lg = a.logits + (size_t)board * N_ACTIONS + sq;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 96; c0 += 32) {
+                for (int c0 = 0; c0 < n_item && cb + c0 < POLICY_PLANES; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
                     if (live) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            if (c0 + j < POLICY_PLANES) lg[(c0 + j) * 64] = __uint_as_float(v[j]) + bias_sh[acc][c0 + j];
+                            if (cb + c0 + j < POLICY_PLANES) lg[(cb + c0 + j) * 64] = __uint_as_float(v[j]) + bias_sh[acc][cb + c0 + j];
                     }
                 }
                 tc_fence_before();
@@ -718,24 +862,19 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 if (lane == 0) mbar_arrive_leader(smem_u32(&bar_acc_empty[acc]));      // last layer: nothing waits on its counter
                 continue;
             }
-            const __nv_bfloat16* resp = (L.res != 255 && live) ? a.act[L.res] + pix * C_TOWER : nullptr;
-            __nv_bfloat16* outp = a.act[L.out] + pix * C_TOWER;
-            uint4 rnext[4];
-            if (resp) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) rnext[q] = __ldcg(reinterpret_cast<const uint4*>(resp) + q);      // written by another SM: bypass L1
-            }
+            __nv_bfloat16* outp = a.act[L.out] + pix * C_TOWER + cb;
+            const float* bias = bias_sh[acc] + cb;
 #pragma unroll 1
-            for (int c0 = 0; c0 < C_TOWER; c0 += 32) {
+            for (int c0 = 0; c0 < n_item; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c0, v);
                 uint4 rcur[4];
                 if (resp) {
 #pragma unroll
-                    for (int q = 0; q < 4; q++) rcur[q] = rnext[q];
-                    if (c0 + 32 < C_TOWER) {
+                    for (int u = 0; u < 4; u++) rcur[u] = rnext[u];
+                    if (c0 + 32 < n_item) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) rnext[q] = __ldcg(reinterpret_cast<const uint4*>(resp + c0 + 32) + q);
+                        for (int u = 0; u < 4; u++) rnext[u] = __ldcg(reinterpret_cast<const uint4*>(resp + c0 + 32) + u);
                     }
                 }
                 tmem_ld_wait();
@@ -745,8 +884,8 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(rcur);
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
-                        float x0 = __uint_as_float(v[2 * j]) + bias_sh[acc][c0 + 2 * j];
-                        float x1 = __uint_as_float(v[2 * j + 1]) + bias_sh[acc][c0 + 2 * j + 1];
+                        float x0 = __uint_as_float(v[2 * j]) + bias[c0 + 2 * j];
+                        float x1 = __uint_as_float(v[2 * j + 1]) + bias[c0 + 2 * j + 1];
                         if (resp) {
                             const float2 r = __bfloat1622float2(rb[j]);
                             x0 += r.x;
@@ -757,16 +896,18 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     }
                     uint4* op = reinterpret_cast<uint4*>(outp + c0);
 #pragma unroll
-                    for (int q = 0; q < 4; q++) op[q] = o[q];
+                    for (int u = 0; u < 4; u++) op[u] = o[u];
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive_leader(smem_u32(&bar_acc_empty[acc]));            // accumulator stage free again (leader's barrier)
-                __threadfence();
+                // the warp's stores happen-before this lane's release (__syncwarp above; release is cumulative); the reader
+                // orders its TMA (async-proxy) loads after its acquire with fence.proxy.async
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(a.ready + (size_t)l * a.n_pair_tiles + t), "r"(1) : "memory");
+                if (tracer) a.trace[(size_t)item * 4 + 3] = global_ns();                // outputs stored and released
             }
         }
     }
@@ -1108,9 +1249,18 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(policy weights) failed: %d", (int)r);
+        CUtensorMap* small[2] = {&net->tower_maps->w32, &net->tower_maps->w16};
+        for (int i = 0; i < 2; i++) {
+            box[1] = 32u >> i;
+            r = g_encode(small[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, net->w16_all, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(N-split weights) failed: %d", (int)r);
+        }
     }
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
+    const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
+    if (ns && (ns[0] == '1' || ns[0] == '2' || ns[0] == '4')) net->tower_nsplit = ns[0] - '0';
     ctx->net_tower_mode = net->tower_mode;
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1135,7 +1285,19 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     a.ready = net->ready + (size_t)MAX_TOWER_LAYERS * (b0 / 4);      // cohorts (disjoint board ranges) get disjoint counter regions
     if (layer_end - layer_begin > 1)
         SZB_CUDA(ctx, cudaMemsetAsync(a.ready, 0, sizeof(int32_t) * (size_t)MAX_TOWER_LAYERS * a.n_pair_tiles, ctx->work));
-    const int grid = 2 * std::min(a.n_pair_tiles, net->num_sms / 2);
+    // Small batches leave most CTA pairs idle and the launch becomes a chain of 41 dependent layers: cut every (layer, tile)
+    // into 2 or 4 items of N / nsplit output channels so that up to all pairs work on one layer.  Same MMAs per output, same K
+    // order: bit-identical results.  Measured (scripts/small_batch.py, ms per launch, split 1 / 2 / 4): 64 boards 0.75 / - / 0.33,
+    // 148 boards 0.79 / 0.44 / -, 200 boards 0.72 / 0.49 / -, 296 boards 0.73 / 0.70 / -, 512 boards 0.89 / 1.24 / -.
+    const int pairs = net->num_sms / 2;
+    a.nsplit = 1;
+    if (layer_end - layer_begin > 1) {
+        if (net->tower_nsplit) a.nsplit = net->tower_nsplit;
+        else if (a.n_pair_tiles * 4 <= pairs) a.nsplit = 4;
+        else if (a.n_pair_tiles <= pairs) a.nsplit = 2;
+    }
+    net->last_nsplit = a.nsplit;
+    const int grid = 2 * std::min(a.n_pair_tiles * a.nsplit, pairs);
     k_tower_tc2<<<grid, TC_THREADS, T2_SMEM, ctx->work>>>(*net->tower_maps, a);
     ctx->launches++;
     return 0;
@@ -1442,6 +1604,35 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc) return rc;
+    const char* trace_path = getenv("SZB_TOWER_TRACE");      // measurement aid: per-item device timestamps of one more launch as CSV
+    if (which == 5 && trace_path && trace_path[0]) {
+        const int tiles = (n + 3) / 4;
+        const size_t slots = (size_t)MAX_TOWER_LAYERS * tiles * 4 * 4;
+        unsigned long long* d_tr = nullptr;
+        SZB_CUDA(ctx, cudaMalloc((void**)&d_tr, slots * 8));
+        SZB_CUDA(ctx, cudaMemsetAsync(d_tr, 0, slots * 8, ctx->stream));
+        net->tower_args->trace = d_tr;
+        rc = launch_tower(ctx, net, 0, n, 0, MAX_TOWER_LAYERS);
+        net->tower_args->trace = nullptr;
+        std::vector<unsigned long long> h(slots);
+        cudaMemcpyAsync(h.data(), d_tr, slots * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_tr);
+        if (rc) return rc;
+        unsigned long long t0 = ~0ull;
+        for (unsigned long long v : h) if (v && v < t0) t0 = v;
+        if (FILE* f = fopen(trace_path, "a")) {
+            fprintf(f, "boards,nsplit,item,layer,tile,q,dep_ns,operands_ns,acc_ns,released_ns\n");
+            const int nsplit = net->last_nsplit;
+            for (int item = 0; item < MAX_TOWER_LAYERS * tiles * nsplit; item++) {
+                const int ti = item / nsplit;
+                fprintf(f, "%d,%d,%d,%d,%d,%d", n, nsplit, item, ti / tiles, ti % tiles, item % nsplit);
+                for (int k = 0; k < 4; k++) fprintf(f, ",%lld", h[(size_t)item * 4 + k] ? (long long)(h[(size_t)item * 4 + k] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     SZB_CUDA(ctx, cudaGetLastError());
     return net_check_error(ctx);
 }

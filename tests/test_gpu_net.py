@@ -153,3 +153,30 @@ def test_tower_kernel_variants_bit_identical(monkeypatch):
         assert np.array_equal(l, outs[0][0]) and np.array_equal(v, outs[0][1])
     # and the batch really is periodic: every copy of a position gives the same logits
     assert np.array_equal(outs[2][0][:len(packed)], outs[2][0][len(packed):2 * len(packed)])
+
+
+def test_tower_n_split_bit_identical(monkeypatch):
+    """small batches cut every (layer, tile) of the persistent tower launch into 2 or 4 work items of N / nsplit output
+    channels (more CTA pairs per layer, shorter dependency chain): the same MMAs per output in the same K order, so forced
+    splits 1 / 2 / 4 and the per-layer launch must agree bit for bit -- ragged last tile, residual and policy layers included"""
+    from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
+    torch.manual_seed(3)
+    model = ref_path.build_policy_nn().eval()
+    _randomise_bn(model, 13)
+    x = _positions(9, seed=22)
+    packed = np.stack([hash_eval.pack_planes(p) for p in x])
+    for n in (1, 37, 150):
+        big = packed[np.arange(n) % len(packed)]
+        outs = []
+        for mode, split in (("1", None), ("2", "1"), ("2", "2"), ("2", "4"), ("2", None)):
+            monkeypatch.setenv("SZB_TOWER_MODE", mode)
+            if split is None:
+                monkeypatch.delenv("SZB_TOWER_NSPLIT", raising=False)
+            else:
+                monkeypatch.setenv("SZB_TOWER_NSPLIT", split)
+            eng = Engine(max_games=n, max_searches=4)
+            eng.load_state_dict(model.state_dict())
+            outs.append(eng.net_forward(big, EVAL_NET_BF16, logits=True))
+            eng.close()
+        for l, v in outs[1:]:
+            assert np.array_equal(l, outs[0][0]) and np.array_equal(v, outs[0][1]), n
