@@ -82,7 +82,7 @@ struct Net {
     struct TowerArgs* tower_args = nullptr;
     int final_x = 0, final_y = 0;        // activation buffers holding the tower output / the policy-head hidden layer
     int tower_mode = 2;                  // 0: single-CTA kernel per layer, 1: pair kernel per layer, 2: pair kernel, one launch
-    int tower_nsplit = 0;                // 0: automatic (launch_tower), else forced 1 / 2 / 4
+    int tower_nsplit = 0;                // 0: automatic (launch_tower), else forced 1 / 2 / 4 / 8
     int last_nsplit = 1;                 // what the last multi-layer launch used (trace aid)
     int num_sms = 148;
     std::vector<void*> allocs;
@@ -462,6 +462,7 @@ struct alignas(64) TowerMaps {
     CUtensorMap w64;     // same buffer, box 64 k x 64 rows (policy output layer; N-split launches)
     CUtensorMap w32;     // box 64 k x 32 rows
     CUtensorMap w16;     // box 64 k x 16 rows
+    CUtensorMap w8;      // box 64 k x 8 rows
 };
 
 struct TowerArgs {
@@ -469,7 +470,7 @@ struct TowerArgs {
     int n_boards;
     int board0;          // first board of this launch inside the activation buffers (cohort offset, multiple of 4)
     int layer_begin, layer_end;
-    int nsplit;          // 1, 2 or 4: a (layer, tile) is cut into nsplit work items of N / nsplit output channels each (small batches)
+    int nsplit;          // 1, 2, 4 or 8: a (layer, tile) is cut into nsplit work items of N / nsplit output channels each (small batches)
     int32_t* ready;      // [MAX_TOWER_LAYERS][n_pair_tiles] completion counters, zeroed before the launch
     const float* bias;   // [MAX_TOWER_LAYERS][256]
     __nv_bfloat16* act[3];
@@ -697,7 +698,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 const int nh = L.n_half / a.nsplit;                               // weight rows per CTA of this item
                 const int tps = L.taps == 9 ? a.nsplit : 1;                       // weight tiles per stage (3x3 layers: 128 / nh)
                 const int wrow = l * C_TOWER + q * 2 * nh + (int)rank * nh;
-                const CUtensorMap* tm_w = nh == 64 ? &maps.w64 : nh == 32 ? &maps.w32 : &maps.w16;
+                const CUtensorMap* tm_w = nh == 64 ? &maps.w64 : nh == 32 ? &maps.w32 : nh == 16 ? &maps.w16 : &maps.w8;
                 const uint32_t tile_bytes = (uint32_t)nh * TC_BLOCK_K * 2;
                 const int n_b = L.taps * L.kchunks;
                 int jb = 0, kc_b = 0, tap_b = 0;
@@ -773,6 +774,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                         // a weight stage holds nsplit consecutive taps of 128 / nsplit rows per CTA (see the producer)
                         ok = a.nsplit == 1   ? mma_chunk_3x3<1>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
                              : a.nsplit == 2 ? mma_chunk_3x3<2>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                             : a.nsplit == 8 ? mma_chunk_3x3<8>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
                                              : mma_chunk_3x3<4>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag);
                     } else {
                         // 1x1 convolution = centre tap, one weight tile per stage
@@ -854,7 +856,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     if (live) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            if (cb + c0 + j < POLICY_PLANES) lg[(cb + c0 + j) * 64] = __uint_as_float(v[j]) + bias_sh[acc][cb + c0 + j];
+                            if (c0 + j < n_item && cb + c0 + j < POLICY_PLANES) lg[(cb + c0 + j) * 64] = __uint_as_float(v[j]) + bias_sh[acc][cb + c0 + j];
                     }
                 }
                 tc_fence_before();
@@ -1249,8 +1251,8 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(policy weights) failed: %d", (int)r);
-        CUtensorMap* small[2] = {&net->tower_maps->w32, &net->tower_maps->w16};
-        for (int i = 0; i < 2; i++) {
+        CUtensorMap* small[3] = {&net->tower_maps->w32, &net->tower_maps->w16, &net->tower_maps->w8};
+        for (int i = 0; i < 3; i++) {
             box[1] = 32u >> i;
             r = g_encode(small[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, net->w16_all, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1260,7 +1262,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
-    if (ns && (ns[0] == '1' || ns[0] == '2' || ns[0] == '4')) net->tower_nsplit = ns[0] - '0';
+    if (ns && (ns[0] == '1' || ns[0] == '2' || ns[0] == '4' || ns[0] == '8')) net->tower_nsplit = ns[0] - '0';
     ctx->net_tower_mode = net->tower_mode;
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1293,6 +1295,7 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     a.nsplit = 1;
     if (layer_end - layer_begin > 1) {
         if (net->tower_nsplit) a.nsplit = net->tower_nsplit;
+        else if (a.n_pair_tiles * 8 <= pairs) a.nsplit = 8;
         else if (a.n_pair_tiles * 4 <= pairs) a.nsplit = 4;
         else if (a.n_pair_tiles <= pairs) a.nsplit = 2;
     }
@@ -1607,7 +1610,7 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
     const char* trace_path = getenv("SZB_TOWER_TRACE");      // measurement aid: per-item device timestamps of one more launch as CSV
     if (which == 5 && trace_path && trace_path[0]) {
         const int tiles = (n + 3) / 4;
-        const size_t slots = (size_t)MAX_TOWER_LAYERS * tiles * 4 * 4;
+        const size_t slots = (size_t)MAX_TOWER_LAYERS * tiles * 8 * 4;
         unsigned long long* d_tr = nullptr;
         SZB_CUDA(ctx, cudaMalloc((void**)&d_tr, slots * 8));
         SZB_CUDA(ctx, cudaMemsetAsync(d_tr, 0, slots * 8, ctx->stream));

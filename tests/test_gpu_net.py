@@ -156,9 +156,9 @@ def test_tower_kernel_variants_bit_identical(monkeypatch):
 
 
 def test_tower_n_split_bit_identical(monkeypatch):
-    """small batches cut every (layer, tile) of the persistent tower launch into 2 or 4 work items of N / nsplit output
+    """small batches cut every (layer, tile) of the persistent tower launch into 2, 4 or 8 work items of N / nsplit output
     channels (more CTA pairs per layer, shorter dependency chain): the same MMAs per output in the same K order, so forced
-    splits 1 / 2 / 4 and the per-layer launch must agree bit for bit -- ragged last tile, residual and policy layers included"""
+    splits 1 / 2 / 4 / 8 and the per-layer launch must agree bit for bit -- ragged last tile, residual and policy layers included"""
     from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
     torch.manual_seed(3)
     model = ref_path.build_policy_nn().eval()
@@ -168,7 +168,7 @@ def test_tower_n_split_bit_identical(monkeypatch):
     for n in (1, 37, 150):
         big = packed[np.arange(n) % len(packed)]
         outs = []
-        for mode, split in (("1", None), ("2", "1"), ("2", "2"), ("2", "4"), ("2", None)):
+        for mode, split in (("1", None), ("2", "1"), ("2", "2"), ("2", "4"), ("2", "8"), ("2", None)):
             monkeypatch.setenv("SZB_TOWER_MODE", mode)
             if split is None:
                 monkeypatch.delenv("SZB_TOWER_NSPLIT", raising=False)
