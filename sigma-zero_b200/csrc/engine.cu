@@ -182,7 +182,7 @@ __global__ void k_unpack_planes_f32(int n, const uint64_t* planes, float* out) {
 // ------------------------------------------------------------------------------------------------
 // search step kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void k_search_begin(Dev d) {
+__global__ void k_search_begin(Dev d, int num_searches) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) *d.edge_top = 0ull;
     if (g >= d.n_games) return;
@@ -193,19 +193,55 @@ __global__ void k_search_begin(Dev d) {
     d.node_pedge[r] = -1;
     d.node_pnode[r] = 0;
     const Pos& p = d.pool[(size_t)g * d.pool_stride + d.cur[g]];
-    d.node_term[r] = p.outcome != OUT_NONE;
-    d.node_tval[r] = p.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
-    d.root_n[g] = 1;
-    d.root_w[g] = 0.0;
+    const bool term = p.outcome != OUT_NONE;
+    const float tval = p.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
+    d.node_term[r] = term;
+    d.node_tval[r] = tval;
+    if (!term) {
+        d.root_n[g] = 1;
+        d.root_w[g] = 0.0;
+    } else {
+        // terminal root: every simulation of mcts.py:49 finds the childless root, reads its constant value and backs it up
+        // (:104-109) -- done here in closed form (the sum of num_searches equal doubles 0 or -1 is exact); the game takes no slot
+        d.root_n[g] = 1 + num_searches;
+        d.root_w[g] = (double)tval * (double)num_searches;
+        unsigned long long* gs = d.gstats + (size_t)g * 8;
+        gs[0] += (unsigned long long)num_searches;
+        gs[2] += (unsigned long long)num_searches;
+    }
+}
+
+// slot -> game list of the games to search (root not terminal), ascending.  One block.
+__global__ void __launch_bounds__(1024) k_active_list(Dev d) {
+    __shared__ int warp_tot[32];
+    __shared__ int base_sh;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_sh = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < d.n_games; g0 += 1024) {
+        const int g = g0 + threadIdx.x;
+        const bool live = g < d.n_games && !d.node_term[(size_t)g * d.nodes_per_game];
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, live);
+        if (lane == 0) warp_tot[wid] = __popc(ballot);
+        __syncthreads();
+        int before = base_sh;
+        for (int w = 0; w < wid; w++) before += warp_tot[w];
+        if (live) d.order[before + __popc(ballot & ((1u << lane) - 1))] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; w++) t += warp_tot[w]; base_sh += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *d.n_active = base_sh;
 }
 
 // warp per tree.  Two dependent memory round trips per level: (child count, first edge) of the node, then the four edge
 // arrays of its children read side by side; the parent's visit count and the chosen child's node index travel down in
 // registers (the winning lane already holds them) instead of being re-read through node_pedge / e_child.
 __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
-    const int g = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (g >= d.g_end) return;
+    if (slot >= d.g_end) return;
+    const int g = d.order[slot];
     const size_t r = (size_t)g * d.nodes_per_game;
     int node = 0, depth = 0;
     int np = d.root_n[g];                                  // visit count of the node being expanded (root: mcts.py:46)
@@ -258,8 +294,9 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
 __global__ void __launch_bounds__(32) k_expand(Dev d) {
     __shared__ Tables T;
     load_tables(&T, d.tables);
-    const int g = d.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= d.g_end) return;
+    const int slot = d.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= d.g_end) return;
+    const int g = d.order[slot];
     const size_t r = (size_t)g * d.nodes_per_game;
     Pos* gp = d.pool + (size_t)g * d.pool_stride;
     const int e = d.sel_edge[g];
@@ -295,28 +332,28 @@ __global__ void __launch_bounds__(32) k_expand(Dev d) {
         d.need_eval[g] = 0;
         return;
     }
-    uint64_t* mrow = d.mask + (size_t)g * MASK_STRIDE;
+    uint64_t* mrow = d.mask + (size_t)slot * MASK_STRIDE;
     for (int w = 0; w < MASK_STRIDE; w++) mrow[w] = 0;
     for (int k = 0; k < cnt; k++) {
         const int idx = move_to_index(q, mv[k]);
         mrow[idx >> 6] |= bit(idx & 63);
     }
-    pack_planes(gp, q, d.planes + (size_t)g * PLANE_STRIDE);
+    pack_planes(gp, q, d.planes + (size_t)slot * PLANE_STRIDE);
     d.need_eval[g] = 1;
 }
 
 // block per tree: policy[i] / value from the integer hash of the packed planes
 __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
-    const int g = d.g_begin + blockIdx.x;
-    if (!d.need_eval[g]) return;
+    const int slot = d.g_begin + blockIdx.x;
+    if (!d.need_eval[d.order[slot]]) return;
     __shared__ uint64_t h_sh;
     if (threadIdx.x == 0) {
-        h_sh = he_fold(d.planes + (size_t)g * PLANE_STRIDE);
-        d.value[g] = he_value(h_sh);
+        h_sh = he_fold(d.planes + (size_t)slot * PLANE_STRIDE);
+        d.value[slot] = he_value(h_sh);
     }
     __syncthreads();
     const uint64_t h = h_sh;
-    float* pol = d.policy + (size_t)g * N_ACTIONS;
+    float* pol = d.policy + (size_t)slot * N_ACTIONS;
     for (int i = threadIdx.x; i < N_ACTIONS; i += blockDim.x) pol[i] = he_policy(h, i);
 }
 
@@ -324,14 +361,15 @@ __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
 __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
     __shared__ int want_sh[4];
     __shared__ unsigned long long base_sh;
-    const int g = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const bool active = g < d.g_end;
+    const bool active = slot < d.g_end;
+    const int g = active ? d.order[slot] : 0;
     const bool eval = active && d.need_eval[g];
     // children to allocate: one bump of the shared edge arena per BLOCK (four trees), not one same-address atomic per tree
     int n_legal = 0;
     if (eval) {
-        const uint64_t* mk = d.mask + (size_t)g * MASK_STRIDE;
+        const uint64_t* mk = d.mask + (size_t)slot * MASK_STRIDE;
         for (int w = lane; w < MASK_WORDS; w += 32) n_legal += popc(mk[w]);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) n_legal += __shfl_xor_sync(0xFFFFFFFFu, n_legal, off);
@@ -348,8 +386,8 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
     const int node = d.sel_node[g];
     float v;
     if (eval) {
-        const float* pol = d.policy + (size_t)g * N_ACTIONS;
-        const uint64_t* mk = d.mask + (size_t)g * MASK_STRIDE;
+        const float* pol = d.policy + (size_t)slot * N_ACTIONS;
+        const uint64_t* mk = d.mask + (size_t)slot * MASK_STRIDE;
         const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
         const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
         unsigned long long e0 = base_sh;
@@ -381,7 +419,7 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
             d.node_edge0[r + node] = (int32_t)e0;
             d.node_nchild[r + node] = (uint16_t)count;
         }
-        v = d.value[g];
+        v = d.value[slot];
         if (node == 0 && lane == 0) d.root_val[g] = v;
     } else {
         v = d.leaf_value[g];
@@ -722,6 +760,7 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     A(e_n, d.edge_cap); A(e_w, d.edge_cap); A(e_p, d.edge_cap); A(e_move, d.edge_cap); A(e_child, d.edge_cap);
     A(edge_top, 1); A(error_flag, 1);
     A(sel_node, G); A(sel_edge, G); A(need_eval, G); A(leaf_value, G);
+    A(order, G); A(n_active, 1);
     A(planes, G * PLANE_STRIDE); A(mask, G * MASK_STRIDE);
     A(policy, G * N_ACTIONS); A(value, G); A(root_val, G);
     A(stats, 8); A(gstats, G * 8);
@@ -884,8 +923,13 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     SZB_CUDA(ctx, cudaMemsetAsync(d.error_flag, 0, sizeof(int32_t), st));
     d.g_begin = 0;
     d.g_end = G;
-    k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d);
-    ctx->launches++;
+    k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d, num_searches);
+    k_active_list<<<1, 1024, 0, st>>>(d);
+    ctx->launches += 2;
+    // the games still running take the slots 0 .. n_slots-1 of this search; everything below is sized by that count
+    int32_t n_slots = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(&n_slots, d.n_active, sizeof n_slots, cudaMemcpyDeviceToHost, st));
+    SZB_CUDA(ctx, cudaStreamSynchronize(st));
     const bool prof = ctx->profiling;
     const char* trace_path = getenv("SZB_TRACE");            // debugging aid: per-cohort phase timestamps of this search as CSV
     const bool trace = prof && trace_path && trace_path[0];
@@ -902,16 +946,17 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     // alternating (scripts/ab_cohorts.py, 1024 games): 2.33 ms per simulation step with two cohorts vs 2.37-2.44 with one
     // (the tower is power-capped either way, so only the ~0.2 ms of small kernels can be hidden).  Profiling keeps one
     // cohort on the context's stream so that per-phase and per-kernel durations mean what they say.
-    int n_cohorts = ctx->cohorts ? ctx->cohorts : (G >= 1024 ? 2 : 1);
-    if ((prof && !trace) || G < 8) n_cohorts = 1;
-    int bounds[3] = {0, G, G};
-    if (n_cohorts == 2) bounds[1] = ((G / 2 + 3) / 4) * 4;        // network tiles are 4 boards wide
+    const int NS = n_slots;
+    int n_cohorts = ctx->cohorts ? ctx->cohorts : (NS >= 1024 ? 2 : 1);
+    if ((prof && !trace) || NS < 8) n_cohorts = 1;
+    int bounds[3] = {0, NS, NS};
+    if (n_cohorts == 2) bounds[1] = ((NS / 2 + 3) / 4) * 4;       // network tiles are 4 boards wide
     if (n_cohorts == 2) {
         SZB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         for (int c = 0; c < 2; c++) SZB_CUDA(ctx, cudaStreamWaitEvent(ctx->cohort_stream[c], ctx->ev_fork, 0));
     }
     int rc = 0;
-    for (int s = 0; s < num_searches && !rc; s++) {
+    for (int s = 0; s < num_searches && !rc && NS > 0; s++) {
         for (int c = 0; c < n_cohorts && !rc; c++) {
             Dev dc = d;
             dc.g_begin = bounds[c];
@@ -955,7 +1000,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     SZB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->edges_high_water = std::max<uint64_t>(ctx->edges_high_water, top);
     if (flag) return fail(ctx, flag, "tree arena exhausted (%llu edges): raise szb_config.edges_per_node", d.edge_cap);
-    if (trace) {
+    if (trace && NS > 0) {
         if (FILE* f = fopen(trace_path, "w")) {
             fprintf(f, "step,cohort,select_start_ms,expand_start_ms,eval_start_ms,finish_start_ms,finish_end_ms\n");
             for (int s = 0; s < num_searches; s++)
@@ -973,7 +1018,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         }
         return 0;
     }
-    if (prof) {
+    if (prof && NS > 0) {
         for (int s = 0; s < num_searches; s++) {
             cudaEvent_t* ev = &ctx->prof_events[5 * (size_t)s];
             for (int k = 0; k < 4; k++) {
@@ -1110,6 +1155,7 @@ int szb_set_profiling(szb_ctx* ctx, int32_t on) {
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->conv_events_used = 0;
     ctx->conv_ms = 0; ctx->conv_launches = 0;
+    ctx->conv_recorded = 0; ctx->conv_boards = 0; ctx->conv_flop = 0;
     k_fold_stats<<<1, 256, 0, ctx->stream>>>(ctx->d, ctx->cfg.max_games);
     SZB_CUDA(ctx, cudaMemsetAsync(ctx->d.stats + 4, 0, 4 * sizeof(unsigned long long), ctx->stream));
     return 0;
@@ -1126,7 +1172,11 @@ int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
     out->steps = ctx->phase_steps; out->reserved = 0;
     out->select_edges = h[4]; out->select_levels = h[5]; out->backup_levels = h[6]; out->edges_written = h[7];
     net_collect_conv_times(ctx);
-    out->conv_ms = ctx->conv_ms; out->conv_launches = ctx->conv_launches; out->conv_boards = ctx->conv_boards; out->conv_kind = ctx->net_tower_mode; out->conv_flop = ctx->conv_flop;
+    out->conv_ms = ctx->conv_ms; out->conv_launches = ctx->conv_launches; out->conv_kind = ctx->net_tower_mode;
+    // per-launch averages (the launches of a chunked evaluation need not be equally large)
+    const uint64_t rec = ctx->conv_recorded > 0 ? (uint64_t)ctx->conv_recorded : 1;
+    out->conv_boards = (int32_t)(ctx->conv_boards / rec);
+    out->conv_flop = ctx->conv_flop / rec;
     return 0;
 }
 

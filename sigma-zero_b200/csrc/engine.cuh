@@ -25,7 +25,11 @@ struct Dev {
     const Tables* tables;
     int pool_stride;
     int n_games;
-    int g_begin, g_end;      // game range the step kernels of this launch work on (a cohort of the search batch)
+    int g_begin, g_end;      // SLOT range the step kernels of this launch work on (a cohort of the search batch)
+    int32_t* order;          // [max_games] slot -> game: the games whose root is not terminal, ascending (k_active_list).  Finished
+                             // games take no slot: no step kernel, no network row (the reference never searches a finished game,
+                             // sim.py:46; a search on a terminal root only backs up its constant value, mcts.py:49-70,104-109)
+    int32_t* n_active;       // device: number of slots
     // ---- tree: visited nodes (one per simulation) -------------------------------------------------
     int nodes_per_game;      // max_searches + 1
     int32_t* node_edge0;     // first child edge (global index)
@@ -51,10 +55,10 @@ struct Dev {
     int32_t* sel_edge;       // edge to create a node for, -1 when the leaf already exists
     uint8_t* need_eval;
     float* leaf_value;
-    uint64_t* planes;        // [max_games][PLANE_STRIDE]
-    uint64_t* mask;          // [max_games][MASK_STRIDE]
-    float* policy;           // [max_games][4672] evaluator output ("softmax over everything")
-    float* value;            // [max_games]
+    uint64_t* planes;        // [slot][PLANE_STRIDE]   (these four are indexed by SLOT: the network reads contiguous rows)
+    uint64_t* mask;          // [slot][MASK_STRIDE]
+    float* policy;           // [slot][4672] evaluator output ("softmax over everything")
+    float* value;            // [slot]
     float* root_val;         // [max_games] evaluator value of the root position
     unsigned long long* stats;   // totals: 0 simulations, 1 evaluations, 2 terminal visits, 3 max depth,
                                  // 4 select edges, 5 select levels, 6 backup levels, 7 edges written
@@ -98,8 +102,10 @@ struct szb_ctx {
     std::vector<cudaEvent_t> conv_events;      // pairs around the timed tower convolution (net.cu)
     size_t conv_events_used = 0;
     float conv_ms = 0;
-    int conv_launches = 0, conv_boards = 0;
-    uint64_t conv_flop = 0;                    // algorithmic FLOP of one timed launch
+    int conv_launches = 0;                     // launches folded into conv_ms
+    int conv_recorded = 0;                     // launches bracketed by events since profiling was switched on
+    uint64_t conv_boards = 0;                  // boards of the bracketed launches (sum)
+    uint64_t conv_flop = 0;                    // algorithmic FLOP of the bracketed launches (sum)
     int net_tower_mode = 2;                    // which bf16 tower kernel runs (net.cu: Net::tower_mode)
 };
 

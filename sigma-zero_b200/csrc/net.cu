@@ -84,6 +84,7 @@ struct Net {
     int tower_mode = 2;                  // 0: single-CTA kernel per layer, 1: pair kernel per layer, 2: pair kernel, one launch
     int tower_nsplit = 0;                // 0: automatic (launch_tower), else forced 1 / 2 / 4 / 8
     int last_nsplit = 1;                 // what the last multi-layer launch used (trace aid)
+    int chunk = 512;                     // boards per tower launch of a large evaluation (net_forward_chunked); 0 = unlimited
     int num_sms = 148;
     std::vector<void*> allocs;
 };
@@ -1261,6 +1262,8 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     }
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
+    const char* ck = getenv("SZB_TOWER_CHUNK");              // measurement aid: boards per tower launch (0 = whole batch)
+    if (ck && ck[0]) net->chunk = std::max(0, atoi(ck)) & ~3;
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
     if (ns && (ns[0] == '1' || ns[0] == '2' || ns[0] == '4' || ns[0] == '8')) net->tower_nsplit = ns[0] - '0';
     ctx->net_tower_mode = net->tower_mode;
@@ -1272,7 +1275,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
 // host: forward
 // =================================================================================================
 // layers [layer_begin, layer_end) of the tower for n boards in one persistent CTA-pair launch
-static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, int layer_end) {
+static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, int layer_end, int out_row = -1) {
     static bool attr_set = false;
     if (!attr_set) {
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
@@ -1284,6 +1287,7 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     a.board0 = b0;
     a.layer_begin = layer_begin;
     a.layer_end = layer_end;
+    if (out_row >= 0) a.logits = net->logits + (size_t)(out_row - b0) * N_ACTIONS;      // board b0 + i -> logits row out_row + i
     a.ready = net->ready + (size_t)MAX_TOWER_LAYERS * (b0 / 4);      // cohorts (disjoint board ranges) get disjoint counter regions
     if (layer_end - layer_begin > 1)
         SZB_CUDA(ctx, cudaMemsetAsync(a.ready, 0, sizeof(int32_t) * (size_t)MAX_TOWER_LAYERS * a.n_pair_tiles, ctx->work));
@@ -1369,8 +1373,11 @@ void net_collect_conv_times(szb_ctx* ctx) {
 // planes (device, row stride `stride` uint64; row 0 = board b0) -> net->logits[b0..] + value_out[0..n) (device).
 // b0 is the first board inside the activation buffers (a multiple of 4): cohorts of one search use disjoint ranges.
 // All launches go to ctx->work.
-static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out) {
+static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out, int out_row = -1) {
     Net* net = ctx->net;
+    if (out_row < 0) out_row = b0;
+    if (out_row != b0 && !(evaluator == SZB_EVAL_NET_BF16 && net && net->tower_mode == 2))
+        return fail(ctx, SZB_ERR_ARG, "only the one-launch bf16 tower writes logits rows apart from its activation rows");
     if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
     if (b0 + n > net->cap || (b0 & 3)) return fail(ctx, SZB_ERR_ARG, "batch [%d, %d) outside capacity %d", b0, b0 + n, net->cap);
     cudaStream_t st = ctx->work;
@@ -1391,7 +1398,7 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
                 cudaEvent_t* cev = (ctx->profiling && blk == 9) ? conv_event_pair(ctx) : nullptr;
                 if (cev) cudaEventRecord(cev[0], st);
                 if ((rc = launch_tc<256, 0>(ctx, net, net->tm_act16[yy], net->tower[2 * blk + 1], net->act16[x], net->act16[o], nullptr, n, 1, b0))) return rc;
-                if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_LAYER * (uint64_t)n; }
+                if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_LAYER * (uint64_t)n; }
                 x = o;
             }
             y = (x + 1) % 3;
@@ -1401,15 +1408,15 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
                 cudaEvent_t* cev = (ctx->profiling && l == 20) ? conv_event_pair(ctx) : nullptr;
                 if (cev) cudaEventRecord(cev[0], st);
                 if ((rc = launch_tower(ctx, net, b0, n, l, l + 1))) return rc;
-                if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_LAYER * (uint64_t)n; }
+                if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_LAYER * (uint64_t)n; }
             }
             x = net->final_x; y = net->final_y;
         } else {
             // stem + 38 tower convolutions + both policy 1x1 layers in ONE persistent launch; the measurement hook brackets exactly that launch
             cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
             if (cev) cudaEventRecord(cev[0], st);
-            if ((rc = launch_tower(ctx, net, b0, n, 0, MAX_TOWER_LAYERS))) return rc;
-            if (cev) { cudaEventRecord(cev[1], st); ctx->conv_boards = n; ctx->conv_flop = FLOP_TOWER_ALL * (uint64_t)n; }
+            if ((rc = launch_tower(ctx, net, b0, n, 0, MAX_TOWER_LAYERS, out_row))) return rc;
+            if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_ALL * (uint64_t)n; }
             x = net->final_x; y = net->final_y;
         }
         // (the one-launch tower ends with the policy output layer; the per-layer modes use the single-CTA kernel for it)
@@ -1441,9 +1448,25 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
     return 0;
 }
 
-// evaluate games [g0, g0 + n) of the search batch (g0 a multiple of 4): d.planes -> d.policy (softmax) / d.value, on ctx->work
+// The bf16 tower of a large batch runs as a sequence of launches of at most `chunk` boards that all use the SAME activation rows
+// [b0, b0 + chunk): three activation buffers of 512 boards (79 MB) + the weights stay in the 126 MB L2, those of 1024+ boards do
+// not (ncu: 0.42 GB of DRAM traffic per 512-board launch, 2.68 GB per 1024-board launch), and under the 1 kW power cap DRAM
+// traffic costs clock.  Planes in, logits / values out keep their own rows.
+static int net_forward_chunked(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out) {
+    Net* net = ctx->net;
+    if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
+    const int chunk = (evaluator == SZB_EVAL_NET_BF16 && net->tower_mode == 2 && net->chunk > 0) ? net->chunk : n;
+    for (int off = 0; off < n; off += chunk) {
+        const int m = std::min(chunk, n - off);
+        int rc = net_forward_device(ctx, evaluator, b0, m, planes + (size_t)off * stride, stride, value_out + off, b0 + off);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// evaluate slots [g0, g0 + n) of the search batch (g0 a multiple of 4): d.planes -> d.policy (softmax) / d.value, on ctx->work
 int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n) {
-    int rc = net_forward_device(ctx, evaluator, g0, n, ctx->d.planes + (size_t)g0 * PLANE_STRIDE, PLANE_STRIDE, ctx->d.value + g0);
+    int rc = net_forward_chunked(ctx, evaluator, g0, n, ctx->d.planes + (size_t)g0 * PLANE_STRIDE, PLANE_STRIDE, ctx->d.value + g0);
     if (rc) return rc;
     k_softmax<<<n, 256, 0, ctx->work>>>(ctx->net->logits + (size_t)g0 * N_ACTIONS, ctx->d.policy + (size_t)g0 * N_ACTIONS, n);
     ctx->launches++;
@@ -1559,7 +1582,7 @@ static int net_forward_common(szb_ctx* ctx, int32_t n, const uint64_t* planes, i
     for (int lo = 0; lo < n; lo += cap) {
         const int m = std::min(cap, n - lo);
         SZB_CUDA(ctx, cudaMemcpyAsync(d_pl, planes + (size_t)lo * N_PLANES, (size_t)m * N_PLANES * 8, cudaMemcpyDefault, ctx->stream));
-        int rc = net_forward_device(ctx, evaluator, 0, m, d_pl, N_PLANES, d_v);
+        int rc = net_forward_chunked(ctx, evaluator, 0, m, d_pl, N_PLANES, d_v);
         if (rc) return rc;
         const float* src = net->logits;
         if (softmax) {
@@ -1591,7 +1614,7 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
         for (int i = 0; i < reps && !rc; i++) {
             switch (which) {
             case 0: rc = launch_tc<256, 0>(ctx, net, net->tm_act16[i & 1], net->tower[1], net->act16[2], net->act16[(i + 1) & 1], nullptr, n, 1); break;
-            case 1: rc = net_forward_device(ctx, SZB_EVAL_NET_BF16, 0, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
+            case 1: rc = net_forward_chunked(ctx, SZB_EVAL_NET_BF16, 0, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
             case 2: rc = net_forward_device(ctx, SZB_EVAL_NET_FP32, 0, n, ctx->d.planes, PLANE_STRIDE, ctx->d.value); break;
             case 3: launch_f32(ctx, net->act32[i & 1], net->tower[1], net->act32[2], net->act32[(i + 1) & 1], n, 1, 0); break;
             case 4: rc = launch_tower(ctx, net, 0, n, 20, 21); break;                       // one tower layer, CTA-pair kernel

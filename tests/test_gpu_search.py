@@ -117,6 +117,41 @@ def test_terminal_root_and_single_search(eng):
     assert visits[1].sum() == 0 and child[1].sum() != 0
 
 
+def test_finished_games_take_no_slot(eng):
+    """games that are over take no slot of the search batch (no step kernels, no network rows): the running games of a mixed
+    batch get exactly the visit counts of a batch holding only them, a finished root still ends with visit_count 1 + num_searches
+    and value_sum num_searches * (-1 | 0) (mcts.py:46,104-109), and the counters say which simulations were evaluations"""
+    from sigma_zero_b200 import _lib
+    from sigma_zero_b200.engine import EVAL_HASH
+    import chess
+    mate = chess.Board("7k/6Q1/6K1/8/8/8/8/8 b - - 0 1")
+    stale = chess.Board("7k/5Q2/6K1/8/8/8/8/8 b - - 0 1")
+    start = chess.Board()
+    kiwi = chess.Board("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1")
+    S = 40
+    eng.set_positions([util.wire_pos(b, _lib) for b in (start, kiwi)])
+    v_ref, c_ref, _ = eng.search(S, 2.0, True, EVAL_HASH)
+    s0 = eng.stats()
+    eng.set_positions([util.wire_pos(b, _lib) for b in (mate, start, stale, kiwi, mate)])
+    v, c, rv = eng.search(S, 2.0, True, EVAL_HASH, want_value=True)
+    s1 = eng.stats()
+    assert np.array_equal(v[[1, 3]], v_ref) and np.array_equal(c[[1, 3]], c_ref)
+    assert v[[0, 2, 4]].sum() == 0 and c[[0, 2, 4]].sum() == 0
+    assert rv[0] == -1.0 and rv[2] == 0.0
+    assert s1["simulations"] - s0["simulations"] == 5 * S
+    assert s1["terminal_visits"] - s0["terminal_visits"] >= 3 * S
+    assert s1["evaluations"] - s0["evaluations"] <= 2 * S
+    for g, (n, w) in {0: (1 + S, -float(S)), 2: (1 + S, 0.0), 4: (1 + S, -float(S))}.items():
+        t = eng.tree_export(g)
+        assert t["root_visits"] == n and t["root_value_sum"] == w and len(t["node_first"]) == 1
+    # all games over: nothing to search, still well defined
+    eng.set_positions([util.wire_pos(mate, _lib), util.wire_pos(stale, _lib)])
+    v, c, _ = eng.search(S, 2.0, False, EVAL_HASH)
+    assert v.sum() == 0 and c.sum() == 0
+    moves, active = eng.selfplay_ply(S, 2.0, True, EVAL_HASH, seed=1, sample=True)
+    assert active == 0 and (moves == -1).all()
+
+
 def test_cohort_split_does_not_change_results():
     """the two-cohort pipeline (two game halves stepping on two streams) must give exactly the visit counts of the single
     batch -- with the hash evaluator (exact) and with the bf16 network (batch-invariant kernels)"""
