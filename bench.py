@@ -43,6 +43,11 @@ WORKLOADS = {
                name="c2: 1024 concurrent vanilla-chess games x 800 sims/move, bf16 network, C=2, learning=True"),
     "c3": dict(games=4096, sims=800, chess960=True,
                name="c3: 4096 concurrent Chess960 games x 800 sims/move, bf16 network, C=2, learning=True"),
+    # BASELINE.json configs[4]: one whole self-play iteration, its games split over the ranks (strong scaling); not a bench line
+    # of the driver (a step is a whole iteration of complete games: minutes), run by hand: --workload c4 [--gpus N]
+    "c4": dict(games=500, sims=800, chess960=True,
+               name="c4: full self-play iteration, num_selfPlay_iterations=500 Chess960 games x 800 sims/move to the end of every "
+                    "game, sharded over the ranks, NCCL weight broadcast first"),
 }
 C_PUCT = 2.0
 SEED = 0
@@ -412,6 +417,91 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+def run_c4(args, wl):
+    """One whole self-play iteration through the product API (train_RL.selfplay_iteration's sharding + sim.selfplay_records):
+    every game of this rank's block is played to its end on the GPU, records land in packed host arrays."""
+    import torch
+    import torch.distributed as dist
+    from sigma_zero_b200 import runtime
+    from sigma_zero_b200.sim import selfplay_records
+    from sigma_zero_b200.train_RL import broadcast_weights, shard_of
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model, weights = seeded_model()
+    sargs = {"C": C_PUCT, "num_searches": wl["sims"], "num_selfPlay_iterations": wl["games"], "chess960": wl["chess960"]}
+    lo, hi = shard_of(wl["games"], rank, world)
+    # warm-up: two plies of this rank's block (engine creation, weight upload, first launches)
+    selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=2, game_id_base=lo)
+    eng = runtime.get_engine()
+    st0 = eng.stats()
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    bcast_ms = None
+    if world > 1:
+        tb = time.perf_counter()
+        broadcast_weights(model, 0, dev)
+        torch.cuda.synchronize()
+        bcast_ms = (time.perf_counter() - tb) * 1e3
+    rec, counters = selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=args.max_plies, game_id_base=lo)
+    torch.cuda.synchronize()
+    my_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    wall_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st1 = eng.stats()
+
+    def reduce(x, op):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+    R = dist.ReduceOp if world > 1 else None
+    total_s = reduce(wall_s, R.MAX if R else None)
+    sims = reduce(counters["simulations"], R.SUM if R else None)
+    moves = reduce(len(rec["z"]), R.SUM if R else None)
+    evals = reduce(st1["evaluations"] - st0["evaluations"], R.SUM if R else None)
+    launches = reduce(st1["kernel_launches"] - st0["kernel_launches"], R.SUM if R else None)
+    unfinished = reduce(int((rec["result"] == 2).sum()), R.SUM if R else None)
+    longest = reduce(counters["plies"], R.MAX if R else None)
+    slowest_rank_s = reduce(my_s, R.MAX if R else None)
+    fastest_rank_s = -reduce(-my_s, R.MAX if R else None)
+    rec_bytes = reduce(sum(v.nbytes for v in rec.values()), R.SUM if R else None)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": sims / total_s, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 0,
+            "ms_per_step": total_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "games": wl["games"], "games_per_gpu": (wl["games"] + world - 1) // world,
+                       "num_searches": wl["sims"], "C": C_PUCT, "learning": True, "chess960": True, "weights": weights,
+                       "start": "Chess960 ids drawn per game from (seed, global game id)", "max_plies": args.max_plies,
+                       "timed": "weight broadcast + every ply of every game (search, sample, push, packed record to host) until the "
+                                "last game of the slowest rank ends; host wall clock between barriers"},
+            "moves_per_sec": moves / total_s, "evals_per_sec": evals / total_s, "positions_recorded": int(moves),
+            "games_unfinished_at_max_plies": int(unfinished), "longest_game_plies": int(longest),
+            "rank_seconds": {"slowest": slowest_rank_s, "fastest": fastest_rank_s}, "record_bytes": int(rec_bytes),
+            "e2e": {"value": sims / total_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(rec_bytes),
+                    "note": "the timed region is the end-to-end API call: records arrive in host memory every ply"},
+            "gpu_launches": int(launches), "clocks": clocks, "weights_broadcast_ms": bcast_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -425,6 +515,7 @@ def main():
     ap.add_argument("--ref-sims", type=int, default=800, help="--impl reference: simulations per step (bounded sample)")
     ap.add_argument("--cpu-sims", type=int, default=2000, help="cpu_baseline: simulations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-plies", type=int, default=None, help="--workload c4: cut games after this many plies (default: play every game out)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.games:
@@ -435,6 +526,8 @@ def main():
         wl["name"] += " [sims overridden: %d]" % args.sims
     if args.impl == "reference":
         run_reference(args, wl)
+    elif args.workload == "c4":
+        run_c4(args, wl)
     else:
         run_ours(args, wl)
 

@@ -74,6 +74,67 @@ def selfplay_batch(model, args, num_games, c960=False, seed=None, start_ids=None
     return games, {"plies": plies, "simulations": plies * n_search * num_games}
 
 
+def selfplay_records(model, args, num_games, c960=False, seed=None, start_ids=None, max_plies=None, learning=True,
+                     sample=True, game_id_base=0):
+    """The same games as selfplay_batch, recorded straight into the packed training format of records.py (no per-move
+    Python objects): returns (records, counters).  records["game"] numbers the games of this call from 0; rows are ordered
+    by game, then ply -- exactly records.pack_records(selfplay_batch(...)[0]).  records["result"] holds one outcome code
+    per game: 1 white won, -1 black won, 0 draw, 2 unfinished (max_plies)."""
+    n_search = int(args['num_searches'])
+    eng = runtime.get_engine(min_games=num_games, min_searches=n_search)
+    runtime.sync_weights(eng, model)
+    eng.owner = None
+    if seed is None:
+        seed = int(np.random.default_rng().integers(0, 2 ** 62))
+    if start_ids is None:
+        start_ids = ([int(np.random.default_rng([int(seed), int(game_id_base) + g]).integers(0, 960)) for g in range(num_games)]
+                     if c960 else np.full(num_games, -1))
+    eng.reset(start_ids)
+    eng.set_game_id_base(game_id_base)
+    evaluator = runtime.evaluator_of(model)
+    col = np.arange(256)[None, :]
+    st, gm, pl, ix, pr, ln = [], [], [], [], [], []
+    plies, active, sims = 0, num_games, 0
+    while active > 0 and (max_plies is None or plies < max_plies):
+        planes, _ = eng.encode(want_mask=False)
+        moves, active = eng.selfplay_ply(n_search, float(args['C']), learning, evaluator, seed=int(seed), sample=sample)
+        idx, vis, cnt = eng.root_children()
+        live = np.nonzero(moves >= 0)[0]
+        if len(live):
+            k = cnt[live].astype(np.int64)
+            sel = col < k[:, None]
+            v = vis[live].astype(np.int64)
+            tot = (v * sel).sum(axis=1)
+            st.append(planes[live])
+            gm.append(live.astype(np.int32))
+            pl.append(np.full(len(live), plies, dtype=np.int32))
+            ix.append(idx[live][sel])
+            pr.append((v / tot[:, None])[sel].astype(np.float32))      # count / sum(count) in double, like mcts.py:113-122
+            ln.append(k)
+            sims += len(live) * n_search
+        plies += 1
+    final = eng.positions()
+    result = np.array([2 if p.outcome == 0 else (0 if p.outcome != 1 else (-1 if p.turn else 1)) for p in final], dtype=np.int8)
+    if not st:
+        rec = {"states": np.zeros((0, 119), np.uint64), "pi_index": np.zeros(0, np.uint16), "pi_prob": np.zeros(0, np.float32),
+               "pi_off": np.zeros(1, np.int64), "z": np.zeros(0, np.int8), "colour": np.zeros(0, bool), "game": np.zeros(0, np.int32),
+               "result": result}
+        return rec, {"plies": plies, "simulations": sims}
+    states, game, ply, length = np.concatenate(st), np.concatenate(gm), np.concatenate(pl), np.concatenate(ln)
+    start = np.concatenate([[0], np.cumsum(length)])[:-1]              # CSR start of every recorded position, in recording order
+    order = np.lexsort((ply, game))                                     # by game, then ply
+    flat_i, flat_p = np.concatenate(ix), np.concatenate(pr)
+    game, ply, length = game[order], ply[order], length[order]
+    new_off = np.concatenate([[0], np.cumsum(length)])
+    rows = np.repeat(start[order] - new_off[:-1], length) + np.arange(new_off[-1])      # gather of the CSR payload
+    reward = np.where(result == 2, 0, result).astype(np.int8)[game]
+    z = np.where(ply % 2 == 0, reward, -reward).astype(np.int8)          # sim.py:86-97: +r for even positions, -r for odd
+    rec = {"states": states[order], "pi_index": flat_i[rows].astype(np.uint16), "pi_prob": flat_p[rows],
+           "pi_off": new_off.astype(np.int64), "z": z,
+           "colour": states[order][:, 112] != 0, "game": game, "result": result}
+    return rec, {"plies": plies, "simulations": sims}
+
+
 def play_game(model, args, c960=False):
     """One self-play game (reference signature, sim.py:31-99)."""
     games, _ = selfplay_batch(model, args, 1, c960=c960)

@@ -56,19 +56,50 @@ def broadcast_weights(model, src=0, device=None):
     return flat.numel() * 4
 
 
-def selfplay_iteration(model, args, seed=0, max_plies=None):
-    """One outer iteration's self-play: this rank's shard of args['num_selfPlay_iterations'] games."""
+def _iteration_shard(model, args):
+    """broadcast rank 0's weights (the only collective of the path) and return this rank's block of the iteration's games"""
     import torch.distributed as dist
-    from .sim import selfplay_batch
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     if dist.is_initialized() and world > 1:
         dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if torch.cuda.is_available() else None
         broadcast_weights(model, 0, dev)
-    lo, hi = shard_of(int(args['num_selfPlay_iterations']), rank, world)
+    return shard_of(int(args['num_selfPlay_iterations']), rank, world)
+
+
+def selfplay_iteration(model, args, seed=0, max_plies=None):
+    """One outer iteration's self-play: this rank's shard of args['num_selfPlay_iterations'] games, as the reference's
+    per-game history dicts (sim.py:38-43)."""
+    from .sim import selfplay_batch
+    lo, hi = _iteration_shard(model, args)
     games, counters = selfplay_batch(model, args, hi - lo, c960=bool(args.get('chess960', False)),
                                      seed=seed, max_plies=max_plies, game_id_base=lo)
     return games, counters
+
+
+def selfplay_iteration_records(model, args, seed=0, max_plies=None):
+    """The same games recorded straight into the packed training format (sim.selfplay_records); `game` holds global game
+    numbers so that the shards of all ranks concatenate into one record set."""
+    from .sim import selfplay_records
+    lo, hi = _iteration_shard(model, args)
+    rec, counters = selfplay_records(model, args, hi - lo, c960=bool(args.get('chess960', False)),
+                                     seed=seed, max_plies=max_plies, game_id_base=lo)
+    rec["game"] = rec["game"] + lo
+    return rec, counters
+
+
+def concat_records(parts):
+    """record sets of consecutive game blocks -> one record set (CSR offsets re-based)"""
+    import numpy as np
+    out = {k: np.concatenate([p[k] for p in parts]) for k in ("states", "pi_index", "pi_prob", "z", "colour", "game")}
+    off, base = [np.zeros(1, dtype=np.int64)], 0
+    for p in parts:
+        off.append(p["pi_off"][1:] + base)
+        base += int(p["pi_off"][-1])
+    out["pi_off"] = np.concatenate(off)
+    if all("result" in p for p in parts):
+        out["result"] = np.concatenate([p["result"] for p in parts])
+    return out
 
 
 def make_optimiser(model, lr=1e-4, weight_decay=1e-4):
@@ -119,13 +150,11 @@ def rl_iteration(model, args, seed=0, max_plies=None, epochs=None, optimiser=Non
     records gathered on every rank, the same fine-tuning step everywhere (identical data + identical seed => identical
     weights, so the next iteration's broadcast is a formality).  Returns (records, loss history)."""
     import torch.distributed as dist
-    from . import records
-    games, _ = selfplay_iteration(model, args, seed=seed, max_plies=max_plies)
+    rec, _ = selfplay_iteration_records(model, args, seed=seed, max_plies=max_plies)
     if dist.is_initialized() and dist.get_world_size() > 1:
         parts = [None] * dist.get_world_size()
-        dist.all_gather_object(parts, games)
-        games = [g for part in parts for g in part]
-    rec = records.pack_records(games)
+        dist.all_gather_object(parts, rec)
+        rec = concat_records(parts)
     hist = train_on_records(model, rec, epochs=int(args.get('num_epochs', 1)) if epochs is None else epochs,
                             batch_size=int(args.get('batch_size', 64)), optimiser=optimiser, lr_scheduler=lr_scheduler,
                             device=train_device, seed=seed)

@@ -239,3 +239,25 @@ def test_selfplay_train_selfplay_loop():
     assert (after_p - ref_p.cpu()).abs().max().item() <= 2e-2 and (after_v - ref_v.cpu()).abs().max().item() <= 2e-2
     games2, _ = selfplay_batch(model, args, 8, c960=False, seed=1, max_plies=2)
     assert len(games2) == 8 and all(len(g["actions"]) == 2 for g in games2)
+
+
+def test_selfplay_records_equal_packed_dict_histories():
+    """sim.selfplay_records writes the packed training format directly (vectorised, no per-move Python objects): it must be
+    records.pack_records of what selfplay_batch returns for the same seed -- states, CSR policy targets, outcomes, row order --
+    including games that end inside the run (short games from a mating net)"""
+    from sigma_zero_b200 import records
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.sim import selfplay_batch, selfplay_records
+    torch.manual_seed(0)
+    model = policyNN({}).eval()
+    args = {"C": 2, "num_searches": 12}
+    for c960, n, plies in ((True, 7, 9), (False, 3, 5)):
+        games, c0 = selfplay_batch(model, args, n, c960=c960, seed=11, max_plies=plies)
+        want = records.pack_records(games)
+        got, c1 = selfplay_records(model, args, n, c960=c960, seed=11, max_plies=plies)
+        assert c0["plies"] == c1["plies"]
+        for k in ("states", "pi_index", "pi_prob", "pi_off", "z", "colour", "game"):
+            assert np.array_equal(want[k], got[k]), k
+        assert got["result"].shape == (n,) and set(got["result"].tolist()) <= {2, 1, 0, -1}
+        dense = records.dense_policy(got, [0, len(got["z"]) - 1])
+        assert np.allclose(dense.sum(1), 1.0, atol=1e-6)

@@ -205,3 +205,26 @@ def test_training_path_matches_reference_architecture_and_learns():
     hist = train_on_records(model, rec, epochs=6, batch_size=6, optimiser=opt, lr_scheduler=sched, device="cpu")
     assert len(hist) == 6 and sum(hist[-1]) < sum(hist[0])
     assert not model.training and any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+
+
+def test_concat_records_rebases_csr_offsets():
+    """record sets of consecutive game blocks (one per rank) concatenate into one set: CSR offsets re-based, rows kept"""
+    from sigma_zero_b200 import records
+    from sigma_zero_b200.train_RL import concat_records
+    rng = np.random.default_rng(0)
+
+    def fake(n, game0):
+        lens = rng.integers(1, 6, n)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        idx = np.concatenate([np.zeros(0, np.int64)] + [np.sort(rng.choice(4672, k, replace=False)) for k in lens]).astype(np.uint16)
+        prob = np.concatenate([np.zeros(0, np.float32)] + [np.full(k, 1.0 / k, np.float32) for k in lens])
+        return {"states": rng.integers(0, 2 ** 63, (n, 119), dtype=np.uint64), "pi_index": idx, "pi_prob": prob, "pi_off": off,
+                "z": rng.integers(-1, 2, n).astype(np.int8), "colour": rng.integers(0, 2, n).astype(bool),
+                "game": (game0 + np.arange(n) // 2).astype(np.int32), "result": np.zeros((n + 1) // 2, np.int8)}
+    a, b, c = fake(5, 0), fake(0, 3), fake(4, 3)
+    whole = concat_records([a, b, c])
+    assert len(whole["z"]) == 9 and whole["pi_off"][0] == 0 and whole["pi_off"][-1] == len(whole["pi_index"])
+    assert np.all(np.diff(whole["pi_off"]) > 0)
+    d = records.dense_policy(whole)
+    assert np.array_equal(d[:5], records.dense_policy(a)) and np.array_equal(d[5:], records.dense_policy(c))
+    assert np.array_equal(whole["states"][5:], c["states"]) and len(whole["result"]) == 3 + 0 + 2
