@@ -261,3 +261,33 @@ def test_selfplay_records_equal_packed_dict_histories():
         assert got["result"].shape == (n,) and set(got["result"].tolist()) <= {2, 1, 0, -1}
         dense = records.dense_policy(got, [0, len(got["z"]) - 1])
         assert np.allclose(dense.sum(1), 1.0, atol=1e-6)
+
+
+def test_supervised_pgn_to_records_matches_oracle_replay():
+    """PGN games replayed in lock step on the GPU engine -> packed one-hot records; every state, move index,
+    colour and reward must equal what the reference's loop produces (generate_training_supervised.py:60-95, restated over the
+    oracle), and the byte view of the packed planes must be the reference's compressed tensor (:91)"""
+    from sigma_zero_b200.supervised import compressed_states, pgn_to_records, read_pgn, resolve_san, select_balanced
+    games = select_balanced(read_pgn(util.PGN_SAMPLE))
+    rec = pgn_to_records(games, strict=True)
+    want_states, want_idx, want_z, want_col, want_game = [], [], [], [], []
+    for gi, (h, san) in enumerate(games):
+        _, ucis = util.replay_san_on_oracle(san, resolve_san)
+        og = util.oracle_game(False, 518)
+        r = {"1-0": 1, "0-1": -1, "1/2-1/2": 0}[h["Result"]]
+        import chess
+        for ply, u in enumerate(ucis):
+            want_states.append(og.get_representation())
+            want_idx.append(ref_path.move_to_index(chess.Move.from_uci(u), og.board.turn))
+            want_col.append(bool(og.board.turn))
+            want_z.append(r if ply % 2 == 0 else -r)
+            want_game.append(gi)
+            og.move_piece(chess.Move.from_uci(u))
+    n = len(want_z)
+    assert n == 33 + 16 + 4 and len(rec["z"]) == n
+    assert np.array_equal(rec["states"], np.stack([hash_eval.pack_planes(s) for s in want_states]))
+    assert rec["pi_index"].tolist() == want_idx and rec["z"].tolist() == want_z
+    assert rec["colour"].tolist() == want_col and rec["game"].tolist() == want_game
+    assert np.array_equal(rec["pi_off"], np.arange(n + 1)) and (rec["pi_prob"] == 1).all()
+    ref = torch.stack([(torch.from_numpy(s.astype(np.uint8)) << torch.arange(8).view(1, 1, 8)).sum(dim=-1).to(torch.uint8) for s in want_states])
+    assert np.array_equal(compressed_states(rec), ref.numpy())

@@ -228,3 +228,27 @@ def test_concat_records_rebases_csr_offsets():
     d = records.dense_policy(whole)
     assert np.array_equal(d[:5], records.dense_policy(a)) and np.array_equal(d[5:], records.dense_policy(c))
     assert np.array_equal(whole["states"][5:], c["states"]) and len(whole["result"]) == 3 + 0 + 2
+
+
+def test_supervised_pgn_reader_and_san_resolver():
+    """SURVEY 8f rank 3, host side: PGN text -> (headers, SAN main line) with comments / variations / NAGs dropped, the
+    reference's balanced game selection, and SAN resolved against a legal-move list (here the oracle's) -- castling both ways,
+    disambiguation, en passant, promotion by capture, mate"""
+    from sigma_zero_b200.supervised import read_pgn, resolve_san, select_balanced
+    games = list(read_pgn(util.PGN_SAMPLE))
+    assert [h["Result"] for h, _ in games] == ["1-0", "1/2-1/2", "0-1", "*"]
+    assert len(games[0][1]) == 33 and games[0][1][21] == "Nbd7" and games[0][1][22] == "O-O-O" and games[0][1][-1] == "Rd8#"
+    assert games[1][1] == ["e4", "a6", "e5", "d5", "exd6", "Nf6", "dxc7", "Nc6", "cxd8=N", "g6", "Nf3", "Bg7", "Bc4", "O-O", "O-O", "Rxd8"]
+    assert list(read_pgn(util.PGN_SAMPLE.encode())) == games
+    g, ucis = util.replay_san_on_oracle(games[0][1], resolve_san)
+    assert ucis[:3] == ["e2e4", "e7e5", "g1f3"] and ucis[22] == "e1c1" and ucis[21] == "b8d7"
+    assert g.board.outcome() is not None and g.board.result() == "1-0"
+    g, ucis = util.replay_san_on_oracle(games[1][1], resolve_san)
+    assert ucis[4] == "e5d6" and ucis[8] == "c7d8n" and ucis[13] == "e8g8" and ucis[14] == "e1g1"
+    g, _ = util.replay_san_on_oracle(games[2][1], resolve_san)
+    assert g.board.result() == "0-1"
+    with pytest.raises(ValueError):
+        util.replay_san_on_oracle(["e4", "e5", "Ke3"], resolve_san)
+    # selection: one white win + one black win + the draw are balanced; asking for 2 stops the scan after the first two games
+    assert [h["Result"] for h, _ in select_balanced(games)] == ["1-0", "1/2-1/2", "0-1"]
+    assert [h["Result"] for h, _ in select_balanced(games, num_games=1)] == ["1/2-1/2"]

@@ -94,3 +94,46 @@ PERFT_KATS = [
     ("2nnrbkr/p1qppppp/8/1ppb4/6PP/3PP3/PPP2P2/BQNNRBKR w HEhe - 1 9", True, [21, 807, 18002, 667366, 16253601]),
     ("b1q1rrkb/pppppppp/3nn3/8/P7/1PPP4/4PPPP/BQNNRKRB w GE - 1 9", True, [20, 479, 10471, 273318, 6417013]),
 ]
+
+
+PGN_SAMPLE = """[Event "Opera"]
+[Site "Paris"]
+[Result "1-0"]
+[PlyCount "33"]
+
+1.e4 e5 2.Nf3 d6 3.d4 Bg4 {a pin} 4.dxe5 Bxf3 5.Qxf3 dxe5 6.Bc4 Nf6 7.Qb3 Qe7 8.Nc3 c6 9.Bg5 b5 $2 10.Nxb5 cxb5
+11.Bxb5+ Nbd7 12.O-O-O Rd8 (12...Qb4 13.Bxf6) 13.Rxd7 Rxd7 14.Rd1 Qe6 15.Bxd7+ Nxd7 16.Qb8+ Nxb8 17.Rd8# 1-0
+
+[Event "en passant, under-promotion by capture, short castling"]
+[Result "1/2-1/2"]
+
+1. e4 a6 2. e5 d5 3. exd6 Nf6 4. dxc7 Nc6 ; rest of line is a comment
+5. cxd8=N g6 6. Nf3 Bg7 7. Bc4 O-O 8. O-O Rxd8 1/2-1/2
+
+[Event "black wins"]
+[Result "0-1"]
+
+1. f3 e5 2. g4 Qh4# 0-1
+
+[Event "unfinished"]
+[Result "*"]
+
+1. e4 *
+"""
+
+
+def replay_san_on_oracle(san_moves, resolve_san):
+    """plays SAN tokens on the oracle board through the product's SAN resolver; returns (RefGame, [uci moves])"""
+    g = ref_path.RefGame(chess960=False, start_id=None)
+    ucis = []
+    for san in san_moves:
+        b = g.board
+        legal = list(b.legal_moves)
+
+        def piece_at(sq, b=b):
+            p = b.piece_at(sq)
+            return (p.piece_type, p.color) if p else None
+        k = resolve_san(san, [(m.from_square, m.to_square, m.promotion) for m in legal], piece_at)
+        ucis.append(legal[k].uci())
+        g.move_piece(legal[k])
+    return g, ucis
