@@ -71,7 +71,8 @@ def traffic_per_launch(kind, boards):
         return None
     try:
         for e in json.load(open(p)).get("captures", []):
-            if int(e["conv_kind"]) == int(kind) and int(e["boards"]) == int(boards):
+            # (a launch of the timed region may be a few boards short of the captured batch: finished games take no row)
+            if int(e["conv_kind"]) == int(kind) and abs(int(e["boards"]) - int(boards)) <= 0.02 * int(e["boards"]):
                 return e["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -381,6 +382,18 @@ def run_ours(args, wl):
     steps_total = max(1, pt["steps"])
     phases = {k: pt[k] / steps_total for k in ("select_ms", "expand_ms", "eval_ms", "finish_ms")}
     net_tflops = (FLOP_PER_EVAL * G) / (phases["eval_ms"] * 1e-3) / 1e12 if phases["eval_ms"] > 0 else None
+    # the HBM-class kernels of the step against the copy peak, algorithmic bytes of SURVEY.md 8d / DESIGN.md 3.2-3.3: latency-bound
+    # at a search's batch size by construction (a few hundred bytes per tree behind 2-4 dependent round trips)
+    def hbm(bytes_, ms):
+        gbs = bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else None
+        return {"algorithmic_bytes": int(bytes_), "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": (gbs / pk["hbm_gbs"]) if gbs else None}
+    hbm_kernels = {
+        "k_select": hbm(16 * pt["select_edges"] + 16 * pt["select_levels"], pt["select_ms"]),
+        "k_expand": hbm(steps_total * G * (96 + 96 + 7 * 96 + 952 + 584), pt["expand_ms"]),
+        "k_finish": hbm(24 * pt["backup_levels"] + 24 * pt["edges_written"], pt["finish_ms"]),
+        "note": "totals over the profiled step; these kernels move ~2 MB per launch at 1024 trees and are latency-bound (hidden under the "
+                "other cohort's tower in the timed region); their bandwidth-regime numbers (65,536 trees, bulk perft) are in profiles/r01f_*",
+    }
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     cpu = None
@@ -408,7 +421,7 @@ def run_ours(args, wl):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pos_bytes,
                     "d2h_bytes_per_step": G * 4672 * 4 + G * 73 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "szb_games_set(host positions) + szb_search(host visit/child buffers), pinned memory"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
             "weights_broadcast_ms": bcast_ms, "lib": _lib.LIB_PATH.replace(ROOT + os.sep, ""),
         }
         print(json.dumps(line), flush=True)

@@ -2,7 +2,7 @@
 //
 // One simulation step of mcts.py:49-109 for ALL games at once is four launches:
 //   k_select  : warp per tree, PUCT descent with shuffle arg-max           (mctsnode.py:23-37, mcts.py:54-55)
-//   k_expand  : thread per tree, make-move + legality + terminal + planes    (mcts.py:57-70, chess_tensor.py:88-172)
+//   k_expand  : one thread per tree (own warp at search sizes), make-move + legality + terminal + planes (mcts.py:57-70, chess_tensor.py:88-172)
 //   evaluator : hash kernel or the network (net.cu)                         (mcts.py:72-75)
 //   k_finish  : warp per tree, mask/normalise/noise, child allocation, backup (mcts.py:77-109, mctsnode.py:39-63)
 #include <cstdarg>
@@ -290,11 +290,16 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
     }
 }
 
-// thread per tree
-__global__ void __launch_bounds__(32) k_expand(Dev d) {
+// One thread per tree does the work; LPT = lanes per tree.  LPT = 1 packs 32 trees into a warp (bulk throughput: every lane
+// busy, but the lanes diverge through move generation and run one after the other); LPT = 32 gives every tree its own warp
+// (one active lane, no divergence: the latency of a step at the batch sizes of a search, a few thousand trees at most).
+template <int LPT>
+__global__ void __launch_bounds__(128) k_expand(Dev d) {
     __shared__ Tables T;
     load_tables(&T, d.tables);
-    const int slot = d.g_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (LPT > 1 && (tid % LPT) != 0) return;
+    const int slot = d.g_begin + tid / LPT;
     if (slot >= d.g_end) return;
     const int g = d.order[slot];
     const size_t r = (size_t)g * d.nodes_per_game;
@@ -969,7 +974,8 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             if (prof) cudaEventRecord(ev[0], cs);
             k_select<<<warp_blocks, 128, 0, cs>>>(dc, c_puct);
             if (prof) cudaEventRecord(ev[1], cs);
-            k_expand<<<(n + 31) / 32, 32, 0, cs>>>(dc);
+            if (n <= 8192) k_expand<32><<<(n + 3) / 4, 128, 0, cs>>>(dc);
+            else k_expand<1><<<(n + 127) / 128, 128, 0, cs>>>(dc);
             if (prof) cudaEventRecord(ev[2], cs);
             ctx->launches += 2;
             if (evaluator == SZB_EVAL_HASH) {
