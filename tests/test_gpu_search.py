@@ -174,3 +174,41 @@ def test_cohort_split_does_not_change_results():
         e.close()
     for a, b in zip(out[1], out[2]):
         assert np.array_equal(a, b)
+
+
+def test_full_size_c2_properties():
+    """BASELINE config c2 at full size (1024 concurrent games x 800 simulations, bf16 tcgen05 network, two cohorts, 512-board tower
+    launches): what must hold whatever the size -- every running game's child visits sum to num_searches - 1 (mcts.py:46,113-122),
+    the root children are exactly the legal moves (no softmax underflow with this network), a second identical search and a
+    single-cohort engine reproduce the visit counts bit for bit, and the counters add up"""
+    import torch
+    from sigma_zero_b200.engine import EVAL_NET_BF16, Engine, child_indices
+    torch.manual_seed(0)
+    sd = ref_path.build_policy_nn().eval().state_dict()
+    G, S = 1024, 800
+    rng = np.random.default_rng(5)
+    out = []
+    for cohorts in (0, 1):
+        e = Engine(max_games=G, max_searches=S, cohorts=cohorts)
+        e.load_state_dict(sd)
+        e.reset([-1] * G)
+        plies = rng.integers(0, 12, G) if cohorts == 0 else plies
+        for ply in range(int(plies.max())):                  # a few random legal plies so that the games differ
+            idx, cnt = e.legal_moves()
+            who = [g for g in range(G) if ply < plies[g] and cnt[g] > 0]
+            e.push(who, [int(idx[g, (7 * g + 3 * ply) % cnt[g]]) for g in who])
+        s0 = e.stats()
+        v, c, _ = e.search(S, 2.0, True, EVAL_NET_BF16)
+        s1 = e.stats()
+        out.append((v, c))
+        if cohorts == 0:
+            v2, c2, _ = e.search(S, 2.0, True, EVAL_NET_BF16)
+            assert np.array_equal(v, v2) and np.array_equal(c, c2)
+            idx, cnt = e.legal_moves()
+            for g in range(0, G, 37):
+                assert list(child_indices(c[g])) == idx[g, :cnt[g]].tolist(), g
+        assert (v.sum(axis=1) == S - 1).all()
+        assert s1["simulations"] - s0["simulations"] == G * S
+        assert s1["evaluations"] - s0["evaluations"] + s1["terminal_visits"] - s0["terminal_visits"] == G * S
+        e.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
