@@ -449,7 +449,8 @@ def run_c4(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     model, weights = seeded_model()
-    sargs = {"C": C_PUCT, "num_searches": wl["sims"], "num_selfPlay_iterations": wl["games"], "chess960": wl["chess960"]}
+    sargs = {"C": C_PUCT, "num_searches": wl["sims"], "num_selfPlay_iterations": wl["games"], "chess960": wl["chess960"],
+             "leaves_per_tree": args.leaves_per_tree}
     lo, hi = shard_of(wl["games"], rank, world)
     # warm-up: two plies of this rank's block (engine creation, weight upload, first launches)
     selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=2, game_id_base=lo)
@@ -501,6 +502,9 @@ def run_c4(args, wl):
             "config": {"workload": wl["name"], "games": wl["games"], "games_per_gpu": (wl["games"] + world - 1) // world,
                        "num_searches": wl["sims"], "C": C_PUCT, "learning": True, "chess960": True, "weights": weights,
                        "start": "Chess960 ids drawn per game from (seed, global game id)", "max_plies": args.max_plies,
+                       "leaves_per_tree": args.leaves_per_tree,
+                       "search": "the reference's algorithm (one simulation of a tree at a time)" if args.leaves_per_tree <= 1 else
+                                 "NON-PARITY multi-leaf mode: %d simulations of a tree in flight per step, virtual loss" % args.leaves_per_tree,
                        "timed": "weight broadcast + every ply of every game (search, sample, push, packed record to host) until the "
                                 "last game of the slowest rank ends; host wall clock between barriers"},
             "moves_per_sec": moves / total_s, "evals_per_sec": evals / total_s, "positions_recorded": int(moves),
@@ -528,6 +532,8 @@ def main():
     ap.add_argument("--ref-sims", type=int, default=800, help="--impl reference: simulations per step (bounded sample)")
     ap.add_argument("--cpu-sims", type=int, default=2000, help="cpu_baseline: simulations in the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--leaves-per-tree", type=int, default=1,
+                    help="--workload c4 only: opt-in multi-leaf search with virtual loss (not the reference's algorithm; reported separately)")
     ap.add_argument("--max-plies", type=int, default=None, help="--workload c4: cut games after this many plies (default: play every game out)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

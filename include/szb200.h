@@ -61,6 +61,10 @@ typedef struct szb_config {
     int32_t edges_per_node;        /* tree arena = max_games * (max_searches+1) * edges_per_node edges; 0 -> 48 */
     int32_t cohorts;               /* search pipelining: 2 = the games step as two independent halves on two streams (one half's
                                       tree kernels run under the other half's network kernel), 1 = one batch, 0 = automatic (2 from 1024 games) */
+    int32_t leaves_per_tree;       /* 0 / 1: the reference's algorithm, one simulation of a tree at a time (mcts.py:49) -- every parity
+                                      statement of this library is about this mode.  2..8: that many simulations of a tree in flight per
+                                      step, kept apart by virtual loss: a DIFFERENT search (other visit counts, still exactly
+                                      num_searches simulations per move, deterministic) for the latency-bound regime of few games */
 } szb_config;
 
 /* A position crossing the ABI. */

@@ -18,7 +18,7 @@ class SzbError(RuntimeError):
 
 class Config(ctypes.Structure):
     _fields_ = [("max_games", ctypes.c_int32), ("max_searches", ctypes.c_int32),
-                ("edges_per_node", ctypes.c_int32), ("cohorts", ctypes.c_int32)]
+                ("edges_per_node", ctypes.c_int32), ("cohorts", ctypes.c_int32), ("leaves_per_tree", ctypes.c_int32)]
 
 
 class Pos(ctypes.Structure):

@@ -188,6 +188,7 @@ __global__ void k_search_begin(Dev d, int num_searches) {
     if (g >= d.n_games) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     d.node_count[g] = 0;
+    d.sims_done[g] = 0;
     d.node_edge0[r] = -1;
     d.node_nchild[r] = 0;
     d.node_pedge[r] = -1;
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
         const int n = d.node_nchild[r + node];
         const int e0 = d.node_edge0[r + node];
         if (n == 0) {
-            if (lane == 0) { d.sel_node[g] = node; d.sel_edge[g] = -1; }
+            if (lane == 0) { d.sel_node[slot] = node; d.sel_edge[slot] = -1; }
             break;
         }
         const float sq = sqrt_parent(np);
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
         depth++;
         scanned += (unsigned long long)n;
         if (c == NO_CHILD) {
-            if (lane == 0) { d.sel_node[g] = node; d.sel_edge[g] = e; }
+            if (lane == 0) { d.sel_node[slot] = node; d.sel_edge[slot] = e; }
             break;
         }
         node = c;
@@ -299,19 +300,21 @@ __global__ void __launch_bounds__(128) k_expand(Dev d) {
     load_tables(&T, d.tables);
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (LPT > 1 && (tid % LPT) != 0) return;
-    const int slot = d.g_begin + tid / LPT;
-    if (slot >= d.g_end) return;
-    const int g = d.order[slot];
+    // a path slot = one in-flight simulation: slot * K + j (K = leaves per tree and step; 1 in the reference-exact mode)
+    const int ps = d.g_begin * d.K + tid / LPT;
+    if (ps >= d.g_end * d.K) return;
+    const int g = d.order[ps / d.K];
     const size_t r = (size_t)g * d.nodes_per_game;
     Pos* gp = d.pool + (size_t)g * d.pool_stride;
-    const int e = d.sel_edge[g];
-    int node = d.sel_node[g];
+    const int e = d.sel_edge[ps];
+    if (e == PATH_DROPPED) { d.need_eval[ps] = 0; return; }
+    int node = d.sel_node[ps];
     uint16_t mv[MAX_MOVES];
     int cnt = 0;
     Pos q;
     if (e >= 0) {
         const int parent = node;
-        node = ++d.node_count[g];
+        node = d.K == 1 ? ++d.node_count[g] : d.sel_new[ps];      // multi-leaf mode: numbered by k_select_vl
         const int pslot = state_slot(d, g, parent);
         const Pos pp = gp[pslot];
         const uint16_t m = index_to_move(pp, d.e_move[e]);
@@ -327,39 +330,76 @@ __global__ void __launch_bounds__(128) k_expand(Dev d) {
         d.node_term[r + node] = q.outcome != OUT_NONE;
         d.node_tval[r + node] = q.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
         d.e_child[e] = (uint16_t)node;
-        d.sel_node[g] = node;
+        d.sel_node[ps] = node;
     } else {
         q = gp[state_slot(d, g, node)];
         if (!d.node_term[r + node]) cnt = gen_legal(T, q, mv);
     }
     if (d.node_term[r + node]) {
-        d.leaf_value[g] = d.node_tval[r + node];
-        d.need_eval[g] = 0;
+        d.leaf_value[ps] = d.node_tval[r + node];
+        d.need_eval[ps] = 0;
         return;
     }
-    uint64_t* mrow = d.mask + (size_t)slot * MASK_STRIDE;
+    uint64_t* mrow = d.mask + (size_t)ps * MASK_STRIDE;
     for (int w = 0; w < MASK_STRIDE; w++) mrow[w] = 0;
     for (int k = 0; k < cnt; k++) {
         const int idx = move_to_index(q, mv[k]);
         mrow[idx >> 6] |= bit(idx & 63);
     }
-    pack_planes(gp, q, d.planes + (size_t)slot * PLANE_STRIDE);
-    d.need_eval[g] = 1;
+    pack_planes(gp, q, d.planes + (size_t)ps * PLANE_STRIDE);
+    d.need_eval[ps] = 1;
 }
 
 // block per tree: policy[i] / value from the integer hash of the packed planes
 __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
-    const int slot = d.g_begin + blockIdx.x;
-    if (!d.need_eval[d.order[slot]]) return;
+    const int ps = d.g_begin * d.K + blockIdx.x;
+    if (!d.need_eval[ps]) return;
     __shared__ uint64_t h_sh;
     if (threadIdx.x == 0) {
-        h_sh = he_fold(d.planes + (size_t)slot * PLANE_STRIDE);
-        d.value[slot] = he_value(h_sh);
+        h_sh = he_fold(d.planes + (size_t)ps * PLANE_STRIDE);
+        d.value[ps] = he_value(h_sh);
     }
     __syncthreads();
     const uint64_t h = h_sh;
-    float* pol = d.policy + (size_t)slot * N_ACTIONS;
+    float* pol = d.policy + (size_t)ps * N_ACTIONS;
     for (int i = threadIdx.x; i < N_ACTIONS; i += blockDim.x) pol[i] = he_policy(h, i);
+}
+
+// warp-cooperative pieces of the expansion (mcts.py:77-96, mctsnode.py:39-54), shared by k_finish and k_finish_vl
+__device__ __forceinline__ int count_legal(const Dev& d, int ps, int lane) {
+    const uint64_t* mk = d.mask + (size_t)ps * MASK_STRIDE;
+    int n = 0;
+    for (int w = lane; w < MASK_WORDS; w += 32) n += popc(mk[w]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, off);
+    return n;
+}
+// children of the node evaluated in path slot ps, written from edge e0 on; returns how many (zero-prior moves are dropped)
+__device__ __forceinline__ int create_children(const Dev& d, int ps, unsigned long long e0, int learning, int lane) {
+    const float* pol = d.policy + (size_t)ps * N_ACTIONS;
+    const uint64_t* mk = d.mask + (size_t)ps * MASK_STRIDE;
+    const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
+    const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
+    int count = 0;
+    for (int chunk = 0; chunk < N_ACTIONS / 32; chunk++) {
+        const uint32_t bits = (uint32_t)(mk[chunk >> 1] >> ((chunk & 1) * 32));
+        if (bits == 0) continue;
+        const int e = chunk * 32 + lane;
+        float pr = 0.0f;
+        bool has = (bits >> lane) & 1u;
+        if (has) { pr = f_div(pol[e], total); has = pr != 0.0f; }     // zero-prior children are dropped (mcts.py:87-89)
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
+        if (has) {
+            const unsigned long long at = e0 + count + __popc(ballot & ((1u << lane) - 1));
+            d.e_n[at] = 0;
+            d.e_w[at] = 0.0;
+            d.e_p[at] = learning ? noisy_prior(pr) : pr;
+            d.e_move[at] = (uint16_t)e;
+            d.e_child[at] = NO_CHILD;
+        }
+        count += __popc(ballot);
+    }
+    return count;
 }
 
 // warp per tree
@@ -370,15 +410,9 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool active = slot < d.g_end;
     const int g = active ? d.order[slot] : 0;
-    const bool eval = active && d.need_eval[g];
+    const bool eval = active && d.need_eval[slot];
     // children to allocate: one bump of the shared edge arena per BLOCK (four trees), not one same-address atomic per tree
-    int n_legal = 0;
-    if (eval) {
-        const uint64_t* mk = d.mask + (size_t)slot * MASK_STRIDE;
-        for (int w = lane; w < MASK_WORDS; w += 32) n_legal += popc(mk[w]);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) n_legal += __shfl_xor_sync(0xFFFFFFFFu, n_legal, off);
-    }
+    const int n_legal = eval ? count_legal(d, slot, lane) : 0;
     if (lane == 0) want_sh[wib] = n_legal;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -388,37 +422,16 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
     __syncthreads();
     if (!active) return;
     const size_t r = (size_t)g * d.nodes_per_game;
-    const int node = d.sel_node[g];
+    const int node = d.sel_node[slot];
     float v;
     if (eval) {
-        const float* pol = d.policy + (size_t)slot * N_ACTIONS;
-        const uint64_t* mk = d.mask + (size_t)slot * MASK_STRIDE;
-        const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
-        const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
         unsigned long long e0 = base_sh;
         for (int k = 0; k < wib; k++) e0 += (unsigned long long)want_sh[k];
         int count = 0;
         if (e0 + (unsigned long long)n_legal > d.edge_cap) {
             if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
         } else {
-            for (int chunk = 0; chunk < N_ACTIONS / 32; chunk++) {
-                const uint32_t bits = (uint32_t)(mk[chunk >> 1] >> ((chunk & 1) * 32));
-                if (bits == 0) continue;
-                const int e = chunk * 32 + lane;
-                float pr = 0.0f;
-                bool has = (bits >> lane) & 1u;
-                if (has) { pr = f_div(pol[e], total); has = pr != 0.0f; }     // zero-prior children are dropped (mcts.py:87-89)
-                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
-                if (has) {
-                    const unsigned long long at = e0 + count + __popc(ballot & ((1u << lane) - 1));
-                    d.e_n[at] = 0;
-                    d.e_w[at] = 0.0;
-                    d.e_p[at] = learning ? noisy_prior(pr) : pr;
-                    d.e_move[at] = (uint16_t)e;
-                    d.e_child[at] = NO_CHILD;
-                }
-                count += __popc(ballot);
-            }
+            count = create_children(d, slot, e0, learning, lane);
         }
         if (lane == 0) {
             d.node_edge0[r + node] = (int32_t)e0;
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
         v = d.value[slot];
         if (node == 0 && lane == 0) d.root_val[g] = v;
     } else {
-        v = d.leaf_value[g];
+        v = d.leaf_value[slot];
     }
     if (lane == 0) {
         // backup (mctsnode.py:56-63): value_sum accumulates python doubles
@@ -445,11 +458,196 @@ __global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
         }
         unsigned long long* gs = d.gstats + (size_t)g * 8;
         gs[6] += levels;
-        if (d.need_eval[g]) gs[7] += (unsigned long long)d.node_nchild[r + node];
+        if (d.need_eval[slot]) gs[7] += (unsigned long long)d.node_nchild[r + node];
         d.root_w[g] += val;
         d.root_n[g] += 1;
         gs[0] += 1ull;
-        gs[d.need_eval[g] ? 1 : 2] += 1ull;
+        gs[d.need_eval[slot] ? 1 : 2] += 1ull;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-leaf mode (szb_config.leaves_per_tree = K > 1): K simulations of a tree in flight per step, kept apart by virtual loss.
+// A DIFFERENT ALGORITHM from the reference's one-simulation-at-a-time search (different visit counts): opt-in, for the
+// latency-bound regime of few games (interactive play, arena, the tail of a self-play iteration), never used by the parity tests
+// or the benchmark.  Deterministic: one warp walks a tree's K paths one after the other, one thread backs them up in order.
+// ------------------------------------------------------------------------------------------------
+// warp per tree.  Every edge of an in-flight path carries a virtual visit that counts as a loss for the side choosing it
+// (N + 1, W + 1: the child's value sum is from the child's mover's view), so later paths of the step look elsewhere.  A path that
+// runs into a node still being created by an earlier path of the step is dropped (its virtual loss taken back).
+__global__ void __launch_bounds__(128) k_select_vl(Dev d, float c_puct, int num_searches) {
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= d.g_end) return;
+    const int g = d.order[slot];
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int budget = num_searches - d.sims_done[g];
+    const int nc = d.node_count[g];
+    int new_nodes = 0, inflight = 0, max_depth = 0;
+    bool root_pending = false;
+    unsigned long long scanned = 0, levels = 0;
+    for (int j = 0; j < d.K; j++) {
+        const int ps = slot * d.K + j;
+        if (inflight >= budget) {
+            if (lane == 0) d.sel_edge[ps] = PATH_DROPPED;
+            continue;
+        }
+        int node = 0, depth = 0;
+        int np = d.root_n[g] + inflight;
+        bool dropped = false;
+        for (;;) {
+            const int n = d.node_nchild[r + node];
+            const int e0 = d.node_edge0[r + node];
+            if (n == 0) {
+                // a node without children that already exists: a terminal node, or the root before its first expansion
+                if (!d.node_term[r + node]) {
+                    if (root_pending) { dropped = true; break; }
+                    root_pending = true;
+                }
+                if (lane == 0) { d.sel_node[ps] = node; d.sel_edge[ps] = -1; }
+                break;
+            }
+            const float sq = sqrt_parent(np);
+            float best = -INFINITY;
+            int besti = 0x7FFFFFFF, best_n = 0;
+            uint16_t best_child = NO_CHILD;
+            for (int i = lane; i < n; i += 32) {
+                const int cn = d.e_n[e0 + i];
+                const uint16_t cc = d.e_child[e0 + i];
+                const float sc = puct_score(cn, d.e_w[e0 + i], d.e_p[e0 + i], sq, c_puct);
+                if (sc > best || besti == 0x7FFFFFFF) { best = sc; besti = i; best_n = cn; best_child = cc; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_down_sync(0xFFFFFFFFu, best, off);
+                const int oi = __shfl_down_sync(0xFFFFFFFFu, besti, off);
+                if (oi != 0x7FFFFFFF && (besti == 0x7FFFFFFF || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+            }
+            besti = __shfl_sync(0xFFFFFFFFu, besti, 0);
+            np = __shfl_sync(0xFFFFFFFFu, best_n, besti & 31);
+            const uint16_t c = (uint16_t)__shfl_sync(0xFFFFFFFFu, (int)best_child, besti & 31);
+            const int e = e0 + besti;
+            depth++;
+            scanned += (unsigned long long)n;
+            if (c == CHILD_PENDING) { dropped = true; break; }
+            if (lane == 0) {
+                d.e_n[e] += 1;                                   // virtual visit ...
+                d.e_w[e] += 1.0;                                 // ... lost by the side that chose this edge
+                if (c == NO_CHILD) {
+                    d.e_child[e] = CHILD_PENDING;
+                    d.sel_node[ps] = node;
+                    d.sel_edge[ps] = e;
+                    d.sel_new[ps] = nc + 1 + new_nodes;
+                }
+            }
+            __syncwarp();
+            if (c == NO_CHILD) { new_nodes++; break; }
+            node = c;
+        }
+        if (dropped) {
+            if (lane == 0) {
+                d.sel_edge[ps] = PATH_DROPPED;
+                for (int nd = node;;) {                          // take the virtual loss of this path back
+                    const int pe = d.node_pedge[r + nd];
+                    if (pe < 0) break;
+                    d.e_n[pe] -= 1;
+                    d.e_w[pe] -= 1.0;
+                    nd = d.node_pnode[r + nd];
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        inflight++;
+        levels += (unsigned long long)depth;
+        max_depth = depth > max_depth ? depth : max_depth;
+    }
+    if (lane == 0) {
+        d.node_count[g] = nc + new_nodes;
+        unsigned long long* gs = d.gstats + (size_t)g * 8;
+        if ((unsigned long long)max_depth > gs[3]) gs[3] = (unsigned long long)max_depth;
+        gs[4] += scanned;
+        gs[5] += levels;
+    }
+}
+
+// block per tree, warp j = path j: expansions in parallel, then one thread backs the paths up in order (the virtual loss of an edge
+// becomes the real result: N keeps its + 1, W gets value - 1)
+__global__ void __launch_bounds__(32 * MAX_LEAVES) k_finish_vl(Dev d, int learning) {
+    __shared__ int want_sh[MAX_LEAVES];
+    __shared__ unsigned long long base_sh;
+    const int slot = d.g_begin + blockIdx.x;
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int g = d.order[slot];
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int ps = slot * d.K + j;
+    const bool live = j < d.K && d.sel_edge[ps] != PATH_DROPPED;
+    const bool eval = live && d.need_eval[ps];
+    const int n_legal = eval ? count_legal(d, ps, lane) : 0;
+    if (lane == 0) want_sh[j] = n_legal;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < MAX_LEAVES; k++) tot += want_sh[k];
+        base_sh = tot ? atomicAdd(d.edge_top, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (eval) {
+        const int node = d.sel_node[ps];
+        unsigned long long e0 = base_sh;
+        for (int k = 0; k < j; k++) e0 += (unsigned long long)want_sh[k];
+        int count = 0;
+        if (e0 + (unsigned long long)n_legal > d.edge_cap) {
+            if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
+        } else {
+            count = create_children(d, ps, e0, learning, lane);
+        }
+        if (lane == 0) {
+            d.node_edge0[r + node] = (int32_t)e0;
+            d.node_nchild[r + node] = (uint16_t)count;
+            if (node == 0) d.root_val[g] = d.value[ps];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned long long* gs = d.gstats + (size_t)g * 8;
+    int done = 0;
+    for (int k = 0; k < d.K; k++) {
+        const int pk = slot * d.K + k;
+        if (d.sel_edge[pk] == PATH_DROPPED) continue;
+        const bool ev = d.need_eval[pk];
+        const int node = d.sel_node[pk];
+        double val = (double)(ev ? d.value[pk] : d.leaf_value[pk]);
+        unsigned long long levels = 0;
+        for (int nd = node;;) {
+            const int pe = d.node_pedge[r + nd];
+            if (pe < 0) break;
+            d.e_w[pe] += val - 1.0;
+            val = -val;
+            nd = d.node_pnode[r + nd];
+            levels++;
+        }
+        d.root_w[g] += val;
+        gs[6] += levels;
+        if (ev) gs[7] += (unsigned long long)d.node_nchild[r + node];
+        gs[ev ? 1 : 2] += 1ull;
+        done++;
+    }
+    d.root_n[g] += done;
+    d.sims_done[g] += done;
+    gs[0] += (unsigned long long)done;
+}
+
+// fewest simulations completed over the slots of this search.  One block.
+__global__ void __launch_bounds__(256) k_min_done(Dev d, int n_slots, int32_t* out) {
+    __shared__ int part[256];
+    int m = 0x7FFFFFFF;
+    for (int i = threadIdx.x; i < n_slots; i += 256) m = min(m, d.sims_done[d.order[i]]);
+    part[threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 256; i++) m = min(m, part[i]);
+        *out = m;
     }
 }
 
@@ -742,10 +940,13 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     }
     SZB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     ctx->cohorts = cfg->cohorts;
+    if (cfg->leaves_per_tree < 0 || cfg->leaves_per_tree > MAX_LEAVES)
+        return fail(ctx, SZB_ERR_ARG, "szb_config.leaves_per_tree must be 0 / 1 (the reference's algorithm) or 2..%d", MAX_LEAVES);
     if (ctx->cohorts < 0 || ctx->cohorts > 2) return fail(ctx, SZB_ERR_ARG, "szb_config.cohorts must be 0 (automatic), 1 or 2");
     if (const char* e = getenv("SZB_COHORTS")) { if (e[0] == '1' || e[0] == '2') ctx->cohorts = e[0] - '0'; }   // measurement aid
     Dev& d = ctx->d;
     const size_t G = (size_t)cfg->max_games;
+    d.K = cfg->leaves_per_tree > 1 ? cfg->leaves_per_tree : 1;
     d.nodes_per_game = cfg->max_searches + 1;
     d.pool_stride = RING + d.nodes_per_game + 1;
     d.n_games = 0;
@@ -764,10 +965,11 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     A(node_count, G); A(root_n, G); A(root_w, G);
     A(e_n, d.edge_cap); A(e_w, d.edge_cap); A(e_p, d.edge_cap); A(e_move, d.edge_cap); A(e_child, d.edge_cap);
     A(edge_top, 1); A(error_flag, 1);
-    A(sel_node, G); A(sel_edge, G); A(need_eval, G); A(leaf_value, G);
-    A(order, G); A(n_active, 1);
-    A(planes, G * PLANE_STRIDE); A(mask, G * MASK_STRIDE);
-    A(policy, G * N_ACTIONS); A(value, G); A(root_val, G);
+    const size_t P = G * (size_t)d.K;                       // path slots
+    A(sel_node, P); A(sel_edge, P); A(sel_new, P); A(need_eval, P); A(leaf_value, P);
+    A(order, G); A(n_active, 1); A(sims_done, G);
+    A(planes, P * PLANE_STRIDE); A(mask, P * MASK_STRIDE);
+    A(policy, P * N_ACTIONS); A(value, P); A(root_val, G);
     A(stats, 8); A(gstats, G * 8);
 #undef A
     if ((rc = dev_alloc(ctx, &ctx->d_moves, G + 1))) return rc;
@@ -938,8 +1140,12 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     const bool prof = ctx->profiling;
     const char* trace_path = getenv("SZB_TRACE");            // debugging aid: per-cohort phase timestamps of this search as CSV
     const bool trace = prof && trace_path && trace_path[0];
+    // steps of this search: one simulation per tree and step in the reference's algorithm; in multi-leaf mode up to K per step
+    // (a few steps more than num_searches / K are planned because paths can be dropped; stragglers are caught up below)
+    const int K = d.K;
+    const int n_steps = K == 1 ? num_searches : (num_searches + K - 1) / K + 2;
     if (prof) {
-        while ((int)ctx->prof_events.size() < 5 * num_searches * (trace ? 2 : 1)) {
+        while ((int)ctx->prof_events.size() < 5 * n_steps * (trace ? 2 : 1)) {
             cudaEvent_t e;
             SZB_CUDA(ctx, cudaEventCreate(&e));
             ctx->prof_events.push_back(e);
@@ -952,7 +1158,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     // (the tower is power-capped either way, so only the ~0.2 ms of small kernels can be hidden).  Profiling keeps one
     // cohort on the context's stream so that per-phase and per-kernel durations mean what they say.
     const int NS = n_slots;
-    int n_cohorts = ctx->cohorts ? ctx->cohorts : (NS >= 1024 ? 2 : 1);
+    int n_cohorts = ctx->cohorts ? ctx->cohorts : (NS * K >= 1024 ? 2 : 1);
     if ((prof && !trace) || NS < 8) n_cohorts = 1;
     int bounds[3] = {0, NS, NS};
     if (n_cohorts == 2) bounds[1] = ((NS / 2 + 3) / 4) * 4;       // network tiles are 4 boards wide
@@ -960,34 +1166,41 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         SZB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         for (int c = 0; c < 2; c++) SZB_CUDA(ctx, cudaStreamWaitEvent(ctx->cohort_stream[c], ctx->ev_fork, 0));
     }
+    // one simulation step of the slots [dc.g_begin, dc.g_end) on stream cs; ev: five events around its four phases, or null
+    auto launch_step = [&](const Dev& dc, cudaStream_t cs, cudaEvent_t* ev) -> int {
+        const int n = dc.g_end - dc.g_begin, paths = n * K;
+        const int warp_blocks = (n * 32 + 127) / 128;
+        ctx->work = cs;
+        if (ev) cudaEventRecord(ev[0], cs);
+        if (K == 1) k_select<<<warp_blocks, 128, 0, cs>>>(dc, c_puct);
+        else k_select_vl<<<warp_blocks, 128, 0, cs>>>(dc, c_puct, num_searches);
+        if (ev) cudaEventRecord(ev[1], cs);
+        if (paths <= 8192) k_expand<32><<<(paths + 3) / 4, 128, 0, cs>>>(dc);
+        else k_expand<1><<<(paths + 127) / 128, 128, 0, cs>>>(dc);
+        if (ev) cudaEventRecord(ev[2], cs);
+        ctx->launches += 2;
+        int rc_eval = 0;
+        if (evaluator == SZB_EVAL_HASH) {
+            k_hash_eval<<<paths, 128, 0, cs>>>(dc);
+            ctx->launches++;
+        } else {
+            rc_eval = net_evaluate_batch(ctx, evaluator, dc.g_begin * K, paths);
+        }
+        if (ev) cudaEventRecord(ev[3], cs);
+        if (K == 1) k_finish<<<warp_blocks, 128, 0, cs>>>(dc, learning);
+        else k_finish_vl<<<n, 32 * MAX_LEAVES, 0, cs>>>(dc, learning);
+        if (ev) cudaEventRecord(ev[4], cs);
+        ctx->launches++;
+        return rc_eval;
+    };
     int rc = 0;
-    for (int s = 0; s < num_searches && !rc && NS > 0; s++) {
+    for (int s = 0; s < n_steps && !rc && NS > 0; s++) {
         for (int c = 0; c < n_cohorts && !rc; c++) {
             Dev dc = d;
             dc.g_begin = bounds[c];
             dc.g_end = bounds[c + 1];
-            const int n = dc.g_end - dc.g_begin;
-            cudaStream_t cs = n_cohorts == 2 ? ctx->cohort_stream[c] : st;
-            ctx->work = cs;
-            const int warp_blocks = (n * 32 + 127) / 128;
             cudaEvent_t* ev = prof ? &ctx->prof_events[5 * ((size_t)s * (trace ? 2 : 1) + (trace ? c : 0))] : nullptr;
-            if (prof) cudaEventRecord(ev[0], cs);
-            k_select<<<warp_blocks, 128, 0, cs>>>(dc, c_puct);
-            if (prof) cudaEventRecord(ev[1], cs);
-            if (n <= 8192) k_expand<32><<<(n + 3) / 4, 128, 0, cs>>>(dc);
-            else k_expand<1><<<(n + 127) / 128, 128, 0, cs>>>(dc);
-            if (prof) cudaEventRecord(ev[2], cs);
-            ctx->launches += 2;
-            if (evaluator == SZB_EVAL_HASH) {
-                k_hash_eval<<<n, 128, 0, cs>>>(dc);
-                ctx->launches++;
-            } else {
-                rc = net_evaluate_batch(ctx, evaluator, dc.g_begin, n);
-            }
-            if (prof) cudaEventRecord(ev[3], cs);
-            k_finish<<<warp_blocks, 128, 0, cs>>>(dc, learning);
-            if (prof) cudaEventRecord(ev[4], cs);
-            ctx->launches++;
+            rc = launch_step(dc, n_cohorts == 2 ? ctx->cohort_stream[c] : st, ev);
         }
     }
     ctx->work = st;
@@ -999,6 +1212,25 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     }
     if (rc) { cudaStreamSynchronize(st); return rc; }
     SZB_CUDA(ctx, cudaGetLastError());
+    if (K > 1 && NS > 0) {
+        // multi-leaf mode: trees that dropped paths are still short of num_searches simulations -- step everything (finished trees
+        // select nothing) until the slowest tree is done
+        Dev dc = d;
+        dc.g_begin = 0;
+        dc.g_end = NS;
+        for (int guard = 0; guard <= 2 * num_searches; guard++) {
+            int32_t least = 0;
+            k_min_done<<<1, 256, 0, st>>>(d, NS, d.n_active);
+            ctx->launches++;
+            SZB_CUDA(ctx, cudaMemcpyAsync(&least, d.n_active, sizeof least, cudaMemcpyDeviceToHost, st));
+            SZB_CUDA(ctx, cudaStreamSynchronize(st));
+            if (least >= num_searches) break;
+            const int more = (num_searches - least + K - 1) / K;
+            for (int k = 0; k < more && !rc; k++) rc = launch_step(dc, st, nullptr);
+            if (rc) { cudaStreamSynchronize(st); return rc; }
+        }
+        ctx->work = st;
+    }
     int32_t flag = 0;
     unsigned long long top = 0;
     SZB_CUDA(ctx, cudaMemcpyAsync(&flag, d.error_flag, sizeof flag, cudaMemcpyDeviceToHost, st));
@@ -1009,7 +1241,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     if (trace && NS > 0) {
         if (FILE* f = fopen(trace_path, "w")) {
             fprintf(f, "step,cohort,select_start_ms,expand_start_ms,eval_start_ms,finish_start_ms,finish_end_ms\n");
-            for (int s = 0; s < num_searches; s++)
+            for (int s = 0; s < n_steps; s++)
                 for (int c = 0; c < n_cohorts; c++) {
                     cudaEvent_t* ev = &ctx->prof_events[5 * ((size_t)s * 2 + c)];
                     fprintf(f, "%d,%d", s, c);
@@ -1025,7 +1257,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         return 0;
     }
     if (prof && NS > 0) {
-        for (int s = 0; s < num_searches; s++) {
+        for (int s = 0; s < n_steps; s++) {
             cudaEvent_t* ev = &ctx->prof_events[5 * (size_t)s];
             for (int k = 0; k < 4; k++) {
                 float ms = 0;
@@ -1033,7 +1265,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
                 ctx->phase_ms[k] += ms;
             }
         }
-        ctx->phase_steps += num_searches;
+        ctx->phase_steps += n_steps;
         net_collect_conv_times(ctx);
     }
     if (evaluator == SZB_EVAL_NET_BF16) return net_check_error(ctx);

@@ -14,6 +14,9 @@ constexpr int RING = 256;                  // real-game positions kept per game 
 constexpr int PLANE_STRIDE = 120;          // uint64 per packed plane row (119 + 1 pad, 16-byte aligned rows)
 constexpr int MASK_STRIDE = 80;            // uint64 per legal-mask row (73 + pad)
 constexpr uint16_t NO_CHILD = 0xFFFF;
+constexpr uint16_t CHILD_PENDING = 0xFFFE;  // multi-leaf mode: the edge's node is being created by an earlier path of this step
+constexpr int PATH_DROPPED = -2;           // multi-leaf mode, sel_edge: this path slot carries no simulation in this step
+constexpr int MAX_LEAVES = 8;              // szb_config.leaves_per_tree <= 8 (one warp per path in k_finish_vl)
 
 struct Net;                                // net.cu
 
@@ -25,6 +28,7 @@ struct Dev {
     const Tables* tables;
     int pool_stride;
     int n_games;
+    int K;                   // leaves (in-flight simulations) per tree and step: 1 = the reference's algorithm
     int g_begin, g_end;      // SLOT range the step kernels of this launch work on (a cohort of the search batch)
     int32_t* order;          // [max_games] slot -> game: the games whose root is not terminal, ascending (k_active_list).  Finished
                              // games take no slot: no step kernel, no network row (the reference never searches a finished game,
@@ -51,14 +55,17 @@ struct Dev {
     unsigned long long* edge_top;
     int32_t* error_flag;
     // ---- per simulation step ------------------------------------------------------------------
+    // (indexed by PATH slot = slot * K + j; the network reads contiguous rows of planes / writes contiguous rows of policy)
     int32_t* sel_node;       // leaf (or, before expansion, its parent)
-    int32_t* sel_edge;       // edge to create a node for, -1 when the leaf already exists
+    int32_t* sel_edge;       // edge to create a node for, -1 when the leaf already exists, PATH_DROPPED
+    int32_t* sel_new;        // multi-leaf mode: node index the expansion must use
     uint8_t* need_eval;
     float* leaf_value;
-    uint64_t* planes;        // [slot][PLANE_STRIDE]   (these four are indexed by SLOT: the network reads contiguous rows)
-    uint64_t* mask;          // [slot][MASK_STRIDE]
-    float* policy;           // [slot][4672] evaluator output ("softmax over everything")
-    float* value;            // [slot]
+    int32_t* sims_done;      // [max_games] multi-leaf mode: simulations completed in this search
+    uint64_t* planes;        // [path slot][PLANE_STRIDE]
+    uint64_t* mask;          // [path slot][MASK_STRIDE]
+    float* policy;           // [path slot][4672] evaluator output ("softmax over everything")
+    float* value;            // [path slot]
     float* root_val;         // [max_games] evaluator value of the root position
     unsigned long long* stats;   // totals: 0 simulations, 1 evaluations, 2 terminal visits, 3 max depth,
                                  // 4 select edges, 5 select levels, 6 backup levels, 7 edges written

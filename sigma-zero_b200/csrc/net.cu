@@ -1514,7 +1514,7 @@ int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, cons
     cudaDeviceProp prop;
     SZB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
     net->num_sms = prop.multiProcessorCount;
-    net->cap = (ctx->cfg.max_games + 1) & ~1;
+    net->cap = (ctx->cfg.max_games * ctx->d.K + 1) & ~1;          // one activation row per path slot
 
     const float* w;
     BN bn;

@@ -15,10 +15,13 @@ def _ptr(a):
 
 
 class Engine:
-    def __init__(self, max_games=1024, max_searches=800, device=0, edges_per_node=0, cohorts=0):
+    def __init__(self, max_games=1024, max_searches=800, device=0, edges_per_node=0, cohorts=0, leaves_per_tree=1):
+        """leaves_per_tree: 1 = the reference's search (one simulation of a tree at a time; what every parity test runs);
+        2..8 = that many simulations of a tree in flight per step with virtual loss -- a different, opt-in search"""
         self.lib = _lib.load()
         self.max_games, self.max_searches = int(max_games), int(max_searches)
-        cfg = _lib.Config(self.max_games, self.max_searches, int(edges_per_node), int(cohorts))
+        self.leaves_per_tree = int(leaves_per_tree)
+        cfg = _lib.Config(self.max_games, self.max_searches, int(edges_per_node), int(cohorts), self.leaves_per_tree)
         h = ctypes.c_void_p()
         rc = self.lib.szb_create(int(device), ctypes.byref(cfg), ctypes.byref(h))
         self._h = h

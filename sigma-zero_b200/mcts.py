@@ -21,7 +21,7 @@ class MCTS0:
     def search(self, state, verbose=True, learning=False):
         args = self.args
         n = int(args['num_searches'])
-        eng = runtime.get_engine(min_games=1, min_searches=n)
+        eng = runtime.get_engine(min_games=1, min_searches=n, leaves_per_tree=runtime.leaves_of(args))
         runtime.sync_weights(eng, self.model)
         eng = self.game._engine()                    # replays the game into slot 0 if another game was there
         white = bool(state.turn)

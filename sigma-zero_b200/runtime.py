@@ -16,18 +16,25 @@ def device_ordinal():
     return int(os.environ.get("LOCAL_RANK", os.environ.get("SZB_DEVICE", "0")))
 
 
-def get_engine(min_games=1, min_searches=800):
-    """An Engine with at least the requested capacity (re-created, and weights re-sent, when it must grow)."""
+def get_engine(min_games=1, min_searches=800, leaves_per_tree=None):
+    """An Engine with at least the requested capacity (re-created, and weights re-sent, when it must grow or when the
+    search mode changes).  leaves_per_tree: None = keep the current engine's mode (1 for a new one)."""
     global _engine, _weights_key
-    if _engine is None or _engine.max_games < min_games or _engine.max_searches < min_searches:
+    want_k = (_engine.leaves_per_tree if _engine else 1) if leaves_per_tree is None else int(leaves_per_tree)
+    if _engine is None or _engine.max_games < min_games or _engine.max_searches < min_searches or _engine.leaves_per_tree != want_k:
         games = max(min_games, _engine.max_games if _engine else 1)
         searches = max(min_searches, _engine.max_searches if _engine else 1)
         if _engine is not None:
             _engine.close()
-        _engine = Engine(max_games=games, max_searches=searches, device=device_ordinal())
+        _engine = Engine(max_games=games, max_searches=searches, device=device_ordinal(), leaves_per_tree=want_k)
         _engine.owner = None
         _weights_key = None
     return _engine
+
+
+def leaves_of(args):
+    """args['leaves_per_tree'] (an extension of the reference's args dict; default 1 = the reference's search)"""
+    return int((args or {}).get('leaves_per_tree', 1))
 
 
 def evaluator_of(model):

@@ -23,7 +23,7 @@ def selfplay_batch(model, args, num_games, c960=False, seed=None, start_ids=None
     959), chess_tensor.py:69) and the moves sampled from the visit counts (sim.py:68) -- is a function of (seed, global game
     id = game_id_base + index) only, so a job sharded over ranks plays exactly the games a single process would."""
     n_search = int(args['num_searches'])
-    eng = runtime.get_engine(min_games=num_games, min_searches=n_search)
+    eng = runtime.get_engine(min_games=num_games, min_searches=n_search, leaves_per_tree=runtime.leaves_of(args))
     runtime.sync_weights(eng, model)
     eng.owner = None
     if seed is None:
@@ -81,7 +81,7 @@ def selfplay_records(model, args, num_games, c960=False, seed=None, start_ids=No
     by game, then ply -- exactly records.pack_records(selfplay_batch(...)[0]).  records["result"] holds one outcome code
     per game: 1 white won, -1 black won, 0 draw, 2 unfinished (max_plies)."""
     n_search = int(args['num_searches'])
-    eng = runtime.get_engine(min_games=num_games, min_searches=n_search)
+    eng = runtime.get_engine(min_games=num_games, min_searches=n_search, leaves_per_tree=runtime.leaves_of(args))
     runtime.sync_weights(eng, model)
     eng.owner = None
     if seed is None:

@@ -20,7 +20,7 @@ def test_struct_layouts():
     import ctypes
     from sigma_zero_b200 import _lib
     assert ctypes.sizeof(_lib.Pos) == 112
-    assert ctypes.sizeof(_lib.Config) == 16
+    assert ctypes.sizeof(_lib.Config) == 20
     assert ctypes.sizeof(_lib.Stats) == 48
 
 

@@ -212,3 +212,63 @@ def test_full_size_c2_properties():
         assert s1["evaluations"] - s0["evaluations"] + s1["terminal_visits"] - s0["terminal_visits"] == G * S
         e.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_multi_leaf_virtual_loss_mode():
+    """opt-in szb_config.leaves_per_tree = K > 1 (K simulations of a tree in flight per step, virtual loss): NOT the reference's
+    algorithm, so no visit-count parity -- what must hold: exactly num_searches simulations per game (child visits sum to
+    num_searches - 1, root visit count 1 + num_searches), the same root children as the exact search, bit-identical repeats,
+    a consistent tree (every expanded node's edge count = 1 + its children's, no pending marker or virtual loss left behind),
+    terminal nodes and finished games handled, counters that add up"""
+    from sigma_zero_b200 import _lib
+    from sigma_zero_b200.engine import EVAL_HASH, Engine
+    import chess
+    S = 200
+    boards = [chess.Board(), chess.Board("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"),
+              chess.Board("6k1/5ppp/8/8/8/8/5PPP/3R2K1 w - - 0 1"),             # mate in one: terminal nodes inside the tree
+              chess.Board("7k/6Q1/6K1/8/8/8/8/8 b - - 0 1"),                    # finished game
+              chess.Board("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1")]
+    pos = [util.wire_pos(b, _lib) for b in boards]
+    ref = Engine(max_games=8, max_searches=S)
+    ref.set_positions(pos)
+    v1, c1, _ = ref.search(S, 2.0, True, EVAL_HASH)
+    ref.close()
+    live = [0, 1, 2, 4]
+    for K in (2, 5, 8):
+        e = Engine(max_games=8, max_searches=S, leaves_per_tree=K)
+        e.set_positions(pos)
+        s0 = e.stats()
+        v, c, _ = e.search(S, 2.0, True, EVAL_HASH)
+        s1 = e.stats()
+        assert (v[live].sum(axis=1) == S - 1).all(), (K, v.sum(axis=1))
+        assert v[3].sum() == 0 and np.array_equal(c, c1)
+        assert s1["simulations"] - s0["simulations"] == len(boards) * S
+        assert (s1["evaluations"] - s0["evaluations"]) + (s1["terminal_visits"] - s0["terminal_visits"]) == len(boards) * S
+        for g in live:
+            t = e.tree_export(g)
+            assert t["root_visits"] == 1 + S
+            n_nodes = len(t["node_first"])
+            kids = t["edge_child"]
+            assert ((kids == -1) | ((kids > 0) & (kids < n_nodes))).all()          # no pending marker left
+            assert sorted(kids[kids > 0].tolist()) == list(range(1, n_nodes))      # every node hangs on exactly one edge
+            assert (t["edge_visits"] >= 0).all()
+            for i in range(1, n_nodes):
+                lo, cnt = t["node_first"][i], t["node_count"][i]
+                n_edge = t["edge_visits"][t["node_parent_edge"][i]]
+                if cnt:
+                    assert n_edge == 1 + t["edge_visits"][lo:lo + cnt].sum(), (K, g, i)
+                else:
+                    assert t["node_terminal"][i] and n_edge >= 1
+            unvisited = kids == -1
+            assert (t["edge_visits"][unvisited] == 0).all() and (t["edge_value_sum"][unvisited] == 0).all()
+        v2, c2, _ = e.search(S, 2.0, True, EVAL_HASH)
+        assert np.array_equal(v, v2) and np.array_equal(c, c2)
+        tv = 0.5 * np.abs(v[live].astype(np.float64) - v1[live]).sum(axis=1) / (S - 1)
+        print("leaves_per_tree=%d: total-variation distance to the exact search %s" % (K, np.round(tv, 3)))
+        assert tv.max() < 0.6
+        moves, active = e.selfplay_ply(S, 2.0, True, EVAL_HASH, seed=3, sample=True)
+        assert active >= 3 and moves[3] == -1 and (moves[live] >= 0).all()
+        e.close()
+    # the mate in one is found: Rd8# (d1d8) collects the most visits in every mode
+    best = int(np.argmax(v[2]))
+    assert best == int(np.argmax(v1[2]))
