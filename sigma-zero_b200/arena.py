@@ -16,7 +16,7 @@ def _evaluator(model):
     return EVAL_NET_FP32 if getattr(model, "precision", "bf16") == "fp32" else EVAL_NET_BF16
 
 
-def play_match(model_a, model_b, num_games, args, c960=False, seed=0, max_plies=None, device=0):
+def play_match(model_a, model_b, num_games, args, c960=False, seed=0, max_plies=None, device=0, leaves_per_tree=None):
     """Plays num_games games between model_a and model_b (arg-max of the visit counts, learning=False).
 
     Returns {"score_a": points of model_a (win 1, draw 0.5), "results": per-game "1-0" / "0-1" / "1/2-1/2" / "*",
@@ -28,7 +28,8 @@ def play_match(model_a, model_b, num_games, args, c960=False, seed=0, max_plies=
                  if c960 else [-1] * num_games)                       # both colours of a pair start from the same position
     engines = []
     for model in (model_a, model_b):
-        e = Engine(max_games=num_games, max_searches=n_search, device=device, cohorts=1)
+        e = Engine(max_games=num_games, max_searches=n_search, device=device, cohorts=1,
+                   leaves_per_tree=int(args.get("leaves_per_tree", 1)) if leaves_per_tree is None else int(leaves_per_tree))
         e.load_state_dict(model.state_dict())
         e.reset(start_ids)
         engines.append(e)
