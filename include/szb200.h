@@ -192,11 +192,11 @@ typedef struct szb_phase_times {
     uint64_t backup_levels;    /* edges updated by backup (24 B read-modify-write each) */
     uint64_t edges_written;    /* children created by expansion (20 B each) */
     float conv_ms;             /* total device time of the timed network launches, CUDA events on the context's stream */
-    int32_t conv_launches;     /* how many launches conv_ms covers (one per bf16 forward) */
-    int32_t conv_boards;       /* boards per timed launch (the GEMM's M / 64) */
+    int32_t conv_launches;     /* how many launches conv_ms covers (a bf16 forward of more than 512 boards is several launches) */
+    int32_t conv_boards;       /* boards per timed launch, averaged (the GEMM's M / 64) */
     int32_t conv_kind;         /* what is timed: 2 = k_tower_tc2, the whole tower (stem + 38 convolutions + policy 1x1) in one
                                   launch; 1 = k_tower_tc2 on one 3x3 256->256 layer; 0 = k_conv_tc<256,0> on one such layer */
-    uint64_t conv_flop;        /* algorithmic FLOP (2 x MAC, no padding credit) of one timed launch */
+    uint64_t conv_flop;        /* algorithmic FLOP (2 x MAC, no padding credit) per timed launch, averaged */
 } szb_phase_times;
 int szb_set_profiling(szb_ctx *ctx, int32_t on);
 int szb_get_phase_times(szb_ctx *ctx, szb_phase_times *out);

@@ -1,10 +1,12 @@
 // engine.cu -- games, flat SoA search tree, batched MCTS step kernels, perft, and the C ABI around them.
 //
-// One simulation step of mcts.py:49-109 for ALL games at once is four launches:
+// One simulation step of mcts.py:49-109 for ALL running games at once is four launches (finished games take no slot:
+// k_search_begin closes terminal roots, k_active_list numbers the rest):
 //   k_select  : warp per tree, PUCT descent with shuffle arg-max           (mctsnode.py:23-37, mcts.py:54-55)
 //   k_expand  : one thread per tree (own warp at search sizes), make-move + legality + terminal + planes (mcts.py:57-70, chess_tensor.py:88-172)
 //   evaluator : hash kernel or the network (net.cu)                         (mcts.py:72-75)
 //   k_finish  : warp per tree, mask/normalise/noise, child allocation, backup (mcts.py:77-109, mctsnode.py:39-63)
+// Opt-in multi-leaf mode (szb_config.leaves_per_tree > 1, not the reference's algorithm): k_select_vl / k_finish_vl.
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
