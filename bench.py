@@ -377,6 +377,7 @@ def run_ours(args, wl):
         roof = {"bound": "tensor", "kernel": kernel,
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "frac_of_burst": achieved / pk["bf16_burst"], "peak_kind": "sustained, " + pk["source"],
+                "frac_timed_region_lower_bound": FLOP_PER_EVAL * evals / (ms * 1e-3) / 1e12 / world / pk["bf16_sustained"],
                 "traffic": traffic_per_launch(pt["conv_kind"], pt["conv_boards"]), "ms_per_launch": conv_ms,
                 "launches_timed": pt["conv_launches"], "flop_per_launch": pt["conv_flop"], "boards_per_launch": pt["conv_boards"]}
     steps_total = max(1, pt["steps"])
@@ -416,7 +417,11 @@ def run_ours(args, wl):
                        "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
                              % (G * 100 * 256 * 2 // 2 ** 20)},
             "moves_per_sec": total_moves / (ms * 1e-3), "evals_per_sec": evals / (ms * 1e-3),
-            "network_tflops_in_step": net_tflops, "phase_ms_per_simulation_step": phases,
+            "network_tflops_in_step": net_tflops,
+            # lower bound of the tower's rate inside the timed region itself (two cohorts pipelined): every network evaluation of the
+            # timed steps at its algorithmic FLOP over the whole elapsed time, as if nothing but the tower ran
+            "network_tflops_timed_region": FLOP_PER_EVAL * evals / (ms * 1e-3) / 1e12,
+            "phase_ms_per_simulation_step": phases,
             "phase_note": "phases and roofline come from one extra profiled step (single cohort, CUDA events on the library stream) run right after the timed region",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pos_bytes,
                     "d2h_bytes_per_step": G * 4672 * 4 + G * 73 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
