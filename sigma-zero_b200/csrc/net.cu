@@ -85,6 +85,11 @@ struct Net {
     int tower_nsplit = 0;                // 0: automatic (launch_tower), else forced 1 / 2 / 4 / 8
     int last_nsplit = 1;                 // what the last multi-layer launch used (trace aid)
     int chunk = 512;                     // boards per tower launch of a large evaluation (net_forward_chunked); 0 = unlimited
+    int tower_pairs = 74;                // CTA pairs of an exclusive launch (SZB_TOWER_PAIRS)
+    bool tower_exclusive = false;        // SZB_TOWER_EXCLUSIVE: experiment, see launch_tower
+    unsigned long long* span = nullptr;  // SZB_TOWER_SPAN: [SPAN_CAP][2] device stamps, dumped as CSV when the network is destroyed
+    std::vector<int> span_boards, span_b0;
+    std::string span_path;
     int num_sms = 148;
     std::vector<void*> allocs;
 };
@@ -445,6 +450,7 @@ constexpr int MAX_TOWER_LAYERS = 41;                      // stem + 38 tower con
 constexpr int POLICY_LAYER = MAX_TOWER_LAYERS - 1;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the pair's even CTA
 constexpr int READY_PER_ITEM = 8;                         // 4 epilogue warps x 2 CTAs
+constexpr int SPAN_CAP = 8192;                            // launches recorded by the SZB_TOWER_SPAN aid
 
 struct TowerLayer {
     uint8_t a_map;       // 0: input planes (128 ch), 1..3: activation buffer 0..2
@@ -478,6 +484,7 @@ struct TowerArgs {
     float* logits;       // [boards][4672]
     int32_t* error;
     unsigned long long* trace;   // measurement aid (SZB_TOWER_TRACE): [item][4] %globaltimer stamps of the leader CTA, or null
+    unsigned long long* span;    // measurement aid (SZB_TOWER_SPAN): {first CTA start, last CTA end} of this launch (%globaltimer), or null
     TowerLayer L[MAX_TOWER_LAYERS];
 };
 
@@ -607,6 +614,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
     volatile int* abort_flag = &abort_sh;
 
     if (threadIdx.x == 0) {
+        if (a.span) atomicMin(a.span, global_ns());
         abort_sh = 0;
         for (int s = 0; s < T2_A_CHUNKS; s++) { mbar_init(smem_u32(&bar_a_full[s]), 1); mbar_init(smem_u32(&bar_a_empty[s]), 1); }
         for (int s = 0; s < T2_B_STAGES; s++) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
@@ -922,6 +930,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
     if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+    if (threadIdx.x == 0 && a.span) atomicMax(a.span + 1, global_ns());
 }
 
 // =================================================================================================
@@ -1161,6 +1170,20 @@ static int upload_conv(szb_ctx* ctx, Net* net, ConvLayer& L, const float* w, int
 
 void net_destroy(szb_ctx* ctx) {
     if (!ctx->net) return;
+    if (ctx->net->span && !ctx->net->span_boards.empty()) {
+        Net* net = ctx->net;
+        std::vector<unsigned long long> h(2 * net->span_boards.size());
+        cudaDeviceSynchronize();
+        if (cudaMemcpy(h.data(), net->span, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (FILE* f = fopen(net->span_path.c_str(), "w")) {
+                fprintf(f, "launch,board0,boards,start_ns,end_ns\n");
+                const unsigned long long t0 = h[0];
+                for (size_t i = 0; i < net->span_boards.size(); i++)
+                    fprintf(f, "%zu,%d,%d,%lld,%lld\n", i, net->span_b0[i], net->span_boards[i], (long long)(h[2 * i] - t0), (long long)(h[2 * i + 1] - t0));
+                fclose(f);
+            }
+        }
+    }
     for (void* p : ctx->net->allocs) cudaFree(p);
     delete ctx->net->tower_maps;
     delete ctx->net->tower_args;
@@ -1262,6 +1285,19 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     }
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
+    if (const char* sp = getenv("SZB_TOWER_SPAN")) {         // measurement aid: start / end device time of every whole-tower launch
+        if (sp[0]) {
+            net->span_path = sp;
+            if ((rc = net_alloc(ctx, net, &net->span, (size_t)SPAN_CAP * 2, false))) return rc;
+            std::vector<unsigned long long> init((size_t)SPAN_CAP * 2, 0ull);
+            for (int i = 0; i < SPAN_CAP; i++) init[2 * (size_t)i] = ~0ull;
+            SZB_CUDA(ctx, cudaMemcpyAsync(net->span, init.data(), init.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    net->tower_pairs = net->num_sms / 2;
+    if (const char* e = getenv("SZB_TOWER_PAIRS")) { if (atoi(e) > 0) net->tower_pairs = std::min(atoi(e), net->num_sms / 2); }
+    if (const char* e = getenv("SZB_TOWER_EXCLUSIVE")) net->tower_exclusive = e[0] == '1';
     const char* ck = getenv("SZB_TOWER_CHUNK");              // measurement aid: boards per tower launch (0 = whole batch)
     if (ck && ck[0]) net->chunk = std::max(0, atoi(ck)) & ~3;
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
@@ -1277,8 +1313,14 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
 // layers [layer_begin, layer_end) of the tower for n boards in one persistent CTA-pair launch
 static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, int layer_end, int out_row = -1) {
     static bool attr_set = false;
+    static int smem_exclusive = T2_SMEM;
     if (!attr_set) {
-        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+        // "exclusive" launches ask for all the shared memory a block can have, so that no other block fits on an SM next to a
+        // tower CTA (every block also reserves 1 KiB of system shared memory): see Net::tower_pairs
+        cudaFuncAttributes fa;
+        SZB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_tower_tc2));
+        smem_exclusive = std::max(T2_SMEM, 232448 - (int)fa.sharedSizeBytes);
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_exclusive));
         attr_set = true;
     }
     TowerArgs a = *net->tower_args;
@@ -1295,7 +1337,8 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     // into 2 or 4 items of N / nsplit output channels so that up to all pairs work on one layer.  Same MMAs per output, same K
     // order: bit-identical results.  Measured (scripts/small_batch.py, ms per launch, split 1 / 2 / 4): 64 boards 0.75 / - / 0.33,
     // 148 boards 0.79 / 0.44 / -, 200 boards 0.72 / 0.49 / -, 296 boards 0.73 / 0.70 / -, 512 boards 0.89 / 1.24 / -.
-    const int pairs = net->num_sms / 2;
+    const bool exclusive = net->tower_exclusive && (n + 3) / 4 > net->tower_pairs;      // large launches only
+    const int pairs = exclusive ? net->tower_pairs : net->num_sms / 2;
     a.nsplit = 1;
     if (layer_end - layer_begin > 1) {
         if (net->tower_nsplit) a.nsplit = net->tower_nsplit;
@@ -1304,8 +1347,13 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
         else if (a.n_pair_tiles <= pairs) a.nsplit = 2;
     }
     net->last_nsplit = a.nsplit;
+    if (net->span && (int)net->span_boards.size() < SPAN_CAP && layer_end - layer_begin > 1) {
+        a.span = net->span + 2 * net->span_boards.size();
+        net->span_boards.push_back(n);
+        net->span_b0.push_back(b0);
+    }
     const int grid = 2 * std::min(a.n_pair_tiles * a.nsplit, pairs);
-    k_tower_tc2<<<grid, TC_THREADS, T2_SMEM, ctx->work>>>(*net->tower_maps, a);
+    k_tower_tc2<<<grid, TC_THREADS, exclusive ? smem_exclusive : T2_SMEM, ctx->work>>>(*net->tower_maps, a);
     ctx->launches++;
     return 0;
 }
