@@ -306,6 +306,7 @@ def run_ours(args, wl):
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
+    eng.tower_spans(True)              # k_tower_tc2 stamps its own start / end (%globaltimer): per-launch durations of the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     sims_done = moves_done = 0
@@ -318,6 +319,7 @@ def run_ours(args, wl):
     barrier()
     clocks = sampler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
+    spans = eng.tower_spans(False)
     st1 = eng.stats()
     # measurement pass (not part of `value`): one more step with the library's profiling on, which serialises the two
     # cohorts on the context's stream and brackets every phase and the network's tower launch with CUDA events
@@ -368,18 +370,38 @@ def run_ours(args, wl):
     # ---- roofline of the dominant kernel --------------------------------------------------------------
     pk = peaks()
     roof = None
+    kernel_name = {2: "k_tower_tc2: stem + 38 tower 3x3 convolutions + policy 1x1 in one persistent CTA-pair launch (tcgen05 cta_group::2 implicit GEMM)",
+                   1: "k_tower_tc2 on one 3x3 256->256 tower convolution (CTA-pair tcgen05 implicit GEMM)",
+                   0: "k_conv_tc<256,0> on one 3x3 256->256 tower convolution (single-CTA tcgen05 implicit GEMM)"}[pt["conv_kind"]]
+    profiled = None
     if pt["conv_launches"] > 0:
         conv_ms = pt["conv_ms"] / pt["conv_launches"]
-        achieved = pt["conv_flop"] / (conv_ms * 1e-3) / 1e12
-        kernel = {2: "k_tower_tc2: stem + 38 tower 3x3 convolutions + policy 1x1 in one persistent CTA-pair launch (tcgen05 cta_group::2 implicit GEMM)",
-                  1: "k_tower_tc2 on one 3x3 256->256 tower convolution (CTA-pair tcgen05 implicit GEMM)",
-                  0: "k_conv_tc<256,0> on one 3x3 256->256 tower convolution (single-CTA tcgen05 implicit GEMM)"}[pt["conv_kind"]]
-        roof = {"bound": "tensor", "kernel": kernel,
-                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                "frac_of_burst": achieved / pk["bf16_burst"], "peak_kind": "sustained, " + pk["source"],
+        profiled = {"ms_per_launch": conv_ms, "achieved": pt["conv_flop"] / (conv_ms * 1e-3) / 1e12, "launches": pt["conv_launches"],
+                    "boards_per_launch": pt["conv_boards"],
+                    "note": "CUDA events around every launch of one extra step run serialised (one cohort) right after the timed region; "
+                            "≈ 10 % idle time between launches lets the power-capped clock recover, so this is a little faster than the timed region"}
+    if spans and spans["launches"] > 0:
+        # the timed region itself: every tower launch of the timed steps, timed on the device by the kernel (first CTA start -> last CTA
+        # end); the two cohorts' launches overlap by a few us at their edges, so busy time can exceed wall time slightly
+        ms_launch = spans["busy_ns"] / spans["launches"] * 1e-6
+        achieved = spans["flop"] / (spans["busy_ns"] * 1e-9) / 1e12
+        boards = spans["boards"] / spans["launches"]
+        roof = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_sustained"], "frac_of_burst": achieved / pk["bf16_burst"],
+                "peak_kind": "sustained, " + pk["source"],
+                "how": "per-launch durations of the TIMED REGION, stamped on the device by the kernel itself (%globaltimer, first CTA start to "
+                       "last CTA end): CUDA events cannot bracket kernels of two overlapping streams",
+                "traffic": traffic_per_launch(pt["conv_kind"], round(boards)), "ms_per_launch": ms_launch,
+                "launches_timed": spans["launches"], "flop_per_launch": spans["flop"] / spans["launches"], "boards_per_launch": boards,
+                "tower_busy_share_of_timed_region": spans["busy_ns"] * 1e-6 / ms if world == 1 else None,
                 "frac_timed_region_lower_bound": FLOP_PER_EVAL * evals / (ms * 1e-3) / 1e12 / world / pk["bf16_sustained"],
-                "traffic": traffic_per_launch(pt["conv_kind"], pt["conv_boards"]), "ms_per_launch": conv_ms,
-                "launches_timed": pt["conv_launches"], "flop_per_launch": pt["conv_flop"], "boards_per_launch": pt["conv_boards"]}
+                "profiled_step": profiled}
+    elif profiled:
+        roof = {"bound": "tensor", "kernel": kernel_name, "achieved": profiled["achieved"], "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": profiled["achieved"] / pk["bf16_sustained"], "frac_of_burst": profiled["achieved"] / pk["bf16_burst"],
+                "peak_kind": "sustained, " + pk["source"], "traffic": traffic_per_launch(pt["conv_kind"], pt["conv_boards"]),
+                "ms_per_launch": profiled["ms_per_launch"], "launches_timed": profiled["launches"], "flop_per_launch": pt["conv_flop"],
+                "boards_per_launch": pt["conv_boards"], "profiled_step": profiled}
     steps_total = max(1, pt["steps"])
     phases = {k: pt[k] / steps_total for k in ("select_ms", "expand_ms", "eval_ms", "finish_ms")}
     net_tflops = (FLOP_PER_EVAL * G) / (phases["eval_ms"] * 1e-3) / 1e12 if phases["eval_ms"] > 0 else None
@@ -413,7 +435,7 @@ def run_ours(args, wl):
                        "chess960": wl["chess960"], "positions": "S2 random-played: U{0..40} random legal plies from the start, seed 0",
                        "weights": weights, "parallelism": "games sharded, %d x network replica" % world,
                        "pipelining": ("2 cohorts of %d games on two streams (tree kernels of one run under the other's network kernel)" % (G // 2))
-                                     if G >= 1024 else "one cohort (the library splits batches of >= 1024 games into two)",
+                                     if G >= 768 else "one cohort (the library splits batches of >= 768 running games into two)",
                        "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
                              % (G * 100 * 256 * 2 // 2 ** 20)},
             "moves_per_sec": total_moves / (ms * 1e-3), "evals_per_sec": evals / (ms * 1e-3),
@@ -422,7 +444,7 @@ def run_ours(args, wl):
             # timed steps at its algorithmic FLOP over the whole elapsed time, as if nothing but the tower ran
             "network_tflops_timed_region": FLOP_PER_EVAL * evals / (ms * 1e-3) / 1e12,
             "phase_ms_per_simulation_step": phases,
-            "phase_note": "phases and roofline come from one extra profiled step (single cohort, CUDA events on the library stream) run right after the timed region",
+            "phase_note": "phases (and roofline.profiled_step) come from one extra profiled step (single cohort, CUDA events on the library stream) run right after the timed region; roofline.achieved is timed on the device inside the timed region",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pos_bytes,
                     "d2h_bytes_per_step": G * 4672 * 4 + G * 73 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "szb_games_set(host positions) + szb_search(host visit/child buffers), pinned memory"},

@@ -60,7 +60,7 @@ typedef struct szb_config {
     int32_t max_searches;          /* capacity: num_searches per move (train_RL.py:170) */
     int32_t edges_per_node;        /* tree arena = max_games * (max_searches+1) * edges_per_node edges; 0 -> 48 */
     int32_t cohorts;               /* search pipelining: 2 = the games step as two independent halves on two streams (one half's
-                                      tree kernels run under the other half's network kernel), 1 = one batch, 0 = automatic (2 from 1024 games) */
+                                      tree kernels run under the other half's network kernel), 1 = one batch, 0 = automatic (2 from 768 running games) */
     int32_t leaves_per_tree;       /* 0 / 1: the reference's algorithm, one simulation of a tree at a time (mcts.py:49) -- every parity
                                       statement of this library is about this mode.  2..8: that many simulations of a tree in flight per
                                       step, kept apart by virtual loss: a DIFFERENT search (other visit counts, still exactly
@@ -200,6 +200,18 @@ typedef struct szb_phase_times {
 } szb_phase_times;
 int szb_set_profiling(szb_ctx *ctx, int32_t on);
 int szb_get_phase_times(szb_ctx *ctx, szb_phase_times *out);
+/* device-side timing of the network's whole-tower launches (k_tower_tc2 stamps %globaltimer when its first CTA starts and when
+ * its last CTA ends): unlike event pairs this also works while the two cohorts of a search overlap on two streams.
+ * on = 1: clear and start recording; on = 0: stop and report what was recorded (at most 8192 launches). */
+typedef struct szb_tower_spans {
+    int32_t launches;          /* launches recorded */
+    int32_t reserved;
+    uint64_t boards;           /* boards of those launches (sum) */
+    uint64_t busy_ns;          /* sum of (end - start) over the launches */
+    uint64_t wall_ns;          /* last end - first start */
+    uint64_t flop;             /* algorithmic FLOP of those launches (sum) */
+} szb_tower_spans;
+int szb_tower_spans_record(szb_ctx *ctx, int32_t on, szb_tower_spans *out);
 /* average duration (ms) of one launch of a kernel run `iters` times back to back on n boards:
  * which = 0: one 3x3 256->256 tower convolution (single-CTA tcgen05 kernel, with residual) ; 1: whole bf16 forward ;
  * 2: whole fp32 forward ; 3: one 3x3 256->256 fp32 SIMT convolution ; 4: one 3x3 256->256 tower convolution

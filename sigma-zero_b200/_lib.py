@@ -42,6 +42,11 @@ class PhaseTimes(ctypes.Structure):
                 ("conv_kind", ctypes.c_int32), ("conv_flop", ctypes.c_uint64)]
 
 
+class TowerSpans(ctypes.Structure):
+    _fields_ = [("launches", ctypes.c_int32), ("reserved", ctypes.c_int32), ("boards", ctypes.c_uint64),
+                ("busy_ns", ctypes.c_uint64), ("wall_ns", ctypes.c_uint64), ("flop", ctypes.c_uint64)]
+
+
 _vp, _i32, _u64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float
 SIGNATURES = {
     "szb_version": (ctypes.c_char_p, []),
@@ -73,6 +78,7 @@ SIGNATURES = {
     "szb_set_profiling": (ctypes.c_int, [_vp, _i32]),
     "szb_get_phase_times": (ctypes.c_int, [_vp, ctypes.POINTER(PhaseTimes)]),
     "szb_time_kernel": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(_f32)]),
+    "szb_tower_spans_record": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(TowerSpans)]),
 }
 
 _lib = None

@@ -1160,7 +1160,11 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     // (the tower is power-capped either way, so only the ~0.2 ms of small kernels can be hidden).  Profiling keeps one
     // cohort on the context's stream so that per-phase and per-kernel durations mean what they say.
     const int NS = n_slots;
-    int n_cohorts = ctx->cohorts ? ctx->cohorts : (NS * K >= 1024 ? 2 : 1);
+    // automatic: two cohorts from 768 path slots on.  Measured, alternating on one box (scripts/ab_cohorts.py): 640 games 1.66-1.71 ms
+    // per step with one cohort vs 1.77 with two (a 320-board tower launch is latency-bound and costs more than the overlap saves),
+    // 800 games 2.03 vs 1.98, 1024 games 2.39 vs 2.33.  The count is the RUNNING games: a 1024-game batch with a few finished
+    // games must still pipeline (it fell back to one cohort for a while in round 1: -5 %).
+    int n_cohorts = ctx->cohorts ? ctx->cohorts : (NS * K >= 768 ? 2 : 1);
     if ((prof && !trace) || NS < 8) n_cohorts = 1;
     int bounds[3] = {0, NS, NS};
     if (n_cohorts == 2) bounds[1] = ((NS / 2 + 3) / 4) * 4;       // network tiles are 4 boards wide

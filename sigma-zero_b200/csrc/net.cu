@@ -87,7 +87,8 @@ struct Net {
     int chunk = 512;                     // boards per tower launch of a large evaluation (net_forward_chunked); 0 = unlimited
     int tower_pairs = 74;                // CTA pairs of an exclusive launch (SZB_TOWER_PAIRS)
     bool tower_exclusive = false;        // SZB_TOWER_EXCLUSIVE: experiment, see launch_tower
-    unsigned long long* span = nullptr;  // SZB_TOWER_SPAN: [SPAN_CAP][2] device stamps, dumped as CSV when the network is destroyed
+    unsigned long long* span = nullptr;  // [SPAN_CAP][2] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
+    bool span_on = false;
     std::vector<int> span_boards, span_b0;
     std::string span_path;
     int num_sms = 148;
@@ -1170,7 +1171,7 @@ static int upload_conv(szb_ctx* ctx, Net* net, ConvLayer& L, const float* w, int
 
 void net_destroy(szb_ctx* ctx) {
     if (!ctx->net) return;
-    if (ctx->net->span && !ctx->net->span_boards.empty()) {
+    if (ctx->net->span && !ctx->net->span_path.empty() && !ctx->net->span_boards.empty()) {
         Net* net = ctx->net;
         std::vector<unsigned long long> h(2 * net->span_boards.size());
         cudaDeviceSynchronize();
@@ -1204,6 +1205,16 @@ static int net_alloc_activations(szb_ctx* ctx, Net* net) {
     if ((rc = make_act_map(ctx, &net->tm_in16, net->in16, C_IN_PAD, net->cap))) return rc;
     if ((rc = net_alloc(ctx, net, &net->logits, cap * N_ACTIONS))) return rc;
     if ((rc = net_alloc(ctx, net, &net->tc_error, 1))) return rc;
+    return 0;
+}
+
+static int net_span_reset(szb_ctx* ctx, Net* net) {
+    std::vector<unsigned long long> init((size_t)SPAN_CAP * 2, 0ull);
+    for (int i = 0; i < SPAN_CAP; i++) init[2 * (size_t)i] = ~0ull;
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpy(net->span, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+    net->span_boards.clear();
+    net->span_b0.clear();
     return 0;
 }
 
@@ -1285,15 +1296,11 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     }
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
-    if (const char* sp = getenv("SZB_TOWER_SPAN")) {         // measurement aid: start / end device time of every whole-tower launch
-        if (sp[0]) {
-            net->span_path = sp;
-            if ((rc = net_alloc(ctx, net, &net->span, (size_t)SPAN_CAP * 2, false))) return rc;
-            std::vector<unsigned long long> init((size_t)SPAN_CAP * 2, 0ull);
-            for (int i = 0; i < SPAN_CAP; i++) init[2 * (size_t)i] = ~0ull;
-            SZB_CUDA(ctx, cudaMemcpyAsync(net->span, init.data(), init.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-            SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
+    // start / end device time of whole-tower launches: szb_tower_spans_record, or SZB_TOWER_SPAN=<csv> (every launch, dumped at destroy)
+    if ((rc = net_alloc(ctx, net, &net->span, (size_t)SPAN_CAP * 2, false))) return rc;
+    if ((rc = net_span_reset(ctx, net))) return rc;
+    if (const char* sp = getenv("SZB_TOWER_SPAN")) {
+        if (sp[0]) { net->span_path = sp; net->span_on = true; }
     }
     net->tower_pairs = net->num_sms / 2;
     if (const char* e = getenv("SZB_TOWER_PAIRS")) { if (atoi(e) > 0) net->tower_pairs = std::min(atoi(e), net->num_sms / 2); }
@@ -1347,7 +1354,7 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
         else if (a.n_pair_tiles <= pairs) a.nsplit = 2;
     }
     net->last_nsplit = a.nsplit;
-    if (net->span && (int)net->span_boards.size() < SPAN_CAP && layer_end - layer_begin > 1) {
+    if (net->span_on && (int)net->span_boards.size() < SPAN_CAP && layer_end - layer_begin > 1) {
         a.span = net->span + 2 * net->span_boards.size();
         net->span_boards.push_back(n);
         net->span_b0.push_back(b0);
@@ -1709,6 +1716,38 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
     }
     SZB_CUDA(ctx, cudaGetLastError());
     return net_check_error(ctx);
+}
+
+int szb_tower_spans_record(szb_ctx* ctx, int32_t on, szb_tower_spans* out) {
+    if (!ctx) return SZB_ERR_ARG;
+    Net* net = ctx->net;
+    if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
+    SZB_CUDA(ctx, cudaDeviceSynchronize());
+    if (on) {
+        int rc = net_span_reset(ctx, net);
+        if (rc) return rc;
+        net->span_on = true;
+        return 0;
+    }
+    net->span_on = !net->span_path.empty();
+    if (!out) return 0;
+    memset(out, 0, sizeof *out);
+    const size_t n = net->span_boards.size();
+    if (n == 0) return 0;
+    std::vector<unsigned long long> h(2 * n);
+    SZB_CUDA(ctx, cudaMemcpy(h.data(), net->span, h.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long first = ~0ull, last = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (h[2 * i] == ~0ull || h[2 * i + 1] == 0) continue;                 // launch not run (cannot happen after the sync above)
+        out->launches++;
+        out->boards += (uint64_t)net->span_boards[i];
+        out->busy_ns += h[2 * i + 1] - h[2 * i];
+        out->flop += FLOP_TOWER_ALL * (uint64_t)net->span_boards[i];
+        first = std::min(first, h[2 * i]);
+        last = std::max(last, h[2 * i + 1]);
+    }
+    if (out->launches) out->wall_ns = last - first;
+    return 0;
 }
 
 int szb_net_forward(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* policy_out, float* value_out) {

@@ -217,6 +217,15 @@ class Engine:
         self._check(self.lib.szb_time_kernel(self._h, int(which), int(n), int(iters), ctypes.byref(ms)))
         return ms.value
 
+    def tower_spans(self, on):
+        """on=True: start recording the device start / end time of every whole-tower launch; on=False: stop and return the totals"""
+        if on:
+            self._check(self.lib.szb_tower_spans_record(self._h, 1, None))
+            return None
+        t = _lib.TowerSpans()
+        self._check(self.lib.szb_tower_spans_record(self._h, 0, ctypes.byref(t)))
+        return {n: getattr(t, n) for n, _ in _lib.TowerSpans._fields_ if n != "reserved"}
+
     def stats(self):
         s = _lib.Stats()
         self._check(self.lib.szb_get_stats(self._h, ctypes.byref(s)))
