@@ -393,7 +393,8 @@ def run_ours(args, wl):
                        "last CTA end): CUDA events cannot bracket kernels of two overlapping streams",
                 "traffic": traffic_per_launch(pt["conv_kind"], round(boards)), "ms_per_launch": ms_launch,
                 "launches_timed": spans["launches"], "flop_per_launch": spans["flop"] / spans["launches"], "boards_per_launch": boards,
-                "tower_busy_share_of_timed_region": spans["busy_ns"] * 1e-6 / ms if world == 1 else None,
+                # (share of the window the recorded launches span: the library keeps the first 8192 launches of the timed region)
+                "tower_busy_share_of_timed_region": spans["busy_ns"] / spans["wall_ns"] if spans["wall_ns"] else None,
                 "frac_timed_region_lower_bound": FLOP_PER_EVAL * evals / (ms * 1e-3) / 1e12 / world / pk["bf16_sustained"],
                 "profiled_step": profiled}
     elif profiled:
