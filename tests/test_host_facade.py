@@ -252,3 +252,57 @@ def test_supervised_pgn_reader_and_san_resolver():
     # selection: one white win + one black win + the draw are balanced; asking for 2 stops the scan after the first two games
     assert [h["Result"] for h, _ in select_balanced(games)] == ["1-0", "1/2-1/2", "0-1"]
     assert [h["Result"] for h, _ in select_balanced(games, num_games=1)] == ["1/2-1/2"]
+
+
+def _gather_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from sigma_zero_b200 import records
+    from sigma_zero_b200.train_RL import concat_records, shard_of
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_of(7, rank, world)                       # 7 games over 2 ranks: blocks of 4 and 3
+    rng = np.random.default_rng(40 + rank)
+    n = 3 * (hi - lo)                                       # three positions per game
+    lens = rng.integers(1, 5, n)
+    rec = {"states": rng.integers(0, 2 ** 63, (n, 119), dtype=np.uint64),
+           "pi_index": np.concatenate([np.sort(rng.choice(4672, k, replace=False)) for k in lens]).astype(np.uint16),
+           "pi_prob": np.concatenate([np.full(k, 1.0 / k, np.float32) for k in lens]),
+           "pi_off": np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), "z": rng.integers(-1, 2, n).astype(np.int8),
+           "colour": (np.arange(n) % 2 == 0), "game": (lo + np.arange(n) // 3).astype(np.int32),
+           "result": np.zeros(hi - lo, np.int8)}
+    parts = [None] * world
+    dist.all_gather_object(parts, rec)                      # what train_RL.rl_iteration does with every rank's shard
+    whole = concat_records(parts)
+    digest = (len(whole["z"]), int(whole["pi_off"][-1]), whole["game"].tolist(), float(records.dense_policy(whole).sum()),
+              int(whole["states"].sum(dtype=np.uint64) % np.uint64(1 << 62)))
+    out.put((rank, digest))
+    dist.destroy_process_group()
+
+
+def test_record_gather_gloo_world2():
+    """the N > 1 host path of an iteration: every rank's packed records gathered and concatenated -- both ranks end
+    up with the same record set, games in global order"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == got[1]
+    n, m, games, total, _ = got[0]
+    assert n == 21 and games == sorted(games) and games[0] == 0 and games[-1] == 6 and abs(total - 21.0) < 1e-4
+
+
+def test_product_arm_has_no_cpu_fallback():
+    """without a CUDA device the bench's own arm must stop loudly (the product path never routes through the oracle)"""
+    if torch.cuda.is_available():
+        return
+    for extra in ([], ["--workload", "c4"]):
+        out = subprocess.run([sys.executable, os.path.join(util.ROOT, "bench.py"), "--steps", "1", "--warmup", "1"] + extra,
+                             capture_output=True, text=True, timeout=600, cwd=util.ROOT)
+        assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
