@@ -159,3 +159,77 @@ def rl_iteration(model, args, seed=0, max_plies=None, epochs=None, optimiser=Non
                             batch_size=int(args.get('batch_size', 64)), optimiser=optimiser, lr_scheduler=lr_scheduler,
                             device=train_device, seed=seed)
     return rec, hist
+
+
+def main(args=None, model=None, weights=None, num_games=None, out_dir=".", seed=0, max_plies=None, passes_per_epoch=7,
+         train_device=None, log=print):
+    """The reference's outer loop (train_RL.py:156-264): for epoch in [start_epoch, num_epochs): self-play with the current
+    weights, save the games, fine-tune on them, save weights and optimiser.
+
+    Differences kept deliberately ("do not preserve"): no hard-coded absolute paths -- `weights` is the
+    checkpoint to start from (the reference loads supervised weights, :161-163) and everything is written under `out_dir`; the games
+    are saved in the packed record format (games/RL_960_{epoch}.npz) instead of a pickled list of bool tensors; resuming reads
+    the files this loop writes (saves/RL_960_{epoch}.pt, saves/RL_960_opt_{epoch}.pt -- the reference's resume reads names its
+    training never writes, :191-194 vs :153).  `num_games` games per epoch (the reference's local num_games = 40, :165; default:
+    args['num_selfPlay_iterations']) are split over the ranks of a torchrun job instead of num_process CPU workers; training runs
+    `passes_per_epoch` passes over the epoch's records (the reference's train(total_steps=6) loops range(0, 7), :94,256)."""
+    import time
+
+    import torch.distributed as dist
+    from . import records
+    from .network import policyNN
+    args = dict(DEFAULT_ARGS, **(args or {}))
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if model is None:
+        model = policyNN({})
+    if weights:
+        model.load_state_dict(torch.load(weights, map_location="cpu"))
+    if train_device is not None:
+        model.to(train_device)           # before the optimiser exists: a resumed optimiser state must live where the parameters train
+    model.eval()
+    optimiser, scheduler = make_optimiser(model)
+    start_epoch, num_epochs = int(args.get("start_epoch", 1)), int(args["num_epochs"])
+    os.makedirs(os.path.join(out_dir, "saves"), exist_ok=True)
+    os.makedirs(os.path.join(out_dir, "games"), exist_ok=True)
+    if start_epoch > 1:
+        try:
+            model.load_state_dict(torch.load(os.path.join(out_dir, "saves", "RL_960_%d.pt" % (start_epoch - 1)), map_location="cpu"))
+            optimiser.load_state_dict(torch.load(os.path.join(out_dir, "saves", "RL_960_opt_%d.pt" % (start_epoch - 1)), map_location="cpu"))
+        except OSError:
+            log("No saved weights from epoch %d found!" % (start_epoch - 1))
+            start_epoch = 1
+    run_args = dict(args, num_selfPlay_iterations=int(num_games if num_games is not None else args["num_selfPlay_iterations"]))
+    history = []
+    for epoch in range(start_epoch, num_epochs):
+        log("Epoch %d" % epoch)
+        t1 = time.perf_counter()
+        rec, hist = rl_iteration(model, run_args, seed=seed + epoch, max_plies=max_plies, epochs=passes_per_epoch,
+                                 optimiser=optimiser, lr_scheduler=scheduler, train_device=train_device)
+        if rank == 0:
+            records.save(os.path.join(out_dir, "games", "RL_960_%d.npz" % epoch), rec)
+            torch.save(model.state_dict(), os.path.join(out_dir, "saves", "RL_960_%d.pt" % epoch))
+            torch.save(optimiser.state_dict(), os.path.join(out_dir, "saves", "RL_960_opt_%d.pt" % epoch))
+        history.append({"epoch": epoch, "positions": int(len(rec["z"])), "losses": hist, "seconds": time.perf_counter() - t1})
+        log("Time taken: %0.4f seconds" % history[-1]["seconds"])
+    return model, history
+
+
+if __name__ == "__main__":
+    import argparse
+    ap = argparse.ArgumentParser(description="self-play + fine-tuning loop of the reference's train_RL.py on the B200 engine "
+                                             "(under torchrun the games of an epoch are split over the ranks)")
+    for key, val in DEFAULT_ARGS.items():
+        ap.add_argument("--" + key, type=type(val) if not isinstance(val, bool) else int, default=val)
+    ap.add_argument("--start_epoch", type=int, default=1)
+    ap.add_argument("--num_games", type=int, default=None)
+    ap.add_argument("--weights", default=None, help="state_dict to start from, e.g. supervised_model_best.pt")
+    ap.add_argument("--out_dir", default=".")
+    ap.add_argument("--leaves_per_tree", type=int, default=1)
+    ns = vars(ap.parse_args())
+    if "RANK" in os.environ:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    cli = {k: ns[k] for k in list(DEFAULT_ARGS) + ["start_epoch", "leaves_per_tree"]}
+    cli["chess960"] = bool(cli["chess960"])
+    main(cli, weights=ns["weights"], num_games=ns["num_games"], out_dir=ns["out_dir"], train_device="cuda")

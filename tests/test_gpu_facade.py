@@ -291,3 +291,30 @@ def test_supervised_pgn_to_records_matches_oracle_replay():
     assert np.array_equal(rec["pi_off"], np.arange(n + 1)) and (rec["pi_prob"] == 1).all()
     ref = torch.stack([(torch.from_numpy(s.astype(np.uint8)) << torch.arange(8).view(1, 1, 8)).sum(dim=-1).to(torch.uint8) for s in want_states])
     assert np.array_equal(compressed_states(rec), ref.numpy())
+
+
+def test_train_rl_main_loop_and_resume(tmp_path):
+    """train_RL.main: the reference's outer loop (self-play -> save games -> fine-tune -> save weights and optimiser,
+    train_RL.py:205-264) on the engine, and a resume from the files it wrote"""
+    from sigma_zero_b200 import records
+    from sigma_zero_b200.network import policyNN
+    from sigma_zero_b200.train_RL import main
+    torch.manual_seed(0)
+    args = {"C": 2, "num_searches": 8, "num_epochs": 3, "batch_size": 4, "chess960": True}
+    logs = []
+    model, hist = main(args, model=policyNN({}), num_games=4, out_dir=str(tmp_path), max_plies=3, passes_per_epoch=1,
+                       train_device="cuda", log=logs.append)
+    assert [h["epoch"] for h in hist] == [1, 2] and all(h["positions"] == 12 for h in hist)
+    assert all(np.isfinite(np.array(h["losses"])).all() and len(h["losses"]) == 3 for h in hist)
+    for epoch in (1, 2):
+        rec = records.load(str(tmp_path / "games" / ("RL_960_%d.npz" % epoch)))
+        assert rec["states"].shape == (12, 119) and sorted(set(rec["game"].tolist())) == [0, 1, 2, 3]
+        assert (tmp_path / "saves" / ("RL_960_%d.pt" % epoch)).exists() and (tmp_path / "saves" / ("RL_960_opt_%d.pt" % epoch)).exists()
+    saved = torch.load(str(tmp_path / "saves" / "RL_960_2.pt"), map_location="cpu")
+    assert all(torch.equal(v.cpu(), saved[k]) for k, v in model.state_dict().items())
+    # resume: epoch 3 starts from the weights of epoch 2
+    logs.clear()
+    model2, hist2 = main(dict(args, start_epoch=3, num_epochs=4), model=policyNN({}), num_games=4, out_dir=str(tmp_path),
+                         max_plies=2, passes_per_epoch=1, train_device="cuda", log=logs.append)
+    assert [h["epoch"] for h in hist2] == [3] and not any("No saved weights" in str(l) for l in logs)
+    assert (tmp_path / "saves" / "RL_960_3.pt").exists()
