@@ -216,6 +216,9 @@ int szb_tower_spans_record(szb_ctx *ctx, int32_t on, szb_tower_spans *out);
  * which = 0: one 3x3 256->256 tower convolution (single-CTA tcgen05 kernel, with residual) ; 1: whole bf16 forward ;
  * 2: whole fp32 forward ; 3: one 3x3 256->256 fp32 SIMT convolution ; 4: one 3x3 256->256 tower convolution
  * (CTA-pair kernel) ; 5: the whole tower in one CTA-pair launch */
+/* NOTE: the tower kernels run on whatever the activation buffers hold.  On a fresh context that is all-zero input planes --
+ * constant activations, little switching, far less power -- so many back-to-back launches then sustain a higher clock than real
+ * positions allow (1.5 vs 1.3 PFLOP/s, profiles/r01o_*).  Run a search first when a sustained figure is wanted. */
 int szb_time_kernel(szb_ctx *ctx, int32_t which, int32_t n, int32_t iters, float *ms_avg_out);
 
 #ifdef __cplusplus
