@@ -237,21 +237,19 @@ __global__ void __launch_bounds__(1024) k_active_list(Dev d) {
     if (threadIdx.x == 0) *d.n_active = base_sh;
 }
 
-// warp per tree.  Two dependent memory round trips per level: (child count, first edge) of the node, then the four edge
-// arrays of its children read side by side; the parent's visit count and the chosen child's node index travel down in
-// registers (the winning lane already holds them) instead of being re-read through node_pedge / e_child.
-__global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
-    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (slot >= d.g_end) return;
+// PUCT descent of one tree by one warp (mctsnode.py:23-37, mcts.py:54-55).  One dependent memory round trip per level: the four
+// edge arrays of the node's children are read side by side, and the chosen child's header (child count, first edge) rides on its
+// edge (e_link), like its visit count and node index: the winning lane already holds them.  The edges walked are recorded
+// (d.path) so that the backup of this simulation is one parallel read-modify-write instead of a pointer chase.
+__device__ __forceinline__ void select_tree(const Dev& d, int slot, int lane, float c_puct) {
     const int g = d.order[slot];
     const size_t r = (size_t)g * d.nodes_per_game;
+    int32_t* path = d.path + (size_t)slot * PATH_CAP;
     int node = 0, depth = 0;
     int np = d.root_n[g];                                  // visit count of the node being expanded (root: mcts.py:46)
+    int n = d.node_nchild[r], e0 = d.node_edge0[r];        // the root's header; deeper headers come with the chosen edge
     unsigned long long scanned = 0;
     for (;;) {
-        const int n = d.node_nchild[r + node];
-        const int e0 = d.node_edge0[r + node];
         if (n == 0) {
             if (lane == 0) { d.sel_node[slot] = node; d.sel_edge[slot] = -1; }
             break;
@@ -259,12 +257,12 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
         const float sq = sqrt_parent(np);
         float best = -INFINITY;
         int besti = 0x7FFFFFFF, best_n = 0;
-        uint16_t best_child = NO_CHILD;
+        unsigned long long best_link = 0;
         for (int i = lane; i < n; i += 32) {
             const int cn = d.e_n[e0 + i];
-            const uint16_t cc = d.e_child[e0 + i];
+            const unsigned long long lk = d.e_link[e0 + i];
             const float s = puct_score(cn, d.e_w[e0 + i], d.e_p[e0 + i], sq, c_puct);
-            if (s > best || besti == 0x7FFFFFFF) { best = s; besti = i; best_n = cn; best_child = cc; }
+            if (s > best || besti == 0x7FFFFFFF) { best = s; besti = i; best_n = cn; best_link = lk; }
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -273,19 +271,24 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
             if (oi != 0x7FFFFFFF && (besti == 0x7FFFFFFF || ob > best || (ob == best && oi < besti))) { best = ob; besti = oi; }
         }
         besti = __shfl_sync(0xFFFFFFFFu, besti, 0);
-        // child i was scored by lane i % 32, which still holds its visit count and node index
+        // child i was scored by lane i % 32, which still holds its visit count and link
         np = __shfl_sync(0xFFFFFFFFu, best_n, besti & 31);
-        const uint16_t c = (uint16_t)__shfl_sync(0xFFFFFFFFu, (int)best_child, besti & 31);
+        const unsigned long long lk = __shfl_sync(0xFFFFFFFFu, best_link, besti & 31);
         const int e = e0 + besti;
+        if (lane == 0 && depth < PATH_CAP) path[depth] = e;
         depth++;
         scanned += (unsigned long long)n;
+        const uint16_t c = link_child(lk);
         if (c == NO_CHILD) {
             if (lane == 0) { d.sel_node[slot] = node; d.sel_edge[slot] = e; }
             break;
         }
         node = c;
+        n = link_nchild(lk);
+        e0 = link_edge0(lk);
     }
     if (lane == 0) {
+        d.path_len[slot] = depth;
         unsigned long long* gs = d.gstats + (size_t)g * 8;
         if ((unsigned long long)depth > gs[3]) gs[3] = (unsigned long long)depth;
         gs[4] += scanned;
@@ -293,23 +296,22 @@ __global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
     }
 }
 
-// One thread per tree does the work; LPT = lanes per tree.  LPT = 1 packs 32 trees into a warp (bulk throughput: every lane
-// busy, but the lanes diverge through move generation and run one after the other); LPT = 32 gives every tree its own warp
-// (one active lane, no divergence: the latency of a step at the batch sizes of a search, a few thousand trees at most).
-template <int LPT>
-__global__ void __launch_bounds__(128) k_expand(Dev d) {
-    __shared__ Tables T;
-    load_tables(&T, d.tables);
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (LPT > 1 && (tid % LPT) != 0) return;
-    // a path slot = one in-flight simulation: slot * K + j (K = leaves per tree and step; 1 in the reference-exact mode)
-    const int ps = d.g_begin * d.K + tid / LPT;
-    if (ps >= d.g_end * d.K) return;
+// warp per tree
+__global__ void __launch_bounds__(128) k_select(Dev d, float c_puct) {
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slot >= d.g_end) return;
+    select_tree(d, slot, threadIdx.x & 31, c_puct);
+}
+
+// Expansion of path slot ps by ONE thread (mcts.py:57-70, chess_tensor.py:88-172,190-218): make the selected move, repetition
+// flags, legal moves, outcome, the 119 planes and the 4672-bit legal mask.  Returns whether the leaf needs the evaluator.
+// planes_out: where the packed planes go (the slot's row in d.planes, or a shared-memory copy the caller spreads afterwards).
+__device__ __forceinline__ bool expand_path(const Dev& d, const Tables& T, int ps, uint64_t* planes_out) {
     const int g = d.order[ps / d.K];
     const size_t r = (size_t)g * d.nodes_per_game;
     Pos* gp = d.pool + (size_t)g * d.pool_stride;
     const int e = d.sel_edge[ps];
-    if (e == PATH_DROPPED) { d.need_eval[ps] = 0; return; }
+    if (e == PATH_DROPPED) { d.need_eval[ps] = 0; return false; }
     int node = d.sel_node[ps];
     uint16_t mv[MAX_MOVES];
     int cnt = 0;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(128) k_expand(Dev d) {
         d.node_edge0[r + node] = -1;
         d.node_term[r + node] = q.outcome != OUT_NONE;
         d.node_tval[r + node] = q.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
-        d.e_child[e] = (uint16_t)node;
+        d.e_link[e] = link_pack(-1, 0, (uint32_t)node);
         d.sel_node[ps] = node;
     } else {
         q = gp[state_slot(d, g, node)];
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(128) k_expand(Dev d) {
     if (d.node_term[r + node]) {
         d.leaf_value[ps] = d.node_tval[r + node];
         d.need_eval[ps] = 0;
-        return;
+        return false;
     }
     uint64_t* mrow = d.mask + (size_t)ps * MASK_STRIDE;
     for (int w = 0; w < MASK_STRIDE; w++) mrow[w] = 0;
@@ -348,8 +350,24 @@ __global__ void __launch_bounds__(128) k_expand(Dev d) {
         const int idx = move_to_index(q, mv[k]);
         mrow[idx >> 6] |= bit(idx & 63);
     }
-    pack_planes(gp, q, d.planes + (size_t)ps * PLANE_STRIDE);
+    pack_planes(gp, q, planes_out);
     d.need_eval[ps] = 1;
+    return true;
+}
+
+// One thread per tree does the work; LPT = lanes per tree.  LPT = 1 packs 32 trees into a warp (bulk throughput: every lane
+// busy, but the lanes diverge through move generation and run one after the other); LPT = 32 gives every tree its own warp
+// (one active lane, no divergence: the latency of a step at the batch sizes of a search, a few thousand trees at most).
+template <int LPT>
+__global__ void __launch_bounds__(128) k_expand(Dev d) {
+    __shared__ Tables T;
+    load_tables(&T, d.tables);
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (LPT > 1 && (tid % LPT) != 0) return;
+    // a path slot = one in-flight simulation: slot * K + j (K = leaves per tree and step; 1 in the reference-exact mode)
+    const int ps = d.g_begin * d.K + tid / LPT;
+    if (ps >= d.g_end * d.K) return;
+    expand_path(d, T, ps, d.planes + (size_t)ps * PLANE_STRIDE);
 }
 
 // block per tree: policy[i] / value from the integer hash of the packed planes
@@ -368,103 +386,192 @@ __global__ void __launch_bounds__(128) k_hash_eval(Dev d) {
 }
 
 // warp-cooperative pieces of the expansion (mcts.py:77-96, mctsnode.py:39-54), shared by k_finish and k_finish_vl
-__device__ __forceinline__ int count_legal(const Dev& d, int ps, int lane) {
-    const uint64_t* mk = d.mask + (size_t)ps * MASK_STRIDE;
+__device__ __forceinline__ int count_legal(const uint64_t* mk, int lane) {
     int n = 0;
     for (int w = lane; w < MASK_WORDS; w += 32) n += popc(mk[w]);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, off);
     return n;
 }
-// children of the node evaluated in path slot ps, written from edge e0 on; returns how many (zero-prior moves are dropped)
-__device__ __forceinline__ int create_children(const Dev& d, int ps, unsigned long long e0, int learning, int lane) {
-    const float* pol = d.policy + (size_t)ps * N_ACTIONS;
-    const uint64_t* mk = d.mask + (size_t)ps * MASK_STRIDE;
+// Children of the node evaluated in path slot ps (legal-move bitset mk, evaluator output pol), written from edge e0 on in ascending
+// move-index order; returns how many (zero-prior moves are dropped, mcts.py:87-89).  The 73 mask words are dealt to the lanes in
+// three rounds (word = round * 32 + lane): every lane normalises the priors of its own set bits, a warp scan places them.
+__device__ __forceinline__ int create_children(const Dev& d, const uint64_t* mk, const float* pol, unsigned long long e0, int learning, int lane) {
     const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
     const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
     int count = 0;
-    for (int chunk = 0; chunk < N_ACTIONS / 32; chunk++) {
-        const uint32_t bits = (uint32_t)(mk[chunk >> 1] >> ((chunk & 1) * 32));
-        if (bits == 0) continue;
-        const int e = chunk * 32 + lane;
-        float pr = 0.0f;
-        bool has = (bits >> lane) & 1u;
-        if (has) { pr = f_div(pol[e], total); has = pr != 0.0f; }     // zero-prior children are dropped (mcts.py:87-89)
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, has);
-        if (has) {
-            const unsigned long long at = e0 + count + __popc(ballot & ((1u << lane) - 1));
+#pragma unroll 1
+    for (int w = lane; w < 96; w += 32) {
+        uint64_t keep = 0;
+        if (w < MASK_WORDS) {
+            uint64_t x = mk[w];
+            while (x) {
+                const int b = lsb(x);
+                x &= x - 1;
+                if (f_div(pol[w * 64 + b], total) != 0.0f) keep |= bit(b);       // zero-prior children are dropped
+            }
+        }
+        const int mine = popc(keep);
+        int incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += y;
+        }
+        unsigned long long at = e0 + (unsigned long long)(count + incl - mine);
+        while (keep) {
+            const int b = lsb(keep);
+            keep &= keep - 1;
+            const int e = w * 64 + b;
+            const float pr = f_div(pol[e], total);
             d.e_n[at] = 0;
             d.e_w[at] = 0.0;
             d.e_p[at] = learning ? noisy_prior(pr) : pr;
             d.e_move[at] = (uint16_t)e;
-            d.e_child[at] = NO_CHILD;
+            d.e_link[at] = link_pack(-1, 0, NO_CHILD);
+            at++;
         }
-        count += __popc(ballot);
+        count += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     return count;
 }
 
-// warp per tree
-__global__ void __launch_bounds__(128) k_finish(Dev d, int learning) {
-    __shared__ int want_sh[4];
-    __shared__ unsigned long long base_sh;
-    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const bool active = slot < d.g_end;
+constexpr int FINISH_WARPS = 4;
+
+// Second half of a simulation for the block's four trees (mcts.py:77-109): children of the evaluated node, then backup.  Called by
+// ALL threads of the block (two block-wide barriers inside); mk_sh: 73 words of shared memory per warp.
+__device__ __forceinline__ void finish_block(const Dev& d, int learning, int slot, bool active, int lane, int wib, int* want_sh,
+                                             unsigned long long* base_sh, uint64_t* mk_sh) {
     const int g = active ? d.order[slot] : 0;
     const bool eval = active && d.need_eval[slot];
+    uint64_t* mk = mk_sh + wib * MASK_STRIDE;
     // children to allocate: one bump of the shared edge arena per BLOCK (four trees), not one same-address atomic per tree
-    const int n_legal = eval ? count_legal(d, slot, lane) : 0;
+    int n_legal = 0;
+    if (eval) {
+        const uint64_t* src = d.mask + (size_t)slot * MASK_STRIDE;
+        for (int w = lane; w < MASK_WORDS; w += 32) mk[w] = src[w];
+        __syncwarp();
+        n_legal = count_legal(mk, lane);
+    }
     if (lane == 0) want_sh[wib] = n_legal;
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int tot = want_sh[0] + want_sh[1] + want_sh[2] + want_sh[3];
-        base_sh = tot ? atomicAdd(d.edge_top, (unsigned long long)tot) : 0ull;
+        int tot = 0;
+        for (int k = 0; k < FINISH_WARPS; k++) tot += want_sh[k];
+        *base_sh = tot ? atomicAdd(d.edge_top, (unsigned long long)tot) : 0ull;
     }
     __syncthreads();
     if (!active) return;
     const size_t r = (size_t)g * d.nodes_per_game;
     const int node = d.sel_node[slot];
     float v;
+    int count = 0;
     if (eval) {
-        unsigned long long e0 = base_sh;
+        unsigned long long e0 = *base_sh;
         for (int k = 0; k < wib; k++) e0 += (unsigned long long)want_sh[k];
-        int count = 0;
         if (e0 + (unsigned long long)n_legal > d.edge_cap) {
             if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
         } else {
-            count = create_children(d, slot, e0, learning, lane);
+            count = create_children(d, mk, d.policy + (size_t)slot * N_ACTIONS, e0, learning, lane);
         }
         if (lane == 0) {
             d.node_edge0[r + node] = (int32_t)e0;
             d.node_nchild[r + node] = (uint16_t)count;
+            const int pe = d.node_pedge[r + node];
+            if (pe >= 0) d.e_link[pe] = link_pack((int32_t)e0, (uint32_t)count, (uint32_t)node);     // the header select reads
         }
         v = d.value[slot];
         if (node == 0 && lane == 0) d.root_val[g] = v;
     } else {
         v = d.leaf_value[slot];
     }
-    if (lane == 0) {
-        // backup (mctsnode.py:56-63): value_sum accumulates python doubles
-        double val = (double)v;
-        int nd = node;
-        unsigned long long levels = 0;
-        for (;;) {
+    // backup (mctsnode.py:56-63): value_sum accumulates python doubles; the edge k levels above the leaf gets (-1)^k * value
+    const double val = (double)v;
+    const int L = d.path_len[slot];
+    if (L <= PATH_CAP) {
+        const int32_t* path = d.path + (size_t)slot * PATH_CAP;
+        for (int k = lane; k < L; k += 32) {
+            const int pe = path[k];
+            d.e_w[pe] += ((L - 1 - k) & 1) ? -val : val;
+            d.e_n[pe] += 1;
+        }
+    } else if (lane == 0) {
+        double x = val;
+        for (int nd = node;;) {
             const int pe = d.node_pedge[r + nd];
             if (pe < 0) break;
-            d.e_w[pe] += val;
+            d.e_w[pe] += x;
             d.e_n[pe] += 1;
-            val = -val;
+            x = -x;
             nd = d.node_pnode[r + nd];
-            levels++;
         }
+    }
+    if (lane == 0) {
         unsigned long long* gs = d.gstats + (size_t)g * 8;
-        gs[6] += levels;
-        if (d.need_eval[slot]) gs[7] += (unsigned long long)d.node_nchild[r + node];
-        d.root_w[g] += val;
+        gs[6] += (unsigned long long)L;
+        if (eval) gs[7] += (unsigned long long)count;
+        d.root_w[g] += (L & 1) ? -val : val;
         d.root_n[g] += 1;
         gs[0] += 1ull;
-        gs[d.need_eval[slot] ? 1 : 2] += 1ull;
+        gs[eval ? 1 : 2] += 1ull;
+    }
+}
+
+// warp per tree
+__global__ void __launch_bounds__(32 * FINISH_WARPS) k_finish(Dev d, int learning) {
+    __shared__ int want_sh[FINISH_WARPS];
+    __shared__ unsigned long long base_sh;
+    __shared__ uint64_t mk_sh[FINISH_WARPS * MASK_STRIDE];
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    finish_block(d, learning, slot, slot < d.g_end, threadIdx.x & 31, threadIdx.x >> 5, want_sh, &base_sh, mk_sh);
+}
+
+// One launch per simulation step and cohort in the reference-exact mode: the second half of step s-1 (children + backup of the
+// evaluated leaves), the first half of step s (PUCT descent, then move / legality / planes / mask of the new leaf) -- the same
+// warp owns its tree through all of it -- and the hand-over to the network: the leaf's input planes are written straight into the
+// tower's bf16 NHWC input rows and the tower's per-item completion counters are cleared, so a step is this kernel + one tower
+// launch (k_tower_tc2, whose last layer's epilogue emits the priors and the value k_finish reads: net.cu).
+constexpr int STEP_FINISH = 1, STEP_SELECT = 2;
+__global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_puct, int learning, int phases) {
+    __shared__ Tables T;
+    __shared__ int want_sh[FINISH_WARPS];
+    __shared__ unsigned long long base_sh;
+    __shared__ uint64_t mk_sh[FINISH_WARPS * MASK_STRIDE];
+    __shared__ uint64_t planes_sh[FINISH_WARPS][PLANE_STRIDE];
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const bool active = slot < d.g_end;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.net_ready_n; i += gridDim.x * blockDim.x) d.net_ready[i] = 0;
+    if (phases & STEP_SELECT) load_tables(&T, d.tables);
+    if (phases & STEP_FINISH) finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, mk_sh);
+    if (!(phases & STEP_SELECT) || !active) return;
+    __syncwarp();                                              // this warp's tree updates -> every lane of the descent
+    select_tree(d, slot, lane, c_puct);
+    __syncwarp();
+    uint64_t* pl = planes_sh[wib];
+    int need = 0;
+    if (lane == 0) need = expand_path(d, T, slot, pl);
+    need = __shfl_sync(0xFFFFFFFFu, need, 0);
+    if (!need) return;
+    uint64_t* prow = d.planes + (size_t)slot * PLANE_STRIDE;
+    for (int i = lane; i < N_PLANES; i += 32) prow[i] = pl[i];
+    if (d.net_in16) {
+        // 64 squares x 128 channels of bf16 (0 / 1.0), interior of the slot's zero-haloed [10][10][128] input row: 16 bytes
+        // (8 channels of one square) per lane and store, consecutive lanes -> consecutive 16-byte pieces
+        uint4* in = reinterpret_cast<uint4*>(d.net_in16 + (size_t)slot * 100 * 128);
+#pragma unroll 4
+        for (int it = 0; it < 32; it++) {
+            const int q = it * 32 + lane, sq = q >> 4, cg = q & 15;
+            uint32_t h[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int c = cg * 8 + j;
+                h[j] = (c < N_PLANES && ((pl[c] >> sq) & 1ull)) ? 0x3F80u : 0u;
+            }
+            uint4 o;
+            o.x = h[0] | (h[1] << 16); o.y = h[2] | (h[3] << 16); o.z = h[4] | (h[5] << 16); o.w = h[6] | (h[7] << 16);
+            in[(size_t)(((sq >> 3) + 1) * 10 + (sq & 7) + 1) * 16 + cg] = o;
+        }
     }
 }
 
@@ -515,7 +622,7 @@ __global__ void __launch_bounds__(128) k_select_vl(Dev d, float c_puct, int num_
             uint16_t best_child = NO_CHILD;
             for (int i = lane; i < n; i += 32) {
                 const int cn = d.e_n[e0 + i];
-                const uint16_t cc = d.e_child[e0 + i];
+                const uint16_t cc = link_child(d.e_link[e0 + i]);
                 const float sc = puct_score(cn, d.e_w[e0 + i], d.e_p[e0 + i], sq, c_puct);
                 if (sc > best || besti == 0x7FFFFFFF) { best = sc; besti = i; best_n = cn; best_child = cc; }
             }
@@ -536,7 +643,7 @@ __global__ void __launch_bounds__(128) k_select_vl(Dev d, float c_puct, int num_
                 d.e_n[e] += 1;                                   // virtual visit ...
                 d.e_w[e] += 1.0;                                 // ... lost by the side that chose this edge
                 if (c == NO_CHILD) {
-                    d.e_child[e] = CHILD_PENDING;
+                    d.e_link[e] = link_pack(-1, 0, CHILD_PENDING);
                     d.sel_node[ps] = node;
                     d.sel_edge[ps] = e;
                     d.sel_new[ps] = nc + 1 + new_nodes;
@@ -585,7 +692,8 @@ __global__ void __launch_bounds__(32 * MAX_LEAVES) k_finish_vl(Dev d, int learni
     const int ps = slot * d.K + j;
     const bool live = j < d.K && d.sel_edge[ps] != PATH_DROPPED;
     const bool eval = live && d.need_eval[ps];
-    const int n_legal = eval ? count_legal(d, ps, lane) : 0;
+    const uint64_t* mk = d.mask + (size_t)ps * MASK_STRIDE;
+    const int n_legal = eval ? count_legal(mk, lane) : 0;
     if (lane == 0) want_sh[j] = n_legal;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -602,7 +710,7 @@ __global__ void __launch_bounds__(32 * MAX_LEAVES) k_finish_vl(Dev d, int learni
         if (e0 + (unsigned long long)n_legal > d.edge_cap) {
             if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
         } else {
-            count = create_children(d, ps, e0, learning, lane);
+            count = create_children(d, mk, d.policy + (size_t)ps * N_ACTIONS, e0, learning, lane);
         }
         if (lane == 0) {
             d.node_edge0[r + node] = (int32_t)e0;
@@ -729,7 +837,7 @@ __global__ void k_tree_export(Dev d, int g, int max_nodes, int max_edges, int32_
         for (int k = lane; k < n; k += 32) {
             e_n[off + k] = d.e_n[e0 + k]; e_w[off + k] = d.e_w[e0 + k]; e_p[off + k] = d.e_p[e0 + k];
             e_move[off + k] = d.e_move[e0 + k];
-            const uint16_t c = d.e_child[e0 + k];
+            const uint16_t c = link_child(d.e_link[e0 + k]);
             e_child[off + k] = c == NO_CHILD ? -1 : (int)c;
         }
         off += n;
@@ -898,6 +1006,7 @@ const char* szb_last_error(const szb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 void* szb_stream(szb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int szb_synchronize(szb_ctx* ctx) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx) return SZB_ERR_ARG;
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -954,6 +1063,10 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     d.n_games = 0;
     const size_t NN = G * (size_t)d.nodes_per_game;
     d.edge_cap = (unsigned long long)NN * (unsigned long long)ctx->cfg.edges_per_node;
+    // edges are addressed with 32-bit indices everywhere (node_edge0, node_pedge, path, e_link)
+    if (d.edge_cap > 0x7FFFFFFFull)
+        return fail(ctx, SZB_ERR_ARG, "tree arena of %llu edges (max_games x (max_searches + 1) x edges_per_node) exceeds the 2^31 - 1 edges "
+                    "a context can index: lower max_games / edges_per_node or use one context per game block", d.edge_cap);
     build_tables(ctx->host_tables);
     Tables* dt = nullptr;
     int rc;
@@ -965,10 +1078,11 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     A(cur, G);
     A(node_edge0, NN); A(node_nchild, NN); A(node_pedge, NN); A(node_pnode, NN); A(node_term, NN); A(node_tval, NN);
     A(node_count, G); A(root_n, G); A(root_w, G);
-    A(e_n, d.edge_cap); A(e_w, d.edge_cap); A(e_p, d.edge_cap); A(e_move, d.edge_cap); A(e_child, d.edge_cap);
+    A(e_n, d.edge_cap); A(e_w, d.edge_cap); A(e_p, d.edge_cap); A(e_move, d.edge_cap); A(e_link, d.edge_cap);
     A(edge_top, 1); A(error_flag, 1);
     const size_t P = G * (size_t)d.K;                       // path slots
     A(sel_node, P); A(sel_edge, P); A(sel_new, P); A(need_eval, P); A(leaf_value, P);
+    A(path, G * PATH_CAP); A(path_len, G);
     A(order, G); A(n_active, 1); A(sims_done, G);
     A(planes, P * PLANE_STRIDE); A(mask, P * MASK_STRIDE);
     A(policy, P * N_ACTIONS); A(value, P); A(root_val, G);
@@ -995,6 +1109,7 @@ static int games_upload(szb_ctx* ctx, int n, const std::vector<Pos>& start) {
 }
 
 int szb_games_reset(szb_ctx* ctx, int32_t n, const int16_t* start_id) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || n <= 0 || n > ctx->cfg.max_games) return fail(ctx, SZB_ERR_ARG, "szb_games_reset: n_games out of range");
     std::vector<Pos> start((size_t)n);
     for (int g = 0; g < n; g++) {
@@ -1007,6 +1122,7 @@ int szb_games_reset(szb_ctx* ctx, int32_t n, const int16_t* start_id) {
 }
 
 int szb_games_set(szb_ctx* ctx, int32_t n, const szb_pos* positions) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || !positions || n <= 0 || n > ctx->cfg.max_games) return fail(ctx, SZB_ERR_ARG, "szb_games_set: bad arguments");
     std::vector<Pos> start((size_t)n);
     for (int g = 0; g < n; g++) pos_from_wire(positions[g], start[g]);
@@ -1014,6 +1130,7 @@ int szb_games_set(szb_ctx* ctx, int32_t n, const szb_pos* positions) {
 }
 
 int szb_games_push(szb_ctx* ctx, int32_t n, const int32_t* game, const uint16_t* move_index, int32_t* status) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || n <= 0 || !move_index) return fail(ctx, SZB_ERR_ARG, "szb_games_push: bad arguments");
     if (ctx->d.n_games == 0) return fail(ctx, SZB_ERR_STATE, "no games");
     const size_t bytes = (size_t)n * (4 + 2 + 4) + 64;
@@ -1037,6 +1154,7 @@ int szb_games_push(szb_ctx* ctx, int32_t n, const int32_t* game, const uint16_t*
 }
 
 int szb_games_get(szb_ctx* ctx, int32_t n, const int32_t* game, szb_pos* out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || n <= 0 || !out) return fail(ctx, SZB_ERR_ARG, "szb_games_get: bad arguments");
     char* st = (char*)ctx_stage(ctx, (size_t)n * (sizeof(szb_pos) + 4));
     if (!st) return fail(ctx, SZB_ERR_CUDA, "staging allocation failed");
@@ -1080,14 +1198,17 @@ static int encode_common(szb_ctx* ctx, int32_t n, const int32_t* game, uint16_t*
 }
 
 int szb_legal_moves(szb_ctx* ctx, int32_t n, const int32_t* game, uint16_t* index_out, uint16_t* count_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     return encode_common(ctx, n, game, index_out, count_out, nullptr, nullptr);
 }
 
 int szb_encode(szb_ctx* ctx, int32_t n, const int32_t* game, uint64_t* planes_out, uint64_t* mask_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     return encode_common(ctx, n, game, nullptr, nullptr, planes_out, mask_out);
 }
 
 int szb_unpack_planes_f32(szb_ctx* ctx, int32_t n, const uint64_t* planes_dev, float* out_dev) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || n <= 0 || !planes_dev || !out_dev) return fail(ctx, SZB_ERR_ARG, "bad arguments");
     const size_t total = (size_t)n * N_PLANES * 64;
     k_unpack_planes_f32<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(n, planes_dev, out_dev);
@@ -1098,6 +1219,7 @@ int szb_unpack_planes_f32(szb_ctx* ctx, int32_t n, const uint64_t* planes_dev, f
 
 int szb_perft_timed(szb_ctx* ctx, const szb_pos* pos, int32_t depth, uint64_t* nodes_out, float* ms_last_level,
                     uint64_t* positions_last_level) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || !pos || !nodes_out || depth < 0) return fail(ctx, SZB_ERR_ARG, "szb_perft: bad arguments");
     if (depth == 0) { *nodes_out = 1; return 0; }
     Pos p;
@@ -1118,6 +1240,7 @@ int szb_perft_timed(szb_ctx* ctx, const szb_pos* pos, int32_t depth, uint64_t* n
 }
 
 int szb_perft(szb_ctx* ctx, const szb_pos* pos, int32_t depth, uint64_t* nodes_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     return szb_perft_timed(ctx, pos, depth, nodes_out, nullptr, nullptr);
 }
 
@@ -1129,7 +1252,10 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     if (num_searches < 1 || num_searches > ctx->cfg.max_searches)
         return fail(ctx, SZB_ERR_ARG, "num_searches %d outside [1, max_searches=%d]", num_searches, ctx->cfg.max_searches);
     cudaStream_t st = ctx->stream;
+    int rc0 = 0;
     SZB_CUDA(ctx, cudaMemsetAsync(d.error_flag, 0, sizeof(int32_t), st));
+    if (evaluator == SZB_EVAL_NET_BF16 && (rc0 = net_reset_error(ctx))) return rc0;
+    d.net_in16 = nullptr; d.net_ready = nullptr; d.net_ready_n = 0;
     d.g_begin = 0;
     d.g_end = G;
     k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d, num_searches);
@@ -1190,7 +1316,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             k_hash_eval<<<paths, 128, 0, cs>>>(dc);
             ctx->launches++;
         } else {
-            rc_eval = net_evaluate_batch(ctx, evaluator, dc.g_begin * K, paths);
+            rc_eval = net_evaluate_batch(ctx, evaluator, dc.g_begin * K, paths, false);
         }
         if (ev) cudaEventRecord(ev[3], cs);
         if (K == 1) k_finish<<<warp_blocks, 128, 0, cs>>>(dc, learning);
@@ -1199,14 +1325,42 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         ctx->launches++;
         return rc_eval;
     };
+    // The reference-exact mode outside profiling runs a step as TWO launches: k_tree_step (children + backup of the previous step's
+    // leaves, descent, expansion of the new leaf, the network's input rows) and the evaluator -- for the bf16 network ONE tower launch
+    // whose last epilogue emits the priors of the legal moves and the value (net.cu).  Profiling keeps the phase kernels apart so
+    // that per-phase times mean what they say; both give the same trees (test_fused_step_equals_phase_kernels).
+    const bool fused = K == 1 && !prof && !getenv("SZB_NO_FUSE");
+    const bool net_fused = fused && net_fused_step(ctx, evaluator);
+    auto launch_fused = [&](const Dev& dc0, cudaStream_t cs, int phases) -> int {
+        Dev dc = dc0;
+        const int n = dc.g_end - dc.g_begin;
+        ctx->work = cs;
+        dc.net_in16 = nullptr; dc.net_ready = nullptr; dc.net_ready_n = 0;
+        if (net_fused && (phases & STEP_SELECT)) net_handover(ctx, dc.g_begin, n, &dc.net_in16, &dc.net_ready, &dc.net_ready_n);
+        k_tree_step<<<(n * 32 + 127) / 128, 128, 0, cs>>>(dc, c_puct, learning, phases);
+        ctx->launches++;
+        if (!(phases & STEP_SELECT)) return 0;
+        if (evaluator == SZB_EVAL_HASH) {
+            k_hash_eval<<<n, 128, 0, cs>>>(dc);
+            ctx->launches++;
+            return 0;
+        }
+        return net_evaluate_batch(ctx, evaluator, dc.g_begin, n, net_fused);
+    };
     int rc = 0;
-    for (int s = 0; s < n_steps && !rc && NS > 0; s++) {
+    for (int s = 0; s <= n_steps && !rc && NS > 0; s++) {
+        if (s == n_steps && !fused) break;
         for (int c = 0; c < n_cohorts && !rc; c++) {
             Dev dc = d;
             dc.g_begin = bounds[c];
             dc.g_end = bounds[c + 1];
-            cudaEvent_t* ev = prof ? &ctx->prof_events[5 * ((size_t)s * (trace ? 2 : 1) + (trace ? c : 0))] : nullptr;
-            rc = launch_step(dc, n_cohorts == 2 ? ctx->cohort_stream[c] : st, ev);
+            cudaStream_t cs = n_cohorts == 2 ? ctx->cohort_stream[c] : st;
+            if (fused) {
+                rc = launch_fused(dc, cs, (s > 0 ? STEP_FINISH : 0) | (s < n_steps ? STEP_SELECT : 0));
+            } else {
+                cudaEvent_t* ev = prof ? &ctx->prof_events[5 * ((size_t)s * (trace ? 2 : 1) + (trace ? c : 0))] : nullptr;
+                rc = launch_step(dc, cs, ev);
+            }
         }
     }
     ctx->work = st;
@@ -1280,6 +1434,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
 
 int szb_search(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
                uint32_t* visits_out, uint64_t* child_mask_out, float* root_value_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx) return SZB_ERR_ARG;
     int rc = run_search(ctx, num_searches, c_puct, learning, evaluator);
     if (rc) return rc;
@@ -1305,6 +1460,7 @@ int szb_search(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learnin
 }
 
 int szb_root_children(szb_ctx* ctx, uint16_t* index_out, uint32_t* visits_out, uint16_t* count_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || !index_out || !visits_out || !count_out) return fail(ctx, SZB_ERR_ARG, "szb_root_children: bad arguments");
     Dev& d = ctx->d;
     const size_t G = (size_t)d.n_games;
@@ -1329,6 +1485,7 @@ int szb_tree_export(szb_ctx* ctx, int32_t game, int32_t max_nodes, int32_t max_e
                     int32_t* node_parent, int32_t* node_parent_edge, uint8_t* node_terminal, float* node_terminal_value,
                     int32_t* edge_visits, double* edge_value_sum, float* edge_prior, uint16_t* edge_move, int32_t* edge_child,
                     int32_t* root_visits_out, double* root_value_sum_out, int32_t* n_nodes_out, int32_t* n_edges_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || game < 0 || game >= ctx->d.n_games || max_nodes <= 0 || max_edges <= 0) return fail(ctx, SZB_ERR_ARG, "szb_tree_export: bad arguments");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t mn = (size_t)max_nodes, me = (size_t)max_edges;
@@ -1366,6 +1523,7 @@ int szb_tree_export(szb_ctx* ctx, int32_t game, int32_t max_nodes, int32_t max_e
 
 int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t learning, int32_t evaluator,
                      uint64_t seed, int32_t sample, int32_t* moves_out, int32_t* n_active_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx) return SZB_ERR_ARG;
     int rc = run_search(ctx, num_searches, c_puct, learning, evaluator);
     if (rc) return rc;
@@ -1386,12 +1544,14 @@ int szb_selfplay_ply(szb_ctx* ctx, int32_t num_searches, float c_puct, int32_t l
 }
 
 int szb_set_game_id_base(szb_ctx* ctx, uint64_t base) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx) return SZB_ERR_ARG;
     ctx->game_id_base = base;
     return 0;
 }
 
 int szb_set_profiling(szb_ctx* ctx, int32_t on) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx) return SZB_ERR_ARG;
     ctx->profiling = on != 0;
     for (int k = 0; k < 4; k++) ctx->phase_ms[k] = 0;
@@ -1406,6 +1566,7 @@ int szb_set_profiling(szb_ctx* ctx, int32_t on) {
 }
 
 int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || !out) return SZB_ERR_ARG;
     unsigned long long h[8];
     k_fold_stats<<<1, 256, 0, ctx->stream>>>(ctx->d, ctx->cfg.max_games);
@@ -1425,6 +1586,7 @@ int szb_get_phase_times(szb_ctx* ctx, szb_phase_times* out) {
 }
 
 int szb_get_stats(szb_ctx* ctx, szb_stats* out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || !out) return SZB_ERR_ARG;
     unsigned long long h[8];
     k_fold_stats<<<1, 256, 0, ctx->stream>>>(ctx->d, ctx->cfg.max_games);

@@ -17,6 +17,17 @@ constexpr uint16_t NO_CHILD = 0xFFFF;
 constexpr uint16_t CHILD_PENDING = 0xFFFE;  // multi-leaf mode: the edge's node is being created by an earlier path of this step
 constexpr int PATH_DROPPED = -2;           // multi-leaf mode, sel_edge: this path slot carries no simulation in this step
 constexpr int MAX_LEAVES = 8;              // szb_config.leaves_per_tree <= 8 (one warp per path in k_finish_vl)
+constexpr int PATH_CAP = 64;               // edges of the selected path k_select records per tree (deeper paths: backup walks node_pedge)
+
+// What an edge knows about the node behind it: {first child edge (int32) | child count << 32 | visited-node index << 48}.  PUCT
+// selection reads it next to N / W / P, so the header of the next level arrives with the scan that picks it (one dependent memory
+// round trip per tree level instead of two).
+__host__ __device__ __forceinline__ unsigned long long link_pack(int32_t edge0, uint32_t nchild, uint32_t child) {
+    return (unsigned long long)(uint32_t)edge0 | ((unsigned long long)(nchild & 0xFFFFu) << 32) | ((unsigned long long)(child & 0xFFFFu) << 48);
+}
+__host__ __device__ __forceinline__ int32_t link_edge0(unsigned long long l) { return (int32_t)(uint32_t)l; }
+__host__ __device__ __forceinline__ int link_nchild(unsigned long long l) { return (int)((l >> 32) & 0xFFFFu); }
+__host__ __device__ __forceinline__ uint16_t link_child(unsigned long long l) { return (uint16_t)(l >> 48); }
 
 struct Net;                                // net.cu
 
@@ -50,7 +61,7 @@ struct Dev {
     double* e_w;             // child.value_sum
     float* e_p;              // child.prior
     uint16_t* e_move;        // policy index of child.action_taken
-    uint16_t* e_child;       // visited-node index or NO_CHILD
+    unsigned long long* e_link;   // link_pack(first edge, child count, visited-node index | NO_CHILD) of the node behind the edge
     unsigned long long edge_cap;
     unsigned long long* edge_top;
     int32_t* error_flag;
@@ -59,6 +70,8 @@ struct Dev {
     int32_t* sel_node;       // leaf (or, before expansion, its parent)
     int32_t* sel_edge;       // edge to create a node for, -1 when the leaf already exists, PATH_DROPPED
     int32_t* sel_new;        // multi-leaf mode: node index the expansion must use
+    int32_t* path;           // [slot][PATH_CAP] edges of the path k_select walked, root first (reference-exact mode)
+    int32_t* path_len;       // [slot] its length (backup is one parallel read-modify-write per edge while it fits PATH_CAP)
     uint8_t* need_eval;
     float* leaf_value;
     int32_t* sims_done;      // [max_games] multi-leaf mode: simulations completed in this search
@@ -69,6 +82,10 @@ struct Dev {
     float* root_val;         // [max_games] evaluator value of the root position
     unsigned long long* stats;   // totals: 0 simulations, 1 evaluations, 2 terminal visits, 3 max depth,
                                  // 4 select edges, 5 select levels, 6 backup levels, 7 edges written
+    // ---- hand-over to the network (net.cu), set per launch by run_search ----------------------------
+    unsigned short* net_in16;    // bf16 NHWC input rows [path slot][10][10][128] the expansion writes directly, or null
+    int32_t* net_ready;          // per-item completion counters of the tower launch that follows: zeroed by the tree kernel
+    int net_ready_n;
     unsigned long long* gstats;  // [max_games][8] the same counters per game: the step kernels bump their own game's row
                                  // (no same-address atomics on the hot path), k_fold_stats folds the rows into `stats`
 };
@@ -121,7 +138,10 @@ int fail(szb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(szb_ctx* ctx, cudaError_t e, const char* what);
 void* ctx_stage(szb_ctx* ctx, size_t bytes);
 // net.cu: evaluate games [g0, g0 + n) of d.planes -> d.policy / d.value (softmax policy) on ctx->work.
-int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n);
+int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n, bool fused);
+bool net_fused_step(szb_ctx* ctx, int evaluator);
+void net_handover(szb_ctx* ctx, int g0, int n, unsigned short** in16, int32_t** ready, int* ready_n);
+int net_reset_error(szb_ctx* ctx);
 void net_destroy(szb_ctx* ctx);
 int net_check_error(szb_ctx* ctx);
 // net.cu: fold the recorded conv event pairs into ctx->conv_ms (call after the stream is synchronised)

@@ -87,11 +87,16 @@ struct Net {
     int chunk = 512;                     // boards per tower launch of a large evaluation (net_forward_chunked); 0 = unlimited
     int tower_pairs = 74;                // CTA pairs of an exclusive launch (SZB_TOWER_PAIRS)
     bool tower_exclusive = false;        // SZB_TOWER_EXCLUSIVE: experiment, see launch_tower
+    bool no_fuse = false;                // SZB_NO_FUSE=1: A/B aid, search steps use the separate head kernels
     unsigned long long* span = nullptr;  // [SPAN_CAP][2] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
     bool span_on = false;
     std::vector<int> span_boards, span_b0;
     std::string span_path;
     int num_sms = 148;
+    int pairs_resident = 74;             // CTA pairs of k_tower_tc2 this device holds at once (cudaOccupancyMaxActiveClusters)
+    bool attr_set = false;               // per context (= per device): dynamic shared memory opt-ins done
+    bool attr_set_tc[2] = {false, false};
+    int smem_exclusive = 0;
     std::vector<void*> allocs;
 };
 
@@ -451,7 +456,7 @@ constexpr int MAX_TOWER_LAYERS = 41;                      // stem + 38 tower con
 constexpr int POLICY_LAYER = MAX_TOWER_LAYERS - 1;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;               // shared::cluster address of the same offset in the pair's even CTA
 constexpr int READY_PER_ITEM = 8;                         // 4 epilogue warps x 2 CTAs
-constexpr int SPAN_CAP = 8192;                            // launches recorded by the SZB_TOWER_SPAN aid
+constexpr int SPAN_CAP = 1 << 17;                         // launches recorded by szb_tower_spans_record / SZB_TOWER_SPAN (a c2 bench run: 32,000)
 
 struct TowerLayer {
     uint8_t a_map;       // 0: input planes (128 ch), 1..3: activation buffer 0..2
@@ -473,12 +478,32 @@ struct alignas(64) TowerMaps {
     CUtensorMap w8;      // box 64 k x 8 rows
 };
 
+// Search mode (mcts.py:72-79 fused into the last layer's epilogue): instead of fp32 logits the policy-output layer emits, for every
+// board that needs an evaluation, softmax(logits)[i] for the LEGAL move indices i only (bit-identical to k_softmax over the full
+// row: same maximum, same exp, same summation order) straight into the rows k_finish reads, and the value head
+// (network.py:156-174) of the tile's boards.  mask == null: plain logits output (szb_net_forward*).
+struct TowerHeads {
+    const uint64_t* mask;              // [row][MASK_STRIDE] legal-move bitsets; row = board + row_delta
+    const uint8_t* need_eval;          // [row]
+    float* policy;                     // [row][4672]
+    float* value;                      // [row]
+    const __nv_bfloat16* tower_out;    // activation buffer holding the last residual block's output
+    const float *v_w, *fc1_wT, *fc1_b, *fc2_w;
+    float v_b, fc2_b;
+    int row_delta;
+};
+
 struct TowerArgs {
     int n_pair_tiles;    // ceil(boards / 4)
     int n_boards;
     int board0;          // first board of this launch inside the activation buffers (cohort offset, multiple of 4)
+    int in_delta;        // the input planes of board b are row b + in_delta of the NHWC input buffer (rows written by k_tree_step)
     int layer_begin, layer_end;
     int nsplit;          // 1, 2, 4 or 8: a (layer, tile) is cut into nsplit work items of N / nsplit output channels each (small batches)
+    int n_main;          // work items of the layers cut nsplit ways; the items after them are whole tiles of the LAST layer (fused heads
+                         // need all 73 planes of a board in one accumulator)
+    int n_items;
+    TowerHeads heads;
     int32_t* ready;      // [MAX_TOWER_LAYERS][n_pair_tiles] completion counters, zeroed before the launch
     const float* bias;   // [MAX_TOWER_LAYERS][256]
     __nv_bfloat16* act[3];
@@ -488,6 +513,28 @@ struct TowerArgs {
     unsigned long long* span;    // measurement aid (SZB_TOWER_SPAN): {first CTA start, last CTA end} of this launch (%globaltimer), or null
     TowerLayer L[MAX_TOWER_LAYERS];
 };
+
+struct TowerItem { int l, t, q, ns; };
+__device__ __forceinline__ TowerItem tower_item(const TowerArgs& a, int item) {
+    TowerItem it;
+    if (item < a.n_main) {
+        const int ti = item / a.nsplit;
+        it.q = item - ti * a.nsplit;
+        it.l = a.layer_begin + ti / a.n_pair_tiles;
+        it.t = ti % a.n_pair_tiles;
+        it.ns = a.nsplit;
+    } else {
+        it.l = a.layer_end - 1;
+        it.t = item - a.n_main;
+        it.q = 0;
+        it.ns = 1;
+    }
+    return it;
+}
+
+// one definition for every kernel that must agree bit for bit (k_softmax, the fused heads, k_value_head)
+__device__ __noinline__ float sm_exp(float x, float mx) { return expf(__fsub_rn(x, mx)); }
+__device__ __noinline__ float vh_tanh(float x) { return tanhf(x); }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -605,13 +652,16 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
     __shared__ float bias_sh[2][C_TOWER];
+    // fused heads (this CTA's two boards)
+    __shared__ uint64_t hd_mask[2][MASK_WORDS];
+    __shared__ float hd_red[2][2][4], hd_plane[2][64], hd_vw[C_TOWER], hd_fc[2][8];
 
     const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_b = smem_a + T2_A_CHUNKS * T2_A_CHUNK_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int n_items = (a.layer_end - a.layer_begin) * a.n_pair_tiles * a.nsplit;
+    const int n_items = a.n_items;
     volatile int* abort_flag = &abort_sh;
 
     if (threadIdx.x == 0) {
@@ -665,7 +715,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 if (l > a.layer_begin && !(ok = wait_dependency(l, t))) break;
                 if (a.trace && rank == 0 && lane == 0) a.trace[(size_t)item * 4 + 0] = global_ns();      // dependency resolved
                 const CUtensorMap* tm_a = &maps.a[L.a_map];
-                const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
+                const int board0 = a.board0 + (t * 2 + (int)rank) * 2 + (L.a_map == 0 ? a.in_delta : 0);
                 const int wrow = l * C_TOWER + (int)rank * L.n_half;
                 const CUtensorMap* tm_w = L.n_half == 128 ? &maps.w : &maps.w64;
                 const uint32_t b_tx = 2u * (uint32_t)L.n_half * TC_BLOCK_K * 2;
@@ -700,13 +750,13 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             // the dependency wait (weights do not depend on the previous layer), then all activation chunks at once, then the
             // remaining weight stages.
             for (int item = pair; item < n_items && ok; item += n_pairs) {
-                const int ti = item / a.nsplit, q = item - ti * a.nsplit;
-                const int l = a.layer_begin + ti / a.n_pair_tiles, t = ti % a.n_pair_tiles;
+                const TowerItem it = tower_item(a, item);
+                const int l = it.l, t = it.t, q = it.q;
                 const TowerLayer L = a.L[l];
                 const CUtensorMap* tm_a = &maps.a[L.a_map];
-                const int board0 = a.board0 + (t * 2 + (int)rank) * 2;
-                const int nh = L.n_half / a.nsplit;                               // weight rows per CTA of this item
-                const int tps = L.taps == 9 ? a.nsplit : 1;                       // weight tiles per stage (3x3 layers: 128 / nh)
+                const int board0 = a.board0 + (t * 2 + (int)rank) * 2 + (L.a_map == 0 ? a.in_delta : 0);
+                const int nh = L.n_half / it.ns;                                  // weight rows per CTA of this item
+                const int tps = L.taps == 9 ? it.ns : 1;                          // weight tiles per stage (3x3 layers: 128 / nh)
                 const int wrow = l * C_TOWER + q * 2 * nh + (int)rank * nh;
                 const CUtensorMap* tm_w = nh == 64 ? &maps.w64 : nh == 32 ? &maps.w32 : nh == 16 ? &maps.w16 : &maps.w8;
                 const uint32_t tile_bytes = (uint32_t)nh * TC_BLOCK_K * 2;
@@ -765,8 +815,9 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             int local = 0;
             bool ok = true;
             for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
-                const TowerLayer L = a.L[a.layer_begin + item / (a.n_pair_tiles * a.nsplit)];
-                const uint32_t idesc = IDESC_BASE | ((uint32_t)(2 * L.n_half / a.nsplit >> 3) << 17);
+                const TowerItem it = tower_item(a, item);
+                const TowerLayer L = a.L[it.l];
+                const uint32_t idesc = IDESC_BASE | ((uint32_t)(2 * L.n_half / it.ns >> 3) << 17);
                 const uint32_t acc = local & 1;
                 const uint32_t acc_phase = (local >> 1) & 1;
                 if (!(ok = warp_mbar_wait(bar_ce0 + acc * 8, acc_phase ^ 1, abort_flag))) break;
@@ -782,9 +833,9 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     const uint32_t chunk_lo = a_lo0 + ac * (T2_A_CHUNK_BYTES >> 4);
                     if (L.taps == 9) {
                         // a weight stage holds nsplit consecutive taps of 128 / nsplit rows per CTA (see the producer)
-                        ok = a.nsplit == 1   ? mma_chunk_3x3<1>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
-                             : a.nsplit == 2 ? mma_chunk_3x3<2>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
-                             : a.nsplit == 8 ? mma_chunk_3x3<8>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                        ok = it.ns == 1   ? mma_chunk_3x3<1>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                             : it.ns == 2 ? mma_chunk_3x3<2>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                             : it.ns == 8 ? mma_chunk_3x3<8>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
                                              : mma_chunk_3x3<4>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag);
                     } else {
                         // 1x1 convolution = centre tap, one weight tile per stage
@@ -818,10 +869,10 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         int local = 0;
         bool ok = true;
         for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
-            const int ti = item / a.nsplit, q = item - ti * a.nsplit;
-            const int l = a.layer_begin + ti / a.n_pair_tiles, t = ti % a.n_pair_tiles;
+            const TowerItem it = tower_item(a, item);
+            const int l = it.l, t = it.t, q = it.q;
             const TowerLayer L = a.L[l];
-            const int n_item = 2 * L.n_half / a.nsplit, cb = q * n_item;      // this item's output channels: [cb, cb + n_item)
+            const int n_item = 2 * L.n_half / it.ns, cb = q * n_item;         // this item's output channels: [cb, cb + n_item)
             const int acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
             bias_sh[acc][etid] = a.bias[l * C_TOWER + etid];
@@ -855,6 +906,113 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             }
             const bool tracer = a.trace && rank == 0 && warp == 2 && lane == 0;
             if (tracer) a.trace[(size_t)item * 4 + 2] = global_ns();                    // accumulator complete
+            if (L.mode == 1 && a.heads.mask != nullptr) {
+                // ===== fused heads (an unsplit item: all 73 planes of this CTA's two boards sit in this accumulator) =====
+                // Thread = (board, square) row with its 73 logits in TMEM.  softmax over the board's 4672 logits in the order
+                // k_softmax uses (per square over the planes, then a fixed tree over the squares), so that the priors are
+                // bit-identical to the unfused path's; only the legal moves' entries are written.
+                const int rb = (row >> 3) & 1;                                        // board within this CTA
+                const int cta_board0 = a.board0 + (t * 2 + (int)rank) * 2;
+                const long row_slot = (long)board + a.heads.row_delta;
+                const bool want = live && a.heads.need_eval[row_slot] != 0;
+                for (int i = etid; i < 2 * MASK_WORDS; i += 128) {
+                    const int bb = i >= MASK_WORDS, w = i - bb * MASK_WORDS, brd = cta_board0 + bb;
+                    hd_mask[bb][w] = brd < a.board0 + a.n_boards ? a.heads.mask[(size_t)(brd + a.heads.row_delta) * MASK_STRIDE + w] : 0ull;
+                }
+                hd_vw[etid] = a.heads.v_w[etid];
+                hd_vw[etid + 128] = a.heads.v_w[etid + 128];
+                const float* bias = bias_sh[acc];
+                float mx = -INFINITY;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 96; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (c0 + j < POLICY_PLANES) mx = fmaxf(mx, __fadd_rn(__uint_as_float(v[j]), bias[c0 + j]));
+                }
+                // the 16 squares of this board held by this warp: lane bits 0-2 (file) and 4 (rank parity); lane bit 3 is the board
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 2));
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 4));
+                mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, 16));
+                if ((lane & 0x17) == 0) hd_red[0][rb][lane_group] = mx;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                mx = fmaxf(fmaxf(hd_red[0][rb][0], hd_red[0][rb][1]), fmaxf(hd_red[0][rb][2], hd_red[0][rb][3]));
+                float ssum = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 96; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (c0 + j < POLICY_PLANES) ssum = __fadd_rn(ssum, sm_exp(__fadd_rn(__uint_as_float(v[j]), bias[c0 + j]), mx));
+                }
+                ssum = __fadd_rn(ssum, __shfl_xor_sync(0xFFFFFFFFu, ssum, 1));
+                ssum = __fadd_rn(ssum, __shfl_xor_sync(0xFFFFFFFFu, ssum, 2));
+                ssum = __fadd_rn(ssum, __shfl_xor_sync(0xFFFFFFFFu, ssum, 4));
+                ssum = __fadd_rn(ssum, __shfl_xor_sync(0xFFFFFFFFu, ssum, 16));
+                if ((lane & 0x17) == 0) hd_red[1][rb][lane_group] = ssum;           // squares [16 g, 16 g + 16), g = lane_group
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float tot = __fadd_rn(__fadd_rn(__fadd_rn(hd_red[1][rb][0], hd_red[1][rb][1]), hd_red[1][rb][2]), hd_red[1][rb][3]);
+                float* prow = a.heads.policy + (size_t)row_slot * N_ACTIONS + sq;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 96; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (want) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if (c0 + j < POLICY_PLANES && ((hd_mask[rb][c0 + j] >> sq) & 1ull))
+                                prow[(c0 + j) * 64] = __fdiv_rn(sm_exp(__fadd_rn(__uint_as_float(v[j]), bias[c0 + j]), mx), tot);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(smem_u32(&bar_acc_empty[acc]));      // accumulator free; nothing waits on this layer's counter
+                // ---- value head (network.py:156-174) on the tower output of this thread's pixel, same arithmetic as k_value_head ----
+                float p4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (live) {
+                    const uint4* tp = reinterpret_cast<const uint4*>(a.heads.tower_out + pix * C_TOWER);
+#pragma unroll
+                    for (int part = 0; part < 4; part++) {
+#pragma unroll
+                        for (int qq = 0; qq < 8; qq++) {
+                            const uint4 u = __ldcg(tp + part * 8 + qq);                 // written by other SMs during this launch
+                            const __nv_bfloat16* h8 = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) p4[part] = fmaf(__bfloat162float(h8[j]), hd_vw[part * 64 + qq * 8 + j], p4[part]);
+                        }
+                    }
+                }
+                hd_plane[rb][sq] = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(p4[0], p4[1]), __fadd_rn(p4[2], p4[3])), a.heads.v_b), 0.f);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+                for (int k2 = 0; k2 < 4; k2++) {
+                    const int bb = k2 >> 1, o = etid + 128 * (k2 & 1);
+                    float h = a.heads.fc1_b[o];
+#pragma unroll 8
+                    for (int k = 0; k < 64; k++) h = fmaf(hd_plane[bb][k], a.heads.fc1_wT[k * 256 + o], h);
+                    h = __fmul_rn(fmaxf(h, 0.f), a.heads.fc2_w[o]);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) h = __fadd_rn(h, __shfl_xor_sync(0xFFFFFFFFu, h, off));
+                    if (lane == 0) hd_fc[bb][(k2 & 1) * 4 + (etid >> 5)] = h;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (etid < 2) {
+                    const int brd = cta_board0 + etid;
+                    if (brd < a.board0 + a.n_boards && a.heads.need_eval[brd + a.heads.row_delta]) {
+                        float tt = a.heads.fc2_b;
+#pragma unroll
+                        for (int w = 0; w < 8; w++) tt = __fadd_rn(tt, hd_fc[etid][w]);
+                        a.heads.value[brd + a.heads.row_delta] = vh_tanh(tt);
+                    }
+                }
+                continue;
+            }
             if (L.mode == 1) {
                 // policy logits, plane-major like torch.flatten(conv_p2(x)): index = plane * 64 + row * 8 + col
                 float* lg = a.logits + (size_t)board * N_ACTIONS + sq;
@@ -866,7 +1024,8 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     if (live) {
 #pragma unroll
                         for (int j = 0; j < 32; j++)
-                            if (c0 + j < n_item && cb + c0 + j < POLICY_PLANES) lg[(cb + c0 + j) * 64] = __uint_as_float(v[j]) + bias_sh[acc][cb + c0 + j];
+                            if (c0 + j < n_item && cb + c0 + j < POLICY_PLANES)
+                                lg[(cb + c0 + j) * 64] = __fadd_rn(__uint_as_float(v[j]), bias_sh[acc][cb + c0 + j]);
                     }
                 }
                 tc_fence_before();
@@ -1031,7 +1190,8 @@ __global__ void k_planes_to_nhwc(const uint64_t* planes, int stride, int n, T* o
 }
 
 // value head (network.py:156-174): conv1x1 256->1 (+BN, ReLU) -> fc 64->256 (ReLU) -> fc 256->1 -> tanh.  Block per board.
-// fc1_wT is fc_v1.weight transposed to [64][256] so that the 256 threads read consecutive floats.
+// fc1_wT is fc_v1.weight transposed to [64][256] so that the 256 threads read consecutive floats.  Every rounding is explicit and in
+// the order the fused heads of k_tower_tc2 use, so the two agree bit for bit (test_tower_kernel_variants_bit_identical).
 template <class T>
 __global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v_w, float v_b, const float* fc1_wT, const float* fc1_b,
                                                     const float* fc2_w, float fc2_b, float* value, int n) {
@@ -1063,55 +1223,59 @@ __global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v
             s = fmaf(u.w, vw[q * 4 + 3], s);
         }
     }
-    s += __shfl_xor_sync(0xFFFFFFFFu, s, 1);
-    s += __shfl_xor_sync(0xFFFFFFFFu, s, 2);
-    if (part == 0) plane[sq] = fmaxf(s + v_b, 0.f);
+    s = __fadd_rn(s, __shfl_xor_sync(0xFFFFFFFFu, s, 1));              // (p0 + p1), (p2 + p3)
+    s = __fadd_rn(s, __shfl_xor_sync(0xFFFFFFFFu, s, 2));              // (p0 + p1) + (p2 + p3)
+    if (part == 0) plane[sq] = fmaxf(__fadd_rn(s, v_b), 0.f);
     __syncthreads();
     float h = fc1_b[tid];
 #pragma unroll 8
     for (int k = 0; k < 64; k++) h = fmaf(plane[k], fc1_wT[k * 256 + tid], h);
-    h = fmaxf(h, 0.f) * fc2_w[tid];
+    h = __fmul_rn(fmaxf(h, 0.f), fc2_w[tid]);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, off);
+    for (int off = 16; off > 0; off >>= 1) h = __fadd_rn(h, __shfl_xor_sync(0xFFFFFFFFu, h, off));
     if ((tid & 31) == 0) red[tid >> 5] = h;
     __syncthreads();
     if (tid == 0) {
         float t = fc2_b;
-        for (int w = 0; w < 8; w++) t += red[w];
-        value[b] = tanhf(t);
+#pragma unroll
+        for (int w = 0; w < 8; w++) t = __fadd_rn(t, red[w]);
+        value[b] = vh_tanh(t);
     }
 }
 
-// nn.Softmax(dim=1) over the 4672 logits of every board (network.py:190).  Block per board, fixed reduction order.
+// nn.Softmax(dim=1) over the 4672 logits of every board (network.py:190).  Four boards per block, thread = (board, square).
+// Fixed order, shared with the fused heads of k_tower_tc2 (whose epilogue threads own one square's 73 logits each): maximum (order-free);
+// per square the sum of exp(l - max) over the planes 0..72 in turn; a balanced tree over each group of 16 squares (bits 0..3 of the
+// square index); the four groups in turn.  Batch invariant by construction.
 __global__ void __launch_bounds__(256) k_softmax(const float* logits, float* policy, int n) {
-    __shared__ float red[8];
-    __shared__ float bcast;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const float* l = logits + (size_t)b * N_ACTIONS;
-    float* p = policy + (size_t)b * N_ACTIONS;
+    __shared__ float red[2][4][4];
+    const int tid = threadIdx.x, bl = tid >> 6, sq = tid & 63, lane = tid & 31;
+    const int b = blockIdx.x * 4 + bl;
+    const bool live = b < n;
+    const float* l = logits + (size_t)(live ? b : 0) * N_ACTIONS + sq;
+    float* p = policy + (size_t)(live ? b : 0) * N_ACTIONS + sq;
     float mx = -INFINITY;
-    for (int i = tid; i < N_ACTIONS; i += 256) mx = fmaxf(mx, l[i]);
+    if (live)
+        for (int c = 0; c < POLICY_PLANES; c++) mx = fmaxf(mx, l[c * 64]);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    for (int off = 1; off < 16; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
+    if ((lane & 15) == 0) red[0][bl][sq >> 4] = mx;
     __syncthreads();
-    if (tid == 0) { float m = red[0]; for (int w = 1; w < 8; w++) m = fmaxf(m, red[w]); bcast = m; }
-    __syncthreads();
-    mx = bcast;
-    float e[(N_ACTIONS + 255) / 256];
+    mx = fmaxf(fmaxf(red[0][bl][0], red[0][bl][1]), fmaxf(red[0][bl][2], red[0][bl][3]));
     float s = 0.f;
-    int k = 0;
-    for (int i = tid; i < N_ACTIONS; i += 256, k++) { e[k] = expf(l[i] - mx); s += e[k]; }
+    if (live) {
+#pragma unroll 1
+        for (int c = 0; c < POLICY_PLANES; c++) s = __fadd_rn(s, sm_exp(l[c * 64], mx));
+    }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    for (int off = 1; off < 16; off <<= 1) s = __fadd_rn(s, __shfl_xor_sync(0xFFFFFFFFu, s, off));
+    if ((lane & 15) == 0) red[1][bl][sq >> 4] = s;
     __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = s;
-    __syncthreads();
-    if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; w++) t += red[w]; bcast = t; }
-    __syncthreads();
-    const float tot = bcast;
-    k = 0;
-    for (int i = tid; i < N_ACTIONS; i += 256, k++) p[i] = __fdiv_rn(e[k], tot);
+    const float tot = __fadd_rn(__fadd_rn(__fadd_rn(red[1][bl][0], red[1][bl][1]), red[1][bl][2]), red[1][bl][3]);
+    if (live) {
+#pragma unroll 1
+        for (int c = 0; c < POLICY_PLANES; c++) p[c * 64] = __fdiv_rn(sm_exp(l[c * 64], mx), tot);
+    }
 }
 
 // =================================================================================================
@@ -1305,6 +1469,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     net->tower_pairs = net->num_sms / 2;
     if (const char* e = getenv("SZB_TOWER_PAIRS")) { if (atoi(e) > 0) net->tower_pairs = std::min(atoi(e), net->num_sms / 2); }
     if (const char* e = getenv("SZB_TOWER_EXCLUSIVE")) net->tower_exclusive = e[0] == '1';
+    if (const char* e = getenv("SZB_NO_FUSE")) net->no_fuse = e[0] == '1';
     const char* ck = getenv("SZB_TOWER_CHUNK");              // measurement aid: boards per tower launch (0 = whole batch)
     if (ck && ck[0]) net->chunk = std::max(0, atoi(ck)) & ~3;
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
@@ -1317,35 +1482,63 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
 // =================================================================================================
 // host: forward
 // =================================================================================================
+// how a whole-tower launch is wired into a search step
+struct TowerRun {
+    bool heads = false;          // fused policy / value heads into d.mask / d.policy / d.value rows (else fp32 logits)
+    bool in16_rows = false;      // the input planes of board b0 + i already sit in NHWC input row out_row + i (written by k_tree_step)
+    bool ready_zeroed = false;   // the launch's completion counters were cleared by the kernel before it on the stream
+};
+
 // layers [layer_begin, layer_end) of the tower for n boards in one persistent CTA-pair launch
-static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, int layer_end, int out_row = -1) {
-    static bool attr_set = false;
-    static int smem_exclusive = T2_SMEM;
-    if (!attr_set) {
+static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, int layer_end, int out_row = -1, TowerRun run = TowerRun()) {
+    if (!net->attr_set) {
         // "exclusive" launches ask for all the shared memory a block can have, so that no other block fits on an SM next to a
         // tower CTA (every block also reserves 1 KiB of system shared memory): see Net::tower_pairs
         cudaFuncAttributes fa;
         SZB_CUDA(ctx, cudaFuncGetAttributes(&fa, k_tower_tc2));
-        smem_exclusive = std::max(T2_SMEM, 232448 - (int)fa.sharedSizeBytes);
-        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_exclusive));
-        attr_set = true;
+        net->smem_exclusive = std::max(T2_SMEM, 232448 - (int)fa.sharedSizeBytes);
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, net->smem_exclusive));
+        // The pairs of a launch wait on one another (per-item completion counters), so every pair must be able to become
+        // resident while the others spin: never launch more pairs than this device can hold at once.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(net->num_sms);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = T2_SMEM;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, k_tower_tc2, &cfg) == cudaSuccess && clusters > 0)
+            net->pairs_resident = std::min(net->num_sms / 2, clusters);
+        else
+            cudaGetLastError();
+        net->attr_set = true;
     }
     TowerArgs a = *net->tower_args;
     a.n_pair_tiles = (n + 3) / 4;
     a.n_boards = n;
     a.board0 = b0;
+    a.in_delta = run.in16_rows && out_row >= 0 ? out_row - b0 : 0;
     a.layer_begin = layer_begin;
     a.layer_end = layer_end;
     if (out_row >= 0) a.logits = net->logits + (size_t)(out_row - b0) * N_ACTIONS;      // board b0 + i -> logits row out_row + i
     a.ready = net->ready + (size_t)MAX_TOWER_LAYERS * (b0 / 4);      // cohorts (disjoint board ranges) get disjoint counter regions
-    if (layer_end - layer_begin > 1)
+    if (layer_end - layer_begin > 1 && !run.ready_zeroed)
         SZB_CUDA(ctx, cudaMemsetAsync(a.ready, 0, sizeof(int32_t) * (size_t)MAX_TOWER_LAYERS * a.n_pair_tiles, ctx->work));
+    const bool heads = run.heads && layer_end == MAX_TOWER_LAYERS;
+    if (heads) {
+        const Dev& d = ctx->d;
+        TowerHeads& h = a.heads;
+        h.mask = d.mask; h.need_eval = d.need_eval; h.policy = d.policy; h.value = d.value;
+        h.tower_out = net->act16[net->final_x];
+        h.v_w = net->v_w; h.fc1_wT = net->fc1_w; h.fc1_b = net->fc1_b; h.fc2_w = net->fc2_w; h.v_b = net->v_b; h.fc2_b = net->fc2_b;
+        h.row_delta = (out_row >= 0 ? out_row : b0) - b0;
+    } else {
+        a.heads.mask = nullptr;
+    }
     // Small batches leave most CTA pairs idle and the launch becomes a chain of 41 dependent layers: cut every (layer, tile)
     // into 2 or 4 items of N / nsplit output channels so that up to all pairs work on one layer.  Same MMAs per output, same K
     // order: bit-identical results.  Measured (scripts/small_batch.py, ms per launch, split 1 / 2 / 4): 64 boards 0.75 / - / 0.33,
     // 148 boards 0.79 / 0.44 / -, 200 boards 0.72 / 0.49 / -, 296 boards 0.73 / 0.70 / -, 512 boards 0.89 / 1.24 / -.
     const bool exclusive = net->tower_exclusive && (n + 3) / 4 > net->tower_pairs;      // large launches only
-    const int pairs = exclusive ? net->tower_pairs : net->num_sms / 2;
+    const int pairs = std::min(exclusive ? net->tower_pairs : net->num_sms / 2, net->pairs_resident);
     a.nsplit = 1;
     if (layer_end - layer_begin > 1) {
         if (net->tower_nsplit) a.nsplit = net->tower_nsplit;
@@ -1354,13 +1547,18 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
         else if (a.n_pair_tiles <= pairs) a.nsplit = 2;
     }
     net->last_nsplit = a.nsplit;
+    // with fused heads the last layer's items are whole tiles (a board's 73 planes in one accumulator) whatever the split
+    const int layers = layer_end - layer_begin;
+    const int main_layers = heads && a.nsplit > 1 ? layers - 1 : layers;
+    a.n_main = main_layers * a.n_pair_tiles * a.nsplit;
+    a.n_items = a.n_main + (layers - main_layers) * a.n_pair_tiles;
     if (net->span_on && (int)net->span_boards.size() < SPAN_CAP && layer_end - layer_begin > 1) {
         a.span = net->span + 2 * net->span_boards.size();
         net->span_boards.push_back(n);
         net->span_b0.push_back(b0);
     }
     const int grid = 2 * std::min(a.n_pair_tiles * a.nsplit, pairs);
-    k_tower_tc2<<<grid, TC_THREADS, exclusive ? smem_exclusive : T2_SMEM, ctx->work>>>(*net->tower_maps, a);
+    k_tower_tc2<<<grid, TC_THREADS, exclusive ? net->smem_exclusive : T2_SMEM, ctx->work>>>(*net->tower_maps, a);
     ctx->launches++;
     return 0;
 }
@@ -1368,11 +1566,10 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
 template <int N_TILE, int MODE>
 static int launch_tc(szb_ctx* ctx, Net* net, const CUtensorMap& tm_a, const ConvLayer& L, const __nv_bfloat16* residual,
                      __nv_bfloat16* out, float* logits, int n, int relu, int b0 = 0) {
-    static bool attr_set = false;
     constexpr int smem = TC_STAGES * (TC_A_BYTES + N_TILE * TC_BLOCK_K * 2) + 1024;
-    if (!attr_set) {
+    if (!net->attr_set_tc[MODE]) {
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_conv_tc<N_TILE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        net->attr_set_tc[MODE] = true;
     }
     TcArgs a;
     a.n_tiles = (n + 1) / 2;
@@ -1428,9 +1625,12 @@ void net_collect_conv_times(szb_ctx* ctx) {
 // planes (device, row stride `stride` uint64; row 0 = board b0) -> net->logits[b0..] + value_out[0..n) (device).
 // b0 is the first board inside the activation buffers (a multiple of 4): cohorts of one search use disjoint ranges.
 // All launches go to ctx->work.
-static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out, int out_row = -1) {
+static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out, int out_row = -1,
+                              TowerRun run = TowerRun()) {
     Net* net = ctx->net;
     if (out_row < 0) out_row = b0;
+    if ((run.heads || run.in16_rows) && !(evaluator == SZB_EVAL_NET_BF16 && net && net->tower_mode == 2))
+        return fail(ctx, SZB_ERR_ARG, "only the one-launch bf16 tower has fused heads");
     if (out_row != b0 && !(evaluator == SZB_EVAL_NET_BF16 && net && net->tower_mode == 2))
         return fail(ctx, SZB_ERR_ARG, "only the one-launch bf16 tower writes logits rows apart from its activation rows");
     if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
@@ -1439,8 +1639,10 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
     const unsigned up_blocks = (unsigned)(((size_t)n * 64 * 16 + 255) / 256);
     const size_t in_off = (size_t)b0 * HALO * HALO * C_IN_PAD, act_off = (size_t)b0 * HALO * HALO * C_TOWER;
     if (evaluator == SZB_EVAL_NET_BF16) {
-        k_planes_to_nhwc<__nv_bfloat16><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in16 + in_off);
-        ctx->launches++;
+        if (!run.in16_rows) {
+            k_planes_to_nhwc<__nv_bfloat16><<<up_blocks, 256, 0, st>>>(planes, stride, n, net->in16 + in_off);
+            ctx->launches++;
+        }
         int rc;
         int x, y;
         if (net->tower_mode == 0) {
@@ -1470,9 +1672,13 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
             // stem + 38 tower convolutions + both policy 1x1 layers in ONE persistent launch; the measurement hook brackets exactly that launch
             cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
             if (cev) cudaEventRecord(cev[0], st);
-            if ((rc = launch_tower(ctx, net, b0, n, 0, MAX_TOWER_LAYERS, out_row))) return rc;
+            if ((rc = launch_tower(ctx, net, b0, n, 0, MAX_TOWER_LAYERS, out_row, run))) return rc;
             if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_ALL * (uint64_t)n; }
             x = net->final_x; y = net->final_y;
+            if (run.heads) {                                      // priors and values were written by the tower's last epilogue
+                SZB_CUDA(ctx, cudaGetLastError());
+                return 0;
+            }
         }
         // (the one-launch tower ends with the policy output layer; the per-layer modes use the single-CTA kernel for it)
         if (net->tower_mode != 2 && (rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0, b0))) return rc;
@@ -1507,24 +1713,50 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
 // [b0, b0 + chunk): three activation buffers of 512 boards (79 MB) + the weights stay in the 126 MB L2, those of 1024+ boards do
 // not (ncu: 0.42 GB of DRAM traffic per 512-board launch, 2.68 GB per 1024-board launch), and under the 1 kW power cap DRAM
 // traffic costs clock.  Planes in, logits / values out keep their own rows.
-static int net_forward_chunked(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out) {
+static int net_forward_chunked(szb_ctx* ctx, int evaluator, int b0, int n, const uint64_t* planes, int stride, float* value_out,
+                               TowerRun run = TowerRun()) {
     Net* net = ctx->net;
     if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
     const int chunk = (evaluator == SZB_EVAL_NET_BF16 && net->tower_mode == 2 && net->chunk > 0) ? net->chunk : n;
     for (int off = 0; off < n; off += chunk) {
         const int m = std::min(chunk, n - off);
-        int rc = net_forward_device(ctx, evaluator, b0, m, planes + (size_t)off * stride, stride, value_out + off, b0 + off);
+        int rc = net_forward_device(ctx, evaluator, b0, m, planes + (size_t)off * stride, stride, value_out + off, b0 + off, run);
         if (rc) return rc;
+        run.ready_zeroed = false;                                 // later chunks reuse the first chunk's counters: clear them again
     }
     return 0;
 }
 
-// evaluate slots [g0, g0 + n) of the search batch (g0 a multiple of 4): d.planes -> d.policy (softmax) / d.value, on ctx->work
-int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n) {
-    int rc = net_forward_chunked(ctx, evaluator, g0, n, ctx->d.planes + (size_t)g0 * PLANE_STRIDE, PLANE_STRIDE, ctx->d.value + g0);
-    if (rc) return rc;
-    k_softmax<<<n, 256, 0, ctx->work>>>(ctx->net->logits + (size_t)g0 * N_ACTIONS, ctx->d.policy + (size_t)g0 * N_ACTIONS, n);
+// does a search step with this evaluator run as k_tree_step + one tower launch with fused heads?
+bool net_fused_step(szb_ctx* ctx, int evaluator) {
+    return evaluator == SZB_EVAL_NET_BF16 && ctx->net && ctx->net->loaded && ctx->net->tower_mode == 2 && !ctx->net->no_fuse;
+}
+
+// what k_tree_step hands to the tower launch that evaluates slots [g0, g0 + n): the NHWC input rows it fills and the completion
+// counters (of the first chunk's launch) it clears
+void net_handover(szb_ctx* ctx, int g0, int n, unsigned short** in16, int32_t** ready, int* ready_n) {
+    Net* net = ctx->net;
+    const int first = net->chunk > 0 ? std::min(n, net->chunk) : n;
+    *in16 = reinterpret_cast<unsigned short*>(net->in16);
+    *ready = net->ready + (size_t)MAX_TOWER_LAYERS * (g0 / 4);
+    *ready_n = MAX_TOWER_LAYERS * ((first + 3) / 4);
+}
+
+// evaluate slots [g0, g0 + n) of the search batch (g0 a multiple of 4): d.planes -> d.policy (softmax; the legal entries only when the
+// heads are fused) / d.value, on ctx->work.  fused: the step's k_tree_step filled the input rows and cleared the counters.
+int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n, bool fused) {
+    TowerRun run;
+    run.heads = run.in16_rows = run.ready_zeroed = fused;
+    int rc = net_forward_chunked(ctx, evaluator, g0, n, ctx->d.planes + (size_t)g0 * PLANE_STRIDE, PLANE_STRIDE, ctx->d.value + g0, run);
+    if (rc || fused) return rc;
+    k_softmax<<<(n + 3) / 4, 256, 0, ctx->work>>>(ctx->net->logits + (size_t)g0 * N_ACTIONS, ctx->d.policy + (size_t)g0 * N_ACTIONS, n);
     ctx->launches++;
+    return 0;
+}
+
+// a search starts with a clean pipeline-error flag (a timed-out launch must not poison the context for good)
+int net_reset_error(szb_ctx* ctx) {
+    if (ctx->net && ctx->net->tc_error) SZB_CUDA(ctx, cudaMemsetAsync(ctx->net->tc_error, 0, sizeof(int32_t), ctx->stream));
     return 0;
 }
 
@@ -1544,6 +1776,7 @@ int net_check_error(szb_ctx* ctx) {
 extern "C" {
 
 int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || n_tensors <= 0 || !names || !data || !numel) return fail(ctx, SZB_ERR_ARG, "szb_net_load: bad arguments");
     int rc;
     if ((rc = get_encode(ctx))) return rc;
@@ -1563,6 +1796,22 @@ int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, cons
         if ((r = get(p + ".running_mean", c, &bn->m))) return r;
         return get(p + ".running_var", c, &bn->v);
     };
+    // validate the whole state_dict BEFORE tearing down the network that is loaded and working: a bad checkpoint leaves it in place
+    {
+        const float* probe;
+        BN pb;
+        if ((rc = get("conv1.weight", 256LL * 119 * 9, &probe)) || (rc = get_bn("norm_layer", 256, &pb))) return rc;
+        for (int b = 0; b < N_BLOCKS; b++)
+            for (int j = 1; j <= 2; j++) {
+                const std::string pfx = "resnet_blocks." + std::to_string(b);
+                if ((rc = get(pfx + ".conv" + std::to_string(j) + ".weight", 256LL * 256 * 9, &probe)) || (rc = get_bn(pfx + ".bn" + std::to_string(j), 256, &pb))) return rc;
+            }
+        if ((rc = get("conv_p1.weight", 256LL * 256, &probe)) || (rc = get_bn("p_norm1", 256, &pb))) return rc;
+        if ((rc = get("conv_p2.weight", 73LL * 256, &probe)) || (rc = get("conv_p2.bias", 73, &probe))) return rc;
+        if ((rc = get("conv_v1.weight", 256, &probe)) || (rc = get_bn("v_norm", 1, &pb))) return rc;
+        if ((rc = get("fc_v1.weight", 256LL * 64, &probe)) || (rc = get("fc_v1.bias", 256, &probe))) return rc;
+        if ((rc = get("fc_v2.weight", 256, &probe)) || (rc = get("fc_v2.bias", 1, &probe))) return rc;
+    }
     net_destroy(ctx);
     Net* net = new Net();
     ctx->net = net;
@@ -1641,7 +1890,7 @@ static int net_forward_common(szb_ctx* ctx, int32_t n, const uint64_t* planes, i
         if (rc) return rc;
         const float* src = net->logits;
         if (softmax) {
-            k_softmax<<<m, 256, 0, ctx->work>>>(net->logits, d_p, m);
+            k_softmax<<<(m + 3) / 4, 256, 0, ctx->work>>>(net->logits, d_p, m);
             ctx->launches++;
             src = d_p;
         }
@@ -1655,6 +1904,7 @@ static int net_forward_common(szb_ctx* ctx, int32_t n, const uint64_t* planes, i
 }
 
 int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float* ms_avg_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx || !ms_avg_out || n <= 0 || iters <= 0) return fail(ctx, SZB_ERR_ARG, "szb_time_kernel: bad arguments");
     Net* net = ctx->net;
     if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
@@ -1719,6 +1969,7 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
 }
 
 int szb_tower_spans_record(szb_ctx* ctx, int32_t on, szb_tower_spans* out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     if (!ctx) return SZB_ERR_ARG;
     Net* net = ctx->net;
     if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
@@ -1751,10 +2002,12 @@ int szb_tower_spans_record(szb_ctx* ctx, int32_t on, szb_tower_spans* out) {
 }
 
 int szb_net_forward(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* policy_out, float* value_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     return net_forward_common(ctx, n, planes, evaluator, policy_out, value_out, true);
 }
 
 int szb_net_forward_logits(szb_ctx* ctx, int32_t n, const uint64_t* planes, int32_t evaluator, float* logits_out, float* value_out) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
     return net_forward_common(ctx, n, planes, evaluator, logits_out, value_out, false);
 }
 
