@@ -215,7 +215,8 @@ int szb_tower_spans_record(szb_ctx *ctx, int32_t on, szb_tower_spans *out);
 /* average duration (ms) of one launch of a kernel run `iters` times back to back on n boards:
  * which = 0: one 3x3 256->256 tower convolution (single-CTA tcgen05 kernel, with residual) ; 1: whole bf16 forward ;
  * 2: whole fp32 forward ; 3: one 3x3 256->256 fp32 SIMT convolution ; 4: one 3x3 256->256 tower convolution
- * (CTA-pair kernel) ; 5: the whole tower in one CTA-pair launch */
+ * (CTA-pair kernel) ; 5: the whole tower in one CTA-pair launch ; 6: the whole forward (tower + heads) in the cluster-resident
+ * kernel that serves batches of at most 18 boards */
 /* NOTE: the tower kernels run on whatever the activation buffers hold.  On a fresh context that is all-zero input planes --
  * constant activations, little switching, far less power -- so many back-to-back launches then sustain a higher clock than real
  * positions allow (1.5 vs 1.3 PFLOP/s, profiles/r01o_*).  Run a search first when a sustained figure is wanted. */

@@ -17,9 +17,14 @@ for n in (1, 4, 8, 16, 32, 64, 72, 100, 148, 200, 296, 512):
     ms = eng.time_kernel(5, n, 50)
     res["tower_ms"][n] = ms
     print("%s tower n=%4d  %8.4f ms  (%.2f us/layer)" % (tag, n, ms, ms * 1e3 / 41), flush=True)
+res["cluster_tower_ms"] = {}
+for n in (1, 2, 4, 8, 12, 18):
+    ms = eng.time_kernel(6, n, 50)
+    res["cluster_tower_ms"][n] = ms
+    print("%s cluster tower (k_tower_cl, whole forward) n=%4d  %8.4f ms  (%.2f us/layer)" % (tag, n, ms, ms * 1e3 / 41), flush=True)
 eng.close()
 S = 200
-for G in (1, 8, 63, 125, 250):
+for G in (1, 8, 18, 63, 125, 250):
     eng = Engine(max_games=G, max_searches=S)
     eng.load_state_dict(model.state_dict())
     eng.reset([-1] * G)

@@ -66,6 +66,14 @@ __device__ __forceinline__ void load_tables(Tables* sm, const Tables* g) {
 }
 __device__ __forceinline__ int state_slot(const Dev& d, int g, int node) { return node == 0 ? d.cur[g] : RING + node; }
 
+// predecessor slots of the position in `slot`, whose direct predecessor sits in prev_slot (NO_PREV: a game's first position)
+__device__ __forceinline__ void set_ancestors(const Dev& d, int g, int slot, uint32_t prev_slot) {
+    uint4* row = reinterpret_cast<uint4*>(d.anc + ((size_t)g * d.pool_stride + slot) * 8);
+    if (prev_slot == NO_PREV) { *row = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); return; }
+    const uint4 o = *reinterpret_cast<const uint4*>(d.anc + ((size_t)g * d.pool_stride + prev_slot) * 8);
+    *row = make_uint4((o.x << 16) | (prev_slot & 0xFFFFu), (o.y << 16) | (o.x >> 16), (o.z << 16) | (o.y >> 16), (o.w << 16) | (o.z >> 16));
+}
+
 __device__ __forceinline__ void analyse(const Tables& T, Pos& p, uint16_t* mv, int& n) {
     n = gen_legal(T, p, mv);
     p.n_legal = (uint8_t)n;
@@ -87,6 +95,7 @@ __global__ void k_games_init(Dev d, const Pos* start, int n) {
     analyse(T, p, mv, cnt);
     const int slot = p.ply & (RING - 1);
     d.pool[(size_t)g * d.pool_stride + slot] = p;
+    set_ancestors(d, g, slot, NO_PREV);
     d.cur[g] = slot;
 }
 
@@ -115,6 +124,7 @@ __global__ void k_games_push(Dev d, int n, const int32_t* game, const uint16_t* 
     analyse(T, q, mv, cnt);
     const int slot = q.ply & (RING - 1);
     gp[slot] = q;
+    set_ancestors(d, g, slot, q.prev);
     d.cur[g] = slot;
     status[i] = 0;
 }
@@ -327,6 +337,7 @@ __device__ __forceinline__ bool expand_path(const Dev& d, const Tables& T, int p
         set_repetition_flags(gp, q);
         analyse(T, q, mv, cnt);
         gp[RING + node] = q;
+        set_ancestors(d, g, RING + node, (uint32_t)pslot);
         d.node_pedge[r + node] = e;
         d.node_pnode[r + node] = (uint16_t)parent;
         d.node_nchild[r + node] = 0;
@@ -352,6 +363,126 @@ __device__ __forceinline__ bool expand_path(const Dev& d, const Tables& T, int p
     }
     pack_planes(gp, q, planes_out);
     d.need_eval[ps] = 1;
+    return true;
+}
+
+// The 119 planes of `now` (pool slot qslot of game g) by nine lanes: lane t < 8 packs history step t, whose position it loads
+// through the recorded predecessor slots (d.anc) -- eight independent loads instead of a walk along Pos::prev -- and lane 8 the
+// seven constant planes.  Same planes as pack_planes (chess.cuh), which k_expand / k_games_encode use: a step exists when every
+// link up to it holds (predecessor recorded and exactly one ply older: a recycled ring slot breaks the chain).
+__device__ __forceinline__ void pack_planes_warp(const Dev& d, int g, const Pos* gp, int qslot, const Pos& now, uint64_t* out, int lane) {
+    const bool white = now.flags & F_WHITE;
+    const int own = white ? BB_WHITE : BB_BLACK, opp = white ? BB_BLACK : BB_WHITE;
+    Pos P = now;
+    bool link = lane == 0;
+    if (lane >= 1 && lane < 8) {
+        const uint16_t A = d.anc[((size_t)g * d.pool_stride + qslot) * 8 + lane - 1];
+        if (A != 0xFFFFu) { P = gp[A]; link = true; }
+    }
+    const int ply = link ? (int)P.ply : -7;
+    const int ply_next = __shfl_up_sync(0xFFFFFFFFu, ply, 1);                 // the step nearer to `now`
+    if (lane >= 1) link = link && (uint16_t)(ply + 1) == (uint16_t)ply_next && ply_next >= 0;
+    const unsigned ok = __ballot_sync(0xFFFFFFFFu, link);
+    const int steps = __ffs(~ok) - 1;                                         // trailing ones: steps 0 .. steps-1 exist
+    if (lane < 8) {
+        uint64_t* o = out + 14 * lane;
+        if (lane < steps) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                o[k] = view_bb(P.bb[BB_P + k] & P.bb[own], white);
+                o[6 + k] = view_bb(P.bb[BB_P + k] & P.bb[opp], white);
+            }
+            o[12] = (P.flags & F_REP2) ? ~0ull : 0ull;
+            o[13] = (P.flags & F_REP3) ? ~0ull : 0ull;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 14; k++) o[k] = 0;
+        }
+    } else if (lane == 8) {
+        const int cf = now.ply ? castling_flags(now) : 15;       // hard-coded ones before the first move (chess_tensor.py:82)
+        const int ownc = white ? (cf & 3) : (cf >> 2), oppc = white ? (cf >> 2) : (cf & 3);
+        out[112] = white ? ~0ull : 0ull;
+        out[113] = now.ply ? ~0ull : 0ull;
+        out[114] = (ownc & 1) ? ~0ull : 0ull;
+        out[115] = (ownc & 2) ? ~0ull : 0ull;
+        out[116] = (oppc & 1) ? ~0ull : 0ull;
+        out[117] = (oppc & 2) ? ~0ull : 0ull;
+        out[118] = (now.ply && now.halfmove) ? ~0ull : 0ull;
+    }
+}
+
+// Expansion of the tree in `slot` by its warp (the latency-critical form k_tree_step uses; same results as expand_path): lane 0
+// makes the move and generates the legal moves into shared memory, then the lanes share the rest -- policy indices of the moves
+// into the shared-memory legal mask, history planes from eight independent position loads, coalesced copies out.
+struct ExpandShared {
+    Pos q;
+    uint16_t mv[MAX_MOVES];
+    uint64_t mask[MASK_STRIDE];
+    uint64_t planes[PLANE_STRIDE];
+};
+__device__ __forceinline__ bool expand_warp(const Dev& d, const Tables& T, int slot, int lane, ExpandShared& S, unsigned long long* tr = nullptr) {
+    const int g = d.order[slot];
+    const size_t r = (size_t)g * d.nodes_per_game;
+    Pos* gp = d.pool + (size_t)g * d.pool_stride;
+    for (int w = lane; w < MASK_STRIDE; w += 32) S.mask[w] = 0;
+    int cnt = 0, qslot = 0, term = 0;
+    if (lane == 0) {
+        const int e = d.sel_edge[slot];
+        int node = d.sel_node[slot];
+        Pos q;
+        if (e >= 0) {
+            const int parent = node;
+            node = ++d.node_count[g];
+            const int pslot = state_slot(d, g, parent);
+            const Pos pp = gp[pslot];
+            const uint16_t m = index_to_move(pp, d.e_move[e]);
+            make_move(T, pp, m, q);
+            q.prev = (uint32_t)pslot;
+            set_repetition_flags(gp, q);
+            if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[4] = t; }
+            analyse(T, q, S.mv, cnt);
+            qslot = RING + node;
+            gp[qslot] = q;
+            set_ancestors(d, g, qslot, (uint32_t)pslot);
+            d.node_pedge[r + node] = e;
+            d.node_pnode[r + node] = (uint16_t)parent;
+            d.node_nchild[r + node] = 0;
+            d.node_edge0[r + node] = -1;
+            term = q.outcome != OUT_NONE;
+            d.node_term[r + node] = (uint8_t)term;
+            d.node_tval[r + node] = q.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
+            d.e_link[e] = link_pack(-1, 0, (uint32_t)node);
+            d.sel_node[slot] = node;
+        } else {
+            qslot = state_slot(d, g, node);
+            q = gp[qslot];
+            term = d.node_term[r + node];
+            if (!term) cnt = gen_legal(T, q, S.mv);
+        }
+        if (term) {
+            d.leaf_value[slot] = d.node_tval[r + node];
+            d.need_eval[slot] = 0;
+        } else {
+            d.need_eval[slot] = 1;
+            S.q = q;
+        }
+    }
+    __syncwarp();                                              // lane 0's shared / global writes -> the other lanes
+    if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[5] = t; }
+    term = __shfl_sync(0xFFFFFFFFu, term, 0);
+    if (term) return false;
+    cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0);
+    qslot = __shfl_sync(0xFFFFFFFFu, qslot, 0);
+    for (int k = lane; k < cnt; k += 32) {
+        const int idx = move_to_index(S.q, S.mv[k]);
+        atomicOr(reinterpret_cast<unsigned long long*>(&S.mask[idx >> 6]), 1ull << (idx & 63));
+    }
+    pack_planes_warp(d, g, gp, qslot, S.q, S.planes, lane);
+    __syncwarp();
+    uint64_t* mrow = d.mask + (size_t)slot * MASK_STRIDE;
+    for (int w = lane; w < MASK_STRIDE; w += 32) mrow[w] = S.mask[w];
+    uint64_t* prow = d.planes + (size_t)slot * PLANE_STRIDE;
+    for (int i = lane; i < N_PLANES; i += 32) prow[i] = S.planes[i];
     return true;
 }
 
@@ -537,42 +668,63 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
     __shared__ int want_sh[FINISH_WARPS];
     __shared__ unsigned long long base_sh;
     __shared__ uint64_t mk_sh[FINISH_WARPS * MASK_STRIDE];
-    __shared__ uint64_t planes_sh[FINISH_WARPS][PLANE_STRIDE];
+    __shared__ ExpandShared ex_sh[FINISH_WARPS];
+    __shared__ uint4 lut_sh[256];                              // byte -> eight bf16 (bit ? 1.0 : 0)
     const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool active = slot < d.g_end;
+    if (d.net_in16 && (phases & STEP_SELECT)) {
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+            uint32_t h[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) h[k] = ((b >> (2 * k)) & 1 ? 0x3F80u : 0u) | ((b >> (2 * k + 1)) & 1 ? 0x3F800000u : 0u);
+            lut_sh[b] = make_uint4(h[0], h[1], h[2], h[3]);
+        }                                                      // (load_tables' barrier below publishes it)
+    }
+    unsigned long long* tr = (d.step_trace && slot == d.g_begin && lane == 0) ? d.step_trace : nullptr;
+    auto stamp = [&](int k) { if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[k] = t; } };
+    stamp(0);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.net_ready_n; i += gridDim.x * blockDim.x) d.net_ready[i] = 0;
     if (phases & STEP_SELECT) load_tables(&T, d.tables);
+    stamp(1);
     if (phases & STEP_FINISH) finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, mk_sh);
     if (!(phases & STEP_SELECT) || !active) return;
     __syncwarp();                                              // this warp's tree updates -> every lane of the descent
+    stamp(2);
     select_tree(d, slot, lane, c_puct);
     __syncwarp();
-    uint64_t* pl = planes_sh[wib];
-    int need = 0;
-    if (lane == 0) need = expand_path(d, T, slot, pl);
-    need = __shfl_sync(0xFFFFFFFFu, need, 0);
-    if (!need) return;
-    uint64_t* prow = d.planes + (size_t)slot * PLANE_STRIDE;
-    for (int i = lane; i < N_PLANES; i += 32) prow[i] = pl[i];
+    stamp(3);
+    ExpandShared& S = ex_sh[wib];
+    if (!expand_warp(d, T, slot, lane, S, tr)) return;
+    stamp(6);
+    const uint64_t* pl = S.planes;
     if (d.net_in16) {
-        // 64 squares x 128 channels of bf16 (0 / 1.0), interior of the slot's zero-haloed [10][10][128] input row: 16 bytes
-        // (8 channels of one square) per lane and store, consecutive lanes -> consecutive 16-byte pieces
+        // 64 squares x 128 channels of bf16 (0 / 1.0) into the interior of the slot's zero-haloed [10][10][128] input row.  A lane takes
+        // an 8-plane x 8-square block (channel group cg, board row r): the planes' bytes of that row, an 8 x 8 bit transpose, and
+        // every byte of the result is one square's 8 channels -> one 16-byte store through a 256-entry table (byte -> 8 bf16).
+        // Lanes 0..15 / 16..31 write two squares' 256 contiguous bytes per store.
         uint4* in = reinterpret_cast<uint4*>(d.net_in16 + (size_t)slot * 100 * 128);
-#pragma unroll 4
-        for (int it = 0; it < 32; it++) {
-            const int q = it * 32 + lane, sq = q >> 4, cg = q & 15;
-            uint32_t h[8];
+        const int cg = lane & 15;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int r = it * 2 + (lane >> 4);
+            uint64_t x = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int c = cg * 8 + j;
-                h[j] = (c < N_PLANES && ((pl[c] >> sq) & 1ull)) ? 0x3F80u : 0u;
+                if (c < N_PLANES) x |= ((pl[c] >> (8 * r)) & 0xFFull) << (8 * j);
             }
-            uint4 o;
-            o.x = h[0] | (h[1] << 16); o.y = h[2] | (h[3] << 16); o.z = h[4] | (h[5] << 16); o.w = h[6] | (h[7] << 16);
-            in[(size_t)(((sq >> 3) + 1) * 10 + (sq & 7) + 1) * 16 + cg] = o;
+            uint64_t t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
+            x ^= t ^ (t << 7);
+            t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
+            x ^= t ^ (t << 14);
+            t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
+            x ^= t ^ (t << 28);
+#pragma unroll
+            for (int i = 0; i < 8; i++) in[(size_t)((r + 1) * 10 + i + 1) * 16 + cg] = lut_sh[(x >> (8 * i)) & 0xFFull];
         }
     }
+    stamp(7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -892,6 +1044,7 @@ __global__ void k_push_picked(Dev d, const int32_t* moves, int32_t* n_active) {
     analyse(T, q, mv, cnt);
     const int slot = q.ply & (RING - 1);
     gp[slot] = q;
+    set_ancestors(d, g, slot, q.prev);
     d.cur[g] = slot;
     if (q.outcome == OUT_NONE) atomicAdd(n_active, 1);
 }
@@ -1075,7 +1228,7 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     d.tables = dt;
 #define A(field, count) if ((rc = dev_alloc(ctx, &d.field, (count)))) return rc
     A(pool, G * (size_t)d.pool_stride);
-    A(cur, G);
+    A(cur, G); A(anc, G * (size_t)d.pool_stride * 8);
     A(node_edge0, NN); A(node_nchild, NN); A(node_pedge, NN); A(node_pnode, NN); A(node_term, NN); A(node_tval, NN);
     A(node_count, G); A(root_n, G); A(root_w, G);
     A(e_n, d.edge_cap); A(e_w, d.edge_cap); A(e_p, d.edge_cap); A(e_move, d.edge_cap); A(e_link, d.edge_cap);
@@ -1255,7 +1408,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     int rc0 = 0;
     SZB_CUDA(ctx, cudaMemsetAsync(d.error_flag, 0, sizeof(int32_t), st));
     if (evaluator == SZB_EVAL_NET_BF16 && (rc0 = net_reset_error(ctx))) return rc0;
-    d.net_in16 = nullptr; d.net_ready = nullptr; d.net_ready_n = 0;
+    d.net_in16 = nullptr; d.net_ready = nullptr; d.net_ready_n = 0; d.step_trace = nullptr;
     d.g_begin = 0;
     d.g_end = G;
     k_search_begin<<<(G + 127) / 128, 128, 0, st>>>(d, num_searches);
@@ -1330,6 +1483,13 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
     // whose last epilogue emits the priors of the legal moves and the value (net.cu).  Profiling keeps the phase kernels apart so
     // that per-phase times mean what they say; both give the same trees (test_fused_step_equals_phase_kernels).
     const bool fused = K == 1 && !prof && !getenv("SZB_NO_FUSE");
+    // measurement aid: SZB_STEP_TRACE=<csv> -- device timestamps of the first tree's warp inside every k_tree_step of this search
+    const char* step_trace_path = getenv("SZB_STEP_TRACE");
+    unsigned long long* d_step_trace = nullptr;
+    if (fused && step_trace_path && step_trace_path[0] && NS > 0) {
+        SZB_CUDA(ctx, cudaMalloc((void**)&d_step_trace, (size_t)(n_steps + 1) * 8 * sizeof(unsigned long long)));
+        SZB_CUDA(ctx, cudaMemsetAsync(d_step_trace, 0, (size_t)(n_steps + 1) * 8 * sizeof(unsigned long long), st));
+    }
     const bool net_fused = fused && net_fused_step(ctx, evaluator);
     auto launch_fused = [&](const Dev& dc0, cudaStream_t cs, int phases) -> int {
         Dev dc = dc0;
@@ -1356,6 +1516,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             dc.g_end = bounds[c + 1];
             cudaStream_t cs = n_cohorts == 2 ? ctx->cohort_stream[c] : st;
             if (fused) {
+                dc.step_trace = (d_step_trace && c == 0) ? d_step_trace + (size_t)s * 8 : nullptr;
                 rc = launch_fused(dc, cs, (s > 0 ? STEP_FINISH : 0) | (s < n_steps ? STEP_SELECT : 0));
             } else {
                 cudaEvent_t* ev = prof ? &ctx->prof_events[5 * ((size_t)s * (trace ? 2 : 1) + (trace ? c : 0))] : nullptr;
@@ -1368,6 +1529,21 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         for (int c = 0; c < 2; c++) {
             SZB_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], ctx->cohort_stream[c]));
             SZB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[c], 0));
+        }
+    }
+    if (d_step_trace) {
+        std::vector<unsigned long long> h((size_t)(n_steps + 1) * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), d_step_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_step_trace);
+        if (FILE* f = fopen(step_trace_path, "w")) {
+            fprintf(f, "step,start_ns,tables_ns,finish_ns,select_ns,move_made_ns,movegen_ns,planes_mask_ns,input_rows_ns\n");
+            for (int s = 0; s <= n_steps; s++) {
+                fprintf(f, "%d", s);
+                for (int k = 0; k < 8; k++) fprintf(f, ",%lld", h[(size_t)s * 8 + k] ? (long long)(h[(size_t)s * 8 + k] - h[0]) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
         }
     }
     if (rc) { cudaStreamSynchronize(st); return rc; }

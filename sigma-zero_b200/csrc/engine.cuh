@@ -36,6 +36,8 @@ struct Dev {
     // ---- games --------------------------------------------------------------------------------
     Pos* pool;               // [max_games][pool_stride]: slots [0,RING) real game ring, RING+i = tree node i
     int32_t* cur;            // [max_games] ring slot of the current position
+    uint16_t* anc;           // [max_games][pool_stride][8] pool slots of a position's 8 predecessors, nearest first (0xFFFF: none), recorded
+                             // when the position is made: the history planes load them side by side instead of walking Pos::prev
     const Tables* tables;
     int pool_stride;
     int n_games;
@@ -86,6 +88,7 @@ struct Dev {
     unsigned short* net_in16;    // bf16 NHWC input rows [path slot][10][10][128] the expansion writes directly, or null
     int32_t* net_ready;          // per-item completion counters of the tower launch that follows: zeroed by the tree kernel
     int net_ready_n;
+    unsigned long long* step_trace;  // measurement aid (SZB_STEP_TRACE): %globaltimer stamps of the first tree's warp through k_tree_step, or null
     unsigned long long* gstats;  // [max_games][8] the same counters per game: the step kernels bump their own game's row
                                  // (no same-address atomics on the hot path), k_fold_stats folds the rows into `stats`
 };

@@ -54,6 +54,7 @@ struct ConvLayer {
 
 struct TowerMaps;
 struct TowerArgs;
+constexpr int CL_MAX_BOARDS_DEFAULT = 18;   // k_tower_cl: one 8-CTA cluster per board, 18 clusters = 144 of 148 SMs
 
 struct Net {
     bool loaded = false;
@@ -88,6 +89,9 @@ struct Net {
     int tower_pairs = 74;                // CTA pairs of an exclusive launch (SZB_TOWER_PAIRS)
     bool tower_exclusive = false;        // SZB_TOWER_EXCLUSIVE: experiment, see launch_tower
     bool no_fuse = false;                // SZB_NO_FUSE=1: A/B aid, search steps use the separate head kernels
+    int cluster_max = CL_MAX_BOARDS_DEFAULT;   // batches up to this many boards run the cluster-resident tower (SZB_TOWER_CLUSTER=<n>, 0 = off)
+    bool attr_set_cl = false;
+    int clusters_resident = 0;
     unsigned long long* span = nullptr;  // [SPAN_CAP][2] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
     bool span_on = false;
     std::vector<int> span_boards, span_b0;
@@ -476,6 +480,7 @@ struct alignas(64) TowerMaps {
     CUtensorMap w32;     // box 64 k x 32 rows
     CUtensorMap w16;     // box 64 k x 16 rows
     CUtensorMap w8;      // box 64 k x 8 rows
+    CUtensorMap in1;     // input planes, box 64 ch x 10 x ONE board x 10 (k_tower_cl)
 };
 
 // Search mode (mcts.py:72-79 fused into the last layer's epilogue): instead of fp32 logits the policy-output layer emits, for every
@@ -1094,6 +1099,416 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
 }
 
 // =================================================================================================
+// cluster-resident tower for very small batches: ONE BOARD PER 8-CTA CLUSTER, activations never leave shared memory
+// =================================================================================================
+// k_tower_tc2 at <= 72 boards is a chain of 41 dependent layers at ~6.7-8 us each: every layer hands its output to the next through
+// L2 (epilogue stores -> red.release -> ld.acquire -> TMA reload, ~2.5 us of round trips) and every tensor-core instruction re-reads
+// 128 activation rows per CTA from shared memory whatever the batch (144 x ~40 clk, ~3 us).  For a handful of boards -- a single game
+// (play.py, the reference's real API), an arena pair, the tail of a self-play iteration -- this kernel keeps a board inside one
+// cluster of 8 SMs for the whole tower:
+//   * CTA r of the cluster computes output channels [32 r, 32 r + 32) of every layer: tcgen05.mma.cta_group::1, M = 64 (the board's
+//     squares: half the shared-memory operand traffic of M = 128), N = 32, accumulator in 32 TMEM columns;
+//   * every CTA holds the board's full activation tile (256 channels x 100 halo pixels, bf16, the same 128-byte-swizzled halo layout
+//     k_tower_tc2 stages per K chunk, so all nine taps read it in place through shifted descriptors) TWICE (layer l reads buffer l & 1
+//     and the cluster writes buffer (l + 1) & 1);
+//   * the epilogue (TMEM -> +bias [+residual, kept in registers: a CTA only ever needs its own 32 channels of it] -> ReLU -> bf16)
+//     stores its 64 x 32 slice straight into all eight CTAs' next-layer buffers (st.shared::cluster, distributed shared memory) and
+//     arrives on each CTA's mbarrier (release.cluster); a layer starts when its CTA has collected all 32 arrivals -- no global memory,
+//     no TMA reload, no cluster-wide hardware barrier, the weight producer warp runs ahead freely (7 x 16 KiB ring);
+//   * the heads run inside the same launch: CTA 0 gathers the 73 logit planes (fp32, distributed shared memory) and does the softmax
+//     in k_softmax's order (full logits, or just the priors of the legal moves in search mode), CTA 1 the value head on the tower
+//     output still sitting in its shared memory.
+// Same MMAs per output element in the same K order (K chunk outer, tap inner) -> bit-identical to k_tower_tc2
+// (test_cluster_tower_bit_identical).
+constexpr int CL_SIZE = 8;
+constexpr int CL_N = C_TOWER / CL_SIZE;                       // 32 output channels per CTA
+constexpr int CL_CHUNK_BYTES = 13 * 1024;                     // 100 halo pixels x 128 B = 12800, padded to the 1024-byte swizzle period
+constexpr int CL_BUF_BYTES = 4 * CL_CHUNK_BYTES;              // 256 channels
+constexpr int CL_B_STAGES = 7;
+constexpr int CL_TILE_BYTES = CL_N * TC_BLOCK_K * 2;          // one tap's 32 x 64 weights: 4 KiB
+constexpr int CL_STAGE_BYTES = 4 * CL_TILE_BYTES;             // four taps per stage (a K chunk of a 3x3 layer = 4 + 4 + 1)
+constexpr int CL_SMEM = 2 * CL_BUF_BYTES + CL_B_STAGES * CL_STAGE_BYTES + 1024;
+constexpr int CL_MAX_BOARDS = 18;                             // 18 clusters x 8 = 144 of 148 SMs
+constexpr uint32_t CL_A_HI = (uint32_t)(T2_A_SBO >> 4) | (1u << 14) | (2u << 29);      // 8-row groups one halo row (1280 B) apart
+
+struct ClusterArgs {
+    int n_boards;
+    int board0;                  // first board (row of the NHWC input buffer, before in_delta)
+    int in_delta;
+    const float* bias;           // [MAX_TOWER_LAYERS][256]
+    TowerHeads heads;            // mask == null: full fp32 logits to `logits`; value always written (heads.value)
+    float* logits;               // [row][4672], row = board + heads.row_delta
+    int32_t* error;
+    TowerLayer L[MAX_TOWER_LAYERS];
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait with cluster-scope acquire (the arrivals come from other CTAs after their distributed-shared-memory stores)
+__device__ __forceinline__ bool mbar_wait_cluster(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        if (mbar_try_wait_cluster(bar, parity)) return true;
+        if (*abort_flag) return false;
+        if (clock64() - t0 > TC_TIMEOUT_CYCLES) { *abort_flag = 1; return false; }
+    }
+}
+__device__ __forceinline__ void tc1_mma_bf16_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                   uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// absolute-address 128-byte swizzle (what TMA and tcgen05.mma apply): address bits 4..6 ^= bits 7..9
+__device__ __forceinline__ uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+
+__global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ ClusterArgs a) {
+    constexpr uint32_t IDESC_M64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 4) << 24);        // bf16 x bf16 -> fp32, M = 64
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_b_full[CL_B_STAGES], bar_b_empty[CL_B_STAGES], bar_acc_full, bar_act, bar_in, bar_lg;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+    __shared__ float bias_sh[2][CL_N];
+    __shared__ uint64_t hd_mask[MASK_WORDS];
+    __shared__ float hd_red[2][4], hd_plane[64], hd_vw[C_TOWER], hd_fc[8];
+
+    const uint32_t smem_act = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = smem_act + 2 * CL_BUF_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int board = a.board0 + (int)(blockIdx.x / CL_SIZE);            // this cluster's board
+    volatile int* abort_flag = &abort_sh;
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < CL_B_STAGES; s++) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc_full), 1);
+        mbar_init(smem_u32(&bar_act), 4 * CL_SIZE);                       // one arrival per epilogue warp of every CTA of the cluster
+        mbar_init(smem_u32(&bar_in), 1);
+        mbar_init(smem_u32(&bar_lg), 4 * CL_SIZE);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // both activation buffers start as zeros: the halo pixels are never written afterwards
+    {
+        uint4* z = reinterpret_cast<uint4*>(smem_raw + (smem_act - smem_u32(smem_raw)));
+        for (int i = threadIdx.x; i < 2 * CL_BUF_BYTES / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");                      // the zeros (generic proxy) -> TMA writes / tensor-core reads
+    tc_fence_before();
+    cluster_sync_all();                                                   // every CTA's barriers and zeroed buffers exist from here on
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===== producer: the board's input planes once, then this CTA's weight slices of all 41 layers, as far ahead as the ring allows =====
+        const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
+        if (elect_one()) {
+            const uint32_t in_full = smem_u32(&bar_in);
+            mbar_expect_tx(in_full, 2u * 12800u);
+            for (int kc = 0; kc < C_IN_PAD / TC_BLOCK_K; kc++)
+                tma_load_4d(smem_act + kc * CL_CHUNK_BYTES, &maps.in1, in_full, kc * TC_BLOCK_K, 0, board + a.in_delta, 0);
+        }
+        __syncwarp();
+        uint32_t bs = 0, b_phase = 0;
+        bool ok = true;
+        for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
+            const TowerLayer L = a.L[l];
+            const int n = L.mode == 1 ? 16 : CL_N;
+            const CUtensorMap* tm_w = n == CL_N ? &maps.w32 : &maps.w16;
+            const uint32_t tile_bytes = (uint32_t)n * TC_BLOCK_K * 2;
+            const int wrow = l * C_TOWER + (int)rank * n;
+            for (int kc = 0; kc < L.kchunks && ok; kc++) {
+                for (int s0 = 0; s0 < L.taps && ok; s0 += 4) {
+                    const int cnt = min(4, L.taps - s0);
+                    if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
+                    if (elect_one()) {
+                        const uint32_t full = bar_bf0 + bs * 8;
+                        mbar_expect_tx(full, tile_bytes * (uint32_t)cnt);
+                        for (int u = 0; u < cnt; u++)
+                            tma_load_2d(smem_b + bs * CL_STAGE_BYTES + u * CL_TILE_BYTES, tm_w, full, ((s0 + u) * L.kchunks + kc) * TC_BLOCK_K, wrow);
+                    }
+                    __syncwarp();
+                    if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: warp-convergent loop, one elected lane issues (straight-line taps, see k_tower_tc2) =====
+        constexpr uint32_t LO_FLAGS = 1u << 16;
+        const uint32_t a_lo0 = ((smem_act >> 4) & 0x3FFFu) | LO_FLAGS, b_lo0 = ((smem_b >> 4) & 0x3FFFu) | LO_FLAGS;
+        const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
+        uint32_t bs = 0, b_phase = 0;
+        bool ok = true;
+        for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
+            const TowerLayer L = a.L[l];
+            const int n = L.mode == 1 ? 16 : CL_N;
+            const uint32_t idesc = IDESC_M64 | ((uint32_t)(n >> 3) << 17);
+            // this layer's input: the TMA-loaded planes, or the 32 arrivals of the previous layer's epilogues
+            if (l == 0) ok = warp_mbar_wait(smem_u32(&bar_in), 0, abort_flag);
+            else ok = __all_sync(0xFFFFFFFFu, mbar_wait_cluster(smem_u32(&bar_act), (uint32_t)((l - 1) & 1), abort_flag));
+            if (!ok) break;
+            asm volatile("fence.proxy.async;" ::: "memory");                  // peers' generic-proxy stores -> tensor-core reads
+            tc_fence_after();
+            const uint32_t buf_lo = a_lo0 + (uint32_t)(l & 1) * (CL_BUF_BYTES >> 4);
+            uint32_t accumulate = 0;
+            for (int kc = 0; kc < L.kchunks && ok; kc++) {
+                const uint32_t chunk_lo = buf_lo + (uint32_t)kc * (CL_CHUNK_BYTES >> 4);
+                if (L.taps == 9) {
+#pragma unroll
+                    for (int s0 = 0; s0 < 9; s0 += 4) {
+                        if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                        tc_fence_after();
+                        const uint32_t b_base = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int tap = s0 + u;
+                                if (tap < 9) {
+                                    const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * HALO + tap % 3) * (128 >> 4);     // halo pixel (ky, kx)
+                                    const uint32_t b_lo = b_base + u * (CL_TILE_BYTES >> 4);
+                                    tc1_mma_bf16_split(tmem_base, a_lo, CL_A_HI, b_lo, T2_B_HI, idesc, tap == 0 ? accumulate : 1u);
+                                    tc1_mma_bf16_split(tmem_base, a_lo + 2, CL_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                                    tc1_mma_bf16_split(tmem_base, a_lo + 4, CL_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                                    tc1_mma_bf16_split(tmem_base, a_lo + 6, CL_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                                }
+                            }
+                            tc_commit(bar_be0 + bs * 8);
+                        }
+                        __syncwarp();
+                        if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
+                    }
+                } else {
+                    if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                    tc_fence_after();
+                    const uint32_t a_lo = chunk_lo + (uint32_t)(HALO + 1) * (128 >> 4);                                    // centre tap
+                    const uint32_t b_lo = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
+                    if (elect_one()) {
+                        tc1_mma_bf16_split(tmem_base, a_lo, CL_A_HI, b_lo, T2_B_HI, idesc, accumulate);
+                        tc1_mma_bf16_split(tmem_base, a_lo + 2, CL_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                        tc1_mma_bf16_split(tmem_base, a_lo + 4, CL_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                        tc1_mma_bf16_split(tmem_base, a_lo + 6, CL_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                        tc_commit(bar_be0 + bs * 8);
+                    }
+                    __syncwarp();
+                    if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
+                }
+                accumulate = 1;
+            }
+            if (ok && elect_one()) tc_commit(smem_u32(&bar_acc_full));
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue warps: accumulator rows 16 w .. 16 w + 15 sit in lanes 0..15 of TMEM quarter w (M = 64 layout) =====
+        const int lane_group = warp & 3;
+        const int etid = threadIdx.x - 64;
+        const bool has_row = lane < 16;
+        const int m = lane_group * 16 + (lane & 15);                       // board square: oy = m >> 3, ox = m & 7
+        const int prow = ((m >> 3) + 1) * HALO + (m & 7) + 1;              // its pixel row in the halo tile
+        const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+        const uint32_t bar_act_addr = smem_u32(&bar_act);
+        uint32_t xin[16];                                                  // this CTA's 32 channels of the current residual block's input
+#pragma unroll
+        for (int j = 0; j < 16; j++) xin[j] = 0;
+        bool ok = true;
+        const uint32_t lg_base = smem_act + CL_BUF_BYTES;                  // CTA 0's buffer 1: fp32 logits [plane][64], see the head section
+        for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
+            const TowerLayer L = a.L[l];
+            const int n = L.mode == 1 ? 16 : CL_N;
+            if (etid < n) bias_sh[l & 1][etid] = a.bias[l * C_TOWER + (int)rank * n + etid];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            ok = __all_sync(0xFFFFFFFFu, mbar_wait(smem_u32(&bar_acc_full), (uint32_t)(l & 1), abort_flag));
+            if (!ok) break;
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr, v);                                  // (the last layer only fills 16 columns; the rest is ignored)
+            tmem_ld_wait();
+            tc_fence_before();
+            const float* bias = bias_sh[l & 1];
+            if (L.mode == 1) {
+                // policy logits of this CTA's 16 planes -> CTA 0 (fp32, plane-major like torch.flatten(conv_p2(x)))
+                if (has_row) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int plane = (int)rank * 16 + j;
+                        if (plane < POLICY_PLANES) st_cluster_f32(mapa_u32(lg_base + (uint32_t)(plane * 64 + m) * 4, 0), __fadd_rn(__uint_as_float(v[j]), bias[j]));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_lg), 0));
+                break;
+            }
+            uint4 o[4];
+            {
+                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(xin);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
+                    float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+                    if (L.res != 255) {
+                        const float2 r2 = __bfloat1622float2(rb[j]);
+                        x0 += r2.x;
+                        x1 += r2.y;
+                    }
+                    if (L.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                    ob[j] = __floats2bfloat162_rn(x0, x1);
+                }
+            }
+            if (l == 0 || L.res != 255) {                                   // the stem's and every block's output is the next block's input
+                const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
+#pragma unroll
+                for (int j = 0; j < 16; j++) xin[j] = ow[j];
+            }
+            if (has_row) {
+                // channels [32 r, 32 r + 32) of pixel prow: K chunk r / 2, 16-byte pieces (r & 1) * 4 .. + 3 of its 128-byte row
+                const uint32_t row_addr = smem_act + (uint32_t)((l + 1) & 1) * CL_BUF_BYTES + (rank >> 1) * CL_CHUNK_BYTES + (uint32_t)prow * 128 + (rank & 1) * 64;
+#pragma unroll
+                for (int dst = 0; dst < CL_SIZE; dst++) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) st_cluster_v4(mapa_u32(swz128(row_addr + u * 16), dst), o[u]);
+                }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");                // generic-proxy stores -> the peers' tensor-core reads
+            __syncwarp();
+            if (lane < CL_SIZE) mbar_arrive_cluster(mapa_u32(bar_act_addr, lane));
+        }
+        // ===== heads =====
+        if (ok && rank == 0) {
+            // softmax over the board's 73 x 64 logits gathered in this CTA's buffer 1, in k_softmax's order; thread = square (64 threads)
+            ok = __all_sync(0xFFFFFFFFu, mbar_wait_cluster(smem_u32(&bar_lg), 0, abort_flag));
+            const float* lg = reinterpret_cast<const float*>(smem_raw + (lg_base - smem_u32(smem_raw)));
+            const long row_slot = (long)board + a.heads.row_delta;
+            const bool search = a.heads.mask != nullptr;
+            const bool want = ok && (!search || a.heads.need_eval[row_slot] != 0);
+            if (search)
+                for (int i = etid; i < MASK_WORDS; i += 128) hd_mask[i] = a.heads.mask[(size_t)row_slot * MASK_STRIDE + i];
+            const int sq = etid & 63;
+            float mx = -INFINITY, ssum = 0.f;
+            if (etid < 64) {
+                for (int c = 0; c < POLICY_PLANES; c++) mx = fmaxf(mx, lg[c * 64 + sq]);
+#pragma unroll
+                for (int off = 1; off < 16; off <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
+                if ((lane & 15) == 0) hd_red[0][sq >> 4] = mx;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mx = fmaxf(fmaxf(hd_red[0][0], hd_red[0][1]), fmaxf(hd_red[0][2], hd_red[0][3]));
+            if (etid < 64) {
+#pragma unroll 1
+                for (int c = 0; c < POLICY_PLANES; c++) ssum = __fadd_rn(ssum, sm_exp(lg[c * 64 + sq], mx));
+#pragma unroll
+                for (int off = 1; off < 16; off <<= 1) ssum = __fadd_rn(ssum, __shfl_xor_sync(0xFFFFFFFFu, ssum, off));
+                if ((lane & 15) == 0) hd_red[1][sq >> 4] = ssum;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float tot = __fadd_rn(__fadd_rn(__fadd_rn(hd_red[1][0], hd_red[1][1]), hd_red[1][2]), hd_red[1][3]);
+            if (want) {
+                // two threads per square: planes of equal parity
+                if (search) {
+                    float* prw = a.heads.policy + (size_t)row_slot * N_ACTIONS + sq;
+#pragma unroll 1
+                    for (int c = etid >> 6; c < POLICY_PLANES; c += 2)
+                        if ((hd_mask[c] >> sq) & 1ull) prw[c * 64] = __fdiv_rn(sm_exp(lg[c * 64 + sq], mx), tot);
+                } else {
+                    float* out = a.logits + (size_t)row_slot * N_ACTIONS + sq;
+#pragma unroll 1
+                    for (int c = etid >> 6; c < POLICY_PLANES; c += 2) out[c * 64] = lg[c * 64 + sq];
+                }
+            }
+        } else if (ok && rank == 1) {
+            // value head (network.py:156-174) on the tower output = the input of layer 39, still in this CTA's buffer 1; same arithmetic
+            // as k_value_head.  Two threads per square: channel quarters {0, 1} and {2, 3}.
+            // (complete and visible: this warp's accumulator waits of layers 39 / 40 are ordered after the MMA warp's acquire of it)
+            hd_vw[etid] = a.heads.v_w[etid];
+            hd_vw[etid + 128] = a.heads.v_w[etid + 128];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int sq = etid >> 1, half = etid & 1;
+            const uint32_t px = smem_act + CL_BUF_BYTES + (uint32_t)(((sq >> 3) + 1) * HALO + (sq & 7) + 1) * 128;
+            float p2[2] = {0.f, 0.f};
+#pragma unroll
+            for (int pp = 0; pp < 2; pp++) {
+                const int part = half * 2 + pp;                             // channels [64 part, 64 part + 64) = K chunk `part`
+#pragma unroll
+                for (int qq = 0; qq < 8; qq++) {
+                    const uint32_t ad = swz128(px + (uint32_t)part * CL_CHUNK_BYTES + qq * 16);
+                    const uint4 u = *reinterpret_cast<const uint4*>(smem_raw + (ad - smem_u32(smem_raw)));
+                    const __nv_bfloat16* h8 = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) p2[pp] = fmaf(__bfloat162float(h8[j]), hd_vw[part * 64 + qq * 8 + j], p2[pp]);
+                }
+            }
+            float s = __fadd_rn(p2[0], p2[1]);                               // (p0 + p1) | (p2 + p3)
+            s = __fadd_rn(s, __shfl_xor_sync(0xFFFFFFFFu, s, 1));
+            if (half == 0) hd_plane[sq] = fmaxf(__fadd_rn(s, a.heads.v_b), 0.f);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+            for (int k2 = 0; k2 < 2; k2++) {
+                const int o = etid + 128 * k2;
+                float h = a.heads.fc1_b[o];
+#pragma unroll 8
+                for (int k = 0; k < 64; k++) h = fmaf(hd_plane[k], a.heads.fc1_wT[k * 256 + o], h);
+                h = __fmul_rn(fmaxf(h, 0.f), a.heads.fc2_w[o]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) h = __fadd_rn(h, __shfl_xor_sync(0xFFFFFFFFu, h, off));
+                if (lane == 0) hd_fc[k2 * 4 + (etid >> 5)] = h;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (etid == 0 && ok) {
+                const long row_slot = (long)board + a.heads.row_delta;
+                if (a.heads.mask == nullptr || a.heads.need_eval[row_slot]) {
+                    float tt = a.heads.fc2_b;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) tt = __fadd_rn(tt, hd_fc[w]);
+                    a.heads.value[row_slot] = vh_tanh(tt);
+                }
+            }
+        }
+    }
+    // ===== teardown: nobody leaves while a peer may still store into this CTA's shared memory or arrive on its barriers =====
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+    }
+    if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+}
+
+// =================================================================================================
 // fp32 SIMT convolution (parity path)
 // =================================================================================================
 struct F32Args {
@@ -1437,6 +1852,17 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     for (int i = 0; i < 3; i++)
         if ((rc = make_halo_map(ctx, &net->tower_maps->a[1 + i], net->act16[i], C_TOWER, net->cap))) return rc;
     {
+        // one board's halo tile of the input planes (k_tower_cl): dims (c, x, board, y), box 64 x 10 x 1 x 10
+        cuuint64_t dims[4] = {(cuuint64_t)C_IN_PAD, HALO, (cuuint64_t)net->cap, HALO};
+        cuuint64_t strides[3] = {(cuuint64_t)C_IN_PAD * 2, (cuuint64_t)C_IN_PAD * 2 * HALO * HALO, (cuuint64_t)C_IN_PAD * 2 * HALO};
+        cuuint32_t box[4] = {TC_BLOCK_K, HALO, 1, HALO};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encode(&net->tower_maps->in1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, net->in16, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(single-board input) failed: %d", (int)r);
+    }
+    {
         cuuint64_t dims[2] = {(cuuint64_t)KMAX, (cuuint64_t)MAX_TOWER_LAYERS * C_TOWER};
         cuuint64_t strides[1] = {(cuuint64_t)KMAX * 2};
         cuuint32_t box[2] = {TC_BLOCK_K, 128};
@@ -1470,6 +1896,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     if (const char* e = getenv("SZB_TOWER_PAIRS")) { if (atoi(e) > 0) net->tower_pairs = std::min(atoi(e), net->num_sms / 2); }
     if (const char* e = getenv("SZB_TOWER_EXCLUSIVE")) net->tower_exclusive = e[0] == '1';
     if (const char* e = getenv("SZB_NO_FUSE")) net->no_fuse = e[0] == '1';
+    if (const char* e = getenv("SZB_TOWER_CLUSTER")) net->cluster_max = std::max(0, std::min(atoi(e), CL_MAX_BOARDS));
     const char* ck = getenv("SZB_TOWER_CHUNK");              // measurement aid: boards per tower launch (0 = whole batch)
     if (ck && ck[0]) net->chunk = std::max(0, atoi(ck)) & ~3;
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
@@ -1559,6 +1986,54 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     }
     const int grid = 2 * std::min(a.n_pair_tiles * a.nsplit, pairs);
     k_tower_tc2<<<grid, TC_THREADS, exclusive ? net->smem_exclusive : T2_SMEM, ctx->work>>>(*net->tower_maps, a);
+    ctx->launches++;
+    return 0;
+}
+
+// the whole forward (tower + both heads) of n <= cluster_max boards with one 8-CTA cluster per board; value_out[i] belongs to board b0 + i
+// unless the heads are fused (then d.policy / d.value rows, as in launch_tower)
+static int cluster_setup(szb_ctx* ctx, Net* net) {
+    if (net->attr_set_cl) return 0;
+    SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL_SIZE * CL_MAX_BOARDS);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = CL_SMEM;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, k_tower_cl, &cfg) == cudaSuccess) net->clusters_resident = clusters;
+    else cudaGetLastError();
+    // more boards than clusters fit at once would run in waves: then the pair kernel is the faster one
+    if (net->clusters_resident > 0) net->cluster_max = std::min(net->cluster_max, net->clusters_resident);
+    if (const char* e = getenv("SZB_TOWER_CLUSTER_VERBOSE")) { if (e[0] == '1') fprintf(stderr, "[szb200] k_tower_cl: %d clusters of %d CTAs resident\n", net->clusters_resident, CL_SIZE); }
+    net->attr_set_cl = true;
+    return 0;
+}
+
+static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_row, float* value_out, TowerRun run) {
+    int rc = cluster_setup(ctx, net);
+    if (rc) return rc;
+    if (out_row < 0) out_row = b0;
+    ClusterArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_boards = n;
+    a.board0 = b0;
+    a.in_delta = run.in16_rows ? out_row - b0 : 0;
+    a.bias = net->bias_all;
+    a.error = net->tc_error;
+    a.logits = net->logits;
+    memcpy(a.L, net->tower_args->L, sizeof a.L);
+    TowerHeads& h = a.heads;
+    h.row_delta = out_row - b0;
+    h.v_w = net->v_w; h.fc1_wT = net->fc1_w; h.fc1_b = net->fc1_b; h.fc2_w = net->fc2_w; h.v_b = net->v_b; h.fc2_b = net->fc2_b;
+    h.tower_out = nullptr;                                    // (the tower output never leaves shared memory)
+    if (run.heads) {
+        const Dev& d = ctx->d;
+        h.mask = d.mask; h.need_eval = d.need_eval; h.policy = d.policy; h.value = d.value;
+    } else {
+        h.mask = nullptr; h.need_eval = nullptr; h.policy = nullptr;
+        h.value = value_out - (ptrdiff_t)out_row;             // value[board + row_delta] == value_out[board - b0]
+    }
+    k_tower_cl<<<CL_SIZE * n, TC_THREADS, CL_SMEM, ctx->work>>>(*net->tower_maps, a);
     ctx->launches++;
     return 0;
 }
@@ -1668,6 +2143,14 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
                 if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_LAYER * (uint64_t)n; }
             }
             x = net->final_x; y = net->final_y;
+        } else if (!cluster_setup(ctx, net) && n <= net->cluster_max) {
+            // a handful of boards: the cluster-resident kernel does the whole forward, heads included (fused or not)
+            cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
+            if (cev) cudaEventRecord(cev[0], st);
+            if ((rc = launch_tower_cluster(ctx, net, b0, n, out_row, value_out, run))) return rc;
+            if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_ALL * (uint64_t)n; }
+            SZB_CUDA(ctx, cudaGetLastError());
+            return 0;
         } else {
             // stem + 38 tower convolutions + both policy 1x1 layers in ONE persistent launch; the measurement hook brackets exactly that launch
             cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
@@ -1924,6 +2407,10 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
             case 3: launch_f32(ctx, net->act32[i & 1], net->tower[1], net->act32[2], net->act32[(i + 1) & 1], n, 1, 0); break;
             case 4: rc = launch_tower(ctx, net, 0, n, 20, 21); break;                       // one tower layer, CTA-pair kernel
             case 5: rc = launch_tower(ctx, net, 0, n, 0, MAX_TOWER_LAYERS); break;          // whole tower, one launch
+            case 6:                                                                         // whole forward, cluster-resident kernel
+                rc = n <= CL_MAX_BOARDS ? launch_tower_cluster(ctx, net, 0, n, 0, ctx->d.value, TowerRun())
+                                        : fail(ctx, SZB_ERR_ARG, "the cluster-resident tower takes at most %d boards", CL_MAX_BOARDS);
+                break;
             default: rc = fail(ctx, SZB_ERR_ARG, "unknown kernel selector %d", which);
             }
         }
