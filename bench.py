@@ -13,8 +13,12 @@ then a move sampled from the visit counts and pushed (szb_selfplay_ply; referenc
   e2e     : the same metric through the host-buffer API: every step uploads the batch's positions from pinned
             host memory (szb_games_set), searches, and reads the visit counts + child masks back to pinned host
             memory (szb_search) -- the call the MCTS0.search facade makes;
-  roofline: the dominant kernel (one 3x3 256->256 tcgen05 tower convolution) timed live with CUDA events inside
-            the timed region, against the measured bf16 peak of MEASURED_PEAKS.json;
+  roofline: the dominant kernel -- k_tower_tc2, the whole 41-layer tower as ONE persistent tcgen05 launch per 512 boards -- timed
+            on the device inside the timed region (the kernel stamps %globaltimer at its first CTA's start and its last CTA's end;
+            the two cohorts' launches overlap on two streams, which CUDA events cannot bracket), against the measured sustained
+            bf16 peak of MEASURED_PEAKS.json;
+  extras  : (same JSON line) config c3 (4096 Chess960 games) as a rate, and a bounded config-c4 iteration (500 games sharded over
+            the ranks, strong scaling) next to the weak-scaling headline;
   cpu_baseline / --impl reference: the restated reference search (oracle/ref_path.py: the reference's Python
             control flow + torch CPU fp32 network, batch 1, all host threads) on a bounded sample of the workload.
 
@@ -52,6 +56,13 @@ WORKLOADS = {
 C_PUCT = 2.0
 SEED = 0
 MAX_PREFIX = 40                                # S2 "random-played" start positions: U{0..40} random legal plies
+
+
+def common_config(wl, weights):
+    """the workload description BOTH arms print (identical keys and values, so the driver's same_config check holds)"""
+    return {"workload": wl["name"], "games_per_gpu": wl["games"], "num_searches": wl["sims"], "C": C_PUCT, "learning": True,
+            "chess960": wl["chess960"], "positions": "S2 random-played: U{0..40} random legal plies from the start, seed 0",
+            "weights": weights}
 
 
 def peaks():
@@ -225,8 +236,9 @@ def run_reference(args, wl):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "games": wl["games"], "num_searches": wl["sims"], "C": C_PUCT,
-                   "note": "reference CPU path: python control flow + torch CPU fp32 batch-1 network over the oracle chess stand-in"},
+        "config": common_config(wl, "random-init torch.manual_seed(0)"),
+        "arm": "reference CPU path: python control flow + torch CPU fp32 batch-1 network over the oracle chess stand-in, all host threads",
+        "host_cores": threads,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -250,7 +262,7 @@ def run_ours(args, wl):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
 
     G, S = wl["games"], wl["sims"]
@@ -432,13 +444,15 @@ def run_ours(args, wl):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl["name"], "games_per_gpu": G, "num_searches": S, "C": C_PUCT, "learning": True,
-                       "chess960": wl["chess960"], "positions": "S2 random-played: U{0..40} random legal plies from the start, seed 0",
-                       "weights": weights, "parallelism": "games sharded, %d x network replica" % world,
-                       "pipelining": ("2 cohorts of %d games on two streams (tree kernels of one run under the other's network kernel)" % (G // 2))
-                                     if G >= 768 else "one cohort (the library splits batches of >= 768 running games into two)",
-                       "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
-                             % (G * 100 * 256 * 2 // 2 ** 20)},
+            "config": common_config(wl, weights),
+            "arm": {"parallelism": "games sharded, %d x network replica" % world,
+                    "pipelining": ("2 cohorts of %d games on two streams (tree kernel of one runs under the other's tower)" % (G // 2))
+                                  if G >= 768 else "one cohort (the library splits batches of >= 768 running games into two)",
+                    "step": "k_tree_step (children + backup of the previous leaves, PUCT descent, move generation, planes, network input rows) "
+                            "+ k_tower_tc2 (41 layers, priors of the legal moves and value head in the last epilogue): 2 launches per 512 boards",
+                    "l2": "no flush: per-step working set (3 x %d MB activations + 46 MB weights + tree arena) exceeds the 126 MB L2"
+                          % (min(G, 1024) * 100 * 256 * 2 // 2 ** 20)},
+            "host_cores": os.cpu_count(),
             "moves_per_sec": total_moves / (ms * 1e-3), "evals_per_sec": evals / (ms * 1e-3),
             "network_tflops_in_step": net_tflops,
             # lower bound of the tower's rate inside the timed region itself (two cohorts pipelined): every network evaluation of the
@@ -452,15 +466,70 @@ def run_ours(args, wl):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
             "weights_broadcast_ms": bcast_ms, "lib": _lib.LIB_PATH.replace(ROOT + os.sep, ""),
         }
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
     eng.close()
+    return line
+
+
+def run_extras(args):
+    """Configs c3 and c4 next to the c2 headline, in the same JSON line (`extras`): c3 = 4096 concurrent Chess960 games x 800 sims as a
+    rate (one timed ply, weak scaling like the headline); c4 = one self-play iteration of 500 Chess960 games x 800 sims SHARDED over
+    the ranks (strong scaling: fixed total work), bounded to --extras-c4-plies plies per game so that the default run stays short."""
+    import torch
+    import torch.distributed as dist
+    from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    out = {}
+    model, weights = seeded_model()
+
+    def reduce(x, op):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+    MAX = dist.ReduceOp.MAX if world > 1 else None
+    SUM = dist.ReduceOp.SUM if world > 1 else None
+
+    # ---- c3 -------------------------------------------------------------------------------------------
+    wl = WORKLOADS["c3"]
+    G, S = wl["games"], wl["sims"]
+    eng = Engine(max_games=G, max_searches=S, device=local)
+    eng.load_state_dict(model.state_dict())
+    play_prefixes_gpu(eng, list(range(rank * G, rank * G + G)), True)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)           # warm-up ply
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    moves, _ = eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)
+    e1.record(ext)
+    torch.cuda.synchronize()
+    ms = reduce(e0.elapsed_time(e1), MAX)
+    live = reduce(int((moves >= 0).sum()), SUM)
+    eng.close()
+    out["c3"] = {"workload": wl["name"], "metric": METRIC, "value": live * S / (ms * 1e-3), "unit": UNIT, "scaling": "weak",
+                 "games_per_gpu": G, "running_games": int(live), "steps": 1, "warmup": 1, "ms_per_step": ms, "n_gpus": world}
+    # ---- c4, bounded ------------------------------------------------------------------------------------
+    c4 = c4_measure(args, dict(WORKLOADS["c4"]), args.extras_c4_plies, model, weights)
+    if c4 is not None:
+        out["c4_bounded"] = {k: c4[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "moves_per_sec", "positions_recorded",
+                                                "rank_seconds", "weights_broadcast_ms")}
+        out["c4_bounded"]["workload"] = c4["config"]["workload"] + " [bounded: %d plies per game]" % args.extras_c4_plies
+        out["c4_bounded"]["games_per_gpu"] = c4["config"]["games_per_gpu"]
+    return out if rank == 0 else None
 
 
-def run_c4(args, wl):
+def c4_measure(args, wl, max_plies, model, weights):
     """One whole self-play iteration through the product API (train_RL.selfplay_iteration's sharding + sim.selfplay_records):
-    every game of this rank's block is played to its end on the GPU, records land in packed host arrays."""
+    every game of this rank's block is played to its end (or to max_plies) on the GPU, records land in packed host arrays.
+    Returns the JSON line on rank 0 (None elsewhere); the process group, if any, must be up."""
     import torch
     import torch.distributed as dist
     from sigma_zero_b200 import runtime
@@ -470,13 +539,7 @@ def run_c4(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    model, weights = seeded_model()
     sargs = {"C": C_PUCT, "num_searches": wl["sims"], "num_selfPlay_iterations": wl["games"], "chess960": wl["chess960"],
              "leaves_per_tree": args.leaves_per_tree}
     lo, hi = shard_of(wl["games"], rank, world)
@@ -496,7 +559,7 @@ def run_c4(args, wl):
         broadcast_weights(model, 0, dev)
         torch.cuda.synchronize()
         bcast_ms = (time.perf_counter() - tb) * 1e3
-    rec, counters = selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=args.max_plies, game_id_base=lo)
+    rec, counters = selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=max_plies, game_id_base=lo)
     torch.cuda.synchronize()
     my_s = time.perf_counter() - t0
     if world > 1:
@@ -529,7 +592,7 @@ def run_c4(args, wl):
             "data": "synthetic",
             "config": {"workload": wl["name"], "games": wl["games"], "games_per_gpu": (wl["games"] + world - 1) // world,
                        "num_searches": wl["sims"], "C": C_PUCT, "learning": True, "chess960": True, "weights": weights,
-                       "start": "Chess960 ids drawn per game from (seed, global game id)", "max_plies": args.max_plies,
+                       "start": "Chess960 ids drawn per game from (seed, global game id)", "max_plies": max_plies,
                        "leaves_per_tree": args.leaves_per_tree,
                        "search": "the reference's algorithm (one simulation of a tree at a time)" if args.leaves_per_tree <= 1 else
                                  "NON-PARITY multi-leaf mode: %d simulations of a tree in flight per step, virtual loss" % args.leaves_per_tree,
@@ -542,9 +605,20 @@ def run_c4(args, wl):
                     "note": "the timed region is the end-to-end API call: records arrive in host memory every ply"},
             "gpu_launches": int(launches), "clocks": clocks, "weights_broadcast_ms": bcast_ms,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
+
+
+def init_dist():
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist
 
 
 def main():
@@ -563,6 +637,8 @@ def main():
     ap.add_argument("--leaves-per-tree", type=int, default=1,
                     help="--workload c4 only: opt-in multi-leaf search with virtual loss (not the reference's algorithm; reported separately)")
     ap.add_argument("--max-plies", type=int, default=None, help="--workload c4: cut games after this many plies (default: play every game out)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3 rate and the bounded c4 iteration that ride on the default (c2) line")
+    ap.add_argument("--extras-c4-plies", type=int, default=24, help="plies per game of the bounded c4 iteration in `extras`")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.games:
@@ -573,10 +649,22 @@ def main():
         wl["name"] += " [sims overridden: %d]" % args.sims
     if args.impl == "reference":
         run_reference(args, wl)
-    elif args.workload == "c4":
-        run_c4(args, wl)
+        return
+    dist = init_dist()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.workload == "c4":
+        model, weights = seeded_model()
+        line = c4_measure(args, wl, args.max_plies, model, weights)
     else:
-        run_ours(args, wl)
+        line = run_ours(args, wl)
+        if args.workload == "c2" and not args.no_extras and not args.games and not args.sims:
+            extras = run_extras(args)
+            if line is not None:
+                line["extras"] = extras
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

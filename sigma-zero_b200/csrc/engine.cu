@@ -683,9 +683,11 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
     }
     unsigned long long* tr = (d.step_trace && slot == d.g_begin && lane == 0) ? d.step_trace : nullptr;
     auto stamp = [&](int k) { if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[k] = t; } };
+    pdl_trigger();                                             // the tower launch behind me may begin its set-up and weight prefetch
+    if (phases & STEP_SELECT) load_tables(&T, d.tables);       // (constant tables: before the wait)
+    pdl_wait();                                                // the evaluator's priors / values; its completion counters are idle now
     stamp(0);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.net_ready_n; i += gridDim.x * blockDim.x) d.net_ready[i] = 0;
-    if (phases & STEP_SELECT) load_tables(&T, d.tables);
     stamp(1);
     if (phases & STEP_FINISH) finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, mk_sh);
     if (!(phases & STEP_SELECT) || !active) return;
@@ -1491,13 +1493,16 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         SZB_CUDA(ctx, cudaMemsetAsync(d_step_trace, 0, (size_t)(n_steps + 1) * 8 * sizeof(unsigned long long), st));
     }
     const bool net_fused = fused && net_fused_step(ctx, evaluator);
+    // programmatic dependent launch chains the two kernels of a step when one cohort runs alone (the latency-bound regime); the
+    // two-cohort pipeline already overlaps one cohort's tree kernel with the other's tower
+    ctx->pdl = net_fused && n_cohorts == 1 && !getenv("SZB_NO_PDL");
     auto launch_fused = [&](const Dev& dc0, cudaStream_t cs, int phases) -> int {
         Dev dc = dc0;
         const int n = dc.g_end - dc.g_begin;
         ctx->work = cs;
         dc.net_in16 = nullptr; dc.net_ready = nullptr; dc.net_ready_n = 0;
         if (net_fused && (phases & STEP_SELECT)) net_handover(ctx, dc.g_begin, n, &dc.net_in16, &dc.net_ready, &dc.net_ready_n);
-        k_tree_step<<<(n * 32 + 127) / 128, 128, 0, cs>>>(dc, c_puct, learning, phases);
+        launch_kernel(k_tree_step, dim3((n * 32 + 127) / 128), dim3(128), 0, cs, ctx->pdl, dc, c_puct, learning, phases);
         ctx->launches++;
         if (!(phases & STEP_SELECT)) return 0;
         if (evaluator == SZB_EVAL_HASH) {
@@ -1525,6 +1530,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         }
     }
     ctx->work = st;
+    ctx->pdl = false;
     if (n_cohorts == 2) {
         for (int c = 0; c < 2; c++) {
             SZB_CUDA(ctx, cudaEventRecord(ctx->ev_join[c], ctx->cohort_stream[c]));

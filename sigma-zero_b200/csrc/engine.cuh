@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/szb200.h"
 #include "chess.cuh"
@@ -134,9 +135,30 @@ struct szb_ctx {
     uint64_t conv_boards = 0;                  // boards of the bracketed launches (sum)
     uint64_t conv_flop = 0;                    // algorithmic FLOP of the bracketed launches (sum)
     int net_tower_mode = 2;                    // which bf16 tower kernel runs (net.cu: Net::tower_mode)
+    bool pdl = false;                          // the launches of the search step in flight use programmatic dependent launch
 };
 
 namespace szb {
+// Programmatic dependent launch (one-cohort searches): a kernel launched with this attribute may start while its predecessor on the
+// stream is still running; it does its set-up, then griddepcontrol.wait blocks until the predecessor has completed and flushed.
+// Both kernels of a search step call pdl_trigger() first (let the successor's set-up overlap me) and pdl_wait() before they touch
+// anything the predecessor wrote.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 int fail(szb_ctx* ctx, int code, const char* fmt, ...);
 int cuda_fail(szb_ctx* ctx, cudaError_t e, const char* what);
 void* ctx_stage(szb_ctx* ctx, size_t bytes);

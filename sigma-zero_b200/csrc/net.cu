@@ -91,6 +91,7 @@ struct Net {
     bool no_fuse = false;                // SZB_NO_FUSE=1: A/B aid, search steps use the separate head kernels
     int cluster_max = CL_MAX_BOARDS_DEFAULT;   // batches up to this many boards run the cluster-resident tower (SZB_TOWER_CLUSTER=<n>, 0 = off)
     bool attr_set_cl = false;
+    unsigned long long* cl_trace = nullptr;
     int clusters_resident = 0;
     unsigned long long* span = nullptr;  // [SPAN_CAP][2] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
     bool span_on = false;
@@ -669,6 +670,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
     const int n_items = a.n_items;
     volatile int* abort_flag = &abort_sh;
 
+    pdl_trigger();                                                // the next tree kernel may start its set-up; it waits for my completion
     if (threadIdx.x == 0) {
         if (a.span) atomicMin(a.span, global_ns());
         abort_sh = 0;
@@ -714,6 +716,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         if (a.nsplit == 1) {
             // large batches: per K chunk the activation chunk, then its weight tiles (one per stage) -- in steady state the rings
             // keep the loads ~7 taps ahead of the MMAs
+            pdl_wait();                                           // input rows and cleared counters come from the kernel before me
             for (int item = pair; item < n_items && ok; item += n_pairs) {
                 const int l = a.layer_begin + item / a.n_pair_tiles, t = item % a.n_pair_tiles;
                 const TowerLayer L = a.L[l];
@@ -787,6 +790,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 };
                 for (int k = 0; k < T2_B_STAGES && jb < n_b && ok; k++) ok = issue_b_stage();
                 if (!ok) break;
+                pdl_wait();                                       // (weights above do not depend on the kernel before me; everything below does)
                 if (l > a.layer_begin && !(ok = wait_dependency(l, t))) break;
                 if (a.trace && rank == 0 && lane == 0) a.trace[(size_t)item * 4 + 0] = global_ns();      // dependency resolved
                 for (int kc = 0; kc < L.kchunks && ok; kc++) {
@@ -869,6 +873,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         }
     } else {
         // ===== epilogue (4 warps in each CTA): TMEM -> +bias [+residual] -> ReLU -> bf16 NHWC store =====
+        pdl_wait();
         const int lane_group = warp & 3;
         const int etid = threadIdx.x - 64;                         // 0..127
         int local = 0;
@@ -1128,6 +1133,7 @@ constexpr int CL_B_STAGES = 7;
 constexpr int CL_TILE_BYTES = CL_N * TC_BLOCK_K * 2;          // one tap's 32 x 64 weights: 4 KiB
 constexpr int CL_STAGE_BYTES = 4 * CL_TILE_BYTES;             // four taps per stage (a K chunk of a 3x3 layer = 4 + 4 + 1)
 constexpr int CL_SMEM = 2 * CL_BUF_BYTES + CL_B_STAGES * CL_STAGE_BYTES + 1024;
+constexpr uint32_t CL_LAYER_BYTES = 64 * C_TOWER * 2;         // a layer's output for one board
 constexpr int CL_MAX_BOARDS = 18;                             // 18 clusters x 8 = 144 of 148 SMs
 constexpr uint32_t CL_A_HI = (uint32_t)(T2_A_SBO >> 4) | (1u << 14) | (2u << 29);      // 8-row groups one halo row (1280 B) apart
 
@@ -1139,6 +1145,7 @@ struct ClusterArgs {
     TowerHeads heads;            // mask == null: full fp32 logits to `logits`; value always written (heads.value)
     float* logits;               // [row][4672], row = board + heads.row_delta
     int32_t* error;
+    unsigned long long* trace;   // measurement aid (SZB_TOWER_TRACE with szb_time_kernel(6)): [layer][8] %globaltimer stamps of cluster 0, CTA 0
     TowerLayer L[MAX_TOWER_LAYERS];
 };
 
@@ -1149,6 +1156,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// asynchronous 16-byte store into a peer's shared memory; the peer's mbarrier counts the bytes (complete_tx, release.cluster)
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, const uint4& v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
@@ -1196,7 +1208,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
     constexpr uint32_t IDESC_M64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 4) << 24);        // bf16 x bf16 -> fp32, M = 64
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_b_full[CL_B_STAGES], bar_b_empty[CL_B_STAGES], bar_acc_full, bar_act, bar_in, bar_lg;
+    __shared__ __align__(8) uint64_t bar_b_full[CL_B_STAGES], bar_b_empty[CL_B_STAGES], bar_acc_full, bar_act[2], bar_in, bar_lg;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
     __shared__ float bias_sh[2][CL_N];
@@ -1210,14 +1222,20 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
     const int board = a.board0 + (int)(blockIdx.x / CL_SIZE);            // this cluster's board
     volatile int* abort_flag = &abort_sh;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         abort_sh = 0;
         for (int s = 0; s < CL_B_STAGES; s++) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
         mbar_init(smem_u32(&bar_acc_full), 1);
-        mbar_init(smem_u32(&bar_act), 4 * CL_SIZE);                       // one arrival per epilogue warp of every CTA of the cluster
+        // layer l's output (32 KiB: 64 squares x 256 channels, from the eight CTAs' asynchronous stores) is counted in BYTES on
+        // bar_act[l & 1]; its one arrival is this CTA's own expect_tx, posted two layers ahead
+        mbar_init(smem_u32(&bar_act[0]), 1);
+        mbar_init(smem_u32(&bar_act[1]), 1);
         mbar_init(smem_u32(&bar_in), 1);
         mbar_init(smem_u32(&bar_lg), 4 * CL_SIZE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(smem_u32(&bar_act[0]), CL_LAYER_BYTES);            // layer 0's and layer 1's outputs
+        mbar_expect_tx(smem_u32(&bar_act[1]), CL_LAYER_BYTES);
     }
     // both activation buffers start as zeros: the halo pixels are never written afterwards
     {
@@ -1237,13 +1255,19 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
     if (warp == 0) {
         // ===== producer: the board's input planes once, then this CTA's weight slices of all 41 layers, as far ahead as the ring allows =====
         const uint32_t bar_bf0 = smem_u32(&bar_b_full[0]), bar_be0 = smem_u32(&bar_b_empty[0]);
-        if (elect_one()) {
-            const uint32_t in_full = smem_u32(&bar_in);
-            mbar_expect_tx(in_full, 2u * 12800u);
-            for (int kc = 0; kc < C_IN_PAD / TC_BLOCK_K; kc++)
-                tma_load_4d(smem_act + kc * CL_CHUNK_BYTES, &maps.in1, in_full, kc * TC_BLOCK_K, 0, board + a.in_delta, 0);
-        }
-        __syncwarp();
+        // the weight ring is primed first (weights do not depend on the kernel before this one: with programmatic dependent launch
+        // they stream in while the tree kernel still runs); then the dependency wait, then the board's input planes
+        int issued = 0;
+        auto send_input = [&]() {
+            pdl_wait();
+            if (elect_one()) {
+                const uint32_t in_full = smem_u32(&bar_in);
+                mbar_expect_tx(in_full, 2u * 12800u);
+                for (int kc = 0; kc < C_IN_PAD / TC_BLOCK_K; kc++)
+                    tma_load_4d(smem_act + kc * CL_CHUNK_BYTES, &maps.in1, in_full, kc * TC_BLOCK_K, 0, board + a.in_delta, 0);
+            }
+            __syncwarp();
+        };
         uint32_t bs = 0, b_phase = 0;
         bool ok = true;
         for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
@@ -1255,6 +1279,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             for (int kc = 0; kc < L.kchunks && ok; kc++) {
                 for (int s0 = 0; s0 < L.taps && ok; s0 += 4) {
                     const int cnt = min(4, L.taps - s0);
+                    if (issued++ == CL_B_STAGES) send_input();
                     if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
                     if (elect_one()) {
                         const uint32_t full = bar_bf0 + bs * 8;
@@ -1280,10 +1305,14 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             const uint32_t idesc = IDESC_M64 | ((uint32_t)(n >> 3) << 17);
             // this layer's input: the TMA-loaded planes, or the 32 arrivals of the previous layer's epilogues
             if (l == 0) ok = warp_mbar_wait(smem_u32(&bar_in), 0, abort_flag);
-            else ok = __all_sync(0xFFFFFFFFu, mbar_wait_cluster(smem_u32(&bar_act), (uint32_t)((l - 1) & 1), abort_flag));
+            else ok = __all_sync(0xFFFFFFFFu, mbar_wait_cluster(smem_u32(&bar_act[(l - 1) & 1]), (uint32_t)(((l - 1) >> 1) & 1), abort_flag));
             if (!ok) break;
+            // re-arm that barrier for the output of layer l + 1 (bytes of it cannot be sent before this CTA has finished layer l)
+            if (l >= 1 && l + 1 <= POLICY_LAYER - 1 && elect_one()) mbar_expect_tx(smem_u32(&bar_act[(l - 1) & 1]), CL_LAYER_BYTES);
+            __syncwarp();
             asm volatile("fence.proxy.async;" ::: "memory");                  // peers' generic-proxy stores -> tensor-core reads
             tc_fence_after();
+            if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[l * 8 + 0] = global_ns();
             const uint32_t buf_lo = a_lo0 + (uint32_t)(l & 1) * (CL_BUF_BYTES >> 4);
             uint32_t accumulate = 0;
             for (int kc = 0; kc < L.kchunks && ok; kc++) {
@@ -1331,16 +1360,17 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             }
             if (ok && elect_one()) tc_commit(smem_u32(&bar_acc_full));
             __syncwarp();
+            if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[l * 8 + 1] = global_ns();
         }
     } else {
         // ===== epilogue warps: accumulator rows 16 w .. 16 w + 15 sit in lanes 0..15 of TMEM quarter w (M = 64 layout) =====
+        pdl_wait();
         const int lane_group = warp & 3;
         const int etid = threadIdx.x - 64;
         const bool has_row = lane < 16;
         const int m = lane_group * 16 + (lane & 15);                       // board square: oy = m >> 3, ox = m & 7
         const int prow = ((m >> 3) + 1) * HALO + (m & 7) + 1;              // its pixel row in the halo tile
         const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
-        const uint32_t bar_act_addr = smem_u32(&bar_act);
         uint32_t xin[16];                                                  // this CTA's 32 channels of the current residual block's input
 #pragma unroll
         for (int j = 0; j < 16; j++) xin[j] = 0;
@@ -1354,10 +1384,13 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             ok = __all_sync(0xFFFFFFFFu, mbar_wait(smem_u32(&bar_acc_full), (uint32_t)(l & 1), abort_flag));
             if (!ok) break;
             tc_fence_after();
+            const bool tracer = a.trace && blockIdx.x == 0 && warp == 2 && lane == 0;
+            if (tracer) a.trace[l * 8 + 2] = global_ns();
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr, v);                                  // (the last layer only fills 16 columns; the rest is ignored)
             tmem_ld_wait();
             tc_fence_before();
+            if (tracer) a.trace[l * 8 + 3] = global_ns();
             const float* bias = bias_sh[l & 1];
             if (L.mode == 1) {
                 // policy logits of this CTA's 16 planes -> CTA 0 (fp32, plane-major like torch.flatten(conv_p2(x)))
@@ -1394,18 +1427,28 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
 #pragma unroll
                 for (int j = 0; j < 16; j++) xin[j] = ow[j];
             }
-            if (has_row) {
-                // channels [32 r, 32 r + 32) of pixel prow: K chunk r / 2, 16-byte pieces (r & 1) * 4 .. + 3 of its 128-byte row
+            {
+                // channels [32 r, 32 r + 32) of pixel prow: K chunk r / 2, 16-byte pieces (r & 1) * 4 .. + 3 of its 128-byte row.  Lanes
+                // 0..15 hold the rows; lanes 16..31 take a copy and serve the peers 4..7, so every lane issues 16 asynchronous stores.
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    o[u].x = __shfl_sync(0xFFFFFFFFu, o[u].x, lane & 15);
+                    o[u].y = __shfl_sync(0xFFFFFFFFu, o[u].y, lane & 15);
+                    o[u].z = __shfl_sync(0xFFFFFFFFu, o[u].z, lane & 15);
+                    o[u].w = __shfl_sync(0xFFFFFFFFu, o[u].w, lane & 15);
+                }
                 const uint32_t row_addr = smem_act + (uint32_t)((l + 1) & 1) * CL_BUF_BYTES + (rank >> 1) * CL_CHUNK_BYTES + (uint32_t)prow * 128 + (rank & 1) * 64;
+                const uint32_t bar_local = smem_u32(&bar_act[l & 1]);
 #pragma unroll
-                for (int dst = 0; dst < CL_SIZE; dst++) {
+                for (int k = 0; k < CL_SIZE / 2; k++) {
+                    const uint32_t dst = (uint32_t)(lane >> 4) * (CL_SIZE / 2) + k;
+                    const uint32_t rbar = mapa_u32(bar_local, dst);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) st_cluster_v4(mapa_u32(swz128(row_addr + u * 16), dst), o[u]);
+                    for (int u = 0; u < 4; u++) st_async_v4(mapa_u32(swz128(row_addr + u * 16), dst), o[u], rbar);
                 }
             }
-            asm volatile("fence.proxy.async;" ::: "memory");                // generic-proxy stores -> the peers' tensor-core reads
-            __syncwarp();
-            if (lane < CL_SIZE) mbar_arrive_cluster(mapa_u32(bar_act_addr, lane));
+            if (tracer) a.trace[l * 8 + 4] = global_ns();
+            if (tracer) a.trace[l * 8 + 5] = global_ns();
         }
         // ===== heads =====
         if (ok && rank == 0) {
@@ -1914,6 +1957,7 @@ struct TowerRun {
     bool heads = false;          // fused policy / value heads into d.mask / d.policy / d.value rows (else fp32 logits)
     bool in16_rows = false;      // the input planes of board b0 + i already sit in NHWC input row out_row + i (written by k_tree_step)
     bool ready_zeroed = false;   // the launch's completion counters were cleared by the kernel before it on the stream
+    bool pdl = false;            // programmatic dependent launch behind the step's tree kernel
 };
 
 // layers [layer_begin, layer_end) of the tower for n boards in one persistent CTA-pair launch
@@ -1985,7 +2029,8 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
         net->span_b0.push_back(b0);
     }
     const int grid = 2 * std::min(a.n_pair_tiles * a.nsplit, pairs);
-    k_tower_tc2<<<grid, TC_THREADS, exclusive ? net->smem_exclusive : T2_SMEM, ctx->work>>>(*net->tower_maps, a);
+    SZB_CUDA(ctx, launch_kernel(k_tower_tc2, dim3(grid), dim3(TC_THREADS), (size_t)(exclusive ? net->smem_exclusive : T2_SMEM), ctx->work,
+                                run.pdl, *net->tower_maps, a));
     ctx->launches++;
     return 0;
 }
@@ -2021,6 +2066,7 @@ static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_r
     a.bias = net->bias_all;
     a.error = net->tc_error;
     a.logits = net->logits;
+    a.trace = net->cl_trace;
     memcpy(a.L, net->tower_args->L, sizeof a.L);
     TowerHeads& h = a.heads;
     h.row_delta = out_row - b0;
@@ -2033,7 +2079,7 @@ static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_r
         h.mask = nullptr; h.need_eval = nullptr; h.policy = nullptr;
         h.value = value_out - (ptrdiff_t)out_row;             // value[board + row_delta] == value_out[board - b0]
     }
-    k_tower_cl<<<CL_SIZE * n, TC_THREADS, CL_SMEM, ctx->work>>>(*net->tower_maps, a);
+    SZB_CUDA(ctx, launch_kernel(k_tower_cl, dim3(CL_SIZE * n), dim3(TC_THREADS), (size_t)CL_SMEM, ctx->work, run.pdl, *net->tower_maps, a));
     ctx->launches++;
     return 0;
 }
@@ -2206,6 +2252,7 @@ static int net_forward_chunked(szb_ctx* ctx, int evaluator, int b0, int n, const
         int rc = net_forward_device(ctx, evaluator, b0, m, planes + (size_t)off * stride, stride, value_out + off, b0 + off, run);
         if (rc) return rc;
         run.ready_zeroed = false;                                 // later chunks reuse the first chunk's counters: clear them again
+        run.pdl = false;
     }
     return 0;
 }
@@ -2230,6 +2277,7 @@ void net_handover(szb_ctx* ctx, int g0, int n, unsigned short** in16, int32_t** 
 int net_evaluate_batch(szb_ctx* ctx, int evaluator, int g0, int n, bool fused) {
     TowerRun run;
     run.heads = run.in16_rows = run.ready_zeroed = fused;
+    run.pdl = fused && ctx->pdl;
     int rc = net_forward_chunked(ctx, evaluator, g0, n, ctx->d.planes + (size_t)g0 * PLANE_STRIDE, PLANE_STRIDE, ctx->d.value + g0, run);
     if (rc || fused) return rc;
     k_softmax<<<(n + 3) / 4, 256, 0, ctx->work>>>(ctx->net->logits + (size_t)g0 * N_ACTIONS, ctx->d.policy + (size_t)g0 * N_ACTIONS, n);
@@ -2423,6 +2471,30 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
     cudaEventDestroy(e1);
     if (rc) return rc;
     const char* trace_path = getenv("SZB_TOWER_TRACE");      // measurement aid: per-item device timestamps of one more launch as CSV
+    if (which == 6 && trace_path && trace_path[0]) {
+        unsigned long long* d_tr = nullptr;
+        const size_t slots = (size_t)MAX_TOWER_LAYERS * 8;
+        SZB_CUDA(ctx, cudaMalloc((void**)&d_tr, slots * 8));
+        SZB_CUDA(ctx, cudaMemsetAsync(d_tr, 0, slots * 8, ctx->stream));
+        net->cl_trace = d_tr;
+        rc = launch_tower_cluster(ctx, net, 0, n, 0, ctx->d.value, TowerRun());
+        net->cl_trace = nullptr;
+        std::vector<unsigned long long> h(slots);
+        cudaMemcpyAsync(h.data(), d_tr, slots * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_tr);
+        if (rc) return rc;
+        if (FILE* f = fopen(trace_path, "a")) {
+            fprintf(f, "boards,layer,input_ready_ns,mma_issued_ns,acc_ready_ns,tmem_read_ns,stores_issued_ns,arrived_ns\n");
+            const unsigned long long t0 = h[0];
+            for (int l = 0; l < MAX_TOWER_LAYERS; l++) {
+                fprintf(f, "%d,%d", n, l);
+                for (int k = 0; k < 6; k++) fprintf(f, ",%lld", h[(size_t)l * 8 + k] ? (long long)(h[(size_t)l * 8 + k] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     if (which == 5 && trace_path && trace_path[0]) {
         const int tiles = (n + 3) / 4;
         const size_t slots = (size_t)MAX_TOWER_LAYERS * tiles * 8 * 4;
