@@ -65,6 +65,11 @@ def common_config(wl, weights):
             "weights": weights}
 
 
+def runtime_flat(model, dev):
+    from sigma_zero_b200 import runtime
+    return runtime.flat_weights(model, dev)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,12 +274,12 @@ def run_ours(args, wl):
     eng = Engine(max_games=G, max_searches=S, device=local)
     model, weights = seeded_model()
 
-    # weights: rank 0's flat fp32 buffer broadcast over NCCL (the only collective of the path), then szb_net_load
+    # weights: rank 0's flat fp32 buffer broadcast over NCCL (the only collective of the path) and folded + packed ON THE GPU straight
+    # from the broadcast buffer (szb_net_load_device): nothing crosses the host
+    from sigma_zero_b200 import runtime
+    keys, numels, flat = runtime.flat_weights(model, dev)
     bcast_ms = None
     if world > 1:
-        from sigma_zero_b200.train_RL import flatten_state_dict, unflatten_into
-        keys, flat = flatten_state_dict(model.state_dict())
-        flat = flat.to(dev)
         dist.broadcast(flat, src=0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -283,8 +288,20 @@ def run_ours(args, wl):
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
-        unflatten_into(model, keys, flat.cpu())
-    eng.load_state_dict(model.state_dict())
+    eng.load_flat_device(keys, numels, flat)                      # first load: allocations, tensor maps
+    torch.cuda.synchronize()
+    t_load = time.perf_counter()
+    eng.load_flat_device(keys, numels, flat)                      # steady state (what every later iteration pays): in-place refill
+    load_ms = (time.perf_counter() - t_load) * 1e3
+    digest = eng.net_checksum()
+    digests_equal = None
+    if world > 1:
+        lo_hi = torch.tensor([digest & 0xFFFFFFFF, digest >> 32], dtype=torch.int64, device=dev)
+        mine = lo_hi.clone()
+        dist.broadcast(lo_hi, src=0)
+        same = torch.tensor([int(bool((lo_hi == mine).all()))], dtype=torch.int64, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        digests_equal = bool(int(same.item()))
 
     # weak scaling: every rank owns its own block of G games (global game ids rank*G .. rank*G+G-1)
     game_ids = list(range(rank * G, rank * G + G))
@@ -464,7 +481,10 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": G * 4672 * 4 + G * 73 * 8, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "szb_games_set(host positions) + szb_search(host visit/child buffers), pinned memory"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu,
-            "weights_broadcast_ms": bcast_ms, "lib": _lib.LIB_PATH.replace(ROOT + os.sep, ""),
+            "weights_broadcast_ms": bcast_ms, "weights_load_ms": load_ms, "weights_digest_equal_on_all_ranks": digests_equal,
+            "weights_note": "flat fp32 state_dict (91 MB) broadcast over NCCL, then BatchNorm fold + bf16/fp32 packing by the library's kernels "
+                            "from the device buffer (szb_net_load_device, host wall clock incl. the stream sync); digest = szb_net_checksum",
+            "lib": _lib.LIB_PATH.replace(ROOT + os.sep, ""),
         }
     else:
         line = None
@@ -499,7 +519,7 @@ def run_extras(args):
     wl = WORKLOADS["c3"]
     G, S = wl["games"], wl["sims"]
     eng = Engine(max_games=G, max_searches=S, device=local)
-    eng.load_state_dict(model.state_dict())
+    eng.load_flat_device(*runtime_flat(model, dev))
     play_prefixes_gpu(eng, list(range(rank * G, rank * G + G)), True)
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
     eng.selfplay_ply(S, C_PUCT, True, EVAL_NET_BF16, seed=SEED, sample=True)           # warm-up ply
@@ -556,7 +576,7 @@ def c4_measure(args, wl, max_plies, model, weights):
     bcast_ms = None
     if world > 1:
         tb = time.perf_counter()
-        broadcast_weights(model, 0, dev)
+        broadcast_weights(model, 0, dev, eng)                 # NCCL broadcast + GPU-side fold straight from the broadcast buffer
         torch.cuda.synchronize()
         bcast_ms = (time.perf_counter() - tb) * 1e3
     rec, counters = selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=max_plies, game_id_base=lo)

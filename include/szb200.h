@@ -120,10 +120,19 @@ int szb_perft_timed(szb_ctx *ctx, const szb_pos *pos, int32_t depth, uint64_t *n
 
 /* ---- network: replaces policyNN.load_state_dict / forward (network.py:100-192, play.py:25-28) ---- */
 /* tensors of the fp32 state_dict by name (252 entries; *.num_batches_tracked may be omitted).
- * data[i] are HOST pointers to contiguous fp32; the library folds BatchNorm (eval mode) into the
- * convolutions and builds the fp32 and bf16 device packs. */
+ * data[i] are HOST pointers to contiguous fp32; the library stages them on the device, folds BatchNorm (eval mode) into the
+ * convolutions there and builds the fp32 and bf16 device packs.  The whole state_dict is validated before anything loaded
+ * earlier is touched. */
 int szb_net_load(szb_ctx *ctx, int32_t n_tensors, const char *const *names, const float *const *data,
                  const int64_t *numel);
+/* The same with DEVICE pointers (e.g. slices of the flat fp32 buffer torch.distributed just broadcast over NCCL: the weight
+ * path of train_RL.py:211-227 with no host round trip).  BatchNorm folding and all packing run on the GPU, asynchronously on the
+ * context's stream; the tensors may be released once the stream has passed this call.  A context that already holds a network
+ * refills its buffers in place (no allocation, no synchronisation). */
+int szb_net_load_device(szb_ctx *ctx, int32_t n_tensors, const char *const *names, const float *const *data_dev,
+                        const int64_t *numel);
+/* 64-bit digest of the packed device weights (what the kernels actually read): equal on every rank after a broadcast */
+int szb_net_checksum(szb_ctx *ctx, uint64_t *digest_out);
 /* policyNN.forward(x, inference=True): planes uint64[n][119] -> softmax policy float[n][4672], value float[n] */
 int szb_net_forward(szb_ctx *ctx, int32_t n, const uint64_t *planes, int32_t evaluator,
                     float *policy_out, float *value_out);

@@ -66,6 +66,8 @@ SIGNATURES = {
     "szb_perft_timed": (ctypes.c_int, [_vp, ctypes.POINTER(Pos), _i32, ctypes.POINTER(_u64),
                                        ctypes.POINTER(_f32), ctypes.POINTER(_u64)]),
     "szb_net_load": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "szb_net_load_device": (ctypes.c_int, [_vp, _i32, _vp, _vp, _vp]),
+    "szb_net_checksum": (ctypes.c_int, [_vp, ctypes.POINTER(_u64)]),
     "szb_net_forward": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "szb_net_forward_logits": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "szb_search": (ctypes.c_int, [_vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp]),

@@ -58,15 +58,16 @@ constexpr int CL_MAX_BOARDS_DEFAULT = 18;   // k_tower_cl: one 8-CTA cluster per
 
 struct Net {
     bool loaded = false;
+    bool allocated = false;              // buffers, tensor maps and layer table exist (net_ensure_allocated)
+    unsigned long long* digest = nullptr;
     int cap = 0;                         // boards the activation buffers hold (even)
     ConvLayer stem, tower[2 * N_BLOCKS], p1, p2;
     // value head (fp32 everywhere)
     float* v_w = nullptr;                // [256] conv_v1 * bn scale
-    float v_b = 0.f;
+    float* head_scalars = nullptr;       // device: {v_norm shift (conv_v1 BN folded), fc_v2.bias}
     float* fc1_w = nullptr;              // [64][256] (fc_v1.weight transposed)
     float* fc1_b = nullptr;              // [256]
     float* fc2_w = nullptr;              // [256]
-    float fc2_b = 0.f;
     // activations
     __nv_bfloat16* in16 = nullptr;       // [cap][10][10][128]
     __nv_bfloat16* act16[3] = {nullptr, nullptr, nullptr};     // [cap][10][10][256]
@@ -495,7 +496,7 @@ struct TowerHeads {
     float* value;                      // [row]
     const __nv_bfloat16* tower_out;    // activation buffer holding the last residual block's output
     const float *v_w, *fc1_wT, *fc1_b, *fc2_w;
-    float v_b, fc2_b;
+    const float* scalars;              // {value-conv BN shift, fc_v2 bias}
     int row_delta;
 };
 
@@ -998,7 +999,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                         }
                     }
                 }
-                hd_plane[rb][sq] = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(p4[0], p4[1]), __fadd_rn(p4[2], p4[3])), a.heads.v_b), 0.f);
+                hd_plane[rb][sq] = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(p4[0], p4[1]), __fadd_rn(p4[2], p4[3])), a.heads.scalars[0]), 0.f);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
                 for (int k2 = 0; k2 < 4; k2++) {
@@ -1015,7 +1016,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                 if (etid < 2) {
                     const int brd = cta_board0 + etid;
                     if (brd < a.board0 + a.n_boards && a.heads.need_eval[brd + a.heads.row_delta]) {
-                        float tt = a.heads.fc2_b;
+                        float tt = a.heads.scalars[1];
 #pragma unroll
                         for (int w = 0; w < 8; w++) tt = __fadd_rn(tt, hd_fc[etid][w]);
                         a.heads.value[brd + a.heads.row_delta] = vh_tanh(tt);
@@ -1516,7 +1517,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             }
             float s = __fadd_rn(p2[0], p2[1]);                               // (p0 + p1) | (p2 + p3)
             s = __fadd_rn(s, __shfl_xor_sync(0xFFFFFFFFu, s, 1));
-            if (half == 0) hd_plane[sq] = fmaxf(__fadd_rn(s, a.heads.v_b), 0.f);
+            if (half == 0) hd_plane[sq] = fmaxf(__fadd_rn(s, a.heads.scalars[0]), 0.f);
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
             for (int k2 = 0; k2 < 2; k2++) {
@@ -1533,7 +1534,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             if (etid == 0 && ok) {
                 const long row_slot = (long)board + a.heads.row_delta;
                 if (a.heads.mask == nullptr || a.heads.need_eval[row_slot]) {
-                    float tt = a.heads.fc2_b;
+                    float tt = a.heads.scalars[1];
 #pragma unroll
                     for (int w = 0; w < 8; w++) tt = __fadd_rn(tt, hd_fc[w]);
                     a.heads.value[row_slot] = vh_tanh(tt);
@@ -1651,8 +1652,9 @@ __global__ void k_planes_to_nhwc(const uint64_t* planes, int stride, int n, T* o
 // fc1_wT is fc_v1.weight transposed to [64][256] so that the 256 threads read consecutive floats.  Every rounding is explicit and in
 // the order the fused heads of k_tower_tc2 use, so the two agree bit for bit (test_tower_kernel_variants_bit_identical).
 template <class T>
-__global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v_w, float v_b, const float* fc1_wT, const float* fc1_b,
-                                                    const float* fc2_w, float fc2_b, float* value, int n) {
+__global__ void __launch_bounds__(256) k_value_head(const T* act, const float* v_w, const float* scalars, const float* fc1_wT, const float* fc1_b,
+                                                    const float* fc2_w, float* value, int n) {
+    const float v_b = scalars[0], fc2_b = scalars[1];
     __shared__ float plane[64];
     __shared__ float red[8];
     __shared__ float vw_sh[C_TOWER];
@@ -1739,14 +1741,6 @@ __global__ void __launch_bounds__(256) k_softmax(const float* logits, float* pol
 // =================================================================================================
 // host: weights
 // =================================================================================================
-static uint16_t f2bf(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-
 template <class T>
 static int net_alloc(szb_ctx* ctx, Net* net, T** out, size_t count, bool zero = true) {
     void* p = nullptr;
@@ -1757,38 +1751,75 @@ static int net_alloc(szb_ctx* ctx, Net* net, T** out, size_t count, bool zero = 
     return 0;
 }
 
-struct BN { const float *g, *b, *m, *v; };
+struct BN { const float *g, *b, *m, *v; };          // DEVICE pointers
 
-// conv weight [cout][cin_src][kh][kw] (+ optional BN, + optional conv bias) -> folded device packs
-static int upload_conv(szb_ctx* ctx, Net* net, ConvLayer& L, const float* w, int cout, int cin_src, int cin, int taps, int cout_pad,
-                       const BN* bn, const float* conv_bias) {
-    L.taps = taps; L.cin = cin; L.cout = cout; L.cout_pad = cout_pad;
-    const int K = taps * cin;
-    std::vector<float> w32((size_t)taps * cin * cout_pad, 0.f), bias((size_t)cout_pad, 0.f);
-    std::vector<uint16_t> w16((size_t)cout_pad * K, 0);
-    for (int co = 0; co < cout; co++) {
-        double scale = 1.0, shift = conv_bias ? conv_bias[co] : 0.0;
-        if (bn) {
-            scale = (double)bn->g[co] / std::sqrt((double)bn->v[co] + 1e-5);
-            shift = (double)bn->b[co] - (double)bn->m[co] * scale;
-        }
+// BatchNorm folding and packing ON THE GPU (eval mode, eps 1e-5; the arithmetic of the former host loop: double precision, one
+// rounding to fp32): conv weight [cout][cin_src][taps] (+ BN | + conv bias) -> fp32 [tap][cin][cout_pad] (SIMT path), bf16 K-major
+// [cout_pad][taps * cin] (tensor-core paths), bias [cout_pad].  One thread per (co, ci, tap) of the padded pack.
+__global__ void k_fold_conv(const float* w, BN bn, int has_bn, const float* conv_bias, int cout, int cin_src, int cin, int taps, int cout_pad,
+                            float* w32, float* bias, __nv_bfloat16* w16) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)cout_pad * cin * taps;
+    if (i >= total) return;
+    const int t = (int)(i % taps), ci = (int)((i / taps) % cin), co = (int)(i / ((size_t)taps * cin));
+    double scale = 1.0;
+    if (co < cout && has_bn) scale = (double)bn.g[co] / sqrt((double)bn.v[co] + 1e-5);
+    float f = 0.f;
+    if (co < cout && ci < cin_src) f = (float)((double)w[((size_t)co * cin_src + ci) * taps + t] * scale);
+    w32[((size_t)t * cin + ci) * cout_pad + co] = f;
+    w16[(size_t)co * taps * cin + (size_t)t * cin + ci] = __float2bfloat16_rn(f);
+    if (ci == 0 && t == 0) {
+        double shift = 0.0;
+        if (co < cout) shift = has_bn ? (double)bn.b[co] - (double)bn.m[co] * scale : (conv_bias ? (double)conv_bias[co] : 0.0);
         bias[co] = (float)shift;
-        for (int ci = 0; ci < cin_src; ci++)
-            for (int t = 0; t < taps; t++) {
-                const float f = (float)((double)w[((size_t)co * cin_src + ci) * taps + t] * scale);
-                w32[((size_t)t * cin + ci) * cout_pad + co] = f;
-                w16[(size_t)co * K + (size_t)t * cin + ci] = f2bf(f);
-            }
     }
+}
+// value head packs: conv_v1 x BN scale, {BN shift, fc_v2.bias}, fc_v1.weight transposed to [64][256]
+__global__ void k_fold_value_head(const float* vw, BN bn, const float* f1w, const float* f1b, const float* f2w, const float* f2b,
+                                  float* v_w, float* scalars, float* fc1_wT, float* fc1_b, float* fc2_w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;                  // 0 .. 256 * 64
+    const double scale = (double)bn.g[0] / sqrt((double)bn.v[0] + 1e-5);
+    if (i < 256) {
+        v_w[i] = (float)((double)vw[i] * scale);
+        fc1_b[i] = f1b[i];
+        fc2_w[i] = f2w[i];
+    }
+    if (i == 0) {
+        scalars[0] = (float)((double)bn.b[0] - (double)bn.m[0] * scale);
+        scalars[1] = f2b[0];
+    }
+    if (i < 256 * 64) {
+        const int o = i / 64, k = i % 64;
+        fc1_wT[k * 256 + o] = f1w[o * 64 + k];
+    }
+}
+// 64-bit digest of a device buffer (order-independent sum of mixed words): szb_net_checksum
+__global__ void k_digest(const uint32_t* p, size_t n_words, uint64_t salt, unsigned long long* out) {
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x)
+        acc += mix64(((uint64_t)p[i] << 20) ^ (uint64_t)i ^ salt);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+static int alloc_conv(szb_ctx* ctx, Net* net, ConvLayer& L, int cin, int taps, int cout, int cout_pad) {
+    L.taps = taps; L.cin = cin; L.cout = cout; L.cout_pad = cout_pad;
+    const size_t K = (size_t)taps * cin;
     int rc;
-    if ((rc = net_alloc(ctx, net, &L.w32, w32.size(), false))) return rc;
-    if ((rc = net_alloc(ctx, net, &L.bias, bias.size(), false))) return rc;
-    if ((rc = net_alloc(ctx, net, &L.w16, w16.size(), false))) return rc;
-    SZB_CUDA(ctx, cudaMemcpyAsync(L.w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    SZB_CUDA(ctx, cudaMemcpyAsync(L.bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-    SZB_CUDA(ctx, cudaMemcpyAsync(L.w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // host vectors die at scope exit
-    return make_w_map(ctx, &L.tm_w, L.w16, K, cout_pad);
+    if ((rc = net_alloc(ctx, net, &L.w32, K * cout_pad, false))) return rc;
+    if ((rc = net_alloc(ctx, net, &L.bias, (size_t)cout_pad, false))) return rc;
+    if ((rc = net_alloc(ctx, net, &L.w16, K * cout_pad, false))) return rc;
+    return make_w_map(ctx, &L.tm_w, L.w16, (int)K, cout_pad);
+}
+static int fold_conv(szb_ctx* ctx, ConvLayer& L, const float* w, int cin_src, const BN* bn, const float* conv_bias) {
+    const size_t total = (size_t)L.cout_pad * L.cin * L.taps;
+    BN z = {nullptr, nullptr, nullptr, nullptr};
+    k_fold_conv<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(w, bn ? *bn : z, bn != nullptr, conv_bias, L.cout, cin_src, L.cin, L.taps,
+                                                                         L.cout_pad, L.w32, L.bias, L.w16);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
 }
 
 void net_destroy(szb_ctx* ctx) {
@@ -1853,35 +1884,22 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     net->tower_args = new TowerArgs();
     TowerArgs& a = *net->tower_args;
     memset(&a, 0, sizeof a);
-    auto put = [&](int l, const ConvLayer& L) -> int {
-        const int K = L.taps * L.cin;
-        SZB_CUDA(ctx, cudaMemcpy2DAsync(net->w16_all + (size_t)l * C_TOWER * KMAX, (size_t)KMAX * 2, L.w16, (size_t)K * 2, (size_t)K * 2,
-                                        C_TOWER, cudaMemcpyDeviceToDevice, ctx->stream));
-        SZB_CUDA(ctx, cudaMemcpyAsync(net->bias_all + (size_t)l * C_TOWER, L.bias, C_TOWER * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        return 0;
-    };
     auto layer = [&](int l, int a_map, int taps, int kchunks, int res, int out) {
         TowerLayer& T = a.L[l];
         T.a_map = (uint8_t)a_map; T.taps = (uint8_t)taps; T.kchunks = (uint8_t)kchunks;
         T.res = (uint8_t)res; T.out = (uint8_t)out; T.relu = 1; T.mode = 0; T.n_half = 128;
     };
-    if ((rc = put(0, net->stem))) return rc;
     layer(0, 0, 9, C_IN_PAD / TC_BLOCK_K, 255, 0);
     int x = 0;
     for (int blk = 0; blk < N_BLOCKS; blk++) {
         const int y = (x + 1) % 3, o = (x + 2) % 3;
-        if ((rc = put(1 + 2 * blk, net->tower[2 * blk])) || (rc = put(2 + 2 * blk, net->tower[2 * blk + 1]))) return rc;
         layer(1 + 2 * blk, 1 + x, 9, C_TOWER / TC_BLOCK_K, 255, y);
         layer(2 + 2 * blk, 1 + y, 9, C_TOWER / TC_BLOCK_K, x, o);
         x = o;
     }
     const int y = (x + 1) % 3;
-    if ((rc = put(POLICY_LAYER - 1, net->p1))) return rc;
     layer(POLICY_LAYER - 1, 1 + x, 1, C_TOWER / TC_BLOCK_K, 255, y);
     // policy output 256 -> 73 (+ conv bias): N = 128 (two halves of 64 rows, the 73 planes zero-padded), fp32 logits epilogue
-    SZB_CUDA(ctx, cudaMemcpy2DAsync(net->w16_all + (size_t)POLICY_LAYER * C_TOWER * KMAX, (size_t)KMAX * 2, net->p2.w16, (size_t)C_TOWER * 2,
-                                    (size_t)C_TOWER * 2, 128, cudaMemcpyDeviceToDevice, ctx->stream));
-    SZB_CUDA(ctx, cudaMemcpyAsync(net->bias_all + (size_t)POLICY_LAYER * C_TOWER, net->p2.bias, 128 * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     layer(POLICY_LAYER, 1 + y, 1, C_TOWER / TC_BLOCK_K, 255, 0);
     a.L[POLICY_LAYER].relu = 0; a.L[POLICY_LAYER].mode = 1; a.L[POLICY_LAYER].n_half = 64;
     a.logits = net->logits;
@@ -1949,6 +1967,25 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     return 0;
 }
 
+// the folded per-layer packs -> the one [41 * 256][2304] bf16 weight buffer and [41][256] bias table the tower kernels read
+// (device-to-device, asynchronous on the context's stream: part of every weight load)
+static int net_assemble_tower(szb_ctx* ctx, Net* net) {
+    constexpr int KMAX = 9 * C_TOWER;
+    auto put = [&](int l, const ConvLayer& L, int rows) -> int {
+        const int K = L.taps * L.cin;
+        SZB_CUDA(ctx, cudaMemcpy2DAsync(net->w16_all + (size_t)l * C_TOWER * KMAX, (size_t)KMAX * 2, L.w16, (size_t)K * 2, (size_t)K * 2,
+                                        rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaMemcpyAsync(net->bias_all + (size_t)l * C_TOWER, L.bias, (size_t)rows * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    };
+    int rc;
+    if ((rc = put(0, net->stem, C_TOWER))) return rc;
+    for (int i = 0; i < 2 * N_BLOCKS; i++)
+        if ((rc = put(1 + i, net->tower[i], C_TOWER))) return rc;
+    if ((rc = put(POLICY_LAYER - 1, net->p1, C_TOWER))) return rc;
+    return put(POLICY_LAYER, net->p2, 128);
+}
+
 // =================================================================================================
 // host: forward
 // =================================================================================================
@@ -1999,7 +2036,7 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
         TowerHeads& h = a.heads;
         h.mask = d.mask; h.need_eval = d.need_eval; h.policy = d.policy; h.value = d.value;
         h.tower_out = net->act16[net->final_x];
-        h.v_w = net->v_w; h.fc1_wT = net->fc1_w; h.fc1_b = net->fc1_b; h.fc2_w = net->fc2_w; h.v_b = net->v_b; h.fc2_b = net->fc2_b;
+        h.v_w = net->v_w; h.fc1_wT = net->fc1_w; h.fc1_b = net->fc1_b; h.fc2_w = net->fc2_w; h.scalars = net->head_scalars;
         h.row_delta = (out_row >= 0 ? out_row : b0) - b0;
     } else {
         a.heads.mask = nullptr;
@@ -2070,7 +2107,7 @@ static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_r
     memcpy(a.L, net->tower_args->L, sizeof a.L);
     TowerHeads& h = a.heads;
     h.row_delta = out_row - b0;
-    h.v_w = net->v_w; h.fc1_wT = net->fc1_w; h.fc1_b = net->fc1_b; h.fc2_w = net->fc2_w; h.v_b = net->v_b; h.fc2_b = net->fc2_b;
+    h.v_w = net->v_w; h.fc1_wT = net->fc1_w; h.fc1_b = net->fc1_b; h.fc2_w = net->fc2_w; h.scalars = net->head_scalars;
     h.tower_out = nullptr;                                    // (the tower output never leaves shared memory)
     if (run.heads) {
         const Dev& d = ctx->d;
@@ -2211,8 +2248,8 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
         }
         // (the one-launch tower ends with the policy output layer; the per-layer modes use the single-CTA kernel for it)
         if (net->tower_mode != 2 && (rc = launch_tc<POLICY_PAD, 1>(ctx, net, net->tm_act16[y], net->p2, nullptr, nullptr, net->logits, n, 0, b0))) return rc;
-        k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x] + act_off, net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w,
-                                                       net->fc2_b, value_out, n);
+        k_value_head<__nv_bfloat16><<<n, 256, 0, st>>>(net->act16[x] + act_off, net->v_w, net->head_scalars, net->fc1_w, net->fc1_b, net->fc2_w,
+                                                       value_out, n);
         ctx->launches++;
     } else if (evaluator == SZB_EVAL_NET_FP32) {
         float* a32[3] = {net->act32[0] + act_off, net->act32[1] + act_off, net->act32[2] + act_off};
@@ -2229,7 +2266,7 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
         const int y = (x + 1) % 3;
         launch_f32(ctx, a32[x], net->p1, nullptr, a32[y], n, 1, 0);
         launch_f32(ctx, a32[y], net->p2, nullptr, net->logits + (size_t)b0 * N_ACTIONS, n, 0, 1);
-        k_value_head<float><<<n, 256, 0, st>>>(a32[x], net->v_w, net->v_b, net->fc1_w, net->fc1_b, net->fc2_w, net->fc2_b, value_out, n);
+        k_value_head<float><<<n, 256, 0, st>>>(a32[x], net->v_w, net->head_scalars, net->fc1_w, net->fc1_b, net->fc2_w, value_out, n);
         ctx->launches++;
     } else {
         return fail(ctx, SZB_ERR_ARG, "unknown evaluator %d", evaluator);
@@ -2306,98 +2343,155 @@ int net_check_error(szb_ctx* ctx) {
 // =================================================================================================
 extern "C" {
 
-int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
-    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
-    if (!ctx || n_tensors <= 0 || !names || !data || !numel) return fail(ctx, SZB_ERR_ARG, "szb_net_load: bad arguments");
+// expected tensors of network.py's state_dict (name -> element count), in the order the loader reads them
+static void net_expected_tensors(std::vector<std::pair<std::string, int64_t>>& out) {
+    auto bn = [&](const std::string& p, int c) {
+        out.push_back({p + ".weight", c}); out.push_back({p + ".bias", c}); out.push_back({p + ".running_mean", c}); out.push_back({p + ".running_var", c});
+    };
+    out.push_back({"conv1.weight", 256LL * 119 * 9});
+    bn("norm_layer", 256);
+    for (int b = 0; b < N_BLOCKS; b++)
+        for (int j = 1; j <= 2; j++) {
+            const std::string pfx = "resnet_blocks." + std::to_string(b);
+            out.push_back({pfx + ".conv" + std::to_string(j) + ".weight", 256LL * 256 * 9});
+            bn(pfx + ".bn" + std::to_string(j), 256);
+        }
+    out.push_back({"conv_p1.weight", 256LL * 256});
+    bn("p_norm1", 256);
+    out.push_back({"conv_p2.weight", 73LL * 256}); out.push_back({"conv_p2.bias", 73});
+    out.push_back({"conv_v1.weight", 256});
+    bn("v_norm", 1);
+    out.push_back({"fc_v1.weight", 256LL * 64}); out.push_back({"fc_v1.bias", 256});
+    out.push_back({"fc_v2.weight", 256}); out.push_back({"fc_v2.bias", 1});
+}
+
+// device buffers, tensor maps and layer table of the network: once per context (and again only if the capacity changes)
+static int net_ensure_allocated(szb_ctx* ctx) {
+    const int cap = (ctx->cfg.max_games * ctx->d.K + 1) & ~1;           // one activation row per path slot
+    if (ctx->net && ctx->net->cap == cap && ctx->net->allocated) return 0;
     int rc;
     if ((rc = get_encode(ctx))) return rc;
-    std::map<std::string, std::pair<const float*, int64_t>> sd;
-    for (int i = 0; i < n_tensors; i++) sd[names[i]] = {data[i], numel[i]};
-    auto get = [&](const std::string& k, int64_t want, const float** out) -> int {
-        auto it = sd.find(k);
-        if (it == sd.end()) return fail(ctx, SZB_ERR_ARG, "state_dict is missing '%s'", k.c_str());
-        if (it->second.second != want) return fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.second, (long long)want);
-        *out = it->second.first;
-        return 0;
-    };
-    auto get_bn = [&](const std::string& p, int c, BN* bn) -> int {
-        int r;
-        if ((r = get(p + ".weight", c, &bn->g))) return r;
-        if ((r = get(p + ".bias", c, &bn->b))) return r;
-        if ((r = get(p + ".running_mean", c, &bn->m))) return r;
-        return get(p + ".running_var", c, &bn->v);
-    };
-    // validate the whole state_dict BEFORE tearing down the network that is loaded and working: a bad checkpoint leaves it in place
-    {
-        const float* probe;
-        BN pb;
-        if ((rc = get("conv1.weight", 256LL * 119 * 9, &probe)) || (rc = get_bn("norm_layer", 256, &pb))) return rc;
-        for (int b = 0; b < N_BLOCKS; b++)
-            for (int j = 1; j <= 2; j++) {
-                const std::string pfx = "resnet_blocks." + std::to_string(b);
-                if ((rc = get(pfx + ".conv" + std::to_string(j) + ".weight", 256LL * 256 * 9, &probe)) || (rc = get_bn(pfx + ".bn" + std::to_string(j), 256, &pb))) return rc;
-            }
-        if ((rc = get("conv_p1.weight", 256LL * 256, &probe)) || (rc = get_bn("p_norm1", 256, &pb))) return rc;
-        if ((rc = get("conv_p2.weight", 73LL * 256, &probe)) || (rc = get("conv_p2.bias", 73, &probe))) return rc;
-        if ((rc = get("conv_v1.weight", 256, &probe)) || (rc = get_bn("v_norm", 1, &pb))) return rc;
-        if ((rc = get("fc_v1.weight", 256LL * 64, &probe)) || (rc = get("fc_v1.bias", 256, &probe))) return rc;
-        if ((rc = get("fc_v2.weight", 256, &probe)) || (rc = get("fc_v2.bias", 1, &probe))) return rc;
-    }
     net_destroy(ctx);
     Net* net = new Net();
     ctx->net = net;
     cudaDeviceProp prop;
     SZB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
     net->num_sms = prop.multiProcessorCount;
-    net->cap = (ctx->cfg.max_games * ctx->d.K + 1) & ~1;          // one activation row per path slot
-
-    const float* w;
-    BN bn;
-    // stem: conv1 [256,119,3,3] + norm_layer
-    if ((rc = get("conv1.weight", 256LL * 119 * 9, &w)) || (rc = get_bn("norm_layer", 256, &bn))) return rc;
-    if ((rc = upload_conv(ctx, net, net->stem, w, 256, 119, C_IN_PAD, 9, 256, &bn, nullptr))) return rc;
-    for (int b = 0; b < N_BLOCKS; b++) {
-        for (int j = 0; j < 2; j++) {
-            const std::string p = "resnet_blocks." + std::to_string(b);
-            if ((rc = get(p + ".conv" + std::to_string(j + 1) + ".weight", 256LL * 256 * 9, &w))) return rc;
-            if ((rc = get_bn(p + ".bn" + std::to_string(j + 1), 256, &bn))) return rc;
-            if ((rc = upload_conv(ctx, net, net->tower[2 * b + j], w, 256, 256, 256, 9, 256, &bn, nullptr))) return rc;
-        }
-    }
-    if ((rc = get("conv_p1.weight", 256LL * 256, &w)) || (rc = get_bn("p_norm1", 256, &bn))) return rc;
-    if ((rc = upload_conv(ctx, net, net->p1, w, 256, 256, 256, 1, 256, &bn, nullptr))) return rc;
-    const float* pb;
-    if ((rc = get("conv_p2.weight", 73LL * 256, &w)) || (rc = get("conv_p2.bias", 73, &pb))) return rc;
+    net->cap = cap;
+    if ((rc = alloc_conv(ctx, net, net->stem, C_IN_PAD, 9, 256, 256))) return rc;
+    for (int i = 0; i < 2 * N_BLOCKS; i++)
+        if ((rc = alloc_conv(ctx, net, net->tower[i], 256, 9, 256, 256))) return rc;
+    if ((rc = alloc_conv(ctx, net, net->p1, 256, 1, 256, 256))) return rc;
     // the fp32 kernel wants cout_pad % 64 == 0, the tcgen05 kernel reads POLICY_PAD rows: pad to 128 and map the first 80
-    if ((rc = upload_conv(ctx, net, net->p2, w, 73, 256, 256, 1, 128, nullptr, pb))) return rc;
+    if ((rc = alloc_conv(ctx, net, net->p2, 256, 1, 73, 128))) return rc;
     if ((rc = make_w_map(ctx, &net->p2.tm_w, net->p2.w16, 256, POLICY_PAD))) return rc;
-    // value head
-    const float *vw, *f1w, *f1b, *f2w, *f2b;
-    if ((rc = get("conv_v1.weight", 256, &vw)) || (rc = get_bn("v_norm", 1, &bn))) return rc;
-    if ((rc = get("fc_v1.weight", 256LL * 64, &f1w)) || (rc = get("fc_v1.bias", 256, &f1b))) return rc;
-    if ((rc = get("fc_v2.weight", 256, &f2w)) || (rc = get("fc_v2.bias", 1, &f2b))) return rc;
-    {
-        const double scale = (double)bn.g[0] / std::sqrt((double)bn.v[0] + 1e-5);
-        std::vector<float> vws(256);
-        for (int c = 0; c < 256; c++) vws[c] = (float)((double)vw[c] * scale);
-        net->v_b = (float)((double)bn.b[0] - (double)bn.m[0] * scale);
-        net->fc2_b = f2b[0];
-        if ((rc = net_alloc(ctx, net, &net->v_w, 256, false)) || (rc = net_alloc(ctx, net, &net->fc1_w, 256 * 64, false)) ||
-            (rc = net_alloc(ctx, net, &net->fc1_b, 256, false)) || (rc = net_alloc(ctx, net, &net->fc2_w, 256, false)))
-            return rc;
-        SZB_CUDA(ctx, cudaMemcpyAsync(net->v_w, vws.data(), 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        std::vector<float> f1t(256 * 64);                       // [64][256]: coalesced reads in k_value_head
-        for (int o = 0; o < 256; o++)
-            for (int k = 0; k < 64; k++) f1t[k * 256 + o] = f1w[o * 64 + k];
-        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_w, f1t.data(), 256 * 64 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc1_b, f1b, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        SZB_CUDA(ctx, cudaMemcpyAsync(net->fc2_w, f2w, 256 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if ((rc = net_alloc(ctx, net, &net->v_w, 256, false)) || (rc = net_alloc(ctx, net, &net->fc1_w, 256 * 64, false)) ||
+        (rc = net_alloc(ctx, net, &net->fc1_b, 256, false)) || (rc = net_alloc(ctx, net, &net->fc2_w, 256, false)) ||
+        (rc = net_alloc(ctx, net, &net->head_scalars, 2, false)) || (rc = net_alloc(ctx, net, &net->digest, 1)))
+        return rc;
     if ((rc = net_alloc_activations(ctx, net))) return rc;
     if ((rc = net_setup_tower(ctx, net))) return rc;
-    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    net->allocated = true;
+    return 0;
+}
+
+// fold + pack all tensors (DEVICE pointers) into the network's buffers; asynchronous on the context's stream, no host round trip
+static int net_fill_from_device(szb_ctx* ctx, const std::map<std::string, const float*>& sd) {
+    Net* net = ctx->net;
+    auto at = [&](const std::string& k) { return sd.at(k); };
+    auto bn_of = [&](const std::string& p) { return BN{at(p + ".weight"), at(p + ".bias"), at(p + ".running_mean"), at(p + ".running_var")}; };
+    int rc;
+    BN bn = bn_of("norm_layer");
+    if ((rc = fold_conv(ctx, net->stem, at("conv1.weight"), 119, &bn, nullptr))) return rc;
+    for (int b = 0; b < N_BLOCKS; b++)
+        for (int j = 0; j < 2; j++) {
+            const std::string p = "resnet_blocks." + std::to_string(b);
+            bn = bn_of(p + ".bn" + std::to_string(j + 1));
+            if ((rc = fold_conv(ctx, net->tower[2 * b + j], at(p + ".conv" + std::to_string(j + 1) + ".weight"), 256, &bn, nullptr))) return rc;
+        }
+    bn = bn_of("p_norm1");
+    if ((rc = fold_conv(ctx, net->p1, at("conv_p1.weight"), 256, &bn, nullptr))) return rc;
+    if ((rc = fold_conv(ctx, net->p2, at("conv_p2.weight"), 256, nullptr, at("conv_p2.bias")))) return rc;
+    bn = bn_of("v_norm");
+    k_fold_value_head<<<64, 256, 0, ctx->stream>>>(at("conv_v1.weight"), bn, at("fc_v1.weight"), at("fc_v1.bias"), at("fc_v2.weight"), at("fc_v2.bias"),
+                                                   net->v_w, net->head_scalars, net->fc1_w, net->fc1_b, net->fc2_w);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    if ((rc = net_assemble_tower(ctx, net))) return rc;
     net->loaded = true;
+    return 0;
+}
+
+static int net_load_common(szb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel, bool on_device) {
+    if (!ctx || n_tensors <= 0 || !names || !data || !numel) return fail(ctx, SZB_ERR_ARG, "szb_net_load: bad arguments");
+    // validate the whole state_dict BEFORE touching the network that is loaded and working: a bad checkpoint leaves it in place
+    std::map<std::string, std::pair<const float*, int64_t>> given;
+    for (int i = 0; i < n_tensors; i++) given[names[i]] = {data[i], numel[i]};
+    std::vector<std::pair<std::string, int64_t>> want;
+    net_expected_tensors(want);
+    size_t total = 0;
+    for (auto& w : want) {
+        auto it = given.find(w.first);
+        if (it == given.end()) return fail(ctx, SZB_ERR_ARG, "state_dict is missing '%s'", w.first.c_str());
+        if (it->second.second != w.second)
+            return fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", w.first.c_str(), (long long)it->second.second, (long long)w.second);
+        if (!it->second.first) return fail(ctx, SZB_ERR_ARG, "'%s' has a null data pointer", w.first.c_str());
+        total += (size_t)w.second;
+    }
+    int rc;
+    if ((rc = net_ensure_allocated(ctx))) return rc;
+    std::map<std::string, const float*> sd;
+    float* staging = nullptr;
+    if (on_device) {
+        for (auto& w : want) sd[w.first] = given[w.first].first;
+    } else {
+        // host tensors: one staging buffer on the device, then the same GPU fold as szb_net_load_device
+        SZB_CUDA(ctx, cudaMalloc((void**)&staging, total * sizeof(float)));
+        size_t off = 0;
+        for (auto& w : want) {
+            cudaError_t e = cudaMemcpyAsync(staging + off, given[w.first].first, (size_t)w.second * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { cudaFree(staging); return cuda_fail(ctx, e, "cudaMemcpyAsync(state_dict tensor)"); }
+            sd[w.first] = staging + off;
+            off += (size_t)w.second;
+        }
+    }
+    rc = net_fill_from_device(ctx, sd);
+    if (staging) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(staging);
+    }
+    return rc;
+}
+
+int szb_net_load(szb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
+    if (ctx) cudaSetDevice(ctx->device);       // whichever device the calling thread had current
+    return net_load_common(ctx, n_tensors, names, data, numel, false);
+}
+
+int szb_net_load_device(szb_ctx* ctx, int32_t n_tensors, const char* const* names, const float* const* data_dev, const int64_t* numel) {
+    if (ctx) cudaSetDevice(ctx->device);
+    return net_load_common(ctx, n_tensors, names, data_dev, numel, true);
+}
+
+int szb_net_checksum(szb_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    Net* net = ctx->net;
+    if (!net || !net->loaded) return fail(ctx, SZB_ERR_STATE, "network weights not loaded (szb_net_load)");
+    SZB_CUDA(ctx, cudaMemsetAsync(net->digest, 0, sizeof(unsigned long long), ctx->stream));
+    struct { const void* p; size_t bytes; } parts[] = {
+        {net->w16_all, (size_t)MAX_TOWER_LAYERS * C_TOWER * 9 * C_TOWER * 2}, {net->bias_all, (size_t)MAX_TOWER_LAYERS * C_TOWER * 4},
+        {net->v_w, 256 * 4}, {net->fc1_w, 256 * 64 * 4}, {net->fc1_b, 256 * 4}, {net->fc2_w, 256 * 4}, {net->head_scalars, 8}};
+    uint64_t salt = 1;
+    for (auto& part : parts) {
+        const size_t words = part.bytes / 4;
+        k_digest<<<(unsigned)std::min<size_t>((words + 255) / 256, 1184), 256, 0, ctx->stream>>>((const uint32_t*)part.p, words, salt++ * 0x9E3779B97F4A7C15ull, net->digest);
+        ctx->launches++;
+    }
+    unsigned long long h = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(&h, net->digest, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = h;
     return 0;
 }
 

@@ -142,6 +142,30 @@ class Engine:
                                           ctypes.cast(c_data, ctypes.c_void_p), ctypes.cast(c_numel, ctypes.c_void_p)))
         self.weights_loaded = True
 
+    def load_flat_device(self, keys, numels, flat):
+        """Weights from ONE flat fp32 CUDA tensor (torch) laid out as the concatenation of the state_dict tensors `keys` with
+        `numels` elements each -- e.g. the buffer torch.distributed just broadcast.  Folding and packing run on the GPU
+        (szb_net_load_device); nothing crosses the host."""
+        import torch
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.device.index == self.device
+        base, n = flat.data_ptr(), len(keys)
+        offs = np.concatenate([[0], np.cumsum(numels)])
+        assert int(offs[-1]) == flat.numel()
+        c_names = (ctypes.c_char_p * n)(*[k.encode() for k in keys])
+        c_data = (ctypes.c_void_p * n)(*[base + 4 * int(o) for o in offs[:-1]])
+        c_numel = (ctypes.c_int64 * n)(*[int(x) for x in numels])
+        # the fold kernels run on the library's stream: order them after the producer of `flat` on torch's current stream
+        torch.cuda.current_stream(flat.device).synchronize()
+        self._check(self.lib.szb_net_load_device(self._h, n, ctypes.cast(c_names, ctypes.c_void_p),
+                                                 ctypes.cast(c_data, ctypes.c_void_p), ctypes.cast(c_numel, ctypes.c_void_p)))
+        self.synchronize()                                   # `flat` may be freed or overwritten by the caller from here on
+        self.weights_loaded = True
+
+    def net_checksum(self):
+        h = ctypes.c_uint64()
+        self._check(self.lib.szb_net_checksum(self._h, ctypes.byref(h)))
+        return h.value
+
     def net_forward(self, planes, evaluator=EVAL_NET_BF16, logits=False):
         planes = np.ascontiguousarray(planes, dtype=np.uint64).reshape(-1, N_PLANES)
         n = planes.shape[0]

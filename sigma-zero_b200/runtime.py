@@ -42,15 +42,36 @@ def evaluator_of(model):
     return EVAL_NET_FP32 if prec == "fp32" else EVAL_NET_BF16
 
 
-def sync_weights(engine, model):
-    """Send the model's state_dict to the GPU library if it changed since the last call."""
-    global _weights_key
+def _key_of(engine, model):
     sd = model.state_dict()
-    key = (id(model), id(engine), tuple(int(getattr(v, "_version", 0)) for v in sd.values()),
-           tuple(v.data_ptr() for v in sd.values()))
+    return (id(model), id(engine), tuple(int(getattr(v, "_version", 0)) for v in sd.values()), tuple(v.data_ptr() for v in sd.values()))
+
+
+def flat_weights(model, device):
+    """(keys, element counts, ONE flat fp32 tensor on `device`) of the model's state_dict, num_batches_tracked left out"""
+    import torch
+    sd = model.state_dict()
+    keys = [k for k in sd if not k.endswith("num_batches_tracked")]
+    flat = torch.cat([sd[k].detach().reshape(-1).float() for k in keys]).to(device)
+    return keys, [int(sd[k].numel()) for k in keys], flat
+
+
+def sync_weights(engine, model):
+    """Send the model's weights to the GPU library if they changed since the last call: one flat fp32 buffer on the device
+    (wherever the parameters live), BatchNorm folding and packing by the library's own kernels (szb_net_load_device)."""
+    global _weights_key
+    key = _key_of(engine, model)
     if key != _weights_key:
-        engine.load_state_dict(sd)
+        import torch
+        keys, numels, flat = flat_weights(model, torch.device("cuda", engine.device))
+        engine.load_flat_device(keys, numels, flat)
         _weights_key = key
+
+
+def mark_synced(engine, model):
+    """the engine was just loaded with exactly this model's weights by other means (train_RL.broadcast_weights)"""
+    global _weights_key
+    _weights_key = _key_of(engine, model)
 
 
 def unpack_planes(words):

@@ -45,14 +45,22 @@ def unflatten_into(model, keys, flat):
         off += n
 
 
-def broadcast_weights(model, src=0, device=None):
-    """one flat-buffer broadcast (NCCL over NVLink on GPUs, gloo in CPU tests); returns the buffer's bytes"""
+def broadcast_weights(model, src=0, device=None, engine=None):
+    """One flat-buffer broadcast (NCCL over NVLink on GPUs, gloo in CPU tests); returns the buffer's bytes.
+    With `engine` (and a CUDA device) the broadcast buffer never leaves the GPU: the library folds and packs it straight from
+    there (szb_net_load_device) and the torch module is updated by a device-side copy when its parameters live on the GPU."""
     import torch.distributed as dist
     keys, flat = flatten_state_dict(model.state_dict())
     if device is not None:
         flat = flat.to(device)
     dist.broadcast(flat, src=src)
-    unflatten_into(model, keys, flat.cpu())
+    param_dev = next(model.parameters()).device
+    unflatten_into(model, keys, flat if flat.device == param_dev else flat.to(param_dev))
+    if engine is not None and flat.is_cuda:
+        from . import runtime
+        sd = model.state_dict()
+        engine.load_flat_device(keys, [int(sd[k].numel()) for k in keys], flat)
+        runtime.mark_synced(engine, model)
     return flat.numel() * 4
 
 
@@ -61,10 +69,16 @@ def _iteration_shard(model, args):
     import torch.distributed as dist
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_of(int(args['num_selfPlay_iterations']), rank, world)
     if dist.is_initialized() and world > 1:
         dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))) if torch.cuda.is_available() else None
-        broadcast_weights(model, 0, dev)
-    return shard_of(int(args['num_selfPlay_iterations']), rank, world)
+        engine = None
+        if dev is not None:
+            from . import runtime
+            engine = runtime.get_engine(min_games=max(1, hi - lo), min_searches=int(args['num_searches']),
+                                        leaves_per_tree=runtime.leaves_of(args))
+        broadcast_weights(model, 0, dev, engine)
+    return lo, hi
 
 
 def selfplay_iteration(model, args, seed=0, max_plies=None):
@@ -125,6 +139,8 @@ def train_on_records(model, rec, epochs=1, batch_size=64, optimiser=None, lr_sch
         order = rng.permutation(n)
         for lo in range(0, n, batch_size):
             rows = order[lo:lo + batch_size]
+            if len(rows) < batch_size and n >= batch_size:
+                continue                                     # DataLoader(drop_last=True), train_RL.py:241-246
             if len(rows) < 2:
                 continue                                     # BatchNorm needs more than one sample in training mode
             x = torch.from_numpy(records.unpack_states(rec, rows)).to(device=device, dtype=torch.float32)
@@ -195,6 +211,9 @@ def main(args=None, model=None, weights=None, num_games=None, out_dir=".", seed=
         try:
             model.load_state_dict(torch.load(os.path.join(out_dir, "saves", "RL_960_%d.pt" % (start_epoch - 1)), map_location="cpu"))
             optimiser.load_state_dict(torch.load(os.path.join(out_dir, "saves", "RL_960_opt_%d.pt" % (start_epoch - 1)), map_location="cpu"))
+            sched_path = os.path.join(out_dir, "saves", "RL_960_sched_%d.pt" % (start_epoch - 1))
+            if os.path.exists(sched_path):                   # the StepLR step counter continues instead of restarting
+                scheduler.load_state_dict(torch.load(sched_path, map_location="cpu"))
         except OSError:
             log("No saved weights from epoch %d found!" % (start_epoch - 1))
             start_epoch = 1
@@ -209,6 +228,7 @@ def main(args=None, model=None, weights=None, num_games=None, out_dir=".", seed=
             records.save(os.path.join(out_dir, "games", "RL_960_%d.npz" % epoch), rec)
             torch.save(model.state_dict(), os.path.join(out_dir, "saves", "RL_960_%d.pt" % epoch))
             torch.save(optimiser.state_dict(), os.path.join(out_dir, "saves", "RL_960_opt_%d.pt" % epoch))
+            torch.save(scheduler.state_dict(), os.path.join(out_dir, "saves", "RL_960_sched_%d.pt" % epoch))
         history.append({"epoch": epoch, "positions": int(len(rec["z"])), "losses": hist, "seconds": time.perf_counter() - t1})
         log("Time taken: %0.4f seconds" % history[-1]["seconds"])
     return model, history

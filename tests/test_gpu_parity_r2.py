@@ -488,3 +488,48 @@ def test_cluster_tower_search_equals_pair_tower(monkeypatch):
         for a, b in zip(res[0], r):
             assert np.array_equal(a, b)
     assert (res[0][0].sum(axis=1) == 149).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# device-resident weight path (train_RL.py:211-227: the weights reach the workers)
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_device_weight_load_equals_host_load_and_refills_in_place():
+    """szb_net_load_device (flat fp32 buffer already on the GPU, BatchNorm folded and packed by kernels) must give exactly the network
+    szb_net_load (host tensors) gives: equal digests of the packed weights, bit-equal fp32 and bf16 outputs; a second, different
+    set of weights refills the same context in place and a reload of the first restores the first digest"""
+    from sigma_zero_b200 import runtime
+    from sigma_zero_b200.engine import EVAL_NET_BF16, EVAL_NET_FP32, Engine
+    models = []
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        m = ref_path.build_policy_nn().eval()
+        g = torch.Generator().manual_seed(40 + seed)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.data = 0.5 + torch.rand(mod.weight.shape, generator=g)
+                mod.bias.data = 0.2 * torch.randn(mod.bias.shape, generator=g)
+                mod.running_mean = 0.1 * torch.randn(mod.running_mean.shape, generator=g)
+                mod.running_var = 0.5 + torch.rand(mod.running_var.shape, generator=g)
+        models.append(m)
+    planes = np.stack([hash_eval.pack_planes(util.oracle_game(c, s, mv).get_representation()) for c, s, mv in _random_specs(5, seed=2)])
+    host = Engine(max_games=8, max_searches=4)
+    host.load_state_dict(models[0].state_dict())
+    dev = Engine(max_games=8, max_searches=4)
+    dev.load_flat_device(*runtime.flat_weights(models[0], torch.device("cuda", 0)))
+    d0 = dev.net_checksum()
+    assert d0 == host.net_checksum()
+    for ev in (EVAL_NET_FP32, EVAL_NET_BF16):
+        a, b = host.net_forward(planes, ev, logits=True), dev.net_forward(planes, ev, logits=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    dev.load_flat_device(*runtime.flat_weights(models[1], torch.device("cuda", 0)))
+    assert dev.net_checksum() != d0
+    dev.load_flat_device(*runtime.flat_weights(models[0], torch.device("cuda", 0)))
+    assert dev.net_checksum() == d0
+    # the fold itself against torch: fp32 path within the north-star tolerance with non-trivial BatchNorm statistics
+    x = torch.from_numpy(np.stack([util.oracle_game(c, s, mv).get_representation() for c, s, mv in _random_specs(5, seed=2)]).astype(np.float32))
+    with torch.no_grad():
+        rp, rv = models[0](x, inference=True)
+    p, v = dev.net_forward(planes, EVAL_NET_FP32)
+    assert np.abs(p - rp.numpy()).max() <= 1e-5 and np.abs(v - rv.numpy().ravel()).max() <= 1e-5
+    host.close()
+    dev.close()
