@@ -17,7 +17,8 @@ if os.path.exists(path):
 os.environ["SZB_TOWER_TRACE"] = path
 ms = eng.time_kernel(6, n, 20)
 eng.close()
-t = np.genfromtxt(path, delimiter=",", skip_header=1)[:, 2:]
+print("".join(l for l in open(path) if l.startswith("#")))
+t = np.genfromtxt(path, delimiter=",", skip_header=1, comments="#")[:, 2:]
 lay = t[2:39]                                 # 3x3 tower layers
 print("k_tower_cl, %d board(s): %.1f us per launch" % (n, ms * 1e3))
 print("per 3x3 layer (us): input->mma issued %.2f | mma issued->acc ready %.2f | tmem read %.2f | stores %.2f | arrive %.2f | arrive->next input ready %.2f | period %.2f" % (

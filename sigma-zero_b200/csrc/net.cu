@@ -78,6 +78,7 @@ struct Net {
     int32_t* tc_error = nullptr;
     // CTA-pair tower kernel (k_tower_tc2): all 40 N=256 layers in one weight / bias buffer + per-item completion counters
     __nv_bfloat16* w16_all = nullptr;    // [MAX_TOWER_LAYERS * 256][2304]
+    __nv_bfloat16* w16_cl[2] = {nullptr, nullptr};   // k_tower_cl<8> / <16> weight streams: [layer][rank][K chunk][tap][rows x 128 B], pre-swizzled smem images
     float* bias_all = nullptr;           // [MAX_TOWER_LAYERS][256]
     int32_t* ready = nullptr;            // [MAX_TOWER_LAYERS][ceil(cap / 4)]
     struct TowerMaps* tower_maps = nullptr;   // host copies, passed by value at launch
@@ -91,9 +92,10 @@ struct Net {
     bool tower_exclusive = false;        // SZB_TOWER_EXCLUSIVE: experiment, see launch_tower
     bool no_fuse = false;                // SZB_NO_FUSE=1: A/B aid, search steps use the separate head kernels
     int cluster_max = CL_MAX_BOARDS_DEFAULT;   // batches up to this many boards run the cluster-resident tower (SZB_TOWER_CLUSTER=<n>, 0 = off)
+    int cluster_force = 0;                     // SZB_TOWER_CLUSTER_SIZE=8|16: A/B aid, use only that cluster size
     bool attr_set_cl = false;
+    int clusters_resident[2] = {0, 0};         // clusters of 8 / 16 CTAs of k_tower_cl this device holds at once
     unsigned long long* cl_trace = nullptr;
-    int clusters_resident = 0;
     unsigned long long* span = nullptr;  // [SPAN_CAP][2] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
     bool span_on = false;
     std::vector<int> span_boards, span_b0;
@@ -1126,23 +1128,55 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
 //     output still sitting in its shared memory.
 // Same MMAs per output element in the same K order (K chunk outer, tap inner) -> bit-identical to k_tower_tc2
 // (test_cluster_tower_bit_identical).
-constexpr int CL_SIZE = 8;
-constexpr int CL_N = C_TOWER / CL_SIZE;                       // 32 output channels per CTA
+// Two cluster sizes: 8 CTAs (N = 32 channels per CTA; the default) and 16 CTAs (N = 16, non-portable cluster size, A/B aid).
+// What a layer costs (device timestamps, scripts/cluster_trace.py, one board): 3.6 us from "input complete" to "last MMA issued",
+// 0.1 us to the accumulator, 1.4 us of distributed-shared-memory stores (32 KiB out of every CTA at ~12 B/clk), 1.3 us until the
+// slowest CTA's bytes have landed and the MMA warp is awake.  The 3.6 us are the ISSUE of the layer's 144 dependent tcgen05.mma by
+// one thread (~28 clk each; per weight stage: 106-152 clk barrier wait + 16 x 28 clk) -- not the tensor core (issuing half of the
+// MMAs: -0.5 us), not the weight stream (16 CTAs per board = a whole layer prefetched, or the contiguous pre-swizzled stream below:
+// no change).  K = 16 per instruction and one accumulation chain per output (bit-identity with the large-batch kernel) fix the
+// count; a shorter chain needs split-K, i.e. other roundings than k_tower_tc2's.
 constexpr int CL_CHUNK_BYTES = 13 * 1024;                     // 100 halo pixels x 128 B = 12800, padded to the 1024-byte swizzle period
 constexpr int CL_BUF_BYTES = 4 * CL_CHUNK_BYTES;              // 256 channels
-constexpr int CL_B_STAGES = 7;
-constexpr int CL_TILE_BYTES = CL_N * TC_BLOCK_K * 2;          // one tap's 32 x 64 weights: 4 KiB
-constexpr int CL_STAGE_BYTES = 4 * CL_TILE_BYTES;             // four taps per stage (a K chunk of a 3x3 layer = 4 + 4 + 1)
-constexpr int CL_SMEM = 2 * CL_BUF_BYTES + CL_B_STAGES * CL_STAGE_BYTES + 1024;
+constexpr int CL_RING_BYTES = 7 * 16384;                      // weight ring
+constexpr int CL_SMEM = 2 * CL_BUF_BYTES + CL_RING_BYTES + 1024;
+constexpr int CL_MAX_STAGES = 14;
+template <int CS> struct ClCfg {
+    static constexpr int N = C_TOWER / CS;                    // output channels per CTA: 32 | 16
+    static constexpr int TILE_BYTES = N * TC_BLOCK_K * 2;     // one tap's N x 64 weights
+    static constexpr int STAGE_BYTES = 4 * TILE_BYTES;        // four taps per stage (a K chunk of a 3x3 layer = 4 + 4 + 1)
+    static constexpr int STAGES = CL_RING_BYTES / STAGE_BYTES;   // 7 | 14
+    static constexpr int NP = 128 / CS;                       // policy planes per CTA (73 padded to 128): 16 | 8
+};
 constexpr uint32_t CL_LAYER_BYTES = 64 * C_TOWER * 2;         // a layer's output for one board
 constexpr int CL_MAX_BOARDS = 18;                             // 18 clusters x 8 = 144 of 148 SMs
 constexpr uint32_t CL_A_HI = (uint32_t)(T2_A_SBO >> 4) | (1u << 14) | (2u << 29);      // 8-row groups one halo row (1280 B) apart
+
+// Weight stream of k_tower_cl.  Through a tensor map a 32-row weight tile arrives as 32 separate 128-byte rows (4608 B apart in
+// w16_all) and a CTA ingests only ~44 GB/s that way -- measured: issuing HALF of a layer's MMAs left the layer's MMA phase at
+// 3.3 of 3.6 us, the phase waits for weights, not for the tensor core.  So the folded weights are stored once more in exactly the
+// order and byte image a CTA consumes them: per (layer, rank) one contiguous run of [K chunk][tap] tiles, each tile the
+// 128-byte-swizzled shared-memory image of its (rows x 64) block; a ring stage is then ONE contiguous bulk copy of up to 16 KiB.
+constexpr size_t CL_W_LAYER_ELEMS = (size_t)C_TOWER * 9 * C_TOWER;          // 2304 x 256: stride of a layer in the stream
+// one thread per 16-byte piece: (layer l, rank, tile = kc * taps + tap, row, piece)
+__global__ void k_pack_cluster_weights(const __nv_bfloat16* w16_all, __nv_bfloat16* out, int l, int taps, int kchunks, int n, int cs) {
+    const int tiles = taps * kchunks;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)cs * tiles * n * 8;
+    if (i >= total) return;
+    const int j = (int)(i & 7), r = (int)((i >> 3) % n), tile = (int)((i / (8 * (size_t)n)) % tiles), rank = (int)(i / (8 * (size_t)n * tiles));
+    const int kc = tile / taps, tap = tile - kc * taps;
+    const uint4 v = *reinterpret_cast<const uint4*>(w16_all + ((size_t)l * C_TOWER + rank * n + r) * (9 * C_TOWER) + (size_t)(tap * kchunks + kc) * TC_BLOCK_K + j * 8);
+    __nv_bfloat16* dst = out + (size_t)l * CL_W_LAYER_ELEMS + (size_t)rank * (CL_W_LAYER_ELEMS / cs) + (size_t)tile * n * TC_BLOCK_K + (size_t)r * TC_BLOCK_K + (size_t)((j ^ (r & 7)) * 8);
+    *reinterpret_cast<uint4*>(dst) = v;
+}
 
 struct ClusterArgs {
     int n_boards;
     int board0;                  // first board (row of the NHWC input buffer, before in_delta)
     int in_delta;
     const float* bias;           // [MAX_TOWER_LAYERS][256]
+    const __nv_bfloat16* w_stream;   // Net::w16_cl
     TowerHeads heads;            // mask == null: full fp32 logits to `logits`; value always written (heads.value)
     float* logits;               // [row][4672], row = board + heads.row_delta
     int32_t* error;
@@ -1150,6 +1184,11 @@ struct ClusterArgs {
     TowerLayer L[MAX_TOWER_LAYERS];
 };
 
+// one contiguous global -> shared bulk copy (no tensor map); the bytes are counted on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
@@ -1204,15 +1243,19 @@ __device__ __forceinline__ void tc1_mma_bf16_split(uint32_t tmem_d, uint32_t a_l
 // absolute-address 128-byte swizzle (what TMA and tcgen05.mma apply): address bits 4..6 ^= bits 7..9
 __device__ __forceinline__ uint32_t swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 
-__global__ void __cluster_dims__(CL_SIZE, 1, 1) __launch_bounds__(TC_THREADS, 1)
+template <int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ ClusterArgs a) {
+    constexpr int CL_SIZE = CS, CL_N = ClCfg<CS>::N, CL_B_STAGES = ClCfg<CS>::STAGES, CL_TILE_BYTES = ClCfg<CS>::TILE_BYTES,
+                  CL_STAGE_BYTES = ClCfg<CS>::STAGE_BYTES, CL_NP = ClCfg<CS>::NP;
+    constexpr size_t CL_W_RANK_ELEMS = CL_W_LAYER_ELEMS / CS;
     constexpr uint32_t IDESC_M64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 4) << 24);        // bf16 x bf16 -> fp32, M = 64
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_b_full[CL_B_STAGES], bar_b_empty[CL_B_STAGES], bar_acc_full, bar_act[2], bar_in, bar_lg;
+    __shared__ __align__(8) uint64_t bar_b_full[CL_MAX_STAGES], bar_b_empty[CL_MAX_STAGES], bar_acc_full, bar_act[2], bar_in, bar_lg;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
-    __shared__ float bias_sh[2][CL_N];
+    __shared__ float bias_sh[2][32];
     __shared__ uint64_t hd_mask[MASK_WORDS];
     __shared__ float hd_red[2][4], hd_plane[64], hd_vw[C_TOWER], hd_fc[8];
 
@@ -1273,10 +1316,10 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
         bool ok = true;
         for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
             const TowerLayer L = a.L[l];
-            const int n = L.mode == 1 ? 16 : CL_N;
-            const CUtensorMap* tm_w = n == CL_N ? &maps.w32 : &maps.w16;
+            const int n = L.mode == 1 ? CL_NP : CL_N;
             const uint32_t tile_bytes = (uint32_t)n * TC_BLOCK_K * 2;
-            const int wrow = l * C_TOWER + (int)rank * n;
+            // this CTA's tiles of the layer, contiguous in consumption order (K chunk outer, tap inner)
+            const __nv_bfloat16* wl = a.w_stream + (size_t)l * CL_W_LAYER_ELEMS + (size_t)rank * CL_W_RANK_ELEMS;
             for (int kc = 0; kc < L.kchunks && ok; kc++) {
                 for (int s0 = 0; s0 < L.taps && ok; s0 += 4) {
                     const int cnt = min(4, L.taps - s0);
@@ -1285,8 +1328,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                     if (elect_one()) {
                         const uint32_t full = bar_bf0 + bs * 8;
                         mbar_expect_tx(full, tile_bytes * (uint32_t)cnt);
-                        for (int u = 0; u < cnt; u++)
-                            tma_load_2d(smem_b + bs * CL_STAGE_BYTES + u * CL_TILE_BYTES, tm_w, full, ((s0 + u) * L.kchunks + kc) * TC_BLOCK_K, wrow);
+                        bulk_load(smem_b + bs * CL_STAGE_BYTES, wl + (size_t)(kc * L.taps + s0) * n * TC_BLOCK_K, tile_bytes * (uint32_t)cnt, full);
                     }
                     __syncwarp();
                     if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
@@ -1302,7 +1344,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
         bool ok = true;
         for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
             const TowerLayer L = a.L[l];
-            const int n = L.mode == 1 ? 16 : CL_N;
+            const int n = L.mode == 1 ? CL_NP : CL_N;
             const uint32_t idesc = IDESC_M64 | ((uint32_t)(n >> 3) << 17);
             // this layer's input: the TMA-loaded planes, or the 32 arrivals of the previous layer's epilogues
             if (l == 0) ok = warp_mbar_wait(smem_u32(&bar_in), 0, abort_flag);
@@ -1321,7 +1363,10 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                 if (L.taps == 9) {
 #pragma unroll
                     for (int s0 = 0; s0 < 9; s0 += 4) {
+                        unsigned long long* st = (a.trace && blockIdx.x == 0 && lane == 0 && l == 5) ? a.trace + MAX_TOWER_LAYERS * 8 + (kc * 3 + s0 / 4) * 4 : nullptr;
+                        if (st) st[0] = clock64();
                         if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                        if (st) st[1] = clock64();
                         tc_fence_after();
                         const uint32_t b_base = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
                         if (elect_one()) {
@@ -1339,7 +1384,9 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                             }
                             tc_commit(bar_be0 + bs * 8);
                         }
+                        if (st) st[2] = clock64();
                         __syncwarp();
+                        if (st) st[3] = clock64();
                         if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
                     }
                 } else {
@@ -1372,14 +1419,14 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
         const int m = lane_group * 16 + (lane & 15);                       // board square: oy = m >> 3, ox = m & 7
         const int prow = ((m >> 3) + 1) * HALO + (m & 7) + 1;              // its pixel row in the halo tile
         const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
-        uint32_t xin[16];                                                  // this CTA's 32 channels of the current residual block's input
+        uint32_t xin[CL_N / 2];                                            // this CTA's channels of the current residual block's input
 #pragma unroll
-        for (int j = 0; j < 16; j++) xin[j] = 0;
+        for (int j = 0; j < CL_N / 2; j++) xin[j] = 0;
         bool ok = true;
         const uint32_t lg_base = smem_act + CL_BUF_BYTES;                  // CTA 0's buffer 1: fp32 logits [plane][64], see the head section
         for (int l = 0; l < MAX_TOWER_LAYERS && ok; l++) {
             const TowerLayer L = a.L[l];
-            const int n = L.mode == 1 ? 16 : CL_N;
+            const int n = L.mode == 1 ? CL_NP : CL_N;
             if (etid < n) bias_sh[l & 1][etid] = a.bias[l * C_TOWER + (int)rank * n + etid];
             asm volatile("bar.sync 1, 128;" ::: "memory");
             ok = __all_sync(0xFFFFFFFFu, mbar_wait(smem_u32(&bar_acc_full), (uint32_t)(l & 1), abort_flag));
@@ -1387,8 +1434,8 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             tc_fence_after();
             const bool tracer = a.trace && blockIdx.x == 0 && warp == 2 && lane == 0;
             if (tracer) a.trace[l * 8 + 2] = global_ns();
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr, v);                                  // (the last layer only fills 16 columns; the rest is ignored)
+            uint32_t v[CL_N];
+            if constexpr (CL_N == 32) tmem_ld_32x32b_x32(taddr, v); else tmem_ld_32x32b_x16(taddr, v);      // (the last layer fills fewer columns)
             tmem_ld_wait();
             tc_fence_before();
             if (tracer) a.trace[l * 8 + 3] = global_ns();
@@ -1397,8 +1444,8 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                 // policy logits of this CTA's 16 planes -> CTA 0 (fp32, plane-major like torch.flatten(conv_p2(x)))
                 if (has_row) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int plane = (int)rank * 16 + j;
+                    for (int j = 0; j < CL_NP; j++) {
+                        const int plane = (int)rank * CL_NP + j;
                         if (plane < POLICY_PLANES) st_cluster_f32(mapa_u32(lg_base + (uint32_t)(plane * 64 + m) * 4, 0), __fadd_rn(__uint_as_float(v[j]), bias[j]));
                     }
                 }
@@ -1406,12 +1453,13 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                 if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bar_lg), 0));
                 break;
             }
-            uint4 o[4];
+            constexpr int PIECES = CL_N / 8;                                // 16-byte pieces of this CTA's slice of a pixel row
+            uint4 o[PIECES];
             {
                 __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
                 const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(xin);
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
+                for (int j = 0; j < CL_N / 2; j++) {
                     float x0 = __uint_as_float(v[2 * j]) + bias[2 * j];
                     float x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
                     if (L.res != 255) {
@@ -1426,26 +1474,27 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             if (l == 0 || L.res != 255) {                                   // the stem's and every block's output is the next block's input
                 const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
 #pragma unroll
-                for (int j = 0; j < 16; j++) xin[j] = ow[j];
+                for (int j = 0; j < CL_N / 2; j++) xin[j] = ow[j];
             }
             {
-                // channels [32 r, 32 r + 32) of pixel prow: K chunk r / 2, 16-byte pieces (r & 1) * 4 .. + 3 of its 128-byte row.  Lanes
-                // 0..15 hold the rows; lanes 16..31 take a copy and serve the peers 4..7, so every lane issues 16 asynchronous stores.
+                // this CTA's channels of pixel prow.  Lanes 0..15 hold the rows; lanes 16..31 take a copy and serve the upper half of the
+                // peers, so every lane issues 16 asynchronous 16-byte stores.
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < PIECES; u++) {
                     o[u].x = __shfl_sync(0xFFFFFFFFu, o[u].x, lane & 15);
                     o[u].y = __shfl_sync(0xFFFFFFFFu, o[u].y, lane & 15);
                     o[u].z = __shfl_sync(0xFFFFFFFFu, o[u].z, lane & 15);
                     o[u].w = __shfl_sync(0xFFFFFFFFu, o[u].w, lane & 15);
                 }
-                const uint32_t row_addr = smem_act + (uint32_t)((l + 1) & 1) * CL_BUF_BYTES + (rank >> 1) * CL_CHUNK_BYTES + (uint32_t)prow * 128 + (rank & 1) * 64;
+                const uint32_t ch0 = rank * CL_N;                            // first channel of the slice: K chunk ch0 / 64, byte (ch0 % 64) * 2 of the row
+                const uint32_t row_addr = smem_act + (uint32_t)((l + 1) & 1) * CL_BUF_BYTES + (ch0 >> 6) * CL_CHUNK_BYTES + (uint32_t)prow * 128 + (ch0 & 63) * 2;
                 const uint32_t bar_local = smem_u32(&bar_act[l & 1]);
 #pragma unroll
                 for (int k = 0; k < CL_SIZE / 2; k++) {
                     const uint32_t dst = (uint32_t)(lane >> 4) * (CL_SIZE / 2) + k;
                     const uint32_t rbar = mapa_u32(bar_local, dst);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) st_async_v4(mapa_u32(swz128(row_addr + u * 16), dst), o[u], rbar);
+                    for (int u = 0; u < PIECES; u++) st_async_v4(mapa_u32(swz128(row_addr + u * 16), dst), o[u], rbar);
                 }
             }
             if (tracer) a.trace[l * 8 + 4] = global_ns();
@@ -1877,6 +1926,8 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     constexpr int KMAX = 9 * C_TOWER;
     if ((rc = net_alloc(ctx, net, &net->w16_all, (size_t)MAX_TOWER_LAYERS * C_TOWER * KMAX))) return rc;
     if ((rc = net_alloc(ctx, net, &net->bias_all, (size_t)MAX_TOWER_LAYERS * C_TOWER))) return rc;
+    for (int v = 0; v < 2; v++)
+        if ((rc = net_alloc(ctx, net, &net->w16_cl[v], (size_t)MAX_TOWER_LAYERS * CL_W_LAYER_ELEMS))) return rc;
     if ((rc = net_alloc(ctx, net, &net->ready, (size_t)MAX_TOWER_LAYERS * ((net->cap + 3) / 4)))) return rc;
     delete net->tower_maps;
     delete net->tower_args;
@@ -1958,6 +2009,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     if (const char* e = getenv("SZB_TOWER_EXCLUSIVE")) net->tower_exclusive = e[0] == '1';
     if (const char* e = getenv("SZB_NO_FUSE")) net->no_fuse = e[0] == '1';
     if (const char* e = getenv("SZB_TOWER_CLUSTER")) net->cluster_max = std::max(0, std::min(atoi(e), CL_MAX_BOARDS));
+    if (const char* e = getenv("SZB_TOWER_CLUSTER_SIZE")) net->cluster_force = atoi(e);
     const char* ck = getenv("SZB_TOWER_CHUNK");              // measurement aid: boards per tower launch (0 = whole batch)
     if (ck && ck[0]) net->chunk = std::max(0, atoi(ck)) & ~3;
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
@@ -1983,7 +2035,20 @@ static int net_assemble_tower(szb_ctx* ctx, Net* net) {
     for (int i = 0; i < 2 * N_BLOCKS; i++)
         if ((rc = put(1 + i, net->tower[i], C_TOWER))) return rc;
     if ((rc = put(POLICY_LAYER - 1, net->p1, C_TOWER))) return rc;
-    return put(POLICY_LAYER, net->p2, 128);
+    if ((rc = put(POLICY_LAYER, net->p2, 128))) return rc;
+    // the same weights once more as k_tower_cl's per-CTA streams
+    for (int v = 0; v < 2; v++) {
+        const int cs = 8 << v;
+        for (int l = 0; l < MAX_TOWER_LAYERS; l++) {
+            const TowerLayer& T = net->tower_args->L[l];
+            const int n = (T.mode == 1 ? 128 : C_TOWER) / cs;
+            const size_t total = (size_t)cs * T.taps * T.kchunks * n * 8;
+            k_pack_cluster_weights<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(net->w16_all, net->w16_cl[v], l, T.taps, T.kchunks, n, cs);
+            ctx->launches++;
+        }
+    }
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
 }
 
 // =================================================================================================
@@ -2074,24 +2139,43 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
 
 // the whole forward (tower + both heads) of n <= cluster_max boards with one 8-CTA cluster per board; value_out[i] belongs to board b0 + i
 // unless the heads are fused (then d.policy / d.value rows, as in launch_tower)
-static int cluster_setup(szb_ctx* ctx, Net* net) {
-    if (net->attr_set_cl) return 0;
-    SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+template <int CS>
+static int cluster_setup_one(szb_ctx* ctx, Net* net, int v) {
+    SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_cl<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, CL_SMEM));
+    if (CS > 8) SZB_CUDA(ctx, cudaFuncSetAttribute(k_tower_cl<CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CL_SIZE * CL_MAX_BOARDS);
+    cfg.gridDim = dim3(CS * CL_MAX_BOARDS);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = CL_SMEM;
     int clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&clusters, k_tower_cl, &cfg) == cudaSuccess) net->clusters_resident = clusters;
+    if (cudaOccupancyMaxActiveClusters(&clusters, k_tower_cl<CS>, &cfg) == cudaSuccess) net->clusters_resident[v] = clusters;
     else cudaGetLastError();
-    // more boards than clusters fit at once would run in waves: then the pair kernel is the faster one
-    if (net->clusters_resident > 0) net->cluster_max = std::min(net->cluster_max, net->clusters_resident);
-    if (const char* e = getenv("SZB_TOWER_CLUSTER_VERBOSE")) { if (e[0] == '1') fprintf(stderr, "[szb200] k_tower_cl: %d clusters of %d CTAs resident\n", net->clusters_resident, CL_SIZE); }
+    return 0;
+}
+static int cluster_setup(szb_ctx* ctx, Net* net) {
+    if (net->attr_set_cl) return 0;
+    int rc;
+    if ((rc = cluster_setup_one<8>(ctx, net, 0)) || (rc = cluster_setup_one<16>(ctx, net, 1))) return rc;
+    if (const char* e = getenv("SZB_TOWER_CLUSTER_VERBOSE")) {
+        if (e[0] == '1') fprintf(stderr, "[szb200] k_tower_cl: %d clusters of 8 CTAs, %d clusters of 16 CTAs resident\n", net->clusters_resident[0], net->clusters_resident[1]);
+    }
     net->attr_set_cl = true;
     return 0;
 }
+// cluster size that serves n boards in one wave (more boards than clusters fit at once would run in waves: then the pair kernel is
+// the faster one), or 0
+static int cluster_size_for(szb_ctx* ctx, Net* net, int n) {
+    if (cluster_setup(ctx, net) || n > net->cluster_max) return 0;
+    // clusters of 8 by default: with 16 CTAs per board a layer's weights fit the ring whole, but the MMA phase is bound by the
+    // issue of its 144 tcgen05.mma (~28 clk each from one thread), not by weights, and the 16-way exchange costs 0.15 us more per
+    // layer (measured 6.54 vs 6.39 us per layer); SZB_TOWER_CLUSTER_SIZE=16 keeps the variant reachable for A/B runs
+    if (net->cluster_force == 16) return n <= net->clusters_resident[1] ? 16 : 0;
+    return n <= net->clusters_resident[0] ? 8 : 0;
+}
 
-static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_row, float* value_out, TowerRun run) {
+// the whole forward (tower + both heads) of n boards with one cluster of cs CTAs per board; value_out[i] belongs to board b0 + i
+// unless the heads are fused (then d.policy / d.value rows, as in launch_tower)
+static int launch_tower_cluster(szb_ctx* ctx, Net* net, int cs, int b0, int n, int out_row, float* value_out, TowerRun run) {
     int rc = cluster_setup(ctx, net);
     if (rc) return rc;
     if (out_row < 0) out_row = b0;
@@ -2101,6 +2185,7 @@ static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_r
     a.board0 = b0;
     a.in_delta = run.in16_rows ? out_row - b0 : 0;
     a.bias = net->bias_all;
+    a.w_stream = net->w16_cl[cs == 16];
     a.error = net->tc_error;
     a.logits = net->logits;
     a.trace = net->cl_trace;
@@ -2116,7 +2201,8 @@ static int launch_tower_cluster(szb_ctx* ctx, Net* net, int b0, int n, int out_r
         h.mask = nullptr; h.need_eval = nullptr; h.policy = nullptr;
         h.value = value_out - (ptrdiff_t)out_row;             // value[board + row_delta] == value_out[board - b0]
     }
-    SZB_CUDA(ctx, launch_kernel(k_tower_cl, dim3(CL_SIZE * n), dim3(TC_THREADS), (size_t)CL_SMEM, ctx->work, run.pdl, *net->tower_maps, a));
+    if (cs == 16) SZB_CUDA(ctx, launch_kernel(k_tower_cl<16>, dim3(16 * n), dim3(TC_THREADS), (size_t)CL_SMEM, ctx->work, run.pdl, *net->tower_maps, a));
+    else SZB_CUDA(ctx, launch_kernel(k_tower_cl<8>, dim3(8 * n), dim3(TC_THREADS), (size_t)CL_SMEM, ctx->work, run.pdl, *net->tower_maps, a));
     ctx->launches++;
     return 0;
 }
@@ -2226,11 +2312,11 @@ static int net_forward_device(szb_ctx* ctx, int evaluator, int b0, int n, const 
                 if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_LAYER * (uint64_t)n; }
             }
             x = net->final_x; y = net->final_y;
-        } else if (!cluster_setup(ctx, net) && n <= net->cluster_max) {
+        } else if (const int cs = cluster_size_for(ctx, net, n)) {
             // a handful of boards: the cluster-resident kernel does the whole forward, heads included (fused or not)
             cudaEvent_t* cev = ctx->profiling ? conv_event_pair(ctx) : nullptr;
             if (cev) cudaEventRecord(cev[0], st);
-            if ((rc = launch_tower_cluster(ctx, net, b0, n, out_row, value_out, run))) return rc;
+            if ((rc = launch_tower_cluster(ctx, net, cs, b0, n, out_row, value_out, run))) return rc;
             if (cev) { cudaEventRecord(cev[1], st); ctx->conv_recorded++; ctx->conv_boards += n; ctx->conv_flop += FLOP_TOWER_ALL * (uint64_t)n; }
             SZB_CUDA(ctx, cudaGetLastError());
             return 0;
@@ -2550,8 +2636,8 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
             case 4: rc = launch_tower(ctx, net, 0, n, 20, 21); break;                       // one tower layer, CTA-pair kernel
             case 5: rc = launch_tower(ctx, net, 0, n, 0, MAX_TOWER_LAYERS); break;          // whole tower, one launch
             case 6:                                                                         // whole forward, cluster-resident kernel
-                rc = n <= CL_MAX_BOARDS ? launch_tower_cluster(ctx, net, 0, n, 0, ctx->d.value, TowerRun())
-                                        : fail(ctx, SZB_ERR_ARG, "the cluster-resident tower takes at most %d boards", CL_MAX_BOARDS);
+                if (const int cs = cluster_size_for(ctx, net, n)) rc = launch_tower_cluster(ctx, net, cs, 0, n, 0, ctx->d.value, TowerRun());
+                else rc = fail(ctx, SZB_ERR_ARG, "no cluster-resident configuration holds %d boards at once on this device", n);
                 break;
             default: rc = fail(ctx, SZB_ERR_ARG, "unknown kernel selector %d", which);
             }
@@ -2567,11 +2653,11 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
     const char* trace_path = getenv("SZB_TOWER_TRACE");      // measurement aid: per-item device timestamps of one more launch as CSV
     if (which == 6 && trace_path && trace_path[0]) {
         unsigned long long* d_tr = nullptr;
-        const size_t slots = (size_t)MAX_TOWER_LAYERS * 8;
+        const size_t slots = (size_t)MAX_TOWER_LAYERS * 8 + 48;
         SZB_CUDA(ctx, cudaMalloc((void**)&d_tr, slots * 8));
         SZB_CUDA(ctx, cudaMemsetAsync(d_tr, 0, slots * 8, ctx->stream));
         net->cl_trace = d_tr;
-        rc = launch_tower_cluster(ctx, net, 0, n, 0, ctx->d.value, TowerRun());
+        rc = launch_tower_cluster(ctx, net, cluster_size_for(ctx, net, n), 0, n, 0, ctx->d.value, TowerRun());
         net->cl_trace = nullptr;
         std::vector<unsigned long long> h(slots);
         cudaMemcpyAsync(h.data(), d_tr, slots * 8, cudaMemcpyDeviceToHost, ctx->stream);
@@ -2585,6 +2671,12 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
                 fprintf(f, "%d,%d", n, l);
                 for (int k = 0; k < 6; k++) fprintf(f, ",%lld", h[(size_t)l * 8 + k] ? (long long)(h[(size_t)l * 8 + k] - t0) : -1ll);
                 fprintf(f, "\n");
+            }
+            fprintf(f, "# layer 5, SM clocks per weight stage of the MMA warp: stage,wait_clk,issue_clk,syncwarp_clk,gap_to_next_clk\n");
+            for (int k = 0; k < 12; k++) {
+                const unsigned long long* q = &h[(size_t)MAX_TOWER_LAYERS * 8 + k * 4];
+                fprintf(f, "# %d,%lld,%lld,%lld,%lld\n", k, (long long)(q[1] - q[0]), (long long)(q[2] - q[1]), (long long)(q[3] - q[2]),
+                        k < 11 ? (long long)(q[4] - q[3]) : 0ll);
             }
             fclose(f);
         }

@@ -439,7 +439,7 @@ def test_playtensor_best_move_equals_reference_first_max():
 # the cluster-resident tower (batches of at most 18 boards) against the CTA-pair tower
 # ---------------------------------------------------------------------------------------------------------------------------
 def test_cluster_tower_bit_identical(monkeypatch):
-    """k_tower_cl (one 8-CTA cluster per board, M = 64 MMAs, activations exchanged through distributed shared memory, heads inside
+    """k_tower_cl (one cluster of 8 or 16 CTAs per board, M = 64 MMAs, activations exchanged through distributed shared memory, heads inside
     the launch) runs the same MMAs per output in the same K order as k_tower_tc2: logits, softmax policy and value must agree bit
     for bit, for 1, 5 and 18 boards, with non-trivial BatchNorm statistics"""
     from sigma_zero_b200.engine import EVAL_NET_BF16, Engine
@@ -456,14 +456,16 @@ def test_cluster_tower_bit_identical(monkeypatch):
     packed = np.stack([hash_eval.pack_planes(util.oracle_game(c, s, mv).get_representation()) for c, s, mv in specs])
     for n in (1, 5, 18):
         outs = []
-        for cluster in ("0", "18"):
+        for cluster, size in (("0", "0"), ("18", "8"), ("18", "16"), ("18", "0")):     # pair kernel | clusters of 8 | of 16 | automatic
             monkeypatch.setenv("SZB_TOWER_CLUSTER", cluster)
+            monkeypatch.setenv("SZB_TOWER_CLUSTER_SIZE", size)
             eng = Engine(max_games=n, max_searches=4)
             eng.load_state_dict(model.state_dict())
             outs.append(eng.net_forward(packed[:n], EVAL_NET_BF16, logits=True) + eng.net_forward(packed[:n], EVAL_NET_BF16))
             eng.close()
-        for a, b in zip(outs[0], outs[1]):
-            assert np.array_equal(a, b), n
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert np.array_equal(a, b), n
         assert np.abs(outs[1][0]).max() > 0.1 and np.isfinite(outs[1][0]).all()
 
 
