@@ -1363,10 +1363,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                 if (L.taps == 9) {
 #pragma unroll
                     for (int s0 = 0; s0 < 9; s0 += 4) {
-                        unsigned long long* st = (a.trace && blockIdx.x == 0 && lane == 0 && l == 5) ? a.trace + MAX_TOWER_LAYERS * 8 + (kc * 3 + s0 / 4) * 4 : nullptr;
-                        if (st) st[0] = clock64();
                         if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
-                        if (st) st[1] = clock64();
                         tc_fence_after();
                         const uint32_t b_base = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
                         if (elect_one()) {
@@ -1384,9 +1381,7 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
                             }
                             tc_commit(bar_be0 + bs * 8);
                         }
-                        if (st) st[2] = clock64();
                         __syncwarp();
-                        if (st) st[3] = clock64();
                         if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
                     }
                 } else {
@@ -2653,7 +2648,7 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
     const char* trace_path = getenv("SZB_TOWER_TRACE");      // measurement aid: per-item device timestamps of one more launch as CSV
     if (which == 6 && trace_path && trace_path[0]) {
         unsigned long long* d_tr = nullptr;
-        const size_t slots = (size_t)MAX_TOWER_LAYERS * 8 + 48;
+        const size_t slots = (size_t)MAX_TOWER_LAYERS * 8;
         SZB_CUDA(ctx, cudaMalloc((void**)&d_tr, slots * 8));
         SZB_CUDA(ctx, cudaMemsetAsync(d_tr, 0, slots * 8, ctx->stream));
         net->cl_trace = d_tr;
@@ -2671,12 +2666,6 @@ int szb_time_kernel(szb_ctx* ctx, int32_t which, int32_t n, int32_t iters, float
                 fprintf(f, "%d,%d", n, l);
                 for (int k = 0; k < 6; k++) fprintf(f, ",%lld", h[(size_t)l * 8 + k] ? (long long)(h[(size_t)l * 8 + k] - t0) : -1ll);
                 fprintf(f, "\n");
-            }
-            fprintf(f, "# layer 5, SM clocks per weight stage of the MMA warp: stage,wait_clk,issue_clk,syncwarp_clk,gap_to_next_clk\n");
-            for (int k = 0; k < 12; k++) {
-                const unsigned long long* q = &h[(size_t)MAX_TOWER_LAYERS * 8 + k * 4];
-                fprintf(f, "# %d,%lld,%lld,%lld,%lld\n", k, (long long)(q[1] - q[0]), (long long)(q[2] - q[1]), (long long)(q[3] - q[2]),
-                        k < 11 ? (long long)(q[4] - q[3]) : 0ll);
             }
             fclose(f);
         }
