@@ -576,6 +576,23 @@ __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slo
     const int g = active ? d.order[slot] : 0;
     const bool eval = active && d.need_eval[slot];
     uint64_t* mk = mk_sh + wib * MASK_STRIDE;
+    // Everything the backup needs is requested NOW, so that these round trips run under the mask -> arena bump -> priors chain
+    // below instead of after it: the path, the statistics of its edges (only this warp touches them; the children created below
+    // are new edges), the leaf's value, the root's sums.
+    const size_t r = (size_t)g * d.nodes_per_game;
+    const int node = active ? d.sel_node[slot] : 0;
+    const int L = active ? d.path_len[slot] : 0;
+    const bool fast = L <= PATH_CAP;
+    const int32_t* path = d.path + (size_t)slot * PATH_CAP;
+    const int pe0 = (fast && lane < L) ? path[lane] : -1, pe1 = (fast && lane + 32 < L) ? path[lane + 32] : -1;
+    double w0 = 0.0, w1 = 0.0;
+    int n0 = 0, n1 = 0;
+    if (pe0 >= 0) { w0 = d.e_w[pe0]; n0 = d.e_n[pe0]; }
+    if (pe1 >= 0) { w1 = d.e_w[pe1]; n1 = d.e_n[pe1]; }
+    const float v = !active ? 0.f : (eval ? d.value[slot] : d.leaf_value[slot]);
+    double root_w = 0.0;
+    int root_n = 0, pedge = -1;
+    if (active && lane == 0) { root_w = d.root_w[g]; root_n = d.root_n[g]; pedge = d.node_pedge[r + node]; }
     // children to allocate: one bump of the shared edge arena per BLOCK (four trees), not one same-address atomic per tree
     int n_legal = 0;
     if (eval) {
@@ -593,9 +610,6 @@ __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slo
     }
     __syncthreads();
     if (!active) return;
-    const size_t r = (size_t)g * d.nodes_per_game;
-    const int node = d.sel_node[slot];
-    float v;
     int count = 0;
     if (eval) {
         unsigned long long e0 = *base_sh;
@@ -608,24 +622,15 @@ __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slo
         if (lane == 0) {
             d.node_edge0[r + node] = (int32_t)e0;
             d.node_nchild[r + node] = (uint16_t)count;
-            const int pe = d.node_pedge[r + node];
-            if (pe >= 0) d.e_link[pe] = link_pack((int32_t)e0, (uint32_t)count, (uint32_t)node);     // the header select reads
+            if (pedge >= 0) d.e_link[pedge] = link_pack((int32_t)e0, (uint32_t)count, (uint32_t)node);     // the header select reads
+            if (node == 0) d.root_val[g] = v;
         }
-        v = d.value[slot];
-        if (node == 0 && lane == 0) d.root_val[g] = v;
-    } else {
-        v = d.leaf_value[slot];
     }
     // backup (mctsnode.py:56-63): value_sum accumulates python doubles; the edge k levels above the leaf gets (-1)^k * value
     const double val = (double)v;
-    const int L = d.path_len[slot];
-    if (L <= PATH_CAP) {
-        const int32_t* path = d.path + (size_t)slot * PATH_CAP;
-        for (int k = lane; k < L; k += 32) {
-            const int pe = path[k];
-            d.e_w[pe] += ((L - 1 - k) & 1) ? -val : val;
-            d.e_n[pe] += 1;
-        }
+    if (fast) {
+        if (pe0 >= 0) { d.e_w[pe0] = w0 + (((L - 1 - lane) & 1) ? -val : val); d.e_n[pe0] = n0 + 1; }
+        if (pe1 >= 0) { d.e_w[pe1] = w1 + (((L - 1 - lane - 32) & 1) ? -val : val); d.e_n[pe1] = n1 + 1; }
     } else if (lane == 0) {
         double x = val;
         for (int nd = node;;) {
@@ -641,8 +646,8 @@ __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slo
         unsigned long long* gs = d.gstats + (size_t)g * 8;
         gs[6] += (unsigned long long)L;
         if (eval) gs[7] += (unsigned long long)count;
-        d.root_w[g] += (L & 1) ? -val : val;
-        d.root_n[g] += 1;
+        d.root_w[g] = root_w + ((L & 1) ? -val : val);
+        d.root_n[g] = root_n + 1;
         gs[0] += 1ull;
         gs[eval ? 1 : 2] += 1ull;
     }

@@ -1320,19 +1320,20 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             const uint32_t tile_bytes = (uint32_t)n * TC_BLOCK_K * 2;
             // this CTA's tiles of the layer, contiguous in consumption order (K chunk outer, tap inner)
             const __nv_bfloat16* wl = a.w_stream + (size_t)l * CL_W_LAYER_ELEMS + (size_t)rank * CL_W_RANK_ELEMS;
-            for (int kc = 0; kc < L.kchunks && ok; kc++) {
-                for (int s0 = 0; s0 < L.taps && ok; s0 += 4) {
-                    const int cnt = min(4, L.taps - s0);
-                    if (issued++ == CL_B_STAGES) send_input();
-                    if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
-                    if (elect_one()) {
-                        const uint32_t full = bar_bf0 + bs * 8;
-                        mbar_expect_tx(full, tile_bytes * (uint32_t)cnt);
-                        bulk_load(smem_b + bs * CL_STAGE_BYTES, wl + (size_t)(kc * L.taps + s0) * n * TC_BLOCK_K, tile_bytes * (uint32_t)cnt, full);
-                    }
-                    __syncwarp();
-                    if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
+            // a stage = four consecutive tiles of the layer's (K chunk, tap) sequence (stages straddle K chunks: a 3x3 layer is nine
+            // full stages, a 1x1 layer one), one contiguous bulk copy
+            const int T = L.taps * L.kchunks;
+            for (int s0 = 0; s0 < T && ok; s0 += 4) {
+                const int cnt = min(4, T - s0);
+                if (issued++ == CL_B_STAGES) send_input();
+                if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
+                if (elect_one()) {
+                    const uint32_t full = bar_bf0 + bs * 8;
+                    mbar_expect_tx(full, tile_bytes * (uint32_t)cnt);
+                    bulk_load(smem_b + bs * CL_STAGE_BYTES, wl + (size_t)s0 * n * TC_BLOCK_K, tile_bytes * (uint32_t)cnt, full);
                 }
+                __syncwarp();
+                if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -1357,49 +1358,54 @@ k_tower_cl(const __grid_constant__ TowerMaps maps, const __grid_constant__ Clust
             tc_fence_after();
             if (a.trace && blockIdx.x == 0 && lane == 0) a.trace[l * 8 + 0] = global_ns();
             const uint32_t buf_lo = a_lo0 + (uint32_t)(l & 1) * (CL_BUF_BYTES >> 4);
-            uint32_t accumulate = 0;
-            for (int kc = 0; kc < L.kchunks && ok; kc++) {
-                const uint32_t chunk_lo = buf_lo + (uint32_t)kc * (CL_CHUNK_BYTES >> 4);
-                if (L.taps == 9) {
+            if (L.taps == 9) {
+                // straight-line issue: stage s holds tiles 4 s .. 4 s + 3 of the layer's (K chunk outer, tap inner) sequence; every
+                // descriptor offset below is an immediate
+                const int T = 9 * L.kchunks;                               // 36, or 18 for the stem
 #pragma unroll
-                    for (int s0 = 0; s0 < 9; s0 += 4) {
-                        if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
-                        tc_fence_after();
-                        const uint32_t b_base = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int tap = s0 + u;
-                                if (tap < 9) {
-                                    const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * HALO + tap % 3) * (128 >> 4);     // halo pixel (ky, kx)
-                                    const uint32_t b_lo = b_base + u * (CL_TILE_BYTES >> 4);
-                                    tc1_mma_bf16_split(tmem_base, a_lo, CL_A_HI, b_lo, T2_B_HI, idesc, tap == 0 ? accumulate : 1u);
-                                    tc1_mma_bf16_split(tmem_base, a_lo + 2, CL_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
-                                    tc1_mma_bf16_split(tmem_base, a_lo + 4, CL_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
-                                    tc1_mma_bf16_split(tmem_base, a_lo + 6, CL_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
-                                }
-                            }
-                            tc_commit(bar_be0 + bs * 8);
-                        }
-                        __syncwarp();
-                        if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
-                    }
-                } else {
+                for (int s = 0; s < 9; s++) {
+                    if (4 * s >= T) break;
                     if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
                     tc_fence_after();
-                    const uint32_t a_lo = chunk_lo + (uint32_t)(HALO + 1) * (128 >> 4);                                    // centre tap
-                    const uint32_t b_lo = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
+                    const uint32_t b_base = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
                     if (elect_one()) {
-                        tc1_mma_bf16_split(tmem_base, a_lo, CL_A_HI, b_lo, T2_B_HI, idesc, accumulate);
-                        tc1_mma_bf16_split(tmem_base, a_lo + 2, CL_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
-                        tc1_mma_bf16_split(tmem_base, a_lo + 4, CL_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
-                        tc1_mma_bf16_split(tmem_base, a_lo + 6, CL_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int t = 4 * s + u, kc = t / 9, tap = t % 9;
+                            if (t < T) {
+                                const uint32_t a_lo = buf_lo + (uint32_t)kc * (CL_CHUNK_BYTES >> 4) + (uint32_t)((tap / 3) * HALO + tap % 3) * (128 >> 4);   // halo pixel (ky, kx)
+                                const uint32_t b_lo = b_base + u * (CL_TILE_BYTES >> 4);
+                                tc1_mma_bf16_split(tmem_base, a_lo, CL_A_HI, b_lo, T2_B_HI, idesc, t == 0 ? 0u : 1u);
+                                tc1_mma_bf16_split(tmem_base, a_lo + 2, CL_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                                tc1_mma_bf16_split(tmem_base, a_lo + 4, CL_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                                tc1_mma_bf16_split(tmem_base, a_lo + 6, CL_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                            }
+                        }
                         tc_commit(bar_be0 + bs * 8);
                     }
                     __syncwarp();
                     if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
                 }
-                accumulate = 1;
+            } else {
+                // 1x1 convolution = centre tap of the four K chunks: one stage of four tiles
+                if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t b_base = b_lo0 + bs * (CL_STAGE_BYTES >> 4);
+                const uint32_t tile_lo = (uint32_t)(n * TC_BLOCK_K * 2) >> 4;
+                if (elect_one()) {
+#pragma unroll
+                    for (int kc = 0; kc < C_TOWER / TC_BLOCK_K; kc++) {
+                        const uint32_t a_lo = buf_lo + (uint32_t)kc * (CL_CHUNK_BYTES >> 4) + (uint32_t)(HALO + 1) * (128 >> 4);
+                        const uint32_t b_lo = b_base + kc * tile_lo;
+                        tc1_mma_bf16_split(tmem_base, a_lo, CL_A_HI, b_lo, T2_B_HI, idesc, kc == 0 ? 0u : 1u);
+                        tc1_mma_bf16_split(tmem_base, a_lo + 2, CL_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                        tc1_mma_bf16_split(tmem_base, a_lo + 4, CL_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                        tc1_mma_bf16_split(tmem_base, a_lo + 6, CL_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                    }
+                    tc_commit(bar_be0 + bs * 8);
+                }
+                __syncwarp();
+                if (++bs == CL_B_STAGES) { bs = 0; b_phase ^= 1; }
             }
             if (ok && elect_one()) tc_commit(smem_u32(&bar_acc_full));
             __syncwarp();
