@@ -138,7 +138,14 @@ def test_bf16_visit_counts_track_the_fp32_search():
     tv = 0.5 * np.abs(v16.astype(np.float64) - v32).sum(1) / 199.0
     same_top = float((v16.argmax(1) == v32.argmax(1)).mean())
     print("bf16 vs fp32 search: mean TV %.4f  max TV %.4f  same top move %.2f" % (tv.mean(), tv.max(), same_top))
-    assert tv.mean() < 0.15 and same_top >= 0.6
+    import json, os
+    out = os.path.join(util.ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump({"games": 32, "sims": 200, "tv_mean": float(tv.mean()), "tv_max": float(tv.max()), "same_top_move": same_top},
+              open(os.path.join(out, "parity_bf16_vs_fp32_32x200.json"), "w"))
+    # observed on B200 (profiles/r02b_parity.json has the at-size figures): mean TV 1.6e-4 at 1024 x 800; the bounds leave a margin
+    # for other weights / positions but no longer admit an unrelated search
+    assert tv.mean() < 0.03 and tv.max() < 0.25 and same_top >= 0.8
     eng.close()
 
 
