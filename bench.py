@@ -563,9 +563,15 @@ def c4_measure(args, wl, max_plies, model, weights):
     sargs = {"C": C_PUCT, "num_searches": wl["sims"], "num_selfPlay_iterations": wl["games"], "chess960": wl["chess960"],
              "leaves_per_tree": args.leaves_per_tree}
     lo, hi = shard_of(wl["games"], rank, world)
-    # warm-up: two plies of this rank's block (engine creation, weight upload, first launches)
+    # the parameters live on the GPU, as in train_RL.main(train_device="cuda"): the broadcast buffer is then built, sent and folded
+    # without leaving the device
+    model.to(dev)
+    # warm-up: two plies of this rank's block (engine creation, weight upload, first launches) and one broadcast (NCCL communicator)
     selfplay_records(model, sargs, hi - lo, c960=wl["chess960"], seed=SEED, max_plies=2, game_id_base=lo)
     eng = runtime.get_engine()
+    if world > 1:
+        broadcast_weights(model, 0, dev, eng)
+        torch.cuda.synchronize()
     st0 = eng.stats()
     sampler = ClockSampler(local)
     if world > 1:
