@@ -567,15 +567,18 @@ __device__ __forceinline__ int create_children(const Dev& d, const uint64_t* mk,
     return count;
 }
 
-constexpr int FINISH_WARPS = 4;
+// Trees per block of the finish / tree-step kernels.  Two, not four: a block of k_tree_step must fit NEXT TO a tower CTA of the other
+// cohort (k_tower_tc2 leaves ~9 KB of an SM's shared memory and half its registers), otherwise the tree kernel of one cohort cannot run
+// under the other cohort's tower and every step pays it in full (measured: tower busy share 1.01 -> 0.976 with four trees and a 4 KB
+// look-up table per block, i.e. 17 KB of shared memory).
+constexpr int FINISH_WARPS = 2;
 
 // Second half of a simulation for the block's four trees (mcts.py:77-109): children of the evaluated node, then backup.  Called by
-// ALL threads of the block (two block-wide barriers inside); mk_sh: 73 words of shared memory per warp.
+// ALL threads of the block (two block-wide barriers inside); mk: 80 words of shared memory of this warp.
 __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slot, bool active, int lane, int wib, int* want_sh,
-                                             unsigned long long* base_sh, uint64_t* mk_sh) {
+                                             unsigned long long* base_sh, uint64_t* mk) {
     const int g = active ? d.order[slot] : 0;
     const bool eval = active && d.need_eval[slot];
-    uint64_t* mk = mk_sh + wib * MASK_STRIDE;
     // Everything the backup needs is requested NOW, so that these round trips run under the mask -> arena bump -> priors chain
     // below instead of after it: the path, the statistics of its edges (only this warp touches them; the children created below
     // are new edges), the leaf's value, the root's sums.
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_finish(Dev d, int learnin
     __shared__ unsigned long long base_sh;
     __shared__ uint64_t mk_sh[FINISH_WARPS * MASK_STRIDE];
     const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    finish_block(d, learning, slot, slot < d.g_end, threadIdx.x & 31, threadIdx.x >> 5, want_sh, &base_sh, mk_sh);
+    finish_block(d, learning, slot, slot < d.g_end, threadIdx.x & 31, threadIdx.x >> 5, want_sh, &base_sh, mk_sh + (threadIdx.x >> 5) * MASK_STRIDE);
 }
 
 // One launch per simulation step and cohort in the reference-exact mode: the second half of step s-1 (children + backup of the
@@ -672,20 +675,10 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
     __shared__ Tables T;
     __shared__ int want_sh[FINISH_WARPS];
     __shared__ unsigned long long base_sh;
-    __shared__ uint64_t mk_sh[FINISH_WARPS * MASK_STRIDE];
-    __shared__ ExpandShared ex_sh[FINISH_WARPS];
-    __shared__ uint4 lut_sh[256];                              // byte -> eight bf16 (bit ? 1.0 : 0)
+    __shared__ ExpandShared ex_sh[FINISH_WARPS];               // (its mask also stages the finish phase's legal mask: 6.4 KB per block)
     const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool active = slot < d.g_end;
-    if (d.net_in16 && (phases & STEP_SELECT)) {
-        for (int b = threadIdx.x; b < 256; b += blockDim.x) {
-            uint32_t h[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) h[k] = ((b >> (2 * k)) & 1 ? 0x3F80u : 0u) | ((b >> (2 * k + 1)) & 1 ? 0x3F800000u : 0u);
-            lut_sh[b] = make_uint4(h[0], h[1], h[2], h[3]);
-        }                                                      // (load_tables' barrier below publishes it)
-    }
     unsigned long long* tr = (d.step_trace && slot == d.g_begin && lane == 0) ? d.step_trace : nullptr;
     auto stamp = [&](int k) { if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[k] = t; } };
     pdl_trigger();                                             // the tower launch behind me may begin its set-up and weight prefetch
@@ -694,7 +687,7 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
     stamp(0);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.net_ready_n; i += gridDim.x * blockDim.x) d.net_ready[i] = 0;
     stamp(1);
-    if (phases & STEP_FINISH) finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, mk_sh);
+    if (phases & STEP_FINISH) finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, ex_sh[wib].mask);
     if (!(phases & STEP_SELECT) || !active) return;
     __syncwarp();                                              // this warp's tree updates -> every lane of the descent
     stamp(2);
@@ -708,7 +701,8 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
     if (d.net_in16) {
         // 64 squares x 128 channels of bf16 (0 / 1.0) into the interior of the slot's zero-haloed [10][10][128] input row.  A lane takes
         // an 8-plane x 8-square block (channel group cg, board row r): the planes' bytes of that row, an 8 x 8 bit transpose, and
-        // every byte of the result is one square's 8 channels -> one 16-byte store through a 256-entry table (byte -> 8 bf16).
+        // every byte of the result is one square's 8 channels -> one 16-byte store through a 256-entry table (byte -> 8 bf16, 4 KB in
+        // global memory: L1-resident, and not part of the block's shared-memory footprint).
         // Lanes 0..15 / 16..31 write two squares' 256 contiguous bytes per store.
         uint4* in = reinterpret_cast<uint4*>(d.net_in16 + (size_t)slot * 100 * 128);
         const int cg = lane & 15;
@@ -728,7 +722,7 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
             t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
             x ^= t ^ (t << 28);
 #pragma unroll
-            for (int i = 0; i < 8; i++) in[(size_t)((r + 1) * 10 + i + 1) * 16 + cg] = lut_sh[(x >> (8 * i)) & 0xFFull];
+            for (int i = 0; i < 8; i++) in[(size_t)((r + 1) * 10 + i + 1) * 16 + cg] = __ldg(d.lut_bf16 + ((x >> (8 * i)) & 0xFFull));
         }
     }
     stamp(7);
@@ -1233,6 +1227,17 @@ int szb_create(int device, const szb_config* cfg, szb_ctx** out) {
     if ((rc = dev_alloc(ctx, &dt, 1))) return rc;
     SZB_CUDA(ctx, cudaMemcpyAsync(dt, &ctx->host_tables, sizeof(Tables), cudaMemcpyHostToDevice, ctx->stream));
     d.tables = dt;
+    {
+        // byte -> eight bf16 (bit ? 1.0 : 0): the table k_tree_step expands the input planes with
+        std::vector<uint32_t> lut(256 * 4);
+        for (int b = 0; b < 256; b++)
+            for (int k = 0; k < 4; k++) lut[b * 4 + k] = (((b >> (2 * k)) & 1) ? 0x3F80u : 0u) | (((b >> (2 * k + 1)) & 1) ? 0x3F800000u : 0u);
+        uint4* dl = nullptr;
+        if ((rc = dev_alloc(ctx, &dl, 256))) return rc;
+        SZB_CUDA(ctx, cudaMemcpyAsync(dl, lut.data(), 256 * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        d.lut_bf16 = dl;
+    }
 #define A(field, count) if ((rc = dev_alloc(ctx, &d.field, (count)))) return rc
     A(pool, G * (size_t)d.pool_stride);
     A(cur, G); A(anc, G * (size_t)d.pool_stride * 8);
@@ -1479,7 +1484,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
             rc_eval = net_evaluate_batch(ctx, evaluator, dc.g_begin * K, paths, false);
         }
         if (ev) cudaEventRecord(ev[3], cs);
-        if (K == 1) k_finish<<<warp_blocks, 128, 0, cs>>>(dc, learning);
+        if (K == 1) k_finish<<<(n + FINISH_WARPS - 1) / FINISH_WARPS, 32 * FINISH_WARPS, 0, cs>>>(dc, learning);
         else k_finish_vl<<<n, 32 * MAX_LEAVES, 0, cs>>>(dc, learning);
         if (ev) cudaEventRecord(ev[4], cs);
         ctx->launches++;
@@ -1507,7 +1512,7 @@ static int run_search(szb_ctx* ctx, int num_searches, float c_puct, int learning
         ctx->work = cs;
         dc.net_in16 = nullptr; dc.net_ready = nullptr; dc.net_ready_n = 0;
         if (net_fused && (phases & STEP_SELECT)) net_handover(ctx, dc.g_begin, n, &dc.net_in16, &dc.net_ready, &dc.net_ready_n);
-        launch_kernel(k_tree_step, dim3((n * 32 + 127) / 128), dim3(128), 0, cs, ctx->pdl, dc, c_puct, learning, phases);
+        launch_kernel(k_tree_step, dim3((n + FINISH_WARPS - 1) / FINISH_WARPS), dim3(32 * FINISH_WARPS), 0, cs, ctx->pdl, dc, c_puct, learning, phases);
         ctx->launches++;
         if (!(phases & STEP_SELECT)) return 0;
         if (evaluator == SZB_EVAL_HASH) {

@@ -40,6 +40,7 @@ struct Dev {
     uint16_t* anc;           // [max_games][pool_stride][8] pool slots of a position's 8 predecessors, nearest first (0xFFFF: none), recorded
                              // when the position is made: the history planes load them side by side instead of walking Pos::prev
     const Tables* tables;
+    const uint4* lut_bf16;   // [256] byte -> eight bf16 (0 / 1.0)
     int pool_stride;
     int n_games;
     int K;                   // leaves (in-flight simulations) per tree and step: 1 = the reference's algorithm
