@@ -424,6 +424,10 @@ def run_ours(args, wl):
                 "launches_timed": spans["launches"], "flop_per_launch": spans["flop"] / spans["launches"], "boards_per_launch": boards,
                 # (share of the window the recorded launches span: the library keeps the first 8192 launches of the timed region)
                 "tower_busy_share_of_timed_region": spans["busy_ns"] / spans["wall_ns"] if spans["wall_ns"] else None,
+                # the SM clock the tower actually ran at: clock64 cycles / %globaltimer ns of CTA 0 of every launch (nvidia-smi samples at
+                # 200 ms cannot see the dips of a power-capped step); utilisation = achieved / (148 SMs x 8192 FLOP/clk x that clock)
+                "sm_mhz_inside_launches": 1e3 * spans["sm_cycles"] / spans["sm_ns"] if spans.get("sm_ns") else None,
+                "tensor_pipe_utilisation_at_that_clock": (achieved * 1e12 / (148 * 8192 * 1e9 * spans["sm_cycles"] / spans["sm_ns"])) if spans.get("sm_ns") else None,
                 "frac_timed_region_lower_bound": FLOP_PER_EVAL * evals / (ms * 1e-3) / 1e12 / world / pk["bf16_sustained"],
                 "profiled_step": profiled}
     elif profiled:

@@ -219,6 +219,8 @@ typedef struct szb_tower_spans {
     uint64_t busy_ns;          /* sum of (end - start) over the launches */
     uint64_t wall_ns;          /* last end - first start */
     uint64_t flop;             /* algorithmic FLOP of those launches (sum) */
+    uint64_t sm_cycles;        /* SM clock cycles CTA 0 of every launch lived (clock64), summed ... */
+    uint64_t sm_ns;            /* ... and the nanoseconds it lived (%globaltimer): sm_cycles / sm_ns = the SM clock INSIDE the launches in GHz */
 } szb_tower_spans;
 int szb_tower_spans_record(szb_ctx *ctx, int32_t on, szb_tower_spans *out);
 /* average duration (ms) of one launch of a kernel run `iters` times back to back on n boards:

@@ -44,7 +44,8 @@ class PhaseTimes(ctypes.Structure):
 
 class TowerSpans(ctypes.Structure):
     _fields_ = [("launches", ctypes.c_int32), ("reserved", ctypes.c_int32), ("boards", ctypes.c_uint64),
-                ("busy_ns", ctypes.c_uint64), ("wall_ns", ctypes.c_uint64), ("flop", ctypes.c_uint64)]
+                ("busy_ns", ctypes.c_uint64), ("wall_ns", ctypes.c_uint64), ("flop", ctypes.c_uint64),
+                ("sm_cycles", ctypes.c_uint64), ("sm_ns", ctypes.c_uint64)]
 
 
 _vp, _i32, _u64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float

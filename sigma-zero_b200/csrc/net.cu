@@ -96,7 +96,7 @@ struct Net {
     bool attr_set_cl = false;
     int clusters_resident[2] = {0, 0};         // clusters of 8 / 16 CTAs of k_tower_cl this device holds at once
     unsigned long long* cl_trace = nullptr;
-    unsigned long long* span = nullptr;  // [SPAN_CAP][2] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
+    unsigned long long* span = nullptr;  // [SPAN_CAP][4] device stamps of whole-tower launches (szb_tower_spans_record / SZB_TOWER_SPAN)
     bool span_on = false;
     std::vector<int> span_boards, span_b0;
     std::string span_path;
@@ -519,7 +519,7 @@ struct TowerArgs {
     float* logits;       // [boards][4672]
     int32_t* error;
     unsigned long long* trace;   // measurement aid (SZB_TOWER_TRACE): [item][4] %globaltimer stamps of the leader CTA, or null
-    unsigned long long* span;    // measurement aid (SZB_TOWER_SPAN): {first CTA start, last CTA end} of this launch (%globaltimer), or null
+    unsigned long long* span;    // measurement aid (SZB_TOWER_SPAN): {first CTA start, last CTA end (%globaltimer), CTA 0's SM cycles, CTA 0's ns}, or null
     TowerLayer L[MAX_TOWER_LAYERS];
 };
 
@@ -675,7 +675,10 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
 
     pdl_trigger();                                                // the next tree kernel may start its set-up; it waits for my completion
     if (threadIdx.x == 0) {
-        if (a.span) atomicMin(a.span, global_ns());
+        if (a.span) {
+            atomicMin(a.span, global_ns());
+            if (blockIdx.x == 0) { a.span[3] = global_ns(); a.span[2] = (unsigned long long)clock64(); }
+        }
         abort_sh = 0;
         for (int s = 0; s < T2_A_CHUNKS; s++) { mbar_init(smem_u32(&bar_a_full[s]), 1); mbar_init(smem_u32(&bar_a_empty[s]), 1); }
         for (int s = 0; s < T2_B_STAGES; s++) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
@@ -1103,7 +1106,10 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
     if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
-    if (threadIdx.x == 0 && a.span) atomicMax(a.span + 1, global_ns());
+    if (threadIdx.x == 0 && a.span) {
+        if (blockIdx.x == 0) { a.span[2] = (unsigned long long)clock64() - a.span[2]; a.span[3] = global_ns() - a.span[3]; }   // SM clocks per ns inside this launch
+        atomicMax(a.span + 1, global_ns());
+    }
 }
 
 // =================================================================================================
@@ -1876,14 +1882,14 @@ void net_destroy(szb_ctx* ctx) {
     if (!ctx->net) return;
     if (ctx->net->span && !ctx->net->span_path.empty() && !ctx->net->span_boards.empty()) {
         Net* net = ctx->net;
-        std::vector<unsigned long long> h(2 * net->span_boards.size());
+        std::vector<unsigned long long> h(4 * net->span_boards.size());
         cudaDeviceSynchronize();
         if (cudaMemcpy(h.data(), net->span, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
             if (FILE* f = fopen(net->span_path.c_str(), "w")) {
                 fprintf(f, "launch,board0,boards,start_ns,end_ns\n");
                 const unsigned long long t0 = h[0];
                 for (size_t i = 0; i < net->span_boards.size(); i++)
-                    fprintf(f, "%zu,%d,%d,%lld,%lld\n", i, net->span_b0[i], net->span_boards[i], (long long)(h[2 * i] - t0), (long long)(h[2 * i + 1] - t0));
+                    fprintf(f, "%zu,%d,%d,%lld,%lld\n", i, net->span_b0[i], net->span_boards[i], (long long)(h[4 * i] - t0), (long long)(h[4 * i + 1] - t0));
                 fclose(f);
             }
         }
@@ -1912,8 +1918,8 @@ static int net_alloc_activations(szb_ctx* ctx, Net* net) {
 }
 
 static int net_span_reset(szb_ctx* ctx, Net* net) {
-    std::vector<unsigned long long> init((size_t)SPAN_CAP * 2, 0ull);
-    for (int i = 0; i < SPAN_CAP; i++) init[2 * (size_t)i] = ~0ull;
+    std::vector<unsigned long long> init((size_t)SPAN_CAP * 4, 0ull);
+    for (int i = 0; i < SPAN_CAP; i++) init[4 * (size_t)i] = ~0ull;
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     SZB_CUDA(ctx, cudaMemcpy(net->span, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
     net->span_boards.clear();
@@ -2000,7 +2006,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     const char* mode = getenv("SZB_TOWER_MODE");             // measurement aid: 0 single-CTA per layer, 1 pair per layer, 2 one launch
     if (mode && mode[0] >= '0' && mode[0] <= '2') net->tower_mode = mode[0] - '0';
     // start / end device time of whole-tower launches: szb_tower_spans_record, or SZB_TOWER_SPAN=<csv> (every launch, dumped at destroy)
-    if ((rc = net_alloc(ctx, net, &net->span, (size_t)SPAN_CAP * 2, false))) return rc;
+    if ((rc = net_alloc(ctx, net, &net->span, (size_t)SPAN_CAP * 4, false))) return rc;
     if ((rc = net_span_reset(ctx, net))) return rc;
     if (const char* sp = getenv("SZB_TOWER_SPAN")) {
         if (sp[0]) { net->span_path = sp; net->span_on = true; }
@@ -2127,7 +2133,7 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     a.n_main = main_layers * a.n_pair_tiles * a.nsplit;
     a.n_items = a.n_main + (layers - main_layers) * a.n_pair_tiles;
     if (net->span_on && (int)net->span_boards.size() < SPAN_CAP && layer_end - layer_begin > 1) {
-        a.span = net->span + 2 * net->span_boards.size();
+        a.span = net->span + 4 * net->span_boards.size();
         net->span_boards.push_back(n);
         net->span_b0.push_back(b0);
     }
@@ -2725,17 +2731,19 @@ int szb_tower_spans_record(szb_ctx* ctx, int32_t on, szb_tower_spans* out) {
     memset(out, 0, sizeof *out);
     const size_t n = net->span_boards.size();
     if (n == 0) return 0;
-    std::vector<unsigned long long> h(2 * n);
+    std::vector<unsigned long long> h(4 * n);
     SZB_CUDA(ctx, cudaMemcpy(h.data(), net->span, h.size() * 8, cudaMemcpyDeviceToHost));
     unsigned long long first = ~0ull, last = 0;
     for (size_t i = 0; i < n; i++) {
-        if (h[2 * i] == ~0ull || h[2 * i + 1] == 0) continue;                 // launch not run (cannot happen after the sync above)
+        if (h[4 * i] == ~0ull || h[4 * i + 1] == 0) continue;                 // launch not run (cannot happen after the sync above)
         out->launches++;
         out->boards += (uint64_t)net->span_boards[i];
-        out->busy_ns += h[2 * i + 1] - h[2 * i];
+        out->busy_ns += h[4 * i + 1] - h[4 * i];
         out->flop += FLOP_TOWER_ALL * (uint64_t)net->span_boards[i];
-        first = std::min(first, h[2 * i]);
-        last = std::max(last, h[2 * i + 1]);
+        out->sm_cycles += h[4 * i + 2];
+        out->sm_ns += h[4 * i + 3];
+        first = std::min(first, h[4 * i]);
+        last = std::max(last, h[4 * i + 1]);
     }
     if (out->launches) out->wall_ns = last - first;
     return 0;
