@@ -688,7 +688,10 @@ def main():
     else:
         line = run_ours(args, wl)
         if args.workload == "c2" and not args.no_extras and not args.games and not args.sims:
-            extras = run_extras(args)
+            try:
+                extras = run_extras(args)
+            except Exception as e:                     # the headline line must survive a failure of the riders
+                extras = {"error": "%s: %s" % (type(e).__name__, e)}
             if line is not None:
                 line["extras"] = extras
     if rank == 0:
