@@ -22,7 +22,7 @@ def test_struct_layouts():
     assert ctypes.sizeof(_lib.Pos) == 112
     assert ctypes.sizeof(_lib.Config) == 20
     assert ctypes.sizeof(_lib.Stats) == 48
-    assert ctypes.sizeof(_lib.TowerSpans) == 56 and ctypes.sizeof(_lib.PhaseTimes) == 72
+    assert ctypes.sizeof(_lib.TowerSpans) == 56 and ctypes.sizeof(_lib.PhaseTimes) == 80
 
 
 def test_no_device_fails_loudly():
