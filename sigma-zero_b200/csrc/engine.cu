@@ -152,37 +152,6 @@ __global__ void k_games_get(Dev d, int n, const int32_t* game, szb_pos* out) {
     out[i] = o;
 }
 
-// legal indices (ascending) and/or planes + mask of the current positions
-__global__ void k_games_encode(Dev d, int n, const int32_t* game, uint16_t* index_out, uint16_t* count_out,
-                               uint64_t* planes_out, uint64_t* mask_out) {
-    __shared__ Tables T;
-    load_tables(&T, d.tables);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int g = game ? game[i] : i;
-    if (g < 0 || g >= d.n_games) { if (count_out) count_out[i] = 0; return; }
-    const Pos* gp = d.pool + (size_t)g * d.pool_stride;
-    const Pos p = gp[d.cur[g]];
-    uint16_t mv[MAX_MOVES];
-    const int cnt = gen_legal(T, p, mv);
-    uint64_t m[MASK_WORDS];
-    for (int w = 0; w < MASK_WORDS; w++) m[w] = 0;
-    for (int k = 0; k < cnt; k++) {
-        int idx = move_to_index(p, mv[k]);
-        m[idx >> 6] |= bit(idx & 63);
-    }
-    if (mask_out) for (int w = 0; w < MASK_WORDS; w++) mask_out[(size_t)i * MASK_WORDS + w] = m[w];
-    if (index_out) {
-        int k = 0;
-        for (int w = 0; w < MASK_WORDS; w++) {
-            uint64_t x = m[w];
-            while (x) { index_out[(size_t)i * SZB_MAX_MOVES + k++] = (uint16_t)(w * 64 + lsb(x)); x &= x - 1; }
-        }
-    }
-    if (count_out) count_out[i] = (uint16_t)cnt;
-    if (planes_out) pack_planes(gp, p, planes_out + (size_t)i * N_PLANES);
-}
-
 __global__ void k_unpack_planes_f32(int n, const uint64_t* planes, float* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // one output element
     size_t total = (size_t)n * N_PLANES * 64;
@@ -366,6 +335,181 @@ __device__ __forceinline__ bool expand_path(const Dev& d, const Tables& T, int p
     return true;
 }
 
+// Legal moves of p by a whole warp (same SET as gen_legal, chess.cuh: the order differs, and nothing downstream depends on it).
+// Lane l owns the pieces on squares 2 l and 2 l + 1; besides, lanes 0..7 own the king's steps, lanes 8 / 9 the en-passant capturers,
+// lanes 10..17 castling with the rook on file l - 10.  Check / pin masks are computed by every lane (uniform, no communication).
+// The moves land in `out` (shared memory) through one warp scan of the per-lane counts; returns their number (uniform).
+__device__ __forceinline__ int gen_legal_warp(const Tables& T, const Pos& p, uint16_t* out, int lane) {
+    const bool white = p.flags & F_WHITE;
+    const uint64_t own = p.bb[white ? BB_WHITE : BB_BLACK], opp = p.bb[white ? BB_BLACK : BB_WHITE];
+    const uint64_t occ = own | opp;
+    const uint64_t P = p.bb[BB_P], N = p.bb[BB_N], B = p.bb[BB_B], R = p.bb[BB_R], Q = p.bb[BB_Q], K = p.bb[BB_K];
+    const uint64_t kbb = K & own;
+    if (!kbb) return 0;
+    const int ksq = lsb(kbb);
+    const uint64_t checkers = attackers_to(T, p.bb, ksq, occ) & opp;
+    const bool dbl = (checkers & (checkers - 1)) != 0;              // double check: king moves only
+    const uint64_t last = white ? RANK_8 : RANK_1;
+    // ---- special duty of this lane: at most one move --------------------------------------------------------------------
+    uint16_t special = MOVE_NONE;
+    if (lane < 8) {
+        uint64_t kt = T.king[ksq] & ~own;
+        for (int j = 0; j < lane; j++) kt &= kt - 1;                  // the lane-th step of the king
+        if (kt) {
+            const int t = lsb(kt);
+            if (!(attackers_to(T, p.bb, t, occ ^ kbb) & opp)) special = mk_move(ksq, t, 0);
+        }
+    } else if (lane < 10) {
+        if (!dbl && p.ep >= 0 && !(occ & bit(p.ep))) {
+            const uint64_t eb = bit(p.ep);
+            uint64_t caps = (white ? wpawn_sources(eb) : bpawn_sources(eb)) & P & own & (white ? 0x000000FF00000000ull : 0x00000000FF000000ull);
+            if (lane == 9) caps &= caps - 1;
+            if (caps) {
+                const int s = lsb(caps);
+                const uint64_t victim = white ? (eb >> 8) : (eb << 8);
+                const uint64_t occ2 = (occ ^ bit(s) ^ victim) | eb;
+                if (!(attackers_to(T, p.bb, ksq, occ2) & opp & ~victim)) special = mk_move(s, p.ep, 0);
+            }
+        }
+    } else if (lane < 18) {
+        const uint8_t rights = white ? p.rights_w : p.rights_b;
+        const int br = white ? 0 : 56, rf = lane - 10;
+        if (!dbl && (rights & (1u << rf)) && (kbb & (0xFFull << br))) {
+            const int rook = br + rf;
+            const uint64_t rb = bit(rook);
+            if (R & own & rb) {
+                const bool a_side = rook < ksq;
+                const int kto = br + (a_side ? 2 : 6), rto = br + (a_side ? 3 : 5);
+                const uint64_t kpath = between(T, ksq, kto);
+                const uint64_t must_empty = kpath | between(T, rook, rto) | bit(kto) | bit(rto);
+                if (!((occ ^ kbb ^ rb) & must_empty)) {
+                    uint64_t chk = kpath | kbb;
+                    bool bad = false;
+                    while (chk && !bad) {
+                        const int sq = lsb(chk);
+                        chk &= chk - 1;
+                        bad = (attackers_to(T, p.bb, sq, occ ^ kbb) & opp) != 0;
+                    }
+                    if (!bad && !(attackers_to(T, p.bb, kto, occ ^ kbb ^ rb ^ bit(rto)) & opp)) special = mk_move(ksq, rook, 0);
+                }
+            }
+        }
+    }
+    // ---- the two squares of this lane ---------------------------------------------------------------------------------------
+    uint64_t tgt[2] = {0, 0};
+    bool pawn[2] = {false, false};
+    if (!dbl) {
+        uint64_t target_mask = ~own;
+        if (checkers) target_mask &= between(T, ksq, lsb(checkers)) | checkers;
+        uint64_t pinned = 0;
+        uint64_t snipers = (((rank_mask(ksq) | file_mask(ksq)) & (R | Q)) | ((T.diag[ksq] | T.anti[ksq]) & (B | Q))) & opp;
+        while (snipers) {
+            const int sn = lsb(snipers);
+            snipers &= snipers - 1;
+            const uint64_t b = between(T, ksq, sn) & occ;
+            if (b && !(b & (b - 1)) && (b & own)) pinned |= b;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int s = 2 * lane + h;
+            const uint64_t sb = bit(s);
+            if (!(own & sb) || (K & sb)) continue;
+            uint64_t a = 0;
+            if (N & sb) {
+                if (!(pinned & sb)) a = T.knight[s] & target_mask;
+            } else if (P & sb) {
+                if (white) {
+                    const uint64_t one = (sb << 8) & ~occ;
+                    a = one | (((one << 8) & ~occ) & 0x00000000FF000000ull);
+                    a |= (((sb << 7) & ~FILE_H) | ((sb << 9) & ~FILE_A)) & opp;
+                } else {
+                    const uint64_t one = (sb >> 8) & ~occ;
+                    a = one | (((one >> 8) & ~occ) & 0x000000FF00000000ull);
+                    a |= (((sb >> 7) & ~FILE_A) | ((sb >> 9) & ~FILE_H)) & opp;
+                }
+                a &= target_mask;
+                if (pinned & sb) a &= line_through(T, ksq, s);
+                pawn[h] = true;
+            } else {
+                if ((B | Q) & sb) a |= bishop_att(T, s, occ);
+                if ((R | Q) & sb) a |= rook_att(s, occ);
+                a &= target_mask;
+                if (pinned & sb) a &= line_through(T, ksq, s);
+            }
+            tgt[h] = a;
+        }
+    }
+    int mine = special != MOVE_NONE;
+#pragma unroll
+    for (int h = 0; h < 2; h++) mine += pawn[h] ? popc(tgt[h] & ~last) + 4 * popc(tgt[h] & last) : popc(tgt[h]);
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    int at = incl - mine;
+    if (special != MOVE_NONE) out[at++] = special;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint64_t a = tgt[h];
+        const int s = 2 * lane + h;
+        while (a) {
+            const int t = lsb(a);
+            a &= a - 1;
+            if (pawn[h] && (bit(t) & last)) {
+                out[at++] = mk_move(s, t, PT_QUEEN);
+                out[at++] = mk_move(s, t, PT_ROOK);
+                out[at++] = mk_move(s, t, PT_BISHOP);
+                out[at++] = mk_move(s, t, PT_KNIGHT);
+            } else {
+                out[at++] = mk_move(s, t, 0);
+            }
+        }
+    }
+    return __shfl_sync(0xFFFFFFFFu, incl, 31);
+}
+
+// legal indices (ascending) and/or planes + mask of the current positions.  Warp per game: the same warp-cooperative move
+// generation the search step uses (gen_legal_warp), so every szb_legal_moves / szb_encode call -- and every test built on them --
+// exercises it; perft and szb_games_push use the one-thread form (gen_legal, chess.cuh).
+__global__ void __launch_bounds__(128) k_games_encode(Dev d, int n, const int32_t* game, uint16_t* index_out, uint16_t* count_out,
+                                                      uint64_t* planes_out, uint64_t* mask_out) {
+    __shared__ Tables T;
+    __shared__ Pos p_sh[4];
+    __shared__ uint16_t mv_sh[4][MAX_MOVES];
+    __shared__ uint64_t m_sh[4][MASK_STRIDE];
+    load_tables(&T, d.tables);
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (i >= n) return;
+    const int g = game ? game[i] : i;
+    if (g < 0 || g >= d.n_games) { if (count_out && lane == 0) count_out[i] = 0; return; }
+    const Pos* gp = d.pool + (size_t)g * d.pool_stride;
+    if (lane == 0) p_sh[wib] = gp[d.cur[g]];
+    for (int w = lane; w < MASK_STRIDE; w += 32) m_sh[wib][w] = 0;
+    __syncwarp();
+    const Pos& p = p_sh[wib];
+    const int cnt = gen_legal_warp(T, p, mv_sh[wib], lane);
+    __syncwarp();
+    for (int k = lane; k < cnt; k += 32) {
+        const int idx = move_to_index(p, mv_sh[wib][k]);
+        atomicOr(reinterpret_cast<unsigned long long*>(&m_sh[wib][idx >> 6]), 1ull << (idx & 63));
+    }
+    __syncwarp();
+    if (mask_out) for (int w = lane; w < MASK_WORDS; w += 32) mask_out[(size_t)i * MASK_WORDS + w] = m_sh[wib][w];
+    if (lane == 0) {
+        if (index_out) {
+            int k = 0;
+            for (int w = 0; w < MASK_WORDS; w++) {
+                uint64_t x = m_sh[wib][w];
+                while (x) { index_out[(size_t)i * SZB_MAX_MOVES + k++] = (uint16_t)(w * 64 + lsb(x)); x &= x - 1; }
+            }
+        }
+        if (count_out) count_out[i] = (uint16_t)cnt;
+        if (planes_out) pack_planes(gp, p, planes_out + (size_t)i * N_PLANES);
+    }
+}
+
 // The 119 planes of `now` (pool slot qslot of game g) by nine lanes: lane t < 8 packs history step t, whose position it loads
 // through the recorded predecessor slots (d.anc) -- eight independent loads instead of a walk along Pos::prev -- and lane 8 the
 // seven constant planes.  Same planes as pack_planes (chess.cuh), which k_expand / k_games_encode use: a step exists when every
@@ -425,54 +569,64 @@ __device__ __forceinline__ bool expand_warp(const Dev& d, const Tables& T, int s
     const size_t r = (size_t)g * d.nodes_per_game;
     Pos* gp = d.pool + (size_t)g * d.pool_stride;
     for (int w = lane; w < MASK_STRIDE; w += 32) S.mask[w] = 0;
-    int cnt = 0, qslot = 0, term = 0;
+    // lane 0: the position the leaf stands for (a new node: the parent's position + the selected move; else the node's own)
+    int qslot = 0, term = -1, node = 0, e = 0, parent = 0;      // term: -1 = not known yet (a new node)
     if (lane == 0) {
-        const int e = d.sel_edge[slot];
-        int node = d.sel_node[slot];
-        Pos q;
+        e = d.sel_edge[slot];
+        node = d.sel_node[slot];
         if (e >= 0) {
-            const int parent = node;
+            parent = node;
             node = ++d.node_count[g];
             const int pslot = state_slot(d, g, parent);
             const Pos pp = gp[pslot];
             const uint16_t m = index_to_move(pp, d.e_move[e]);
+            Pos q;
             make_move(T, pp, m, q);
             q.prev = (uint32_t)pslot;
             set_repetition_flags(gp, q);
-            if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[4] = t; }
-            analyse(T, q, S.mv, cnt);
+            S.q = q;
             qslot = RING + node;
-            gp[qslot] = q;
             set_ancestors(d, g, qslot, (uint32_t)pslot);
+        } else {
+            qslot = state_slot(d, g, node);
+            S.q = gp[qslot];
+            term = d.node_term[r + node];
+        }
+    }
+    __syncwarp();                                              // lane 0's shared / global writes -> the other lanes
+    if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[4] = t; }
+    term = __shfl_sync(0xFFFFFFFFu, term, 0);
+    qslot = __shfl_sync(0xFFFFFFFFu, qslot, 0);
+    // all lanes: legal moves into shared memory (a terminal node that already exists needs none), then the outcome
+    int cnt = 0;
+    if (term != 1) cnt = gen_legal_warp(T, S.q, S.mv, lane);
+    __syncwarp();
+    if (lane == 0) {
+        if (e >= 0) {
+            S.q.n_legal = (uint8_t)cnt;
+            S.q.outcome = outcome_of(T, S.q, cnt);
+            term = S.q.outcome != OUT_NONE;
+            gp[qslot] = S.q;
             d.node_pedge[r + node] = e;
             d.node_pnode[r + node] = (uint16_t)parent;
             d.node_nchild[r + node] = 0;
             d.node_edge0[r + node] = -1;
-            term = q.outcome != OUT_NONE;
             d.node_term[r + node] = (uint8_t)term;
-            d.node_tval[r + node] = q.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
+            d.node_tval[r + node] = S.q.outcome == OUT_CHECKMATE ? -1.0f : 0.0f;
             d.e_link[e] = link_pack(-1, 0, (uint32_t)node);
             d.sel_node[slot] = node;
-        } else {
-            qslot = state_slot(d, g, node);
-            q = gp[qslot];
-            term = d.node_term[r + node];
-            if (!term) cnt = gen_legal(T, q, S.mv);
         }
         if (term) {
             d.leaf_value[slot] = d.node_tval[r + node];
             d.need_eval[slot] = 0;
         } else {
             d.need_eval[slot] = 1;
-            S.q = q;
         }
     }
-    __syncwarp();                                              // lane 0's shared / global writes -> the other lanes
+    __syncwarp();
     if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[5] = t; }
     term = __shfl_sync(0xFFFFFFFFu, term, 0);
     if (term) return false;
-    cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0);
-    qslot = __shfl_sync(0xFFFFFFFFu, qslot, 0);
     for (int k = lane; k < cnt; k += 32) {
         const int idx = move_to_index(S.q, S.mv[k]);
         atomicOr(reinterpret_cast<unsigned long long*>(&S.mask[idx >> 6]), 1ull << (idx & 63));
@@ -1349,7 +1503,7 @@ static int encode_common(szb_ctx* ctx, int32_t n, const int32_t* game, uint16_t*
     uint64_t* d_pl = (uint64_t*)st; st += up(b_pl);
     uint64_t* d_mk = (uint64_t*)st;
     if (game) SZB_CUDA(ctx, cudaMemcpyAsync(d_game, game, b_game, cudaMemcpyDefault, ctx->stream));
-    k_games_encode<<<(n + 31) / 32, 32, 0, ctx->stream>>>(ctx->d, n, game ? d_game : nullptr, index_out ? d_idx : nullptr,
+    k_games_encode<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ctx->d, n, game ? d_game : nullptr, index_out ? d_idx : nullptr,
                                                         count_out ? d_cnt : nullptr, planes_out ? d_pl : nullptr,
                                                         mask_out ? d_mk : nullptr);
     ctx->launches++;
