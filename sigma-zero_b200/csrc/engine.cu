@@ -679,44 +679,64 @@ __device__ __forceinline__ int count_legal(const uint64_t* mk, int lane) {
     return n;
 }
 // Children of the node evaluated in path slot ps (legal-move bitset mk, evaluator output pol), written from edge e0 on in ascending
-// move-index order; returns how many (zero-prior moves are dropped, mcts.py:87-89).  The 73 mask words are dealt to the lanes in
-// three rounds (word = round * 32 + lane): every lane normalises the priors of its own set bits, a warp scan places them.
-__device__ __forceinline__ int create_children(const Dev& d, const uint64_t* mk, const float* pol, unsigned long long e0, int learning, int lane) {
-    const float part = cascade_lane_sparse(mk, [&](int e) -> float { return pol[e]; }, lane);
-    const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
-    int count = 0;
+// move-index order; returns how many (zero-prior moves are dropped, mcts.py:87-89).
+//   1. the legal moves are compacted into shared memory (idx_sh / p_sh: index and evaluator output, ascending): the 73 mask words
+//      are dealt to the lanes in three rounds, a warp scan places each lane's set bits, and ALL prior loads are in flight at once;
+//   2. torch.sum's cascade order over the masked policy (tree.cuh): lane t adds the entries with index = t (mod 32) in ascending
+//      order, closing a 16-step block when the next entry belongs to a later one -- cascade_lane_sparse on the compact list;
+//   3. every lane normalises entries lane, lane + 32, ... and a ballot places the survivors.
+__device__ __forceinline__ int create_children(const Dev& d, const uint64_t* mk, const float* pol, unsigned long long e0, int learning, int lane,
+                                               uint16_t* idx_sh, float* p_sh) {
+    int n = 0;
 #pragma unroll 1
     for (int w = lane; w < 96; w += 32) {
-        uint64_t keep = 0;
-        if (w < MASK_WORDS) {
-            uint64_t x = mk[w];
-            while (x) {
-                const int b = lsb(x);
-                x &= x - 1;
-                if (f_div(pol[w * 64 + b], total) != 0.0f) keep |= bit(b);       // zero-prior children are dropped
-            }
-        }
-        const int mine = popc(keep);
+        uint64_t x = w < MASK_WORDS ? mk[w] : 0ull;
+        const int mine = popc(x);
         int incl = mine;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
             if (lane >= off) incl += y;
         }
-        unsigned long long at = e0 + (unsigned long long)(count + incl - mine);
-        while (keep) {
-            const int b = lsb(keep);
-            keep &= keep - 1;
-            const int e = w * 64 + b;
-            const float pr = f_div(pol[e], total);
+        int at = n + incl - mine;
+        while (x) {
+            const int e = w * 64 + lsb(x);
+            x &= x - 1;
+            idx_sh[at] = (uint16_t)e;
+            p_sh[at] = pol[e];
+            at++;
+        }
+        n += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    __syncwarp();
+    float a0 = 0.0f, a1 = 0.0f;
+    int cur = 0;                                             // 16-step block the pending a0 belongs to
+    for (int k = 0; k < n; k++) {
+        const int e = idx_sh[k];
+        if ((e & 31) != lane) continue;
+        const int blk = e >> 9;                              // step e / 32, block step / 16
+        if (blk != cur) { a1 = f_add(a1, a0); a0 = 0.0f; cur = blk; }
+        a0 = f_add(a0, p_sh[k]);
+    }
+    if (cur < CASCADE_STEPS / 16) { a1 = f_add(a1, a0); a0 = 0.0f; }   // pending block was a complete one; the tail block stays in a0
+    const float part = f_add(a0, a1);
+    const float total = cascade_combine([&](int t) -> float { return __shfl_sync(0xFFFFFFFFu, part, t); });
+    int count = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        float pr = 0.0f;
+        bool has = false;
+        if (k < n) { pr = f_div(p_sh[k], total); has = pr != 0.0f; }     // zero-prior children are dropped
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, has);
+        if (has) {
+            const unsigned long long at = e0 + (unsigned long long)(count + __popc(ballot & ((1u << lane) - 1)));
             d.e_n[at] = 0;
             d.e_w[at] = 0.0;
             d.e_p[at] = learning ? noisy_prior(pr) : pr;
-            d.e_move[at] = (uint16_t)e;
+            d.e_move[at] = idx_sh[k];
             d.e_link[at] = link_pack(-1, 0, NO_CHILD);
-            at++;
         }
-        count += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        count += __popc(ballot);
     }
     return count;
 }
@@ -730,7 +750,7 @@ constexpr int FINISH_WARPS = 2;
 // Second half of a simulation for the block's four trees (mcts.py:77-109): children of the evaluated node, then backup.  Called by
 // ALL threads of the block (two block-wide barriers inside); mk: 80 words of shared memory of this warp.
 __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slot, bool active, int lane, int wib, int* want_sh,
-                                             unsigned long long* base_sh, uint64_t* mk) {
+                                             unsigned long long* base_sh, uint64_t* mk, uint16_t* idx_sh, float* p_sh) {
     const int g = active ? d.order[slot] : 0;
     const bool eval = active && d.need_eval[slot];
     // Everything the backup needs is requested NOW, so that these round trips run under the mask -> arena bump -> priors chain
@@ -774,7 +794,7 @@ __device__ __forceinline__ void finish_block(const Dev& d, int learning, int slo
         if (e0 + (unsigned long long)n_legal > d.edge_cap) {
             if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
         } else {
-            count = create_children(d, mk, d.policy + (size_t)slot * N_ACTIONS, e0, learning, lane);
+            count = create_children(d, mk, d.policy + (size_t)slot * N_ACTIONS, e0, learning, lane, idx_sh, p_sh);
         }
         if (lane == 0) {
             d.node_edge0[r + node] = (int32_t)e0;
@@ -815,8 +835,10 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_finish(Dev d, int learnin
     __shared__ int want_sh[FINISH_WARPS];
     __shared__ unsigned long long base_sh;
     __shared__ uint64_t mk_sh[FINISH_WARPS * MASK_STRIDE];
-    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    finish_block(d, learning, slot, slot < d.g_end, threadIdx.x & 31, threadIdx.x >> 5, want_sh, &base_sh, mk_sh + (threadIdx.x >> 5) * MASK_STRIDE);
+    __shared__ uint16_t idx_sh[FINISH_WARPS][MAX_MOVES];
+    __shared__ float p_sh[FINISH_WARPS][MAX_MOVES];
+    const int slot = d.g_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), wib = threadIdx.x >> 5;
+    finish_block(d, learning, slot, slot < d.g_end, threadIdx.x & 31, wib, want_sh, &base_sh, mk_sh + wib * MASK_STRIDE, idx_sh[wib], p_sh[wib]);
 }
 
 // One launch per simulation step and cohort in the reference-exact mode: the second half of step s-1 (children + backup of the
@@ -841,7 +863,8 @@ __global__ void __launch_bounds__(32 * FINISH_WARPS) k_tree_step(Dev d, float c_
     stamp(0);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.net_ready_n; i += gridDim.x * blockDim.x) d.net_ready[i] = 0;
     stamp(1);
-    if (phases & STEP_FINISH) finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, ex_sh[wib].mask);
+    if (phases & STEP_FINISH)      // (the expansion's shared memory is idle during the finish phase: mask, move list and planes serve as its scratch)
+        finish_block(d, learning, slot, active, lane, wib, want_sh, &base_sh, ex_sh[wib].mask, ex_sh[wib].mv, reinterpret_cast<float*>(ex_sh[wib].planes));
     if (!(phases & STEP_SELECT) || !active) return;
     __syncwarp();                                              // this warp's tree updates -> every lane of the descent
     stamp(2);
@@ -991,6 +1014,8 @@ __global__ void __launch_bounds__(128) k_select_vl(Dev d, float c_puct, int num_
 // becomes the real result: N keeps its + 1, W gets value - 1)
 __global__ void __launch_bounds__(32 * MAX_LEAVES) k_finish_vl(Dev d, int learning) {
     __shared__ int want_sh[MAX_LEAVES];
+    __shared__ uint16_t idx_vl[MAX_LEAVES][MAX_MOVES];
+    __shared__ float p_vl[MAX_LEAVES][MAX_MOVES];
     __shared__ unsigned long long base_sh;
     const int slot = d.g_begin + blockIdx.x;
     const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
@@ -1017,7 +1042,7 @@ __global__ void __launch_bounds__(32 * MAX_LEAVES) k_finish_vl(Dev d, int learni
         if (e0 + (unsigned long long)n_legal > d.edge_cap) {
             if (lane == 0) atomicExch(d.error_flag, SZB_ERR_ARENA);
         } else {
-            count = create_children(d, mk, d.policy + (size_t)ps * N_ACTIONS, e0, learning, lane);
+            count = create_children(d, mk, d.policy + (size_t)ps * N_ACTIONS, e0, learning, lane, idx_vl[j], p_vl[j]);
         }
         if (lane == 0) {
             d.node_edge0[r + node] = (int32_t)e0;
