@@ -2046,6 +2046,7 @@ static int net_assemble_tower(szb_ctx* ctx, Net* net) {
     // the same weights once more as k_tower_cl's per-CTA streams
     for (int v = 0; v < 2; v++) {
         const int cs = 8 << v;
+        if (cs == 16 && net->cluster_force != 16) continue;      // the 16-CTA variant only runs when it is asked for (A/B aid)
         for (int l = 0; l < MAX_TOWER_LAYERS; l++) {
             const TowerLayer& T = net->tower_args->L[l];
             const int n = (T.mode == 1 ? 128 : C_TOWER) / cs;
