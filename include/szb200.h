@@ -43,7 +43,8 @@ enum {
     SZB_ERR_ILLEGAL_MOVE = -3,     /* szb_games_push: at least one move was not legal (chess_tensor.py:91-92) */
     SZB_ERR_ARENA = -4,            /* tree arena exhausted: raise szb_config.edges_per_node */
     SZB_ERR_STATE = -5,            /* call made in the wrong state (no games, no weights, ...) */
-    SZB_ERR_UNSUPPORTED = -6
+    SZB_ERR_UNSUPPORTED = -6,
+    SZB_ERR_INTERNAL = -7          /* a kernel reported a failure (pipeline time-out, bad record row) */
 };
 
 /* evaluator used by szb_search / szb_selfplay */
@@ -232,6 +233,46 @@ int szb_tower_spans_record(szb_ctx *ctx, int32_t on, szb_tower_spans *out);
  * constant activations, little switching, far less power -- so many back-to-back launches then sustain a higher clock than real
  * positions allow (1.5 vs 1.3 PFLOP/s, profiles/r01o_*).  Run a search first when a sustained figure is wanted. */
 int szb_time_kernel(szb_ctx *ctx, int32_t which, int32_t n, int32_t iters, float *ms_avg_out);
+
+/* ---- trainer: the fine-tuning half of the self-play loop (train_RL.py:77-154) ---------------------------------------------
+ * Replaces chessDataset / collatefn / train() of the reference for packed self-play records: per batch
+ *     loss = mse_loss(v, z) + cross_entropy(logits, pi)      (train_RL.py:103-113, pi = soft visit-fraction target)
+ *     Adam(lr, weight_decay) with torch's update rule (train_RL.py:187), StepLR(lr_step, lr_gamma) stepped per batch (:199, :123)
+ * on network.py:100-192 in training mode (BatchNorm with batch statistics; running buffers updated with `bn_momentum`).
+ * Mixed precision: fp32 master weights / moments / BatchNorm arithmetic, bf16 tensor-core operands with fp32 accumulation.
+ * One trainer per context; tensors are named as in the reference's state_dict and laid out as torch lays them out. */
+typedef struct szb_train_config {
+    int32_t batch;            /* largest batch (boards) a step may carry */
+    float lr, beta1, beta2, eps, weight_decay;     /* torch.optim.Adam: 1e-4, 0.9, 0.999, 1e-8, 1e-4 in the reference */
+    int32_t lr_step;          /* StepLR step_size (500) */
+    float lr_gamma;           /* StepLR gamma (0.95) */
+    float bn_momentum, bn_eps;                     /* torch.nn.BatchNorm2d defaults 0.1, 1e-5 */
+    int64_t step0;            /* optimiser steps already taken (resume): Adam's bias correction and StepLR continue from here */
+    int32_t probe_lbo, probe_sbo;                  /* 0 (measurement aid: override the wgrad operand descriptor strides) */
+} szb_train_config;
+enum { SZB_TRAIN_FORWARD_ONLY = 1,   /* losses only */
+       SZB_TRAIN_NO_UPDATE = 2 };    /* forward + backward, gradients kept, no optimiser step */
+enum { SZB_TRAIN_PARAMS = 0,         /* parameters and BatchNorm running buffers */
+       SZB_TRAIN_GRADS = 1,          /* gradients of the last step */
+       SZB_TRAIN_EXP_AVG = 2, SZB_TRAIN_EXP_AVG_SQ = 3,    /* Adam moments */
+       SZB_TRAIN_ACTIVATIONS = 4 };  /* read-only: "logits" [n][4672], "value" [n] of the last step */
+int szb_train_create(szb_ctx *ctx, const szb_train_config *cfg);
+int szb_train_destroy(szb_ctx *ctx);
+/* copy named tensors (host or device pointers, fp32, torch layout) into / out of the trainer; `kind` as above.  Setting
+ * SZB_TRAIN_PARAMS needs every parameter and running buffer of the state_dict once before the first step. */
+int szb_train_set(szb_ctx *ctx, int32_t kind, int32_t n_tensors, const char *const *names, const float *const *data,
+                  const int64_t *numel);
+int szb_train_get(szb_ctx *ctx, int32_t kind, int32_t n_tensors, const char *const *names, float *const *data,
+                  const int64_t *numel);
+/* the packed self-play records the steps draw from (copied to the device once): states [n][119] as szb_encode emits them,
+ * CSR policy targets (pi_off [n+1] starting at 0, policy indices, visit fractions), outcomes z [n] from the mover's side */
+int szb_train_records(szb_ctx *ctx, int64_t n, const uint64_t *states, const int64_t *pi_off, const uint16_t *pi_index,
+                      const float *pi_prob, const int8_t *z);
+/* one optimiser step on the batch of record rows `rows` [n] (2 <= n <= cfg.batch); losses_out (may be null: no synchronisation)
+ * receives {mse, cross entropy} of the batch BEFORE the update, as the reference prints them */
+int szb_train_step(szb_ctx *ctx, int32_t n, const int32_t *rows, int32_t flags, float *losses_out);
+/* optimiser step counter: read (set = 0) or overwrite (set = 1) */
+int szb_train_state(szb_ctx *ctx, int64_t *step_inout, int32_t set);
 
 #ifdef __cplusplus
 }

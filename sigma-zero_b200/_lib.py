@@ -48,6 +48,16 @@ class TowerSpans(ctypes.Structure):
                 ("sm_cycles", ctypes.c_uint64), ("sm_ns", ctypes.c_uint64)]
 
 
+class TrainConfig(ctypes.Structure):
+    _fields_ = [("batch", ctypes.c_int32), ("lr", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float),
+                ("eps", ctypes.c_float), ("weight_decay", ctypes.c_float), ("lr_step", ctypes.c_int32), ("lr_gamma", ctypes.c_float),
+                ("bn_momentum", ctypes.c_float), ("bn_eps", ctypes.c_float), ("step0", ctypes.c_int64),
+                ("probe_lbo", ctypes.c_int32), ("probe_sbo", ctypes.c_int32)]
+
+
+TRAIN_FORWARD_ONLY, TRAIN_NO_UPDATE = 1, 2
+TRAIN_PARAMS, TRAIN_GRADS, TRAIN_EXP_AVG, TRAIN_EXP_AVG_SQ, TRAIN_ACTIVATIONS = 0, 1, 2, 3, 4
+
 _vp, _i32, _u64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_float
 SIGNATURES = {
     "szb_version": (ctypes.c_char_p, []),
@@ -82,6 +92,13 @@ SIGNATURES = {
     "szb_get_phase_times": (ctypes.c_int, [_vp, ctypes.POINTER(PhaseTimes)]),
     "szb_time_kernel": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.POINTER(_f32)]),
     "szb_tower_spans_record": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(TowerSpans)]),
+    "szb_train_create": (ctypes.c_int, [_vp, ctypes.POINTER(TrainConfig)]),
+    "szb_train_destroy": (ctypes.c_int, [_vp]),
+    "szb_train_set": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "szb_train_get": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "szb_train_records": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "szb_train_step": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp]),
+    "szb_train_state": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), _i32]),
 }
 
 _lib = None

@@ -1349,6 +1349,7 @@ void szb_destroy(szb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    trainer_destroy(ctx);
     net_destroy(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);

@@ -31,6 +31,7 @@ __host__ __device__ __forceinline__ int link_nchild(unsigned long long l) { retu
 __host__ __device__ __forceinline__ uint16_t link_child(unsigned long long l) { return (uint16_t)(l >> 48); }
 
 struct Net;                                // net.cu
+struct Trainer;                            // train.cu
 
 // Device pointers of one context.  Passed to kernels by value.
 struct Dev {
@@ -120,6 +121,8 @@ struct szb_ctx {
     size_t stage_bytes = 0;
     // network (net.cu)
     szb::Net* net = nullptr;
+    // trainer (train.cu)
+    szb::Trainer* trainer = nullptr;
     // self-play records
     int32_t* d_moves = nullptr;
     uint64_t game_id_base = 0;                 // global id of game 0 of this context (move-sampling RNG key; sharding)
@@ -169,6 +172,7 @@ bool net_fused_step(szb_ctx* ctx, int evaluator);
 void net_handover(szb_ctx* ctx, int g0, int n, unsigned short** in16, int32_t** ready, int* ready_n);
 int net_reset_error(szb_ctx* ctx);
 void net_destroy(szb_ctx* ctx);
+void trainer_destroy(szb_ctx* ctx);
 int net_check_error(szb_ctx* ctx);
 // net.cu: fold the recorded conv event pairs into ctx->conv_ms (call after the stream is synchronised)
 void net_collect_conv_times(szb_ctx* ctx);

@@ -1,0 +1,1322 @@
+// train.cu -- the trainer of the self-play loop (train_RL.py:77-154) as hand-written sm_100a kernels.
+//
+//   loss = mse_loss(v, z) + cross_entropy(logits, pi)   (train_RL.py:103-113; pi = soft visit-fraction target over all 4672 logits)
+//   Adam(lr 1e-4, weight_decay 1e-4) (train_RL.py:187), StepLR(500, 0.95) stepped per batch (:199, :123-124)
+//   network.py:100-192 in TRAINING mode: every BatchNorm normalises with the statistics of the batch and updates its running buffers.
+//
+// Mixed precision: fp32 master weights, Adam moments and BatchNorm arithmetic; bf16 operands on the tensor cores with fp32 accumulation
+// in TMEM; activations and activation gradients are stored as bf16.  Three tcgen05 GEMM shapes do all the heavy work of a step:
+//   forward   Y[pos][co]  = sum_{tap,ci} X[pos+tap][ci] * W[co][tap][ci]          k_tconv   (A: shifted TMA boxes of X, K-major)
+//   dgrad     dX[pos][ci] = sum_{tap,co} dY[pos+tap][co] * W[co][8-tap][ci]       k_tconv   (same kernel, transposed/flipped weight pack)
+//   wgrad     dW[co][tap][ci] = sum_pos dY[pos][co] * X[pos+tap][ci]              k_wgrad   (both operands MN-major: the K dimension is the
+//                                                                                           board square, exactly as the tensors lie in HBM)
+// wgrad is split over the batch (K) into `ksplit` partial sums that a second kernel adds in a fixed order: a step is deterministic.
+// Activations live in HBM as NHWC bf16 with a one-square zero halo, [B][10][10][C], like the inference tower (net.cu).
+//
+// Everything here is reached through szb_train_* (include/szb200.h); there is no CPU path.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include "engine.cuh"
+#include "tc.cuh"
+
+using namespace szb;
+
+namespace szb {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int TH = 10;                       // halo board edge
+constexpr int TPIX = TH * TH;
+constexpr int TC = 256;                      // tower channels
+constexpr int TCIN = 128;                    // 119 input planes padded
+constexpr int T_LAYERS = 41;                 // stem, 38 tower convolutions, conv_p1, conv_p2
+constexpr int T_BN = 40;                     // all of them but conv_p2 carry a BatchNorm
+constexpr int L_P1 = 39, L_P2 = 40;
+constexpr int T_ACTIONS = 4672;
+constexpr int T_PLANES = 119;
+constexpr int DL_C = 128;                    // channels of the logits-gradient buffer (73 policy planes padded)
+
+constexpr int TR_THREADS = 192;              // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int TR_STAGES = 3;
+constexpr int TR_A_BYTES = 128 * 64 * 2;     // 128 board squares x 64 channels
+constexpr int TR_B_BYTES = 128 * 64 * 2;     // 128 output channels x 64 k
+constexpr int TR_STAGE_BYTES = TR_A_BYTES + TR_B_BYTES;
+constexpr int TR_SMEM = TR_STAGES * TR_STAGE_BYTES + 1024;
+
+constexpr int WG_STAGES = 4;
+constexpr int WG_BOX = 64 * 64 * 2;          // one board (64 squares) x 64 channels
+constexpr int WG_MAX_SPLIT = 64;
+
+__device__ __forceinline__ int halo_pix(int sq) { return ((sq >> 3) + 1) * TH + (sq & 7) + 1; }
+
+// MN-major operand, 128-byte swizzle: rows of 128 B are 64 consecutive M (or N) elements of ONE k; 8 consecutive k form a 1024 B atom;
+// SBO = distance between 8-k groups, LBO = distance between 64-element MN atoms (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO))
+// in 16-byte units).
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// =================================================================================================
+// forward / dgrad convolution: one 128-square x 128-channel tile per CTA
+// =================================================================================================
+struct TConvArgs {
+    int taps, kchunks;           // K = taps * kchunks * 64
+    int n_boards;
+    bf16* out;                   // MODE 0: halo NHWC, `ldc` channels per square
+    int ldc;
+    float* logits;               // MODE 1: [board][4672] plane-major (torch.flatten of conv_p2's output), + bias
+    const float* bias;
+    int32_t* error;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TR_THREADS, 2)
+k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TConvArgs a) {
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[TR_STAGES], bar_empty[TR_STAGES], bar_acc;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, nh = blockIdx.y;
+    volatile int* abort_flag = &abort_sh;
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < TR_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    const int k_iters = a.taps * a.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < k_iters; it++) {
+                const int tap = it / a.kchunks, kc = it - tap * a.kchunks;
+                const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
+                if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag)) break;
+                const uint32_t full = smem_u32(&bar_full[stage]);
+                const uint32_t sa = smem_base + stage * TR_STAGE_BYTES;
+                mbar_expect_tx(full, TR_STAGE_BYTES);
+                tma_load_4d(sa, &tm_a, full, kc * 64, kx, ky, tile * 2);
+                tma_load_2d(sa + TR_A_BYTES, &tm_w, full, it * 64, nh * 128);
+                if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int it = 0; it < k_iters; it++) {
+                if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * TR_STAGE_BYTES;
+                const uint32_t sb = sa + TR_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < 4; k++) tc_mma_bf16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it | k) != 0);
+                tc_commit(smem_u32(&bar_empty[stage]));
+                if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (ok) tc_commit(smem_u32(&bar_acc));
+        }
+    } else {
+        const int lane_group = warp & 3;
+        bool ok = mbar_wait(smem_u32(&bar_acc), 0, abort_flag);
+        ok = __all_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            tc_fence_after();
+            const int m = lane_group * 32 + lane;
+            const int board = tile * 2 + (m >> 6), sq = m & 63;
+            const bool live = board < a.n_boards;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+            const size_t pix = (size_t)board * TPIX + halo_pix(sq);
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(taddr + c0, v);
+                tmem_ld_32x32b_x16(taddr + c0 + 16, v + 16);
+                tmem_ld_wait();
+                if (!live) continue;
+                if (MODE == 0) {
+                    uint4 o[4];
+                    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+                    for (int j = 0; j < 16; j++) ob[j] = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.ldc + nh * 128 + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) op[j] = o[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int c = nh * 128 + c0 + j;
+                        if (c < 73) a.logits[(size_t)board * T_ACTIONS + c * 64 + sq] = __uint_as_float(v[j]) + a.bias[c];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+}
+
+// =================================================================================================
+// wgrad: D[co 128][ci N] (+)= sum over the squares of this CTA's boards of dY[sq][co] * X[sq + tap][ci]
+// =================================================================================================
+struct WgArgs {
+    int taps, m_halves, n_boards, ksplit;
+    float* partial;              // [ksplit][cout_pad][ldw]
+    int ldw;                     // taps * cin_pad
+    int cin_pad;
+    size_t split_stride;         // cout_pad * ldw
+    int32_t* error;
+    uint32_t lbo, sbo;           // descriptor strides (probe aid; 8192 / 1024)
+};
+
+template <int NB>                // 64-channel boxes of X: N = NB * 64 input channels
+__global__ void __launch_bounds__(TR_THREADS, 1)
+k_wgrad(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const WgArgs a) {
+    constexpr int N = NB * 64;
+    constexpr int STAGE = (2 + NB) * WG_BOX;
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[WG_STAGES], bar_empty[WG_STAGES], bar_acc;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x / a.m_halves, mh = blockIdx.x - tap * a.m_halves;
+    const int ks = blockIdx.y;
+    const int b_lo = (int)((long long)ks * a.n_boards / a.ksplit), b_hi = (int)((long long)(ks + 1) * a.n_boards / a.ksplit);
+    const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
+    volatile int* abort_flag = &abort_sh;
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < WG_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int b = b_lo; b < b_hi; b++) {
+                if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag)) break;
+                const uint32_t full = smem_u32(&bar_full[stage]);
+                const uint32_t sa = smem_base + stage * STAGE;
+                mbar_expect_tx(full, STAGE);
+                tma_load_4d(sa, &tm_dy, full, mh * 128, 1, 1, b);
+                tma_load_4d(sa + WG_BOX, &tm_dy, full, mh * 128 + 64, 1, 1, b);
+#pragma unroll
+                for (int j = 0; j < NB; j++) tma_load_4d(sa + (2 + j) * WG_BOX, &tm_x, full, j * 64, kx, ky, b);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int b = b_lo; b < b_hi; b++) {
+                if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * STAGE;
+                const uint32_t sb = sa + 2 * WG_BOX;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    tc_mma_bf16(tmem_base, make_smem_desc_mn(sa + k * 2048, a.lbo, a.sbo), make_smem_desc_mn(sb + k * 2048, a.lbo, a.sbo), IDESC,
+                                (b != b_lo) || k != 0);
+                tc_commit(smem_u32(&bar_empty[stage]));
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (ok) tc_commit(smem_u32(&bar_acc));
+        }
+    } else {
+        const int lane_group = warp & 3;
+        bool ok = mbar_wait(smem_u32(&bar_acc), 0, abort_flag);
+        ok = __all_sync(0xFFFFFFFFu, ok);
+        if (ok) {
+            tc_fence_after();
+            const int co = mh * 128 + lane_group * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+            float* dst = a.partial + (size_t)ks * a.split_stride + (size_t)co * a.ldw + (size_t)tap * a.cin_pad;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(taddr + c0, v);
+                tmem_ld_32x32b_x16(taddr + c0 + 16, v + 16);
+                tmem_ld_wait();
+                uint4* op = reinterpret_cast<uint4*>(dst + c0);
+#pragma unroll
+                for (int j = 0; j < 8; j++) op[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+}
+
+// grad[i] = sum_s partial[s][i], s ascending (deterministic)
+__global__ void k_reduce_partials(const float* partial, size_t stride, int ksplit, float* grad, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 acc = *reinterpret_cast<const float4*>(partial + i);
+    for (int s = 1; s < ksplit; s++) {
+        const float4 p = *reinterpret_cast<const float4*>(partial + (size_t)s * stride + i);
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    *reinterpret_cast<float4*>(grad + i) = acc;
+}
+
+// =================================================================================================
+// input: gather packed records -> bf16 NHWC halo planes
+// =================================================================================================
+__global__ void k_gather_input(const uint64_t* states, long long n_records, int32_t* rows, int n, bf16* out, int32_t* error) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;        // (board, square, 8-channel group)
+    if (i >= (size_t)n * 64 * 16) return;
+    const int cg = (int)(i & 15), sq = (int)((i >> 4) & 63);
+    const size_t b = i >> 10;
+    int row = rows[b];
+    if (row < 0 || row >= n_records) {                                     // reported by szb_train_step; the later kernels read row 0 instead
+        if ((i & 1023) == 0) { atomicExch(error, 2); rows[b] = 0; }
+        row = 0;
+    }
+    const uint64_t* p = states + (size_t)row * T_PLANES;
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = cg * 8 + 2 * j;
+        const float f0 = c < T_PLANES ? (float)((p[c] >> sq) & 1ull) : 0.f;
+        const float f1 = c + 1 < T_PLANES ? (float)((p[c + 1] >> sq) & 1ull) : 0.f;
+        ob[j] = __floats2bfloat162_rn(f0, f1);
+    }
+    *reinterpret_cast<uint4*>(out + (b * TPIX + halo_pix(sq)) * TCIN + cg * 8) = o;
+}
+
+// =================================================================================================
+// BatchNorm (training mode), 256 channels
+// =================================================================================================
+struct BnPtrs {
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var;
+    float* mean; float* invstd;          // saved for the backward pass
+    float* scale; float* shift;          // y * scale + shift
+    float* part;                         // [boards][2][256]
+    unsigned int* counter;
+    float momentum, eps;
+};
+
+__global__ void __launch_bounds__(256) k_bn_stats(const bf16* y, int n, BnPtrs p) {
+    const int b = blockIdx.x, c = threadIdx.x;
+    float s1 = 0.f, s2 = 0.f;
+    const bf16* base = y + (size_t)b * TPIX * TC + c;
+#pragma unroll 8
+    for (int sq = 0; sq < 64; sq++) {
+        const float v = __bfloat162float(base[(size_t)halo_pix(sq) * TC]);
+        s1 += v;
+        s2 += v * v;
+    }
+    p.part[(size_t)b * 512 + c] = s1;
+    p.part[(size_t)b * 512 + 256 + c] = s2;
+    __threadfence();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double S1 = 0, S2 = 0;
+    for (int i = 0; i < n; i++) { S1 += (double)__ldcg(&p.part[(size_t)i * 512 + c]); S2 += (double)__ldcg(&p.part[(size_t)i * 512 + 256 + c]); }
+    const double cnt = (double)n * 64.0;
+    const double mean = S1 / cnt;
+    double var = S2 / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    p.mean[c] = (float)mean;
+    p.invstd[c] = invstd;
+    const float sc = p.gamma[c] * invstd;
+    p.scale[c] = sc;
+    p.shift[c] = p.beta[c] - (float)mean * sc;
+    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * cnt / (cnt - 1.0));
+    if (threadIdx.x == 0) *p.counter = 0;
+}
+
+// out = relu(y * scale + shift [+ residual]); 8 channels of one square per thread
+__global__ void __launch_bounds__(256) k_bn_apply(const bf16* y, const float* scale, const float* shift, const bf16* residual, bf16* out, int n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * 64 * 32) return;
+    const int cg = (int)(i & 31), sq = (int)((i >> 5) & 63);
+    const size_t b = i >> 11;
+    const size_t off = (b * TPIX + halo_pix(sq)) * TC + cg * 8;
+    const uint4 yv = *reinterpret_cast<const uint4*>(y + off);
+    const bf16* yb = reinterpret_cast<const bf16*>(&yv);
+    float f[8];
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + cg * 8), s1 = *reinterpret_cast<const float4*>(scale + cg * 8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(shift + cg * 8), h1 = *reinterpret_cast<const float4*>(shift + cg * 8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = __bfloat162float(yb[j]) * sc[j] + sh[j];
+    if (residual) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(residual + off);
+        const bf16* rb = reinterpret_cast<const bf16*>(&rv);
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] += __bfloat162float(rb[j]);
+    }
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) ob[j] = __floats2bfloat162_rn(fmaxf(f[2 * j], 0.f), fmaxf(f[2 * j + 1], 0.f));
+    *reinterpret_cast<uint4*>(out + off) = o;
+}
+
+struct BnBwdPtrs {
+    const float* gamma; const float* mean; const float* invstd;
+    float* g_gamma; float* g_beta;       // gradient slots of the flat gradient buffer
+    float* ca; float* cb; float* cc;     // dy = ca * (g - cb - (y - mean) * invstd * cc)
+    float* part;                         // [boards][2][256]
+    unsigned int* counter;
+};
+
+// g = (d_in [+ skip]) * [out > 0]  -> gm (bf16);  per-channel sums of g and g * xhat;  the last block turns them into d_gamma, d_beta and
+// the coefficients of k_bn_bwd_apply
+__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const bf16* d_in, const bf16* skip, const bf16* out, const bf16* y, bf16* gm, int n, BnBwdPtrs p) {
+    const int b = blockIdx.x, c = threadIdx.x;
+    const float mean = p.mean[c], invstd = p.invstd[c];
+    float s1 = 0.f, s2 = 0.f;
+    const size_t base = (size_t)b * TPIX * TC + c;
+#pragma unroll 4
+    for (int sq = 0; sq < 64; sq++) {
+        const size_t o = base + (size_t)halo_pix(sq) * TC;
+        float g = __bfloat162float(d_in[o]);
+        if (skip) g += __bfloat162float(skip[o]);
+        if (!(__bfloat162float(out[o]) > 0.f)) g = 0.f;
+        const bf16 gb = __float2bfloat16(g);
+        gm[o] = gb;
+        g = __bfloat162float(gb);
+        s1 += g;
+        s2 += g * ((__bfloat162float(y[o]) - mean) * invstd);
+    }
+    p.part[(size_t)b * 512 + c] = s1;
+    p.part[(size_t)b * 512 + 256 + c] = s2;
+    __threadfence();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double S1 = 0, S2 = 0;
+    for (int i = 0; i < n; i++) { S1 += (double)__ldcg(&p.part[(size_t)i * 512 + c]); S2 += (double)__ldcg(&p.part[(size_t)i * 512 + 256 + c]); }
+    const double cnt = (double)n * 64.0;
+    p.g_beta[c] = (float)S1;
+    p.g_gamma[c] = (float)S2;
+    p.ca[c] = p.gamma[c] * invstd;
+    p.cb[c] = (float)(S1 / cnt);
+    p.cc[c] = (float)(S2 / cnt);
+    if (threadIdx.x == 0) *p.counter = 0;
+}
+
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const bf16* gm, const bf16* y, const float* mean, const float* invstd, const float* ca, const float* cb,
+                                                      const float* cc, bf16* dy, int n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * 64 * 32) return;
+    const int cg = (int)(i & 31), sq = (int)((i >> 5) & 63);
+    const size_t b = i >> 11;
+    const size_t off = (b * TPIX + halo_pix(sq)) * TC + cg * 8;
+    const uint4 gv = *reinterpret_cast<const uint4*>(gm + off), yv = *reinterpret_cast<const uint4*>(y + off);
+    const bf16* gb = reinterpret_cast<const bf16*>(&gv);
+    const bf16* yb = reinterpret_cast<const bf16*>(&yv);
+    uint4 o;
+    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = cg * 8 + j;
+        const float xhat = (__bfloat162float(yb[j]) - mean[c]) * invstd[c];
+        f[j] = ca[c] * (__bfloat162float(gb[j]) - cb[c] - xhat * cc[c]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(dy + off) = o;
+}
+
+// =================================================================================================
+// value head (network.py:156-174) forward + backward, fp32 SIMT (0.02 % of the step's FLOP)
+// =================================================================================================
+// yv[b][sq] = sum_c T[b][sq][c] * wv[c]: one warp per square
+__global__ void __launch_bounds__(256) k_vconv(const bf16* T, const float* wv, float* yv, int n) {
+    const int w = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n * 64) return;
+    const int b = w >> 6, sq = w & 63;
+    const uint4 tv = *reinterpret_cast<const uint4*>(T + ((size_t)b * TPIX + halo_pix(sq)) * TC + lane * 8);
+    const bf16* tb = reinterpret_cast<const bf16*>(&tv);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc += __bfloat162float(tb[j]) * wv[lane * 8 + j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) yv[w] = acc;
+}
+
+__device__ __forceinline__ double block_sum_1024(double v, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sh[i];
+    return t;
+}
+
+struct VStat { float mean, invstd; };
+
+// one-channel BatchNorm statistics over all n*64 values (single block)
+__global__ void __launch_bounds__(1024) k_vbn_stats(const float* yv, int n, float* running_mean, float* running_var, VStat* st, float momentum, float eps) {
+    __shared__ double sh[32];
+    double s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < n * 64; i += blockDim.x) { const double v = yv[i]; s1 += v; s2 += v * v; }
+    s1 = block_sum_1024(s1, sh);
+    s2 = block_sum_1024(s2, sh);
+    if (threadIdx.x == 0) {
+        const double cnt = (double)n * 64.0, mean = s1 / cnt;
+        double var = s2 / cnt - mean * mean;
+        if (var < 0) var = 0;
+        st->mean = (float)mean;
+        st->invstd = (float)(1.0 / sqrt(var + (double)eps));
+        *running_mean = (1.f - momentum) * *running_mean + momentum * (float)mean;
+        *running_var = (1.f - momentum) * *running_var + momentum * (float)(var * cnt / (cnt - 1.0));
+    }
+}
+
+struct VHead {
+    const float* yv; const VStat* st;
+    const float* gamma; const float* beta;               // v_norm
+    const float* fc1_w; const float* fc1_b;              // [256][64], [256]
+    const float* fc2_w; const float* fc2_b;              // [256], [1]
+    const int8_t* z; const int32_t* rows;
+    float* value; float* se;                             // [n]: tanh output, squared error
+    float* r; float* dh1; float* h1r; float* du; float* gr;    // saved for the gradient kernels: [n][64], [n][256], [n][256], [n], [n][64]
+    int n;
+};
+
+// per board: BN -> ReLU -> fc1 -> ReLU -> fc2 -> tanh, squared error, and the backward pass down to the gradient of the BN output
+__global__ void __launch_bounds__(256) k_vhead(VHead p) {
+    __shared__ float r_sh[64], dh_sh[256], red[8];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float mean = p.st->mean, invstd = p.st->invstd;
+    if (t < 64) {
+        const float xh = (p.yv[b * 64 + t] - mean) * invstd;
+        const float r = fmaxf(xh * p.gamma[0] + p.beta[0], 0.f);
+        r_sh[t] = r;
+        p.r[b * 64 + t] = r;
+    }
+    __syncthreads();
+    float h = p.fc1_b[t];
+    const float* w1 = p.fc1_w + t * 64;
+#pragma unroll 8
+    for (int s = 0; s < 64; s++) h += w1[s] * r_sh[s];
+    const float hr = fmaxf(h, 0.f);
+    float acc = hr * p.fc2_w[t];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((t & 31) == 0) red[t >> 5] = acc;
+    __syncthreads();
+    float u = p.fc2_b[0];
+#pragma unroll
+    for (int i = 0; i < 8; i++) u += red[i];
+    const float v = tanhf(u);
+    const float zt = (float)p.z[p.rows[b]];
+    const float du = 2.f * (v - zt) / (float)p.n * (1.f - v * v);
+    if (t == 0) { p.value[b] = v; p.se[b] = (v - zt) * (v - zt); p.du[b] = du; }
+    const float dh = h > 0.f ? du * p.fc2_w[t] : 0.f;
+    dh_sh[t] = dh;
+    p.dh1[b * 256 + t] = dh;
+    p.h1r[b * 256 + t] = hr;
+    __syncthreads();
+    if (t < 64) {
+        float dr = 0.f;
+        for (int j = 0; j < 256; j++) dr += dh_sh[j] * p.fc1_w[j * 64 + t];
+        p.gr[b * 64 + t] = r_sh[t] > 0.f ? dr : 0.f;
+    }
+}
+
+// one-channel BatchNorm backward over all n*64 values (single block): dyv, d_gamma, d_beta
+__global__ void __launch_bounds__(1024) k_vbn_bwd(const float* yv, const float* gr, const VStat* st, const float* gamma, float* g_gamma, float* g_beta,
+                                                  float* dyv, int n) {
+    __shared__ double sh[32];
+    const float mean = st->mean, invstd = st->invstd;
+    double s1 = 0, s2 = 0;
+    for (int i = threadIdx.x; i < n * 64; i += blockDim.x) { const double g = gr[i]; s1 += g; s2 += g * (double)((yv[i] - mean) * invstd); }
+    s1 = block_sum_1024(s1, sh);
+    s2 = block_sum_1024(s2, sh);
+    const double cnt = (double)n * 64.0;
+    if (threadIdx.x == 0) { *g_beta = (float)s1; *g_gamma = (float)s2; }
+    const float ca = gamma[0] * invstd, cb = (float)(s1 / cnt), cc = (float)(s2 / cnt);
+    for (int i = threadIdx.x; i < n * 64; i += blockDim.x) dyv[i] = ca * (gr[i] - cb - (yv[i] - mean) * invstd * cc);
+}
+
+// per board: the value branch's share of the tower-output gradient (bf16, added as the "skip" term of the last block) and this board's
+// partial of d conv_v1.weight
+__global__ void __launch_bounds__(256) k_vconv_bwd(const bf16* T, const float* wv, const float* dyv, bf16* skip, float* part) {
+    const int b = blockIdx.x, c = threadIdx.x;
+    const float w = wv[c];
+    float acc = 0.f;
+    for (int sq = 0; sq < 64; sq++) {
+        const size_t o = ((size_t)b * TPIX + halo_pix(sq)) * TC + c;
+        const float d = dyv[b * 64 + sq];
+        acc += d * __bfloat162float(T[o]);
+        skip[o] = __float2bfloat16(d * w);
+    }
+    part[(size_t)b * 256 + c] = acc;
+}
+
+// out[j] = sum_i part[i][j], i ascending
+__global__ void k_colsum(const float* part, int rows, int cols, int ld, float* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    float acc = 0.f;
+    for (int i = 0; i < rows; i++) acc += part[(size_t)i * ld + j];
+    out[j] = acc;
+}
+
+// d fc_v1.weight[j][sq] = sum_b dh1[b][j] * r[b][sq];  d fc_v1.bias[j] = sum_b dh1[b][j];  d fc_v2.weight[j] = sum_b du[b] * h1r[b][j];  d fc_v2.bias
+__global__ void __launch_bounds__(256) k_vhead_grads(const float* dh1, const float* r, const float* h1r, const float* du, int n, float* g_fc1w, float* g_fc1b,
+                                                     float* g_fc2w, float* g_fc2b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 256 * 64) {
+        const int j = i >> 6, sq = i & 63;
+        float acc = 0.f;
+        for (int b = 0; b < n; b++) acc += dh1[b * 256 + j] * r[b * 64 + sq];
+        g_fc1w[i] = acc;
+    } else if (i < 256 * 64 + 256) {
+        const int j = i - 256 * 64;
+        float a1 = 0.f, a2 = 0.f;
+        for (int b = 0; b < n; b++) { a1 += dh1[b * 256 + j]; a2 += du[b] * h1r[b * 256 + j]; }
+        g_fc1b[j] = a1;
+        g_fc2w[j] = a2;
+    } else if (i == 256 * 64 + 256) {
+        float a = 0.f;
+        for (int b = 0; b < n; b++) a += du[b];
+        g_fc2b[0] = a;
+    }
+}
+
+// =================================================================================================
+// policy loss: cross entropy with a soft target over all 4672 logits (torch.nn.functional.cross_entropy with probabilities)
+// =================================================================================================
+struct LossArgs {
+    const float* logits;                 // [n][4672]
+    const int32_t* rows;                 // record row of each batch slot
+    const long long* pi_off; const uint16_t* pi_index; const float* pi_prob;   // CSR over ALL records
+    bf16* dl;                            // [n][10][10][128] halo NHWC gradient of the logits (x 1/n)
+    float* ce;                           // [n]
+    float* db_part;                      // [n][128] per-board sums of the gradient per policy plane (conv_p2.bias)
+    int n;
+};
+
+__global__ void __launch_bounds__(256) k_policy_loss(LossArgs a) {
+    __shared__ float dl[73 * 65];
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float* lg = a.logits + (size_t)b * T_ACTIONS;
+    float m = -INFINITY;
+    for (int j = t; j < T_ACTIONS; j += 256) m = fmaxf(m, lg[j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((t & 31) == 0) red[t >> 5] = m;
+    __syncthreads();
+    if (t == 0) { float x = red[0]; for (int i = 1; i < 8; i++) x = fmaxf(x, red[i]); bc = x; }
+    __syncthreads();
+    m = bc;
+    float s = 0.f;
+    for (int j = t; j < T_ACTIONS; j += 256) s += expf(lg[j] - m);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = s;
+    __syncthreads();
+    if (t == 0) { float x = 0.f; for (int i = 0; i < 8; i++) x += red[i]; bc = m + logf(x); }
+    __syncthreads();
+    const float lse = bc;
+    // target mass and cross entropy over the sparse target
+    const int row = a.rows[b];
+    const long long lo = a.pi_off[row], hi = a.pi_off[row + 1];
+    float mass = 0.f, ce = 0.f;
+    for (long long e = lo + t; e < hi; e += 256) {
+        const float p = a.pi_prob[e];
+        mass += p;
+        ce -= p * (lg[a.pi_index[e]] - lse);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { mass += __shfl_xor_sync(0xFFFFFFFFu, mass, o); ce += __shfl_xor_sync(0xFFFFFFFFu, ce, o); }
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = mass;
+    __syncthreads();
+    if (t == 0) { float x = 0.f; for (int i = 0; i < 8; i++) x += red[i]; bc = x; }
+    __syncthreads();
+    mass = bc;
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = ce;
+    __syncthreads();
+    if (t == 0) { float x = 0.f; for (int i = 0; i < 8; i++) x += red[i]; a.ce[b] = x; }
+    const float inv_n = 1.f / (float)a.n;
+    for (int j = t; j < T_ACTIONS; j += 256) dl[(j >> 6) * 65 + (j & 63)] = expf(lg[j] - lse) * mass * inv_n;
+    __syncthreads();
+    for (long long e = lo + t; e < hi; e += 256) {
+        const int j = a.pi_index[e];
+        dl[(j >> 6) * 65 + (j & 63)] -= a.pi_prob[e] * inv_n;       // indices of one position are distinct
+    }
+    __syncthreads();
+    if (t < DL_C) {
+        float acc = 0.f;
+        if (t < 73) for (int sq = 0; sq < 64; sq++) acc += dl[t * 65 + sq];
+        a.db_part[(size_t)b * DL_C + t] = acc;
+    }
+    for (int e = t; e < 64 * DL_C; e += 256) {
+        const int sq = e >> 7, c = e & (DL_C - 1);
+        a.dl[((size_t)b * TPIX + halo_pix(sq)) * DL_C + c] = __float2bfloat16(c < 73 ? dl[c * 65 + sq] : 0.f);
+    }
+}
+
+// losses[0] = mean squared error, losses[1] = mean cross entropy (sequential sums: deterministic)
+__global__ void k_loss_reduce(const float* se, const float* ce, int n, float* losses) {
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0;
+        for (int i = 0; i < n; i++) { a += se[i]; c += ce[i]; }
+        losses[0] = (float)(a / n);
+        losses[1] = (float)(c / n);
+    }
+}
+
+// =================================================================================================
+// optimiser + weight packs
+// =================================================================================================
+// torch.optim.Adam (weight decay added to the gradient, bias-corrected moments), one thread per parameter of the flat buffer
+__global__ void k_adam(float* w, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2, float eps, float wd, float bc2_sqrt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float p = w[i];
+    const float gg = g[i] + wd * p;
+    const float mm = m[i] + (gg - m[i]) * (1.f - beta1);
+    const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+    m[i] = mm;
+    v[i] = vv;
+    w[i] = p - step_size * (mm / (sqrtf(vv) / bc2_sqrt + eps));
+}
+
+struct PackDesc {
+    const float* w;      // master [cout_pad][taps][cin_pad]
+    bf16* wf;            // forward pack, same layout
+    bf16* wd;            // dgrad pack [cin_pad][taps][cout_pad] with the taps mirrored, or null
+    int cout_pad, taps, cin_pad;
+};
+
+__global__ void k_pack(const PackDesc* descs) {
+    const PackDesc d = descs[blockIdx.y];
+    const size_t n = (size_t)d.cout_pad * d.taps * d.cin_pad;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = d.w[i];
+        const bf16 xb = __float2bfloat16(x);
+        d.wf[i] = xb;
+        if (d.wd) {
+            const int ci = (int)(i % d.cin_pad), tap = (int)((i / d.cin_pad) % d.taps), co = (int)(i / ((size_t)d.cin_pad * d.taps));
+            d.wd[((size_t)ci * d.taps + (d.taps - 1 - tap)) * d.cout_pad + co] = xb;
+        }
+    }
+}
+
+// torch [cout][cin][taps] <-> packed [cout_pad][taps][cin_pad]
+__global__ void k_conv_to_packed(const float* src, float* dst, int cout, int cin, int taps, int cout_pad, int cin_pad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)cout_pad * taps * cin_pad) return;
+    const int ci = (int)(i % cin_pad), tap = (int)((i / cin_pad) % taps), co = (int)(i / ((size_t)cin_pad * taps));
+    dst[i] = (co < cout && ci < cin) ? src[((size_t)co * cin + ci) * taps + tap] : 0.f;
+}
+__global__ void k_packed_to_conv(const float* src, float* dst, int cout, int cin, int taps, int cin_pad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)cout * cin * taps) return;
+    const int tap = (int)(i % taps), ci = (int)((i / taps) % cin), co = (int)(i / ((size_t)taps * cin));
+    dst[i] = src[((size_t)co * taps + tap) * cin_pad + ci];
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct TParam {
+    std::string name;
+    int kind = 0;                // 0: vector (stored as torch has it), 1: convolution weight (stored packed)
+    int64_t numel = 0;           // torch element count
+    size_t off = 0, n = 0;       // slot in the flat buffers
+    int cout = 0, cin = 0, taps = 0, cout_pad = 0, cin_pad = 0;
+};
+struct TBuffer { std::string name; int64_t numel; float* ptr; };
+
+struct TLayer {
+    int taps = 9, cin_pad = 256, cout_pad = 256;
+    int param = -1, gamma = -1, beta = -1;       // indices into Trainer::params
+    bf16* wf = nullptr; bf16* wd = nullptr;
+    CUtensorMap tm_wf, tm_wd;
+    bf16* y = nullptr; bf16* o = nullptr;        // pre-BatchNorm convolution output, layer output
+    CUtensorMap tm_o2, tm_o1;                    // layer output as the next layer's operand: 2-board boxes (forward), 1-board boxes (wgrad)
+    float* bn = nullptr;                         // running_mean, running_var, mean, invstd, scale, shift, ca, cb, cc: 9 x 256
+};
+
+struct Trainer {
+    szb_train_config cfg{};
+    int cap = 0;                                 // boards (even)
+    std::vector<TParam> params;
+    std::map<std::string, int> index;
+    std::vector<TBuffer> buffers;
+    size_t total = 0;
+    float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+    TLayer L[T_LAYERS];
+    bf16* x_in = nullptr; CUtensorMap tm_in2, tm_in1;
+    bf16 *dy = nullptr, *dl = nullptr, *gbuf[2] = {nullptr, nullptr}, *gm1 = nullptr, *skip[2] = {nullptr, nullptr};
+    CUtensorMap tm_dy2, tm_dy1, tm_dl2, tm_dl1;
+    float* logits = nullptr;
+    float* partial = nullptr; size_t partial_floats = 0;
+    float* bn_part = nullptr; unsigned int* counter = nullptr;
+    // value head
+    float *yv = nullptr, *vr = nullptr, *dh1 = nullptr, *h1r = nullptr, *du = nullptr, *gr = nullptr, *dyv = nullptr, *value = nullptr, *se = nullptr, *ce = nullptr;
+    float *vpart = nullptr, *db_part = nullptr, *v_running = nullptr;
+    VStat* vstat = nullptr;
+    float* losses = nullptr;
+    PackDesc* pack_descs = nullptr;
+    int32_t* error = nullptr;
+    int32_t* rows = nullptr;
+    // records on the device
+    uint64_t* rec_states = nullptr; long long* rec_off = nullptr; uint16_t* rec_index = nullptr; float* rec_prob = nullptr; int8_t* rec_z = nullptr;
+    int64_t rec_n = 0;
+    int64_t step = 0;
+    int last_n = 0;
+    bool loaded = false, attr_set = false;
+    std::vector<void*> allocs;
+};
+
+typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnT t_encode = nullptr;
+
+static int t_get_encode(szb_ctx* ctx) {
+    if (t_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    t_encode = (EncodeTiledFnT)fn;
+    return 0;
+}
+// halo activations [B][10][10][C]: box = 64 channels x 8 x 8 x `boards`
+static int t_act_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, int cap, int boards) {
+    cuuint64_t dims[4] = {(cuuint64_t)channels, TH, TH, (cuuint64_t)cap};
+    cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * TH, (cuuint64_t)channels * 2 * TPIX};
+    cuuint32_t box[4] = {64, 8, 8, (cuuint32_t)boards};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = t_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(training activations) failed: %d", (int)r);
+    return 0;
+}
+// weight pack [rows][k]: box = 64 k x 128 rows
+static int t_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = t_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(training weights) failed: %d", (int)r);
+    return 0;
+}
+
+template <class T>
+static int t_alloc(szb_ctx* ctx, Trainer* tr, T** p, size_t count) {
+    SZB_CUDA(ctx, cudaMalloc((void**)p, count * sizeof(T)));
+    tr->allocs.push_back(*p);
+    SZB_CUDA(ctx, cudaMemsetAsync(*p, 0, count * sizeof(T), ctx->stream));
+    return 0;
+}
+
+void trainer_destroy(szb_ctx* ctx) {
+    Trainer* tr = ctx->trainer;
+    if (!tr) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : tr->allocs) cudaFree(p);
+    void* rec[5] = {tr->rec_states, tr->rec_off, tr->rec_index, tr->rec_prob, tr->rec_z};
+    for (void* p : rec) if (p) cudaFree(p);
+    delete tr;
+    ctx->trainer = nullptr;
+}
+
+static void t_add_vec(Trainer* tr, const std::string& name, int64_t n) {
+    TParam p;
+    p.name = name; p.kind = 0; p.numel = n; p.n = (size_t)((n + 3) & ~3LL);
+    tr->index[name] = (int)tr->params.size();
+    tr->params.push_back(p);
+}
+static void t_add_conv(Trainer* tr, const std::string& name, int cout, int cin, int taps, int cout_pad, int cin_pad) {
+    TParam p;
+    p.name = name; p.kind = 1; p.numel = (int64_t)cout * cin * taps;
+    p.cout = cout; p.cin = cin; p.taps = taps; p.cout_pad = cout_pad; p.cin_pad = cin_pad;
+    p.n = (size_t)cout_pad * taps * cin_pad;
+    tr->index[name] = (int)tr->params.size();
+    tr->params.push_back(p);
+}
+
+// the parameters in the order network.py registers them (torch.optim.Adam's state is numbered in this order)
+static void t_build_params(Trainer* tr) {
+    auto bn = [&](const std::string& p, int c) { t_add_vec(tr, p + ".weight", c); t_add_vec(tr, p + ".bias", c); };
+    t_add_conv(tr, "conv1.weight", 256, 119, 9, 256, TCIN);
+    bn("norm_layer", 256);
+    t_add_conv(tr, "conv_p1.weight", 256, 256, 1, 256, 256);
+    bn("p_norm1", 256);
+    t_add_conv(tr, "conv_p2.weight", 73, 256, 1, 128, 256);
+    t_add_vec(tr, "conv_p2.bias", 73);
+    t_add_vec(tr, "conv_v1.weight", 256);
+    bn("v_norm", 1);
+    t_add_vec(tr, "fc_v1.weight", 256 * 64); t_add_vec(tr, "fc_v1.bias", 256);
+    t_add_vec(tr, "fc_v2.weight", 256); t_add_vec(tr, "fc_v2.bias", 1);
+    for (int b = 0; b < 19; b++)
+        for (int j = 1; j <= 2; j++) {
+            const std::string pfx = "resnet_blocks." + std::to_string(b);
+            t_add_conv(tr, pfx + ".conv" + std::to_string(j) + ".weight", 256, 256, 9, 256, 256);
+            bn(pfx + ".bn" + std::to_string(j), 256);
+        }
+    size_t off = 0;
+    for (auto& p : tr->params) { p.off = off; off += p.n; }
+    tr->total = off;
+}
+
+static std::string t_layer_conv_name(int l) {
+    if (l == 0) return "conv1";
+    if (l == L_P1) return "conv_p1";
+    if (l == L_P2) return "conv_p2";
+    return "resnet_blocks." + std::to_string((l - 1) / 2) + ".conv" + std::to_string((l - 1) % 2 + 1);
+}
+static std::string t_layer_bn_name(int l) {
+    if (l == 0) return "norm_layer";
+    if (l == L_P1) return "p_norm1";
+    return "resnet_blocks." + std::to_string((l - 1) / 2) + ".bn" + std::to_string((l - 1) % 2 + 1);
+}
+
+static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
+    int rc;
+    if ((rc = t_get_encode(ctx))) return rc;
+    trainer_destroy(ctx);
+    Trainer* tr = new Trainer();
+    ctx->trainer = tr;
+    tr->cfg = *cfg;
+    tr->cap = (cfg->batch + 1) & ~1;
+    tr->step = cfg->step0;
+    t_build_params(tr);
+    const int cap = tr->cap;
+    const size_t act = (size_t)cap * TPIX * TC;
+    if ((rc = t_alloc(ctx, tr, &tr->w, tr->total)) || (rc = t_alloc(ctx, tr, &tr->g, tr->total)) || (rc = t_alloc(ctx, tr, &tr->m, tr->total)) ||
+        (rc = t_alloc(ctx, tr, &tr->v, tr->total)))
+        return rc;
+    if ((rc = t_alloc(ctx, tr, &tr->x_in, (size_t)cap * TPIX * TCIN))) return rc;
+    if ((rc = t_act_map(ctx, &tr->tm_in2, tr->x_in, TCIN, cap, 2)) || (rc = t_act_map(ctx, &tr->tm_in1, tr->x_in, TCIN, cap, 1))) return rc;
+    for (int l = 0; l < T_LAYERS; l++) {
+        TLayer& L = tr->L[l];
+        L.taps = (l == L_P1 || l == L_P2) ? 1 : 9;
+        L.cin_pad = l == 0 ? TCIN : 256;
+        L.cout_pad = l == L_P2 ? 128 : 256;
+        L.param = tr->index.at(t_layer_conv_name(l) + ".weight");
+        const size_t wn = (size_t)L.cout_pad * L.taps * L.cin_pad;
+        if ((rc = t_alloc(ctx, tr, &L.wf, wn))) return rc;
+        if ((rc = t_w_map(ctx, &L.tm_wf, L.wf, L.taps * L.cin_pad, L.cout_pad))) return rc;
+        if (l != 0) {
+            if ((rc = t_alloc(ctx, tr, &L.wd, wn))) return rc;
+            if ((rc = t_w_map(ctx, &L.tm_wd, L.wd, L.taps * L.cout_pad, L.cin_pad))) return rc;
+        }
+        if (l < T_BN) {
+            L.gamma = tr->index.at(t_layer_bn_name(l) + ".weight");
+            L.beta = tr->index.at(t_layer_bn_name(l) + ".bias");
+            if ((rc = t_alloc(ctx, tr, &L.y, act)) || (rc = t_alloc(ctx, tr, &L.o, act)) || (rc = t_alloc(ctx, tr, &L.bn, 9 * 256))) return rc;
+            if ((rc = t_act_map(ctx, &L.tm_o2, L.o, TC, cap, 2)) || (rc = t_act_map(ctx, &L.tm_o1, L.o, TC, cap, 1))) return rc;
+            tr->buffers.push_back({t_layer_bn_name(l) + ".running_mean", 256, L.bn});
+            tr->buffers.push_back({t_layer_bn_name(l) + ".running_var", 256, L.bn + 256});
+        }
+    }
+    if ((rc = t_alloc(ctx, tr, &tr->dy, act)) || (rc = t_alloc(ctx, tr, &tr->gbuf[0], act)) || (rc = t_alloc(ctx, tr, &tr->gbuf[1], act)) ||
+        (rc = t_alloc(ctx, tr, &tr->gm1, act)) || (rc = t_alloc(ctx, tr, &tr->skip[0], act)) || (rc = t_alloc(ctx, tr, &tr->skip[1], act)) ||
+        (rc = t_alloc(ctx, tr, &tr->dl, (size_t)cap * TPIX * DL_C)))
+        return rc;
+    if ((rc = t_act_map(ctx, &tr->tm_dy2, tr->dy, TC, cap, 2)) || (rc = t_act_map(ctx, &tr->tm_dy1, tr->dy, TC, cap, 1)) ||
+        (rc = t_act_map(ctx, &tr->tm_dl2, tr->dl, DL_C, cap, 2)) || (rc = t_act_map(ctx, &tr->tm_dl1, tr->dl, DL_C, cap, 1)))
+        return rc;
+    tr->partial_floats = (size_t)WG_MAX_SPLIT * 256 * 256;                      // 1x1 layers: up to 64 splits of 256 x 256
+    if (tr->partial_floats < (size_t)8 * 256 * 2304) tr->partial_floats = (size_t)8 * 256 * 2304;
+    if ((rc = t_alloc(ctx, tr, &tr->partial, tr->partial_floats)) || (rc = t_alloc(ctx, tr, &tr->logits, (size_t)cap * T_ACTIONS)) ||
+        (rc = t_alloc(ctx, tr, &tr->bn_part, (size_t)cap * 512)) || (rc = t_alloc(ctx, tr, &tr->counter, 1)) ||
+        (rc = t_alloc(ctx, tr, &tr->yv, (size_t)cap * 64)) || (rc = t_alloc(ctx, tr, &tr->vr, (size_t)cap * 64)) ||
+        (rc = t_alloc(ctx, tr, &tr->dh1, (size_t)cap * 256)) || (rc = t_alloc(ctx, tr, &tr->h1r, (size_t)cap * 256)) ||
+        (rc = t_alloc(ctx, tr, &tr->du, (size_t)cap)) || (rc = t_alloc(ctx, tr, &tr->gr, (size_t)cap * 64)) ||
+        (rc = t_alloc(ctx, tr, &tr->dyv, (size_t)cap * 64)) || (rc = t_alloc(ctx, tr, &tr->value, (size_t)cap)) ||
+        (rc = t_alloc(ctx, tr, &tr->se, (size_t)cap)) || (rc = t_alloc(ctx, tr, &tr->ce, (size_t)cap)) ||
+        (rc = t_alloc(ctx, tr, &tr->vpart, (size_t)cap * 256)) || (rc = t_alloc(ctx, tr, &tr->db_part, (size_t)cap * DL_C)) ||
+        (rc = t_alloc(ctx, tr, &tr->v_running, 4)) || (rc = t_alloc(ctx, tr, &tr->vstat, 1)) || (rc = t_alloc(ctx, tr, &tr->losses, 2)) ||
+        (rc = t_alloc(ctx, tr, &tr->error, 1)) || (rc = t_alloc(ctx, tr, &tr->rows, (size_t)cap)) ||
+        (rc = t_alloc(ctx, tr, &tr->pack_descs, (size_t)T_LAYERS)))
+        return rc;
+    tr->buffers.push_back({"v_norm.running_mean", 1, tr->v_running});
+    tr->buffers.push_back({"v_norm.running_var", 1, tr->v_running + 1});
+    std::vector<PackDesc> pd(T_LAYERS);
+    for (int l = 0; l < T_LAYERS; l++) {
+        const TLayer& L = tr->L[l];
+        pd[l] = PackDesc{tr->w + tr->params[L.param].off, L.wf, L.wd, L.cout_pad, L.taps, L.cin_pad};
+    }
+    SZB_CUDA(ctx, cudaMemcpyAsync(tr->pack_descs, pd.data(), sizeof(PackDesc) * T_LAYERS, cudaMemcpyHostToDevice, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!tr->attr_set) {
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 6 * WG_BOX + 1024));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 4 * WG_BOX + 1024));
+        tr->attr_set = true;
+    }
+    return 0;
+}
+
+static int t_pack(szb_ctx* ctx, Trainer* tr) {
+    k_pack<<<dim3(64, T_LAYERS), 256, 0, ctx->stream>>>(tr->pack_descs);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+static float* t_kind_base(Trainer* tr, int kind) { return kind == 0 ? tr->w : kind == 1 ? tr->g : kind == 2 ? tr->m : kind == 3 ? tr->v : nullptr; }
+
+// copy tensors by name between caller memory (host or device, torch layout) and the flat buffers
+static int t_transfer(szb_ctx* ctx, int kind, int32_t n_tensors, const char* const* names, float* const* data, const int64_t* numel, bool to_trainer) {
+    Trainer* tr = ctx->trainer;
+    if (!tr) return fail(ctx, SZB_ERR_ARG, "no trainer: call szb_train_create first");
+    if (kind < 0 || kind > 4 || n_tensors < 0 || (n_tensors && (!names || !data || !numel))) return fail(ctx, SZB_ERR_ARG, "szb_train_get/set: bad arguments");
+    float* scratch = nullptr;
+    int rc = 0;
+    for (int i = 0; i < n_tensors && !rc; i++) {
+        const std::string name = names[i];
+        if (kind == 4) {
+            if (to_trainer) { rc = fail(ctx, SZB_ERR_ARG, "activations are read-only"); break; }
+            const float* src = nullptr;
+            int64_t cnt = 0;
+            if (name == "logits") { src = tr->logits; cnt = (int64_t)tr->last_n * T_ACTIONS; }
+            else if (name == "value") { src = tr->value; cnt = tr->last_n; }
+            else { rc = fail(ctx, SZB_ERR_ARG, "unknown activation '%s'", name.c_str()); break; }
+            if (numel[i] != cnt) { rc = fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, caller expects %lld", name.c_str(), (long long)cnt, (long long)numel[i]); break; }
+            cudaError_t e = cudaMemcpyAsync(data[i], src, (size_t)cnt * 4, cudaMemcpyDefault, ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemcpyAsync(activation)");
+            continue;
+        }
+        auto it = tr->index.find(name);
+        if (it == tr->index.end()) {
+            const TBuffer* bf = nullptr;
+            for (auto& b : tr->buffers) if (b.name == name) bf = &b;
+            if (!bf || kind != 0) { rc = fail(ctx, SZB_ERR_ARG, "unknown tensor '%s' (kind %d)", name.c_str(), kind); break; }
+            if (numel[i] != bf->numel) { rc = fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", name.c_str(), (long long)numel[i], (long long)bf->numel); break; }
+            cudaError_t e = to_trainer ? cudaMemcpyAsync(bf->ptr, data[i], (size_t)bf->numel * 4, cudaMemcpyDefault, ctx->stream)
+                                       : cudaMemcpyAsync(data[i], bf->ptr, (size_t)bf->numel * 4, cudaMemcpyDefault, ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemcpyAsync(buffer)");
+            continue;
+        }
+        const TParam& p = tr->params[it->second];
+        if (numel[i] != p.numel) { rc = fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", name.c_str(), (long long)numel[i], (long long)p.numel); break; }
+        float* slot = t_kind_base(tr, kind) + p.off;
+        if (p.kind == 0) {
+            cudaError_t e = to_trainer ? cudaMemcpyAsync(slot, data[i], (size_t)p.numel * 4, cudaMemcpyDefault, ctx->stream)
+                                       : cudaMemcpyAsync(data[i], slot, (size_t)p.numel * 4, cudaMemcpyDefault, ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemcpyAsync(parameter)");
+            continue;
+        }
+        // convolution weight: permute through a device scratch tensor in torch layout
+        if (!scratch) {
+            cudaError_t e = cudaMalloc((void**)&scratch, (size_t)256 * 256 * 9 * 4);
+            if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaMalloc(scratch)"); break; }
+        }
+        const int threads = 256;
+        if (to_trainer) {
+            cudaError_t e = cudaMemcpyAsync(scratch, data[i], (size_t)p.numel * 4, cudaMemcpyDefault, ctx->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaMemcpyAsync(weight)"); break; }
+            k_conv_to_packed<<<(unsigned)((p.n + threads - 1) / threads), threads, 0, ctx->stream>>>(scratch, slot, p.cout, p.cin, p.taps, p.cout_pad, p.cin_pad);
+        } else {
+            k_packed_to_conv<<<(unsigned)((p.numel + threads - 1) / threads), threads, 0, ctx->stream>>>(slot, scratch, p.cout, p.cin, p.taps, p.cin_pad);
+            cudaError_t e = cudaMemcpyAsync(data[i], scratch, (size_t)p.numel * 4, cudaMemcpyDefault, ctx->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(ctx, e, "cudaMemcpyAsync(weight)"); break; }
+        }
+        ctx->launches++;
+        // the scratch tensor is reused by the next convolution weight: stream order keeps that safe
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (scratch) cudaFree(scratch);
+    if (!rc && e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaStreamSynchronize");
+    if (!rc && (e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(ctx, e, "szb_train_get/set");
+    if (!rc && to_trainer && kind == 0) { tr->loaded = true; rc = t_pack(ctx, tr); }
+    return rc;
+}
+
+static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUtensorMap& tm_w, int taps, int kchunks, int n_out, int n, bf16* out, int mode,
+                  const float* bias) {
+    TConvArgs a{};
+    a.taps = taps; a.kchunks = kchunks; a.n_boards = n; a.out = out; a.ldc = TC; a.logits = tr->logits; a.bias = bias; a.error = tr->error;
+    const dim3 grid((n + 1) / 2, n_out / 128);
+    if (mode == 0) k_tconv<0><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(tm_a, tm_w, a);
+    else k_tconv<1><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(tm_a, tm_w, a);
+    ctx->launches++;
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int t_ksplit(int n, int tiles_x) {
+    int k = 144 / tiles_x;
+    if (k > WG_MAX_SPLIT) k = WG_MAX_SPLIT;
+    if (k > n) k = n;
+    if (k < 1) k = 1;
+    return k;
+}
+
+// dW of layer l: A = gradient of the convolution output (tm_a: 1-board boxes), X = the layer's input (tm_x)
+static int t_wgrad(szb_ctx* ctx, Trainer* tr, int l, const CUtensorMap& tm_a, const CUtensorMap& tm_x, int n) {
+    const TLayer& L = tr->L[l];
+    const TParam& p = tr->params[L.param];
+    WgArgs a{};
+    a.taps = L.taps; a.m_halves = L.cout_pad / 128; a.n_boards = n;
+    a.ksplit = t_ksplit(n, L.taps * a.m_halves);
+    a.partial = tr->partial; a.ldw = L.taps * L.cin_pad; a.cin_pad = L.cin_pad; a.split_stride = (size_t)L.cout_pad * a.ldw; a.error = tr->error;
+    a.lbo = tr->cfg.probe_lbo ? (uint32_t)tr->cfg.probe_lbo : WG_BOX;
+    a.sbo = tr->cfg.probe_sbo ? (uint32_t)tr->cfg.probe_sbo : 1024;
+    if ((size_t)a.ksplit * a.split_stride > tr->partial_floats) return fail(ctx, SZB_ERR_INTERNAL, "wgrad scratch too small");
+    const dim3 grid(L.taps * a.m_halves, a.ksplit);
+    if (L.cin_pad == 256) k_wgrad<4><<<grid, TR_THREADS, WG_STAGES * 6 * WG_BOX + 1024, ctx->stream>>>(tm_a, tm_x, a);
+    else k_wgrad<2><<<grid, TR_THREADS, WG_STAGES * 4 * WG_BOX + 1024, ctx->stream>>>(tm_a, tm_x, a);
+    const size_t cnt = a.split_stride;
+    k_reduce_partials<<<(unsigned)((cnt / 4 + 255) / 256), 256, 0, ctx->stream>>>(tr->partial, a.split_stride, a.ksplit, tr->g + p.off, cnt);
+    ctx->launches += 2;
+    SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+static float* t_slot(Trainer* tr, float* base, const std::string& name) { return base + tr->params[tr->index.at(name)].off; }
+
+static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, float* losses_out) {
+    Trainer* tr = ctx->trainer;
+    if (!tr || !tr->loaded) return fail(ctx, SZB_ERR_STATE, "trainer has no weights: szb_train_create + szb_train_set(kind 0) first");
+    if (!tr->rec_states) return fail(ctx, SZB_ERR_STATE, "no records: szb_train_records first");
+    if (n < 2 || n > tr->cfg.batch || !rows) return fail(ctx, SZB_ERR_ARG, "szb_train_step: 2 <= n <= %d boards (BatchNorm needs more than one)", tr->cfg.batch);
+    cudaStream_t st = ctx->stream;
+    int rc;
+    tr->last_n = n;
+    SZB_CUDA(ctx, cudaMemcpyAsync(tr->rows, rows, (size_t)n * 4, cudaMemcpyDefault, st));
+    // an odd batch leaves a phantom board in the last 2-board tile: GEMM rows are independent, its rows are computed and never stored
+    const unsigned ew_blocks = (unsigned)(((size_t)n * 64 * 32 + 255) / 256);
+    k_gather_input<<<(unsigned)(((size_t)n * 64 * 16 + 255) / 256), 256, 0, st>>>(tr->rec_states, (long long)tr->rec_n, tr->rows, n, tr->x_in, tr->error);
+    ctx->launches++;
+    // ---------------- forward ----------------
+    for (int l = 0; l < T_BN; l++) {
+        TLayer& L = tr->L[l];
+        const CUtensorMap& tm_a = l == 0 ? tr->tm_in2 : l == L_P1 ? tr->L[38].tm_o2 : tr->L[l - 1].tm_o2;
+        if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr))) return rc;
+        BnPtrs bp{tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768, L.bn + 1024, L.bn + 1280,
+                  tr->bn_part, tr->counter, tr->cfg.bn_momentum, tr->cfg.bn_eps};
+        k_bn_stats<<<n, 256, 0, st>>>(L.y, n, bp);
+        const bf16* res = (l >= 2 && l <= 38 && ((l - 1) & 1)) ? tr->L[l - 2].o : nullptr;
+        k_bn_apply<<<ew_blocks, 256, 0, st>>>(L.y, L.bn + 1024, L.bn + 1280, res, L.o, n);
+        ctx->launches += 2;
+    }
+    if ((rc = t_conv(ctx, tr, tr->L[L_P1].tm_o2, tr->L[L_P2].tm_wf, 1, 4, 128, n, nullptr, 1, t_slot(tr, tr->w, "conv_p2.bias")))) return rc;
+    const bf16* T = tr->L[38].o;
+    k_vconv<<<(unsigned)(((size_t)n * 64 * 32 + 255) / 256), 256, 0, st>>>(T, t_slot(tr, tr->w, "conv_v1.weight"), tr->yv, n);
+    k_vbn_stats<<<1, 1024, 0, st>>>(tr->yv, n, tr->v_running, tr->v_running + 1, tr->vstat, tr->cfg.bn_momentum, tr->cfg.bn_eps);
+    VHead vh{tr->yv, tr->vstat, t_slot(tr, tr->w, "v_norm.weight"), t_slot(tr, tr->w, "v_norm.bias"), t_slot(tr, tr->w, "fc_v1.weight"),
+             t_slot(tr, tr->w, "fc_v1.bias"), t_slot(tr, tr->w, "fc_v2.weight"), t_slot(tr, tr->w, "fc_v2.bias"), tr->rec_z, tr->rows, tr->value, tr->se,
+             tr->vr, tr->dh1, tr->h1r, tr->du, tr->gr, n};
+    k_vhead<<<n, 256, 0, st>>>(vh);
+    LossArgs la{tr->logits, tr->rows, tr->rec_off, tr->rec_index, tr->rec_prob, tr->dl, tr->ce, tr->db_part, n};
+    k_policy_loss<<<n, 256, 0, st>>>(la);
+    k_loss_reduce<<<1, 32, 0, st>>>(tr->se, tr->ce, n, tr->losses);
+    ctx->launches += 5;
+    SZB_CUDA(ctx, cudaGetLastError());
+    if (!(flags & SZB_TRAIN_FORWARD_ONLY)) {
+        // ---------------- backward: heads ----------------
+        k_colsum<<<1, 128, 0, st>>>(tr->db_part, n, 73, DL_C, t_slot(tr, tr->g, "conv_p2.bias"));
+        k_vbn_bwd<<<1, 1024, 0, st>>>(tr->yv, tr->gr, tr->vstat, t_slot(tr, tr->w, "v_norm.weight"), t_slot(tr, tr->g, "v_norm.weight"),
+                                      t_slot(tr, tr->g, "v_norm.bias"), tr->dyv, n);
+        k_vconv_bwd<<<n, 256, 0, st>>>(T, t_slot(tr, tr->w, "conv_v1.weight"), tr->dyv, tr->skip[0], tr->vpart);
+        k_colsum<<<1, 256, 0, st>>>(tr->vpart, n, 256, 256, t_slot(tr, tr->g, "conv_v1.weight"));
+        k_vhead_grads<<<(256 * 64 + 256 + 1 + 255) / 256, 256, 0, st>>>(tr->dh1, tr->vr, tr->h1r, tr->du, n, t_slot(tr, tr->g, "fc_v1.weight"),
+                                                                       t_slot(tr, tr->g, "fc_v1.bias"), t_slot(tr, tr->g, "fc_v2.weight"),
+                                                                       t_slot(tr, tr->g, "fc_v2.bias"));
+        ctx->launches += 5;
+        // conv_p2: weight gradient, then the gradient of its input (conv_p1's output after BN + ReLU)
+        if ((rc = t_wgrad(ctx, tr, L_P2, tr->tm_dl1, tr->L[L_P1].tm_o1, n))) return rc;
+        int cur = 0;                                            // gbuf[cur] holds the gradient arriving at the layer being processed
+        if ((rc = t_conv(ctx, tr, tr->tm_dl2, tr->L[L_P2].tm_wd, 1, DL_C / 64, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
+        int sk = 0;                                             // skip[sk] holds the skip-path gradient for the next residual join
+        for (int l = L_P1; l >= 0; l--) {
+            TLayer& L = tr->L[l];
+            const bool join = l == 0 || (l <= 38 && ((l - 1) & 1));          // layers whose output feeds a residual add as well (or two heads)
+            const bf16* skip_in = join ? tr->skip[sk] : nullptr;
+            bf16* gm = join ? tr->skip[sk ^ 1] : tr->gm1;
+            BnBwdPtrs bp{tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768, tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off,
+                         L.bn + 1536, L.bn + 1792, L.bn + 2048, tr->bn_part, tr->counter};
+            k_bn_bwd_reduce<<<n, 256, 0, st>>>(tr->gbuf[cur], skip_in, L.o, L.y, gm, n, bp);
+            k_bn_bwd_apply<<<ew_blocks, 256, 0, st>>>(gm, L.y, L.bn + 512, L.bn + 768, L.bn + 1536, L.bn + 1792, L.bn + 2048, tr->dy, n);
+            ctx->launches += 2;
+            if (join) sk ^= 1;
+            const CUtensorMap& tm_x = l == 0 ? tr->tm_in1 : l == L_P1 ? tr->L[38].tm_o1 : tr->L[l - 1].tm_o1;
+            if ((rc = t_wgrad(ctx, tr, l, tr->tm_dy1, tm_x, n))) return rc;
+            if (l > 0) {
+                cur ^= 1;
+                if ((rc = t_conv(ctx, tr, tr->tm_dy2, L.tm_wd, L.taps, 4, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
+            }
+        }
+        if (!(flags & SZB_TRAIN_NO_UPDATE)) {
+            tr->step++;
+            const szb_train_config& c = tr->cfg;
+            const double lr = (double)c.lr * pow((double)c.lr_gamma, (double)((tr->step - 1) / (c.lr_step > 0 ? c.lr_step : 1)));
+            const double bc1 = 1.0 - pow((double)c.beta1, (double)tr->step), bc2 = 1.0 - pow((double)c.beta2, (double)tr->step);
+            k_adam<<<(unsigned)((tr->total + 255) / 256), 256, 0, st>>>(tr->w, tr->g, tr->m, tr->v, tr->total, (float)(lr / bc1), c.beta1, c.beta2, c.eps,
+                                                                       c.weight_decay, (float)sqrt(bc2));
+            ctx->launches++;
+            if ((rc = t_pack(ctx, tr))) return rc;
+        }
+    }
+    SZB_CUDA(ctx, cudaGetLastError());
+    if (losses_out) {
+        int32_t err = 0;
+        SZB_CUDA(ctx, cudaMemcpyAsync(losses_out, tr->losses, 8, cudaMemcpyDefault, st));
+        SZB_CUDA(ctx, cudaMemcpyAsync(&err, tr->error, 4, cudaMemcpyDeviceToHost, st));
+        SZB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (err) {
+            cudaMemsetAsync(tr->error, 0, 4, st);
+            return err == 2 ? fail(ctx, SZB_ERR_ARG, "szb_train_step: a row index is outside the %lld records", (long long)tr->rec_n)
+                            : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
+        }
+    }
+    return 0;
+}
+
+}  // namespace szb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int szb_train_create(szb_ctx* ctx, const szb_train_config* cfg) {
+    if (!ctx || !cfg) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (cfg->batch < 2 || cfg->batch > 4096) return fail(ctx, SZB_ERR_ARG, "szb_train_create: batch must be 2..4096");
+    return t_create(ctx, cfg);
+}
+
+int szb_train_destroy(szb_ctx* ctx) {
+    if (!ctx) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    trainer_destroy(ctx);
+    return 0;
+}
+
+int szb_train_set(szb_ctx* ctx, int32_t kind, int32_t n_tensors, const char* const* names, const float* const* data, const int64_t* numel) {
+    if (!ctx) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return t_transfer(ctx, kind, n_tensors, names, const_cast<float* const*>(data), numel, true);
+}
+
+int szb_train_get(szb_ctx* ctx, int32_t kind, int32_t n_tensors, const char* const* names, float* const* data, const int64_t* numel) {
+    if (!ctx) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return t_transfer(ctx, kind, n_tensors, names, data, numel, false);
+}
+
+int szb_train_records(szb_ctx* ctx, int64_t n, const uint64_t* states, const int64_t* pi_off, const uint16_t* pi_index, const float* pi_prob, const int8_t* z) {
+    if (!ctx) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    Trainer* tr = ctx->trainer;
+    if (!tr) return fail(ctx, SZB_ERR_STATE, "no trainer: call szb_train_create first");
+    if (n < 1 || !states || !pi_off || !pi_index || !pi_prob || !z) return fail(ctx, SZB_ERR_ARG, "szb_train_records: bad arguments");
+    cudaStreamSynchronize(ctx->stream);
+    void* old[5] = {tr->rec_states, tr->rec_off, tr->rec_index, tr->rec_prob, tr->rec_z};
+    for (void* p : old) if (p) cudaFree(p);
+    tr->rec_states = nullptr; tr->rec_off = nullptr; tr->rec_index = nullptr; tr->rec_prob = nullptr; tr->rec_z = nullptr;
+    int64_t first = 0, last = 0;
+    SZB_CUDA(ctx, cudaMemcpy(&first, pi_off, 8, cudaMemcpyDefault));
+    SZB_CUDA(ctx, cudaMemcpy(&last, pi_off + n, 8, cudaMemcpyDefault));
+    if (first != 0 || last < 0) return fail(ctx, SZB_ERR_ARG, "szb_train_records: pi_off must start at 0 and ascend");
+    const size_t m = (size_t)last;
+    SZB_CUDA(ctx, cudaMalloc((void**)&tr->rec_states, (size_t)n * T_PLANES * 8));
+    SZB_CUDA(ctx, cudaMalloc((void**)&tr->rec_off, (size_t)(n + 1) * 8));
+    SZB_CUDA(ctx, cudaMalloc((void**)&tr->rec_index, (m ? m : 1) * 2));
+    SZB_CUDA(ctx, cudaMalloc((void**)&tr->rec_prob, (m ? m : 1) * 4));
+    SZB_CUDA(ctx, cudaMalloc((void**)&tr->rec_z, (size_t)n));
+    SZB_CUDA(ctx, cudaMemcpyAsync(tr->rec_states, states, (size_t)n * T_PLANES * 8, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaMemcpyAsync(tr->rec_off, pi_off, (size_t)(n + 1) * 8, cudaMemcpyDefault, ctx->stream));
+    if (m) {
+        SZB_CUDA(ctx, cudaMemcpyAsync(tr->rec_index, pi_index, m * 2, cudaMemcpyDefault, ctx->stream));
+        SZB_CUDA(ctx, cudaMemcpyAsync(tr->rec_prob, pi_prob, m * 4, cudaMemcpyDefault, ctx->stream));
+    }
+    SZB_CUDA(ctx, cudaMemcpyAsync(tr->rec_z, z, (size_t)n, cudaMemcpyDefault, ctx->stream));
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    tr->rec_n = n;
+    return 0;
+}
+
+int szb_train_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, float* losses_out) {
+    if (!ctx) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return t_step(ctx, n, rows, flags, losses_out);
+}
+
+int szb_train_state(szb_ctx* ctx, int64_t* step_inout, int32_t set) {
+    if (!ctx || !step_inout) return SZB_ERR_ARG;
+    if (!ctx->trainer) return fail(ctx, SZB_ERR_STATE, "no trainer");
+    if (set) ctx->trainer->step = *step_inout; else *step_inout = ctx->trainer->step;
+    return 0;
+}
+
+}  // extern "C"
