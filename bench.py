@@ -554,7 +554,85 @@ def run_extras(args):
                                                 "rank_seconds", "weights_broadcast_ms")}
         out["c4_bounded"]["workload"] = c4["config"]["workload"] + " [bounded: %d plies per game]" % args.extras_c4_plies
         out["c4_bounded"]["games_per_gpu"] = c4["config"]["games_per_gpu"]
+    # ---- f1: the fine-tuning step of the same loop (train_RL.py:77-154) on the library's trainer, next to torch eager -----------
+    if rank == 0:
+        try:
+            out["f1_trainer"] = trainer_measure(model, dev, local)
+        except Exception as e:                                     # an extra must never take the headline down
+            out["f1_trainer"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out if rank == 0 else None
+
+
+def trainer_measure(model, dev, local, batch=128, steps=20, warmup=3):
+    """positions/s of one optimiser step (forward + backward + Adam) at the reference's batch size (train_RL.py:175: 128) on synthetic
+    records, through sigma_zero_b200.trainer.Trainer (szb_train_step: row numbers from the host every step), timed with CUDA events on
+    the library's stream; beside it the same step in torch eager on the same GPU (the reference's own trainer code path, convolutions
+    in torch's default TF32 mode), inputs already on the device"""
+    import numpy as np
+    import torch
+    from sigma_zero_b200 import records as records_mod
+    from sigma_zero_b200.engine import Engine
+    from sigma_zero_b200.trainer import Trainer
+    rng = np.random.default_rng(SEED)
+    n = 8 * batch
+    bits = rng.random((n, 119, 64)) < 0.12
+    idx, prob, off = [], [], [0]
+    for _ in range(n):
+        k = int(rng.integers(5, 45))
+        idx.extend(np.sort(rng.choice(4672, size=k, replace=False)).tolist())
+        p = rng.random(k).astype(np.float32)
+        prob.extend((p / p.sum()).tolist())
+        off.append(len(idx))
+    rec = {"states": np.packbits(bits, axis=-1, bitorder="little").view("<u8").reshape(n, 119).astype(np.uint64),
+           "pi_index": np.array(idx, np.uint16), "pi_prob": np.array(prob, np.float32), "pi_off": np.array(off, np.int64),
+           "z": rng.integers(-1, 2, n).astype(np.int8)}
+    batches = [rng.permutation(n)[:batch].astype(np.int32) for _ in range(8)]
+    eng = Engine(max_games=2, max_searches=8, device=local)
+    tr = Trainer(eng, model, batch_size=batch)
+    tr.set_records(rec)
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    first = tr.step(batches[0])
+    for i in range(1, warmup):
+        tr.step(batches[i % 8], want_losses=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for i in range(steps):
+        last = tr.step(batches[i % 8], want_losses=(i == steps - 1))
+    e1.record(ext)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tr.close()
+    eng.close()
+    # torch eager, same step
+    ref = type(model)({}).to(dev).train()
+    ref.load_state_dict(model.state_dict())
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-4, weight_decay=1e-4)
+    x = torch.from_numpy(records_mod.unpack_states(rec, batches[0])).to(device=dev, dtype=torch.float32)
+    pi = torch.from_numpy(records_mod.dense_policy(rec, batches[0])).to(dev)
+    z = torch.from_numpy(rec["z"][batches[0]].astype(np.float32)).to(dev)
+
+    def torch_step():
+        opt.zero_grad(set_to_none=True)
+        p, v = ref.forward_torch(x)
+        (torch.nn.functional.mse_loss(v.squeeze(-1), z) + torch.nn.functional.cross_entropy(p, pi)).backward()
+        opt.step()
+    for _ in range(warmup):
+        torch_step()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(10):
+        torch_step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms_torch = t0.elapsed_time(t1) / 10
+    flop = 3 * 2 * 64 * batch * (256 * (119 * 9 + 38 * 2304 + 256) + 73 * 256)       # forward + dgrad + wgrad of every convolution (no dgrad for the stem: ~1 % less)
+    return {"metric": "trained_positions_per_sec", "value": batch / (ms * 1e-3), "unit": "positions/s", "batch": batch, "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "tflops": flop / (ms * 1e-3) / 1e12, "dtype": "bf16 operands, fp32 accumulate / master weights / Adam",
+            "loss_first_step": list(first), "loss_last_step": list(last),
+            "torch_eager_same_gpu": {"ms_per_step": ms_torch, "value": batch / (ms_torch * 1e-3), "mode": "fp32 parameters, TF32 convolutions (torch default)"},
+            "speedup_vs_torch_eager": ms_torch / ms, "data": "synthetic records, resident on the GPU; row numbers sent from the host every step"}
 
 
 def c4_measure(args, wl, max_plies, model, weights):

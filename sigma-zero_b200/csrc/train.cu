@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -43,15 +44,16 @@ constexpr int T_PLANES = 119;
 constexpr int DL_C = 128;                    // channels of the logits-gradient buffer (73 policy planes padded)
 
 constexpr int TR_THREADS = 192;              // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
-constexpr int TR_STAGES = 3;
-constexpr int TR_A_BYTES = 128 * 64 * 2;     // 128 board squares x 64 channels
-constexpr int TR_B_BYTES = 128 * 64 * 2;     // 128 output channels x 64 k
-constexpr int TR_STAGE_BYTES = TR_A_BYTES + TR_B_BYTES;
-constexpr int TR_SMEM = TR_STAGES * TR_STAGE_BYTES + 1024;
+constexpr int TR_A_CHUNKS = 3;
+constexpr int TR_A_CHUNK_BYTES = 2 * TPIX * 128;      // two boards with their halo x 64 channels: 25600 = 25 * 1024
+constexpr int TR_B_STAGES = 6;
+constexpr int TR_B_BYTES = 128 * 64 * 2;              // 128 output channels x 64 k
+constexpr int TR_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TR_B_STAGES * TR_B_BYTES + 1024;
 
 constexpr int WG_STAGES = 4;
 constexpr int WG_BOX = 64 * 64 * 2;          // one board (64 squares) x 64 channels
 constexpr int WG_MAX_SPLIT = 64;
+constexpr int ROWS_RING = 8;
 
 __device__ __forceinline__ int halo_pix(int sq) { return ((sq >> 3) + 1) * TH + (sq & 7) + 1; }
 
@@ -81,23 +83,30 @@ struct TConvArgs {
     int32_t* error;
 };
 
+// Shared memory: a ring of TR_A_CHUNKS activation chunks and a ring of TR_B_STAGES weight tiles.  An activation chunk is one 64-channel
+// slice of the tile's two boards INCLUDING the halo, 200 rows of 128 bytes in the order [y][board][x] (one TMA box through a tensor map
+// with dims (c, x, board, y)); all nine taps read it in place: the A descriptor of tap (ky, kx) starts (ky * 20 + kx) rows into the chunk
+// and strides 10 rows between 8-row groups, so MMA row m = (oy * 2 + board) * 8 + ox reads halo square (oy + ky, ox + kx) -- the layout
+// k_tower_tc2 (net.cu) uses.  An activation byte enters the SM once per layer instead of once per tap.
 template <int MODE>
-__global__ void __launch_bounds__(TR_THREADS, 2)
+__global__ void __launch_bounds__(TR_THREADS, 1)
 k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TConvArgs a) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[TR_STAGES], bar_empty[TR_STAGES], bar_acc;
+    __shared__ __align__(8) uint64_t bar_af[TR_A_CHUNKS], bar_ae[TR_A_CHUNKS], bar_bf[TR_B_STAGES], bar_be[TR_B_STAGES], bar_acc;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
 
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = smem_a + TR_A_CHUNKS * TR_A_CHUNK_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, nh = blockIdx.y;
     volatile int* abort_flag = &abort_sh;
 
     if (threadIdx.x == 0) {
         abort_sh = 0;
-        for (int s = 0; s < TR_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < TR_A_CHUNKS; s++) { mbar_init(smem_u32(&bar_af[s]), 1); mbar_init(smem_u32(&bar_ae[s]), 1); }
+        for (int s = 0; s < TR_B_STAGES; s++) { mbar_init(smem_u32(&bar_bf[s]), 1); mbar_init(smem_u32(&bar_be[s]), 1); }
         mbar_init(smem_u32(&bar_acc), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -109,38 +118,50 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
-    const int k_iters = a.taps * a.kchunks;
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int it = 0; it < k_iters; it++) {
-                const int tap = it / a.kchunks, kc = it - tap * a.kchunks;
-                const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
-                if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1, abort_flag)) break;
-                const uint32_t full = smem_u32(&bar_full[stage]);
-                const uint32_t sa = smem_base + stage * TR_STAGE_BYTES;
-                mbar_expect_tx(full, TR_STAGE_BYTES);
-                tma_load_4d(sa, &tm_a, full, kc * 64, kx, ky, tile * 2);
-                tma_load_2d(sa + TR_A_BYTES, &tm_w, full, it * 64, nh * 128);
-                if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+            int ac = 0, bs = 0;
+            uint32_t a_phase = 0, b_phase = 0;
+            bool ok = true;
+            for (int kc = 0; kc < a.kchunks && ok; kc++) {
+                if (!(ok = mbar_wait(smem_u32(&bar_ae[ac]), a_phase ^ 1, abort_flag))) break;
+                const uint32_t af = smem_u32(&bar_af[ac]);
+                mbar_expect_tx(af, TR_A_CHUNK_BYTES);
+                tma_load_4d(smem_a + ac * TR_A_CHUNK_BYTES, &tm_a, af, kc * 64, 0, tile * 2, 0);
+                if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
+                for (int tap = 0; tap < a.taps; tap++) {
+                    if (!(ok = mbar_wait(smem_u32(&bar_be[bs]), b_phase ^ 1, abort_flag))) break;
+                    const uint32_t bf = smem_u32(&bar_bf[bs]);
+                    mbar_expect_tx(bf, TR_B_BYTES);
+                    tma_load_2d(smem_b + bs * TR_B_BYTES, &tm_w, bf, (tap * a.kchunks + kc) * 64, nh * 128);
+                    if (++bs == TR_B_STAGES) { bs = 0; b_phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int ac = 0, bs = 0;
+            uint32_t a_phase = 0, b_phase = 0;
             bool ok = true;
-            for (int it = 0; it < k_iters; it++) {
-                if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
+            for (int kc = 0; kc < a.kchunks && ok; kc++) {
+                if (!(ok = mbar_wait(smem_u32(&bar_af[ac]), a_phase, abort_flag))) break;
                 tc_fence_after();
-                const uint32_t sa = smem_base + stage * TR_STAGE_BYTES;
-                const uint32_t sb = sa + TR_A_BYTES;
+                const uint32_t chunk = smem_a + ac * TR_A_CHUNK_BYTES;
+                for (int tap = 0; tap < a.taps; tap++) {
+                    const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
+                    if (!(ok = mbar_wait(smem_u32(&bar_bf[bs]), b_phase, abort_flag))) break;
+                    tc_fence_after();
+                    const uint32_t sa = chunk + (uint32_t)(ky * 2 * TH + kx) * 128u;
+                    const uint32_t sb = smem_b + bs * TR_B_BYTES;
 #pragma unroll
-                for (int k = 0; k < 4; k++) tc_mma_bf16(tmem_base, make_smem_desc(sa + k * 32), make_smem_desc(sb + k * 32), IDESC, (it | k) != 0);
-                tc_commit(smem_u32(&bar_empty[stage]));
-                if (++stage == TR_STAGES) { stage = 0; phase ^= 1; }
+                    for (int k = 0; k < 4; k++)
+                        tc_mma_bf16(tmem_base, make_smem_desc(sa + k * 32, TH * 128), make_smem_desc(sb + k * 32), IDESC, (kc | tap | k) != 0);
+                    tc_commit(smem_u32(&bar_be[bs]));
+                    if (++bs == TR_B_STAGES) { bs = 0; b_phase ^= 1; }
+                }
+                if (ok) tc_commit(smem_u32(&bar_ae[ac]));
+                if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
             }
             if (ok) tc_commit(smem_u32(&bar_acc));
         }
@@ -150,8 +171,8 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
         ok = __all_sync(0xFFFFFFFFu, ok);
         if (ok) {
             tc_fence_after();
-            const int m = lane_group * 32 + lane;
-            const int board = tile * 2 + (m >> 6), sq = m & 63;
+            const int m = lane_group * 32 + lane;                          // row (oy * 2 + board) * 8 + ox
+            const int board = tile * 2 + ((m >> 3) & 1), sq = (m >> 4) * 8 + (m & 7);
             const bool live = board < a.n_boards;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
             const size_t pix = (size_t)board * TPIX + halo_pix(sq);
@@ -338,149 +359,213 @@ __global__ void k_gather_input(const uint64_t* states, long long n_records, int3
 // =================================================================================================
 // BatchNorm (training mode), 256 channels
 // =================================================================================================
-struct BnPtrs {
+constexpr int BN_SLICES = 8;                 // blocks own 32 channels ...
+constexpr int BN_GROUPS = 18;                // ... of one group of boards: 144 blocks, all resident at once (the kernels carry a grid barrier)
+
+struct GridBar { unsigned int count, gen; };
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Every block of the grid arrives before any leaves.  Sense reversing (the last block clears the count and bumps the generation), so the
+// same two words serve every launch, and a replayed CUDA graph too.  `my_gen` is the generation read before arriving.
+__device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int my_gen, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&bar->count, 1u) == nblocks - 1) {
+            bar->count = 0;
+            __threadfence();
+            atomicAdd(&bar->gen, 1u);
+        } else {
+            while (ld_acquire_u32(&bar->gen) == my_gen) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// per-channel sums of a [64 squares][32 channels] register tile spread over 256 threads (thread = (square, 8 channels)): fixed order
+__device__ __forceinline__ void bn_block_sums(float (*red)[64][33], const float* s1, const float* s2, float* part, int grp, int slice) {
+    const int t = threadIdx.x, cq = t & 3, pos = t >> 2;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { red[0][pos][cq * 8 + j] = s1[j]; red[1][pos][cq * 8 + j] = s2[j]; }
+    __syncthreads();
+    if (t < 64) {
+        const int which = t >> 5, c = t & 31;
+        float a = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 64; i++) a += red[which][i][c];
+        part[(grp * 2 + which) * 256 + slice * 32 + c] = a;
+    }
+}
+
+struct BnFwd {
+    const bf16* y; const bf16* residual; bf16* out;
     const float* gamma; const float* beta;
     float* running_mean; float* running_var;
     float* mean; float* invstd;          // saved for the backward pass
-    float* scale; float* shift;          // y * scale + shift
-    float* part;                         // [boards][2][256]
-    unsigned int* counter;
+    float* part;                         // [BN_GROUPS][2][256]
+    GridBar* bar;
+    int n;
     float momentum, eps;
 };
 
-__global__ void __launch_bounds__(256) k_bn_stats(const bf16* y, int n, BnPtrs p) {
-    const int b = blockIdx.x, c = threadIdx.x;
-    float s1 = 0.f, s2 = 0.f;
-    const bf16* base = y + (size_t)b * TPIX * TC + c;
-#pragma unroll 8
-    for (int sq = 0; sq < 64; sq++) {
-        const float v = __bfloat162float(base[(size_t)halo_pix(sq) * TC]);
-        s1 += v;
-        s2 += v * v;
+// Training-mode BatchNorm + ReLU (+ residual) in ONE launch: batch statistics of the block's 32 channels over its boards, grid barrier,
+// every block folds the 18 partials of its channels (fixed order) into scale / shift, then normalises the same boards.
+__global__ void __launch_bounds__(256) k_bn_fwd(BnFwd p) {
+    __shared__ float red[2][64][33];
+    __shared__ float sc_sh[32], sh_sh[32];
+    __shared__ unsigned int gen_sh;
+    const int slice = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
+    const int t = threadIdx.x, cq = t & 3, pos = t >> 2;
+    const int b_lo = (int)((long long)grp * p.n / G), b_hi = (int)((long long)(grp + 1) * p.n / G);
+    if (t == 0) gen_sh = ld_acquire_u32(&p.bar->gen);
+    const size_t coff = (size_t)halo_pix(pos) * TC + slice * 32 + cq * 8;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s1[j] = s2[j] = 0.f;
+#pragma unroll 4
+    for (int b = b_lo; b < b_hi; b++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p.y + (size_t)b * TPIX * TC + coff);
+        const bf16* vb = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const float f = __bfloat162float(vb[j]); s1[j] += f; s2[j] += f * f; }
     }
-    p.part[(size_t)b * 512 + c] = s1;
-    p.part[(size_t)b * 512 + 256 + c] = s2;
-    __threadfence();
-    __shared__ bool last;
+    bn_block_sums(red, s1, s2, p.part, grp, slice);
+    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y);
+    if (t < 32) {
+        const int c = slice * 32 + t;
+        double S1 = 0, S2 = 0;
+        for (int g = 0; g < G; g++) { S1 += (double)__ldcg(&p.part[(g * 2) * 256 + c]); S2 += (double)__ldcg(&p.part[(g * 2 + 1) * 256 + c]); }
+        const double cnt = (double)p.n * 64.0, mean = S1 / cnt;
+        double var = S2 / cnt - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
+        const float sc = p.gamma[c] * invstd;
+        sc_sh[t] = sc;
+        sh_sh[t] = p.beta[c] - (float)mean * sc;
+        if (grp == 0) {
+            p.mean[c] = (float)mean;
+            p.invstd[c] = invstd;
+            p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
+            p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * cnt / (cnt - 1.0));
+        }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    double S1 = 0, S2 = 0;
-    for (int i = 0; i < n; i++) { S1 += (double)__ldcg(&p.part[(size_t)i * 512 + c]); S2 += (double)__ldcg(&p.part[(size_t)i * 512 + 256 + c]); }
-    const double cnt = (double)n * 64.0;
-    const double mean = S1 / cnt;
-    double var = S2 / cnt - mean * mean;
-    if (var < 0) var = 0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)p.eps));
-    p.mean[c] = (float)mean;
-    p.invstd[c] = invstd;
-    const float sc = p.gamma[c] * invstd;
-    p.scale[c] = sc;
-    p.shift[c] = p.beta[c] - (float)mean * sc;
-    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (float)mean;
-    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)(var * cnt / (cnt - 1.0));
-    if (threadIdx.x == 0) *p.counter = 0;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sc[j] = sc_sh[cq * 8 + j]; sh[j] = sh_sh[cq * 8 + j]; }
+#pragma unroll 4
+    for (int b = b_lo; b < b_hi; b++) {
+        const size_t off = (size_t)b * TPIX * TC + coff;
+        const uint4 v = *reinterpret_cast<const uint4*>(p.y + off);
+        const bf16* vb = reinterpret_cast<const bf16*>(&v);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = __bfloat162float(vb[j]) * sc[j] + sh[j];
+        if (p.residual) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + off);
+            const bf16* rb = reinterpret_cast<const bf16*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 8; j++) f[j] += __bfloat162float(rb[j]);
+        }
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) ob[j] = __floats2bfloat162_rn(fmaxf(f[2 * j], 0.f), fmaxf(f[2 * j + 1], 0.f));
+        *reinterpret_cast<uint4*>(p.out + off) = o;
+    }
 }
 
-// out = relu(y * scale + shift [+ residual]); 8 channels of one square per thread
-__global__ void __launch_bounds__(256) k_bn_apply(const bf16* y, const float* scale, const float* shift, const bf16* residual, bf16* out, int n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n * 64 * 32) return;
-    const int cg = (int)(i & 31), sq = (int)((i >> 5) & 63);
-    const size_t b = i >> 11;
-    const size_t off = (b * TPIX + halo_pix(sq)) * TC + cg * 8;
-    const uint4 yv = *reinterpret_cast<const uint4*>(y + off);
-    const bf16* yb = reinterpret_cast<const bf16*>(&yv);
-    float f[8];
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + cg * 8), s1 = *reinterpret_cast<const float4*>(scale + cg * 8 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + cg * 8), h1 = *reinterpret_cast<const float4*>(shift + cg * 8 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-    for (int j = 0; j < 8; j++) f[j] = __bfloat162float(yb[j]) * sc[j] + sh[j];
-    if (residual) {
-        const uint4 rv = *reinterpret_cast<const uint4*>(residual + off);
-        const bf16* rb = reinterpret_cast<const bf16*>(&rv);
-#pragma unroll
-        for (int j = 0; j < 8; j++) f[j] += __bfloat162float(rb[j]);
-    }
-    uint4 o;
-    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-    for (int j = 0; j < 4; j++) ob[j] = __floats2bfloat162_rn(fmaxf(f[2 * j], 0.f), fmaxf(f[2 * j + 1], 0.f));
-    *reinterpret_cast<uint4*>(out + off) = o;
-}
-
-struct BnBwdPtrs {
+struct BnBwd {
+    const bf16* d_in; const bf16* skip; const bf16* out; const bf16* y;
+    bf16* gm;                            // (d_in [+ skip]) * [out > 0]: the gradient arriving at the BatchNorm output (kept: it is the skip-path gradient below)
+    bf16* dy;                            // gradient of the convolution output
     const float* gamma; const float* mean; const float* invstd;
     float* g_gamma; float* g_beta;       // gradient slots of the flat gradient buffer
-    float* ca; float* cb; float* cc;     // dy = ca * (g - cb - (y - mean) * invstd * cc)
-    float* part;                         // [boards][2][256]
-    unsigned int* counter;
+    float* part;
+    GridBar* bar;
+    int n;
 };
 
-// g = (d_in [+ skip]) * [out > 0]  -> gm (bf16);  per-channel sums of g and g * xhat;  the last block turns them into d_gamma, d_beta and
-// the coefficients of k_bn_bwd_apply
-__global__ void __launch_bounds__(256) k_bn_bwd_reduce(const bf16* d_in, const bf16* skip, const bf16* out, const bf16* y, bf16* gm, int n, BnBwdPtrs p) {
-    const int b = blockIdx.x, c = threadIdx.x;
-    const float mean = p.mean[c], invstd = p.invstd[c];
-    float s1 = 0.f, s2 = 0.f;
-    const size_t base = (size_t)b * TPIX * TC + c;
+// ReLU + residual-join + BatchNorm backward in ONE launch: g = (d_in [+ skip]) * [out > 0]; per-channel sums of g and g * xhat; grid
+// barrier; dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); d_gamma, d_beta by the first board group.
+__global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
+    __shared__ float red[2][64][33];
+    __shared__ float ca_sh[32], cb_sh[32], cc_sh[32];
+    __shared__ unsigned int gen_sh;
+    const int slice = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
+    const int t = threadIdx.x, cq = t & 3, pos = t >> 2;
+    const int b_lo = (int)((long long)grp * p.n / G), b_hi = (int)((long long)(grp + 1) * p.n / G);
+    if (t == 0) gen_sh = ld_acquire_u32(&p.bar->gen);
+    const int c0 = slice * 32 + cq * 8;
+    const size_t coff = (size_t)halo_pix(pos) * TC + c0;
+    float mean[8], invstd[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { mean[j] = p.mean[c0 + j]; invstd[j] = p.invstd[c0 + j]; s1[j] = s2[j] = 0.f; }
+#pragma unroll 2
+    for (int b = b_lo; b < b_hi; b++) {
+        const size_t off = (size_t)b * TPIX * TC + coff;
+        const uint4 dv = *reinterpret_cast<const uint4*>(p.d_in + off), ov = *reinterpret_cast<const uint4*>(p.out + off),
+                    yv = *reinterpret_cast<const uint4*>(p.y + off);
+        const bf16* db = reinterpret_cast<const bf16*>(&dv);
+        const bf16* obf = reinterpret_cast<const bf16*>(&ov);
+        const bf16* yb = reinterpret_cast<const bf16*>(&yv);
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) g[j] = __bfloat162float(db[j]);
+        if (p.skip) {
+            const uint4 sv = *reinterpret_cast<const uint4*>(p.skip + off);
+            const bf16* sb = reinterpret_cast<const bf16*>(&sv);
+#pragma unroll
+            for (int j = 0; j < 8; j++) g[j] += __bfloat162float(sb[j]);
+        }
+        uint4 o;
+        bf16* gb = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!(__bfloat162float(obf[j]) > 0.f)) g[j] = 0.f;
+            gb[j] = __float2bfloat16(g[j]);
+            const float gr = __bfloat162float(gb[j]);
+            s1[j] += gr;
+            s2[j] += gr * ((__bfloat162float(yb[j]) - mean[j]) * invstd[j]);
+        }
+        *reinterpret_cast<uint4*>(p.gm + off) = o;
+    }
+    bn_block_sums(red, s1, s2, p.part, grp, slice);
+    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y);
+    if (t < 32) {
+        const int c = slice * 32 + t;
+        double S1 = 0, S2 = 0;
+        for (int g = 0; g < G; g++) { S1 += (double)__ldcg(&p.part[(g * 2) * 256 + c]); S2 += (double)__ldcg(&p.part[(g * 2 + 1) * 256 + c]); }
+        const double cnt = (double)p.n * 64.0;
+        ca_sh[t] = p.gamma[c] * p.invstd[c];
+        cb_sh[t] = (float)(S1 / cnt);
+        cc_sh[t] = (float)(S2 / cnt);
+        if (grp == 0) { p.g_beta[c] = (float)S1; p.g_gamma[c] = (float)S2; }
+    }
+    __syncthreads();
+    float ca[8], cb[8], cc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ca[j] = ca_sh[cq * 8 + j]; cb[j] = cb_sh[cq * 8 + j]; cc[j] = cc_sh[cq * 8 + j]; }
 #pragma unroll 4
-    for (int sq = 0; sq < 64; sq++) {
-        const size_t o = base + (size_t)halo_pix(sq) * TC;
-        float g = __bfloat162float(d_in[o]);
-        if (skip) g += __bfloat162float(skip[o]);
-        if (!(__bfloat162float(out[o]) > 0.f)) g = 0.f;
-        const bf16 gb = __float2bfloat16(g);
-        gm[o] = gb;
-        g = __bfloat162float(gb);
-        s1 += g;
-        s2 += g * ((__bfloat162float(y[o]) - mean) * invstd);
-    }
-    p.part[(size_t)b * 512 + c] = s1;
-    p.part[(size_t)b * 512 + 256 + c] = s2;
-    __threadfence();
-    __shared__ bool last;
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    double S1 = 0, S2 = 0;
-    for (int i = 0; i < n; i++) { S1 += (double)__ldcg(&p.part[(size_t)i * 512 + c]); S2 += (double)__ldcg(&p.part[(size_t)i * 512 + 256 + c]); }
-    const double cnt = (double)n * 64.0;
-    p.g_beta[c] = (float)S1;
-    p.g_gamma[c] = (float)S2;
-    p.ca[c] = p.gamma[c] * invstd;
-    p.cb[c] = (float)(S1 / cnt);
-    p.cc[c] = (float)(S2 / cnt);
-    if (threadIdx.x == 0) *p.counter = 0;
-}
-
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const bf16* gm, const bf16* y, const float* mean, const float* invstd, const float* ca, const float* cb,
-                                                      const float* cc, bf16* dy, int n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n * 64 * 32) return;
-    const int cg = (int)(i & 31), sq = (int)((i >> 5) & 63);
-    const size_t b = i >> 11;
-    const size_t off = (b * TPIX + halo_pix(sq)) * TC + cg * 8;
-    const uint4 gv = *reinterpret_cast<const uint4*>(gm + off), yv = *reinterpret_cast<const uint4*>(y + off);
-    const bf16* gb = reinterpret_cast<const bf16*>(&gv);
-    const bf16* yb = reinterpret_cast<const bf16*>(&yv);
-    uint4 o;
-    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
-    float f[8];
+    for (int b = b_lo; b < b_hi; b++) {
+        const size_t off = (size_t)b * TPIX * TC + coff;
+        const uint4 gv = *reinterpret_cast<const uint4*>(p.gm + off), yv = *reinterpret_cast<const uint4*>(p.y + off);   // gm: this thread's own stores
+        const bf16* gb = reinterpret_cast<const bf16*>(&gv);
+        const bf16* yb = reinterpret_cast<const bf16*>(&yv);
+        float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int c = cg * 8 + j;
-        const float xhat = (__bfloat162float(yb[j]) - mean[c]) * invstd[c];
-        f[j] = ca[c] * (__bfloat162float(gb[j]) - cb[c] - xhat * cc[c]);
-    }
+        for (int j = 0; j < 8; j++) f[j] = ca[j] * (__bfloat162float(gb[j]) - cb[j] - (__bfloat162float(yb[j]) - mean[j]) * invstd[j] * cc[j]);
+        uint4 o;
+        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-    for (int j = 0; j < 4; j++) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-    *reinterpret_cast<uint4*>(dy + off) = o;
+        for (int j = 0; j < 4; j++) ob[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p.dy + off) = o;
+    }
 }
 
 // =================================================================================================
@@ -738,9 +823,19 @@ __global__ void k_loss_reduce(const float* se, const float* ce, int n, float* lo
 // optimiser + weight packs
 // =================================================================================================
 // torch.optim.Adam (weight decay added to the gradient, bias-corrected moments), one thread per parameter of the flat buffer
-__global__ void k_adam(float* w, const float* g, float* m, float* v, size_t n, float step_size, float beta1, float beta2, float eps, float wd, float bc2_sqrt) {
+// advances the optimiser step counter ON THE DEVICE and derives what k_adam needs from it (StepLR learning rate over Adam's first bias
+// correction, square root of the second): a captured step replays without any host-side parameter
+__global__ void k_hyper(long long* step, float lr0, float lr_gamma, int lr_step, float beta1, float beta2, float* hyper) {
+    const long long t = ++*step;
+    const double lr = (double)lr0 * pow((double)lr_gamma, (double)((t - 1) / (lr_step > 0 ? lr_step : 1)));
+    hyper[0] = (float)(lr / (1.0 - pow((double)beta1, (double)t)));
+    hyper[1] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
+}
+
+__global__ void k_adam(float* w, const float* g, float* m, float* v, size_t n, const float* hyper, float beta1, float beta2, float eps, float wd) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const float step_size = hyper[0], bc2_sqrt = hyper[1];
     const float p = w[i];
     const float gg = g[i] + wd * p;
     const float mm = m[i] + (gg - m[i]) * (1.f - beta1);
@@ -757,17 +852,29 @@ struct PackDesc {
     int cout_pad, taps, cin_pad;
 };
 
-__global__ void k_pack(const PackDesc* descs) {
+// 32 x 32 (co, ci) tiles of one tap through shared memory: the master is read once, both packs are written in 64-byte runs
+__global__ void __launch_bounds__(256) k_pack(const PackDesc* descs) {
+    __shared__ float tile[32][33];
     const PackDesc d = descs[blockIdx.y];
-    const size_t n = (size_t)d.cout_pad * d.taps * d.cin_pad;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float x = d.w[i];
-        const bf16 xb = __float2bfloat16(x);
-        d.wf[i] = xb;
-        if (d.wd) {
-            const int ci = (int)(i % d.cin_pad), tap = (int)((i / d.cin_pad) % d.taps), co = (int)(i / ((size_t)d.cin_pad * d.taps));
-            d.wd[((size_t)ci * d.taps + (d.taps - 1 - tap)) * d.cout_pad + co] = xb;
+    const int tiles_ci = d.cin_pad / 32, tiles_co = d.cout_pad / 32;
+    const int n_tiles = d.taps * tiles_co * tiles_ci;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int tci = tl % tiles_ci, tco = (tl / tiles_ci) % tiles_co, tap = tl / (tiles_ci * tiles_co);
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const size_t i = ((size_t)(tco * 32 + r) * d.taps + tap) * d.cin_pad + tci * 32 + tx;
+            const float x = d.w[i];
+            d.wf[i] = __float2bfloat16(x);
+            tile[r][tx] = x;
         }
+        __syncthreads();
+        if (d.wd) {
+#pragma unroll
+            for (int r = ty; r < 32; r += 8)
+                d.wd[((size_t)(tci * 32 + r) * d.taps + (d.taps - 1 - tap)) * d.cout_pad + tco * 32 + tx] = __float2bfloat16(tile[tx][r]);
+        }
+        __syncthreads();
     }
 }
 
@@ -804,7 +911,7 @@ struct TLayer {
     CUtensorMap tm_wf, tm_wd;
     bf16* y = nullptr; bf16* o = nullptr;        // pre-BatchNorm convolution output, layer output
     CUtensorMap tm_o2, tm_o1;                    // layer output as the next layer's operand: 2-board boxes (forward), 1-board boxes (wgrad)
-    float* bn = nullptr;                         // running_mean, running_var, mean, invstd, scale, shift, ca, cb, cc: 9 x 256
+    float* bn = nullptr;                         // running_mean, running_var, mean, invstd: 4 x 256
 };
 
 struct Trainer {
@@ -821,7 +928,7 @@ struct Trainer {
     CUtensorMap tm_dy2, tm_dy1, tm_dl2, tm_dl1;
     float* logits = nullptr;
     float* partial = nullptr; size_t partial_floats = 0;
-    float* bn_part = nullptr; unsigned int* counter = nullptr;
+    float* bn_part = nullptr; GridBar* bar = nullptr;
     // value head
     float *yv = nullptr, *vr = nullptr, *dh1 = nullptr, *h1r = nullptr, *du = nullptr, *gr = nullptr, *dyv = nullptr, *value = nullptr, *se = nullptr, *ce = nullptr;
     float *vpart = nullptr, *db_part = nullptr, *v_running = nullptr;
@@ -833,7 +940,15 @@ struct Trainer {
     // records on the device
     uint64_t* rec_states = nullptr; long long* rec_off = nullptr; uint16_t* rec_index = nullptr; float* rec_prob = nullptr; int8_t* rec_z = nullptr;
     int64_t rec_n = 0;
-    int64_t step = 0;
+    int64_t step = 0;                            // host mirror of *d_step
+    long long* d_step = nullptr; float* hyper = nullptr;
+    int32_t* rows_host = nullptr;                // [ROWS_RING][cap] pinned staging of the steps' row numbers
+    cudaEvent_t rows_ev[8] = {};
+    bool rows_used[8] = {};
+    uint64_t steps_queued = 0;
+    std::map<std::pair<int, int>, cudaGraphExec_t> graphs;     // (boards, flags) -> the captured step
+    bool use_graph = true;
+    std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
     bool loaded = false, attr_set = false;
     std::vector<void*> allocs;
@@ -863,6 +978,17 @@ static int t_act_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, in
     if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(training activations) failed: %d", (int)r);
     return 0;
 }
+// halo activations seen as (c, x, board, y): box = 64 channels x 10 x 2 boards x 10 -> shared-memory rows [y][board][x] (k_tconv's chunk)
+static int t_halo_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, int cap) {
+    cuuint64_t dims[4] = {(cuuint64_t)channels, TH, (cuuint64_t)cap, TH};
+    cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * TPIX, (cuuint64_t)channels * 2 * TH};
+    cuuint32_t box[4] = {64, TH, 2, TH};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = t_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(training halo activations) failed: %d", (int)r);
+    return 0;
+}
 // weight pack [rows][k]: box = 64 k x 128 rows
 static int t_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int rows) {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
@@ -888,6 +1014,9 @@ void trainer_destroy(szb_ctx* ctx) {
     if (!tr) return;
     cudaStreamSynchronize(ctx->stream);
     for (void* p : tr->allocs) cudaFree(p);
+    for (auto& kv : tr->graphs) cudaGraphExecDestroy(kv.second);
+    if (tr->rows_host) cudaFreeHost(tr->rows_host);
+    for (int i = 0; i < ROWS_RING; i++) if (tr->rows_ev[i]) cudaEventDestroy(tr->rows_ev[i]);
     void* rec[5] = {tr->rec_states, tr->rec_off, tr->rec_index, tr->rec_prob, tr->rec_z};
     for (void* p : rec) if (p) cudaFree(p);
     delete tr;
@@ -961,7 +1090,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         (rc = t_alloc(ctx, tr, &tr->v, tr->total)))
         return rc;
     if ((rc = t_alloc(ctx, tr, &tr->x_in, (size_t)cap * TPIX * TCIN))) return rc;
-    if ((rc = t_act_map(ctx, &tr->tm_in2, tr->x_in, TCIN, cap, 2)) || (rc = t_act_map(ctx, &tr->tm_in1, tr->x_in, TCIN, cap, 1))) return rc;
+    if ((rc = t_halo_map(ctx, &tr->tm_in2, tr->x_in, TCIN, cap)) || (rc = t_act_map(ctx, &tr->tm_in1, tr->x_in, TCIN, cap, 1))) return rc;
     for (int l = 0; l < T_LAYERS; l++) {
         TLayer& L = tr->L[l];
         L.taps = (l == L_P1 || l == L_P2) ? 1 : 9;
@@ -978,8 +1107,8 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         if (l < T_BN) {
             L.gamma = tr->index.at(t_layer_bn_name(l) + ".weight");
             L.beta = tr->index.at(t_layer_bn_name(l) + ".bias");
-            if ((rc = t_alloc(ctx, tr, &L.y, act)) || (rc = t_alloc(ctx, tr, &L.o, act)) || (rc = t_alloc(ctx, tr, &L.bn, 9 * 256))) return rc;
-            if ((rc = t_act_map(ctx, &L.tm_o2, L.o, TC, cap, 2)) || (rc = t_act_map(ctx, &L.tm_o1, L.o, TC, cap, 1))) return rc;
+            if ((rc = t_alloc(ctx, tr, &L.y, act)) || (rc = t_alloc(ctx, tr, &L.o, act)) || (rc = t_alloc(ctx, tr, &L.bn, 4 * 256))) return rc;
+            if ((rc = t_halo_map(ctx, &L.tm_o2, L.o, TC, cap)) || (rc = t_act_map(ctx, &L.tm_o1, L.o, TC, cap, 1))) return rc;
             tr->buffers.push_back({t_layer_bn_name(l) + ".running_mean", 256, L.bn});
             tr->buffers.push_back({t_layer_bn_name(l) + ".running_var", 256, L.bn + 256});
         }
@@ -988,13 +1117,13 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         (rc = t_alloc(ctx, tr, &tr->gm1, act)) || (rc = t_alloc(ctx, tr, &tr->skip[0], act)) || (rc = t_alloc(ctx, tr, &tr->skip[1], act)) ||
         (rc = t_alloc(ctx, tr, &tr->dl, (size_t)cap * TPIX * DL_C)))
         return rc;
-    if ((rc = t_act_map(ctx, &tr->tm_dy2, tr->dy, TC, cap, 2)) || (rc = t_act_map(ctx, &tr->tm_dy1, tr->dy, TC, cap, 1)) ||
-        (rc = t_act_map(ctx, &tr->tm_dl2, tr->dl, DL_C, cap, 2)) || (rc = t_act_map(ctx, &tr->tm_dl1, tr->dl, DL_C, cap, 1)))
+    if ((rc = t_halo_map(ctx, &tr->tm_dy2, tr->dy, TC, cap)) || (rc = t_act_map(ctx, &tr->tm_dy1, tr->dy, TC, cap, 1)) ||
+        (rc = t_halo_map(ctx, &tr->tm_dl2, tr->dl, DL_C, cap)) || (rc = t_act_map(ctx, &tr->tm_dl1, tr->dl, DL_C, cap, 1)))
         return rc;
     tr->partial_floats = (size_t)WG_MAX_SPLIT * 256 * 256;                      // 1x1 layers: up to 64 splits of 256 x 256
     if (tr->partial_floats < (size_t)8 * 256 * 2304) tr->partial_floats = (size_t)8 * 256 * 2304;
     if ((rc = t_alloc(ctx, tr, &tr->partial, tr->partial_floats)) || (rc = t_alloc(ctx, tr, &tr->logits, (size_t)cap * T_ACTIONS)) ||
-        (rc = t_alloc(ctx, tr, &tr->bn_part, (size_t)cap * 512)) || (rc = t_alloc(ctx, tr, &tr->counter, 1)) ||
+        (rc = t_alloc(ctx, tr, &tr->bn_part, (size_t)BN_GROUPS * 512)) || (rc = t_alloc(ctx, tr, &tr->bar, 1)) ||
         (rc = t_alloc(ctx, tr, &tr->yv, (size_t)cap * 64)) || (rc = t_alloc(ctx, tr, &tr->vr, (size_t)cap * 64)) ||
         (rc = t_alloc(ctx, tr, &tr->dh1, (size_t)cap * 256)) || (rc = t_alloc(ctx, tr, &tr->h1r, (size_t)cap * 256)) ||
         (rc = t_alloc(ctx, tr, &tr->du, (size_t)cap)) || (rc = t_alloc(ctx, tr, &tr->gr, (size_t)cap * 64)) ||
@@ -1003,8 +1132,15 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         (rc = t_alloc(ctx, tr, &tr->vpart, (size_t)cap * 256)) || (rc = t_alloc(ctx, tr, &tr->db_part, (size_t)cap * DL_C)) ||
         (rc = t_alloc(ctx, tr, &tr->v_running, 4)) || (rc = t_alloc(ctx, tr, &tr->vstat, 1)) || (rc = t_alloc(ctx, tr, &tr->losses, 2)) ||
         (rc = t_alloc(ctx, tr, &tr->error, 1)) || (rc = t_alloc(ctx, tr, &tr->rows, (size_t)cap)) ||
-        (rc = t_alloc(ctx, tr, &tr->pack_descs, (size_t)T_LAYERS)))
+        (rc = t_alloc(ctx, tr, &tr->pack_descs, (size_t)T_LAYERS)) || (rc = t_alloc(ctx, tr, &tr->d_step, 1)) || (rc = t_alloc(ctx, tr, &tr->hyper, 2)))
         return rc;
+    SZB_CUDA(ctx, cudaMallocHost((void**)&tr->rows_host, (size_t)ROWS_RING * cap * 4));
+    for (int i = 0; i < ROWS_RING; i++) SZB_CUDA(ctx, cudaEventCreateWithFlags(&tr->rows_ev[i], cudaEventDisableTiming));
+    {
+        const long long s0 = cfg->step0;
+        SZB_CUDA(ctx, cudaMemcpyAsync(tr->d_step, &s0, 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     tr->buffers.push_back({"v_norm.running_mean", 1, tr->v_running});
     tr->buffers.push_back({"v_norm.running_var", 1, tr->v_running + 1});
     std::vector<PackDesc> pd(T_LAYERS);
@@ -1025,7 +1161,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
 }
 
 static int t_pack(szb_ctx* ctx, Trainer* tr) {
-    k_pack<<<dim3(64, T_LAYERS), 256, 0, ctx->stream>>>(tr->pack_descs);
+    k_pack<<<dim3(144, T_LAYERS), 256, 0, ctx->stream>>>(tr->pack_descs);
     ctx->launches++;
     SZB_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -1143,17 +1279,11 @@ static int t_wgrad(szb_ctx* ctx, Trainer* tr, int l, const CUtensorMap& tm_a, co
 
 static float* t_slot(Trainer* tr, float* base, const std::string& name) { return base + tr->params[tr->index.at(name)].off; }
 
-static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, float* losses_out) {
-    Trainer* tr = ctx->trainer;
-    if (!tr || !tr->loaded) return fail(ctx, SZB_ERR_STATE, "trainer has no weights: szb_train_create + szb_train_set(kind 0) first");
-    if (!tr->rec_states) return fail(ctx, SZB_ERR_STATE, "no records: szb_train_records first");
-    if (n < 2 || n > tr->cfg.batch || !rows) return fail(ctx, SZB_ERR_ARG, "szb_train_step: 2 <= n <= %d boards (BatchNorm needs more than one)", tr->cfg.batch);
+// every launch of one step on the context's stream (no synchronisation: this is what a CUDA graph captures)
+static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
     cudaStream_t st = ctx->stream;
     int rc;
-    tr->last_n = n;
-    SZB_CUDA(ctx, cudaMemcpyAsync(tr->rows, rows, (size_t)n * 4, cudaMemcpyDefault, st));
     // an odd batch leaves a phantom board in the last 2-board tile: GEMM rows are independent, its rows are computed and never stored
-    const unsigned ew_blocks = (unsigned)(((size_t)n * 64 * 32 + 255) / 256);
     k_gather_input<<<(unsigned)(((size_t)n * 64 * 16 + 255) / 256), 256, 0, st>>>(tr->rec_states, (long long)tr->rec_n, tr->rows, n, tr->x_in, tr->error);
     ctx->launches++;
     // ---------------- forward ----------------
@@ -1161,12 +1291,11 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
         TLayer& L = tr->L[l];
         const CUtensorMap& tm_a = l == 0 ? tr->tm_in2 : l == L_P1 ? tr->L[38].tm_o2 : tr->L[l - 1].tm_o2;
         if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr))) return rc;
-        BnPtrs bp{tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768, L.bn + 1024, L.bn + 1280,
-                  tr->bn_part, tr->counter, tr->cfg.bn_momentum, tr->cfg.bn_eps};
-        k_bn_stats<<<n, 256, 0, st>>>(L.y, n, bp);
         const bf16* res = (l >= 2 && l <= 38 && ((l - 1) & 1)) ? tr->L[l - 2].o : nullptr;
-        k_bn_apply<<<ew_blocks, 256, 0, st>>>(L.y, L.bn + 1024, L.bn + 1280, res, L.o, n);
-        ctx->launches += 2;
+        BnFwd bp{L.y, res, L.o, tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768,
+                 tr->bn_part, tr->bar, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
+        k_bn_fwd<<<dim3(BN_SLICES, BN_GROUPS), 256, 0, st>>>(bp);
+        ctx->launches++;
     }
     if ((rc = t_conv(ctx, tr, tr->L[L_P1].tm_o2, tr->L[L_P2].tm_wf, 1, 4, 128, n, nullptr, 1, t_slot(tr, tr->w, "conv_p2.bias")))) return rc;
     const bf16* T = tr->L[38].o;
@@ -1202,11 +1331,10 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
             const bool join = l == 0 || (l <= 38 && ((l - 1) & 1));          // layers whose output feeds a residual add as well (or two heads)
             const bf16* skip_in = join ? tr->skip[sk] : nullptr;
             bf16* gm = join ? tr->skip[sk ^ 1] : tr->gm1;
-            BnBwdPtrs bp{tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768, tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off,
-                         L.bn + 1536, L.bn + 1792, L.bn + 2048, tr->bn_part, tr->counter};
-            k_bn_bwd_reduce<<<n, 256, 0, st>>>(tr->gbuf[cur], skip_in, L.o, L.y, gm, n, bp);
-            k_bn_bwd_apply<<<ew_blocks, 256, 0, st>>>(gm, L.y, L.bn + 512, L.bn + 768, L.bn + 1536, L.bn + 1792, L.bn + 2048, tr->dy, n);
-            ctx->launches += 2;
+            BnBwd bp{tr->gbuf[cur], skip_in, L.o, L.y, gm, tr->dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768,
+                     tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off, tr->bn_part, tr->bar, n};
+            k_bn_bwd<<<dim3(BN_SLICES, BN_GROUPS), 256, 0, st>>>(bp);
+            ctx->launches++;
             if (join) sk ^= 1;
             const CUtensorMap& tm_x = l == 0 ? tr->tm_in1 : l == L_P1 ? tr->L[38].tm_o1 : tr->L[l - 1].tm_o1;
             if ((rc = t_wgrad(ctx, tr, l, tr->tm_dy1, tm_x, n))) return rc;
@@ -1216,17 +1344,61 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
             }
         }
         if (!(flags & SZB_TRAIN_NO_UPDATE)) {
-            tr->step++;
             const szb_train_config& c = tr->cfg;
-            const double lr = (double)c.lr * pow((double)c.lr_gamma, (double)((tr->step - 1) / (c.lr_step > 0 ? c.lr_step : 1)));
-            const double bc1 = 1.0 - pow((double)c.beta1, (double)tr->step), bc2 = 1.0 - pow((double)c.beta2, (double)tr->step);
-            k_adam<<<(unsigned)((tr->total + 255) / 256), 256, 0, st>>>(tr->w, tr->g, tr->m, tr->v, tr->total, (float)(lr / bc1), c.beta1, c.beta2, c.eps,
-                                                                       c.weight_decay, (float)sqrt(bc2));
-            ctx->launches++;
+            k_hyper<<<1, 1, 0, st>>>(tr->d_step, c.lr, c.lr_gamma, c.lr_step, c.beta1, c.beta2, tr->hyper);
+            k_adam<<<(unsigned)((tr->total + 255) / 256), 256, 0, st>>>(tr->w, tr->g, tr->m, tr->v, tr->total, tr->hyper, c.beta1, c.beta2, c.eps, c.weight_decay);
+            ctx->launches += 2;
             if ((rc = t_pack(ctx, tr))) return rc;
         }
     }
     SZB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, float* losses_out) {
+    Trainer* tr = ctx->trainer;
+    if (!tr || !tr->loaded) return fail(ctx, SZB_ERR_STATE, "trainer has no weights: szb_train_create + szb_train_set(kind 0) first");
+    if (!tr->rec_states) return fail(ctx, SZB_ERR_STATE, "no records: szb_train_records first");
+    if (n < 2 || n > tr->cfg.batch || !rows) return fail(ctx, SZB_ERR_ARG, "szb_train_step: 2 <= n <= %d boards (BatchNorm needs more than one)", tr->cfg.batch);
+    cudaStream_t st = ctx->stream;
+    int rc;
+    // row numbers: through a ring of pinned staging slots, so that the host can queue several steps ahead of the GPU
+    {
+        const int slot = (int)(tr->steps_queued++ % ROWS_RING);
+        int32_t* stage = tr->rows_host + (size_t)slot * tr->cap;
+        if (tr->rows_used[slot]) SZB_CUDA(ctx, cudaEventSynchronize(tr->rows_ev[slot]));
+        SZB_CUDA(ctx, cudaMemcpy(stage, rows, (size_t)n * 4, cudaMemcpyDefault));
+        SZB_CUDA(ctx, cudaMemcpyAsync(tr->rows, stage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        SZB_CUDA(ctx, cudaEventRecord(tr->rows_ev[slot], st));
+        tr->rows_used[slot] = true;
+    }
+    tr->last_n = n;
+    const uint64_t launches0 = ctx->launches;
+    bool done = false;
+    if (tr->use_graph) {
+        // one graph per (boards, flags): ~210 launches become one submission
+        const std::pair<int, int> key(n, flags);
+        auto it = tr->graphs.find(key);
+        if (it == tr->graphs.end()) {
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                rc = t_step_launches(ctx, tr, n, flags);
+                cudaError_t e = cudaStreamEndCapture(st, &graph);
+                if (!rc && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) it = tr->graphs.emplace(key, exec).first;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            if (it == tr->graphs.end()) { cudaGetLastError(); tr->use_graph = false; }       // capture unavailable: plain launches from here on
+            tr->launches_per_step[key] = ctx->launches - launches0;
+        }
+        if (it != tr->graphs.end()) {
+            SZB_CUDA(ctx, cudaGraphLaunch(it->second, st));
+            ctx->launches = launches0 + tr->launches_per_step[key];
+            done = true;
+        }
+    }
+    if (!done && (rc = t_step_launches(ctx, tr, n, flags))) return rc;
+    if (!(flags & (SZB_TRAIN_NO_UPDATE | SZB_TRAIN_FORWARD_ONLY))) tr->step++;
     if (losses_out) {
         int32_t err = 0;
         SZB_CUDA(ctx, cudaMemcpyAsync(losses_out, tr->losses, 8, cudaMemcpyDefault, st));
@@ -1315,7 +1487,15 @@ int szb_train_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, 
 int szb_train_state(szb_ctx* ctx, int64_t* step_inout, int32_t set) {
     if (!ctx || !step_inout) return SZB_ERR_ARG;
     if (!ctx->trainer) return fail(ctx, SZB_ERR_STATE, "no trainer");
-    if (set) ctx->trainer->step = *step_inout; else *step_inout = ctx->trainer->step;
+    if (set) {
+        cudaSetDevice(ctx->device);
+        ctx->trainer->step = *step_inout;
+        const long long v = *step_inout;
+        SZB_CUDA(ctx, cudaMemcpyAsync(ctx->trainer->d_step, &v, 8, cudaMemcpyHostToDevice, ctx->stream));
+        SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        *step_inout = ctx->trainer->step;
+    }
     return 0;
 }
 

@@ -122,41 +122,99 @@ def make_optimiser(model, lr=1e-4, weight_decay=1e-4):
     return opt, torch.optim.lr_scheduler.StepLR(opt, step_size=500, gamma=0.95)
 
 
-def train_on_records(model, rec, epochs=1, batch_size=64, optimiser=None, lr_scheduler=None, device=None, seed=0, log=None):
+def _batches(n, batch_size, epochs, seed):
+    """the row numbers of every batch: a fresh permutation per epoch, short last batch dropped (DataLoader(drop_last=True),
+    train_RL.py:241-246) unless the whole record set is smaller than one batch; BatchNorm needs more than one sample"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    for epoch in range(epochs):
+        order = rng.permutation(n)
+        for lo in range(0, n, batch_size):
+            rows = order[lo:lo + batch_size]
+            if (len(rows) < batch_size and n >= batch_size) or len(rows) < 2:
+                continue
+            yield rows
+
+
+def train_on_records_cuda(model, rec, epochs=1, batch_size=64, optimiser=None, lr_scheduler=None, seed=0, log=None, engine=None):
+    """train_on_records on the GPU library's trainer (szb_train_*, csrc/train.cu): same batches, same recipe, no torch op in the step.
+    `optimiser` / `lr_scheduler` (torch objects, optional) carry the state between calls and into checkpoints: their moments, step
+    counter and hyper-parameters are loaded into the trainer first and written back after the last batch."""
+    from . import runtime
+    from .trainer import Trainer
+    eng = engine if engine is not None else runtime.get_engine()
+    hp, step0 = {}, 0
+    if optimiser is not None:
+        g = optimiser.param_groups[0]
+        hp = dict(lr=float(g.get("initial_lr", g["lr"])), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]), eps=float(g["eps"]),
+                  weight_decay=float(g["weight_decay"]))
+    if lr_scheduler is not None:
+        hp.update(lr_step=int(lr_scheduler.step_size), lr_gamma=float(lr_scheduler.gamma))
+        step0 = int(lr_scheduler.last_epoch)
+    else:
+        hp.update(lr_step=1 << 30, lr_gamma=1.0)
+    tr = Trainer(eng, model, batch_size=batch_size, step0=step0, **hp)
+    try:
+        if optimiser is not None and optimiser.state_dict()["state"]:
+            tr.load_optimiser_state(optimiser.state_dict())
+            if lr_scheduler is not None:
+                tr.step_count = step0                        # StepLR's counter is the one the learning rate follows
+        tr.set_records(rec)
+        history = []
+        for rows in _batches(len(rec["z"]), batch_size, epochs, seed):
+            history.append(tr.step(rows))
+            if log is not None:
+                log({"MSE Loss": history[-1][0], "CE Loss": history[-1][1]}, len(history))
+        flat = tr.write_back(model, steps_taken=len(history))
+        if optimiser is not None:
+            optimiser.load_state_dict(tr.optimiser_state(model))
+        if lr_scheduler is not None:
+            lr_scheduler.last_epoch += len(history)
+            lr_scheduler._last_lr = [g["lr"] for g in optimiser.param_groups] if optimiser is not None else lr_scheduler._last_lr
+        # the inference network of the same context gets the new weights straight from the trainer's device buffer
+        eng.load_flat_device(tr.keys, tr.numels, flat)
+        runtime.mark_synced(eng, model)
+    finally:
+        tr.close()
+    model.eval()
+    return history
+
+
+def train_on_records(model, rec, epochs=1, batch_size=64, optimiser=None, lr_scheduler=None, device=None, seed=0, log=None, backend=None):
     """Fine-tunes `model` on packed self-play records (records.pack_records): per batch
     loss = mse_loss(v, z) + cross_entropy(logits, pi) with pi the soft visit-fraction target (train_RL.py:103-113).
-    Returns the per-batch (mse, ce) losses.  The model is left in eval() mode, ready for the next self-play iteration."""
+    Returns the per-batch (mse, ce) losses.  The model is left in eval() mode, ready for the next self-play iteration.
+
+    backend "cuda" (the default whenever the training device is a GPU): the library's own trainer, train_on_records_cuda.
+    backend "torch": torch autograd, the reference's own code path -- what the CUDA trainer is tested against, and what runs when
+    device="cpu" is asked for explicitly."""
     import numpy as np
     from . import records
     if optimiser is None:
         optimiser, lr_scheduler = make_optimiser(model)
     device = torch.device(device) if device is not None else next(model.parameters()).device
+    if backend is None:
+        backend = "cuda" if device.type == "cuda" else "torch"
+    if backend == "cuda":
+        model.to(device)                                     # the module ends up where the caller asked for it, as with the torch path
+        return train_on_records_cuda(model, rec, epochs=epochs, batch_size=batch_size, optimiser=optimiser, lr_scheduler=lr_scheduler, seed=seed, log=log)
     model.to(device).train()
-    n = len(rec["z"])
-    rng = np.random.default_rng(seed)
     history = []
-    for epoch in range(epochs):
-        order = rng.permutation(n)
-        for lo in range(0, n, batch_size):
-            rows = order[lo:lo + batch_size]
-            if len(rows) < batch_size and n >= batch_size:
-                continue                                     # DataLoader(drop_last=True), train_RL.py:241-246
-            if len(rows) < 2:
-                continue                                     # BatchNorm needs more than one sample in training mode
-            x = torch.from_numpy(records.unpack_states(rec, rows)).to(device=device, dtype=torch.float32)
-            pi = torch.from_numpy(records.dense_policy(rec, rows)).to(device)
-            z = torch.from_numpy(rec["z"][rows].astype(np.float32)).to(device)
-            p, v = model(x)
-            mse = torch.nn.functional.mse_loss(v.squeeze(-1), z)
-            ce = torch.nn.functional.cross_entropy(p, pi)
-            optimiser.zero_grad()
-            (mse + ce).backward()
-            optimiser.step()
-            if lr_scheduler is not None:
-                lr_scheduler.step()
-            history.append((float(mse.detach()), float(ce.detach())))
-            if log is not None:
-                log({"MSE Loss": history[-1][0], "CE Loss": history[-1][1]}, len(history))
+    for rows in _batches(len(rec["z"]), batch_size, epochs, seed):
+        x = torch.from_numpy(records.unpack_states(rec, rows)).to(device=device, dtype=torch.float32)
+        pi = torch.from_numpy(records.dense_policy(rec, rows)).to(device)
+        z = torch.from_numpy(rec["z"][rows].astype(np.float32)).to(device)
+        p, v = model(x)
+        mse = torch.nn.functional.mse_loss(v.squeeze(-1), z)
+        ce = torch.nn.functional.cross_entropy(p, pi)
+        optimiser.zero_grad()
+        (mse + ce).backward()
+        optimiser.step()
+        if lr_scheduler is not None:
+            lr_scheduler.step()
+        history.append((float(mse.detach()), float(ce.detach())))
+        if log is not None:
+            log({"MSE Loss": history[-1][0], "CE Loss": history[-1][1]}, len(history))
     model.eval()
     return history
 

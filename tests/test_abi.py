@@ -23,6 +23,7 @@ def test_struct_layouts():
     assert ctypes.sizeof(_lib.Config) == 20
     assert ctypes.sizeof(_lib.Stats) == 48
     assert ctypes.sizeof(_lib.TowerSpans) == 56 and ctypes.sizeof(_lib.PhaseTimes) == 80
+    assert ctypes.sizeof(_lib.TrainConfig) == 56 and _lib.TrainConfig.step0.offset == 40
 
 
 def test_no_device_fails_loudly():
