@@ -118,6 +118,8 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
+    pdl_trigger();                                  // programmatic dependent launch: everything above overlapped the predecessor's tail
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -254,6 +256,8 @@ k_wgrad(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUten
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -320,6 +324,8 @@ k_wgrad(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUten
 
 // grad[i] = sum_s partial[s][i], s ascending (deterministic)
 __global__ void k_reduce_partials(const float* partial, size_t stride, int ksplit, float* grad, size_t n) {
+    pdl_trigger();
+    pdl_wait();
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
     float4 acc = *reinterpret_cast<const float4*>(partial + i);
@@ -416,6 +422,8 @@ struct BnFwd {
 // Training-mode BatchNorm + ReLU (+ residual) in ONE launch: batch statistics of the block's 32 channels over its boards, grid barrier,
 // every block folds the 18 partials of its channels (fixed order) into scale / shift, then normalises the same boards.
 __global__ void __launch_bounds__(256) k_bn_fwd(BnFwd p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[2][64][33];
     __shared__ float sc_sh[32], sh_sh[32];
     __shared__ unsigned int gen_sh;
@@ -494,6 +502,8 @@ struct BnBwd {
 // ReLU + residual-join + BatchNorm backward in ONE launch: g = (d_in [+ skip]) * [out > 0]; per-channel sums of g and g * xhat; grid
 // barrier; dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); d_gamma, d_beta by the first board group.
 __global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[2][64][33];
     __shared__ float ca_sh[32], cb_sh[32], cc_sh[32];
     __shared__ unsigned int gen_sh;
@@ -948,6 +958,7 @@ struct Trainer {
     uint64_t steps_queued = 0;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;     // (boards, flags) -> the captured step
     bool use_graph = true;
+    bool pdl = true;                             // programmatic dependent launch along the convolution / BatchNorm chain (SZB_TRAIN_NO_PDL=1: off)
     std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
     bool loaded = false, attr_set = false;
@@ -1141,6 +1152,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         SZB_CUDA(ctx, cudaMemcpyAsync(tr->d_step, &s0, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
+    if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
     tr->buffers.push_back({"v_norm.running_mean", 1, tr->v_running});
     tr->buffers.push_back({"v_norm.running_var", 1, tr->v_running + 1});
     std::vector<PackDesc> pd(T_LAYERS);
@@ -1241,8 +1253,8 @@ static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUte
     TConvArgs a{};
     a.taps = taps; a.kchunks = kchunks; a.n_boards = n; a.out = out; a.ldc = TC; a.logits = tr->logits; a.bias = bias; a.error = tr->error;
     const dim3 grid((n + 1) / 2, n_out / 128);
-    if (mode == 0) k_tconv<0><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(tm_a, tm_w, a);
-    else k_tconv<1><<<grid, TR_THREADS, TR_SMEM, ctx->stream>>>(tm_a, tm_w, a);
+    if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv<0>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+    else SZB_CUDA(ctx, launch_kernel(k_tconv<1>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
     ctx->launches++;
     SZB_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -1268,10 +1280,11 @@ static int t_wgrad(szb_ctx* ctx, Trainer* tr, int l, const CUtensorMap& tm_a, co
     a.sbo = tr->cfg.probe_sbo ? (uint32_t)tr->cfg.probe_sbo : 1024;
     if ((size_t)a.ksplit * a.split_stride > tr->partial_floats) return fail(ctx, SZB_ERR_INTERNAL, "wgrad scratch too small");
     const dim3 grid(L.taps * a.m_halves, a.ksplit);
-    if (L.cin_pad == 256) k_wgrad<4><<<grid, TR_THREADS, WG_STAGES * 6 * WG_BOX + 1024, ctx->stream>>>(tm_a, tm_x, a);
-    else k_wgrad<2><<<grid, TR_THREADS, WG_STAGES * 4 * WG_BOX + 1024, ctx->stream>>>(tm_a, tm_x, a);
+    if (L.cin_pad == 256) SZB_CUDA(ctx, launch_kernel(k_wgrad<4>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 6 * WG_BOX + 1024), ctx->stream, tr->pdl, tm_a, tm_x, a));
+    else SZB_CUDA(ctx, launch_kernel(k_wgrad<2>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 4 * WG_BOX + 1024), ctx->stream, tr->pdl, tm_a, tm_x, a));
     const size_t cnt = a.split_stride;
-    k_reduce_partials<<<(unsigned)((cnt / 4 + 255) / 256), 256, 0, ctx->stream>>>(tr->partial, a.split_stride, a.ksplit, tr->g + p.off, cnt);
+    SZB_CUDA(ctx, launch_kernel(k_reduce_partials, dim3((unsigned)((cnt / 4 + 255) / 256)), dim3(256), 0, ctx->stream, tr->pdl, (const float*)tr->partial,
+                                a.split_stride, a.ksplit, tr->g + p.off, cnt));
     ctx->launches += 2;
     SZB_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -1294,7 +1307,7 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
         const bf16* res = (l >= 2 && l <= 38 && ((l - 1) & 1)) ? tr->L[l - 2].o : nullptr;
         BnFwd bp{L.y, res, L.o, tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768,
                  tr->bn_part, tr->bar, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
-        k_bn_fwd<<<dim3(BN_SLICES, BN_GROUPS), 256, 0, st>>>(bp);
+        SZB_CUDA(ctx, launch_kernel(k_bn_fwd, dim3(BN_SLICES, BN_GROUPS), dim3(256), 0, st, tr->pdl, bp));
         ctx->launches++;
     }
     if ((rc = t_conv(ctx, tr, tr->L[L_P1].tm_o2, tr->L[L_P2].tm_wf, 1, 4, 128, n, nullptr, 1, t_slot(tr, tr->w, "conv_p2.bias")))) return rc;
@@ -1333,7 +1346,7 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
             bf16* gm = join ? tr->skip[sk ^ 1] : tr->gm1;
             BnBwd bp{tr->gbuf[cur], skip_in, L.o, L.y, gm, tr->dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768,
                      tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off, tr->bn_part, tr->bar, n};
-            k_bn_bwd<<<dim3(BN_SLICES, BN_GROUPS), 256, 0, st>>>(bp);
+            SZB_CUDA(ctx, launch_kernel(k_bn_bwd, dim3(BN_SLICES, BN_GROUPS), dim3(256), 0, st, tr->pdl, bp));
             ctx->launches++;
             if (join) sk ^= 1;
             const CUtensorMap& tm_x = l == 0 ? tr->tm_in1 : l == L_P1 ? tr->L[38].tm_o1 : tr->L[l - 1].tm_o1;

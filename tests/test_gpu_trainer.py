@@ -251,7 +251,7 @@ def test_train_on_records_product_path(setup):
     opt, sched = make_optimiser(model)
     hist = train_on_records(model, rec, epochs=2, batch_size=16, optimiser=opt, lr_scheduler=sched, device="cuda", seed=1)
     assert len(hist) == 8 and all(np.isfinite(h).all() for h in hist)
-    sd = model.state_dict()
+    sd = {k: v.cpu() for k, v in model.state_dict().items()}       # the module now lives on the training device, as with the torch path
     assert not torch.equal(sd["conv1.weight"], before["conv1.weight"]) and not torch.equal(sd["norm_layer.running_mean"], before["norm_layer.running_mean"])
     assert int(sd["norm_layer.num_batches_tracked"]) == int(before["norm_layer.num_batches_tracked"]) + 8
     st = opt.state_dict()
