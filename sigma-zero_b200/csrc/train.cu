@@ -47,6 +47,7 @@ constexpr int TR_THREADS = 192;              // warp 0 TMA, warp 1 MMA + TMEM, w
 constexpr int TR_A_CHUNKS = 3;
 constexpr int TR_A_CHUNK_BYTES = 2 * TPIX * 128;      // two boards with their halo x 64 channels: 25600 = 25 * 1024
 constexpr int TR_B_STAGES = 6;
+constexpr int TR_CLUSTER = 4;                         // CTAs (neighbouring tiles) that share every weight tile through TMA multicast
 constexpr int TR_B_BYTES = 128 * 64 * 2;              // 128 output channels x 64 k
 constexpr int TR_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TR_B_STAGES * TR_B_BYTES + 1024;
 
@@ -81,15 +82,58 @@ struct TConvArgs {
     float* logits;               // MODE 1: [board][4672] plane-major (torch.flatten of conv_p2's output), + bias
     const float* bias;
     int32_t* error;
+    unsigned long long* trace;   // measurement aid (SZB_TRAIN_TRACE): %globaltimer stamps of CTA (0, 0), or null
 };
+
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+                 : "memory");
+}
+// MMA completion -> one arrival on the barrier at this offset in every CTA of the mask
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t t_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void t_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// tcgen05.mma with the 64-bit shared-memory descriptors given as (lo, hi) halves: hi is a constant of the operand's layout, lo = address
+// field, advanced by plain 32-bit adds -- the single issuing thread's instruction stream is what bounds 64-cycle MMAs
+__device__ __forceinline__ void t_mma_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+constexpr uint32_t DESC_LO_FLAGS = 1u << 16;                                                  // LBO field (unused for swizzled K-major) = 1
+constexpr uint32_t DESC_HI_K1024 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);          // K-major, SBO 1024, version 1, SWIZZLE_128B
+constexpr uint32_t DESC_HI_K1280 = (uint32_t)((TH * 128) >> 4) | (1u << 14) | (2u << 29);    // K-major, 8-row groups one halo row apart
+
+__device__ __forceinline__ void t_stamp(unsigned long long* tr, int k) {
+    if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[k] = t; }
+}
 
 // Shared memory: a ring of TR_A_CHUNKS activation chunks and a ring of TR_B_STAGES weight tiles.  An activation chunk is one 64-channel
 // slice of the tile's two boards INCLUDING the halo, 200 rows of 128 bytes in the order [y][board][x] (one TMA box through a tensor map
 // with dims (c, x, board, y)); all nine taps read it in place: the A descriptor of tap (ky, kx) starts (ky * 20 + kx) rows into the chunk
 // and strides 10 rows between 8-row groups, so MMA row m = (oy * 2 + board) * 8 + ox reads halo square (oy + ky, ox + kx) -- the layout
 // k_tower_tc2 (net.cu) uses.  An activation byte enters the SM once per layer instead of once per tap.
+// Weights: the TR_CLUSTER CTAs of a cluster work on neighbouring tiles with the SAME weights; each loads a quarter of every weight tile and
+// multicasts it into all four shared memories, and a stage is refilled only when all four CTAs' MMAs have released it (their commits arrive
+// on every CTA's barrier).  The kernel is bound by L2 -> SM traffic (measured: 6.8 TB/s with one L2 read per CTA and tile); multicast cuts
+// the weight reads four-fold.
 template <int MODE>
-__global__ void __launch_bounds__(TR_THREADS, 1)
+__global__ void __cluster_dims__(TR_CLUSTER, 1, 1) __launch_bounds__(TR_THREADS, 1)
 k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TConvArgs a) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -102,11 +146,13 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, nh = blockIdx.y;
     volatile int* abort_flag = &abort_sh;
+    unsigned long long* trace = (blockIdx.x == 0 && blockIdx.y == 0) ? a.trace : nullptr;
+    if (threadIdx.x == 0) t_stamp(trace, 0);
 
     if (threadIdx.x == 0) {
         abort_sh = 0;
         for (int s = 0; s < TR_A_CHUNKS; s++) { mbar_init(smem_u32(&bar_af[s]), 1); mbar_init(smem_u32(&bar_ae[s]), 1); }
-        for (int s = 0; s < TR_B_STAGES; s++) { mbar_init(smem_u32(&bar_bf[s]), 1); mbar_init(smem_u32(&bar_be[s]), 1); }
+        for (int s = 0; s < TR_B_STAGES; s++) { mbar_init(smem_u32(&bar_bf[s]), 1); mbar_init(smem_u32(&bar_be[s]), TR_CLUSTER); }
         mbar_init(smem_u32(&bar_acc), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -116,10 +162,15 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
     }
     tc_fence_before();
     __syncthreads();
+    t_cluster_sync();                               // every CTA's barriers exist before a peer's multicast or commit can reach them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
+    const uint32_t crank = t_cluster_rank();
+    constexpr uint16_t CMASK = (uint16_t)((1u << TR_CLUSTER) - 1);
+    if (threadIdx.x == 0) t_stamp(trace, 1);
     pdl_trigger();                                  // programmatic dependent launch: everything above overlapped the predecessor's tail
     pdl_wait();
+    if (threadIdx.x == 0) t_stamp(trace, 2);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -135,42 +186,70 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
                 for (int tap = 0; tap < a.taps; tap++) {
                     if (!(ok = mbar_wait(smem_u32(&bar_be[bs]), b_phase ^ 1, abort_flag))) break;
                     const uint32_t bf = smem_u32(&bar_bf[bs]);
-                    mbar_expect_tx(bf, TR_B_BYTES);
-                    tma_load_2d(smem_b + bs * TR_B_BYTES, &tm_w, bf, (tap * a.kchunks + kc) * 64, nh * 128);
+                    mbar_expect_tx(bf, TR_B_BYTES);                  // four quarters, one from each CTA of the cluster
+                    tma_load_2d_mc(smem_b + bs * TR_B_BYTES + crank * (TR_B_BYTES / TR_CLUSTER), &tm_w, bf, (tap * a.kchunks + kc) * 64,
+                                   nh * 128 + (int)crank * (128 / TR_CLUSTER), CMASK);
                     if (++bs == TR_B_STAGES) { bs = 0; b_phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int ac = 0, bs = 0;
-            uint32_t a_phase = 0, b_phase = 0;
-            bool ok = true;
-            for (int kc = 0; kc < a.kchunks && ok; kc++) {
-                if (!(ok = mbar_wait(smem_u32(&bar_af[ac]), a_phase, abort_flag))) break;
-                tc_fence_after();
-                const uint32_t chunk = smem_a + ac * TR_A_CHUNK_BYTES;
-                for (int tap = 0; tap < a.taps; tap++) {
-                    const int ky = a.taps == 9 ? tap / 3 : 1, kx = a.taps == 9 ? tap - (tap / 3) * 3 : 1;
-                    if (!(ok = mbar_wait(smem_u32(&bar_bf[bs]), b_phase, abort_flag))) break;
-                    tc_fence_after();
-                    const uint32_t sa = chunk + (uint32_t)(ky * 2 * TH + kx) * 128u;
-                    const uint32_t sb = smem_b + bs * TR_B_BYTES;
+        // The whole warp runs the loop convergently (descriptors and barrier addresses stay in uniform registers), one elected lane issues;
+        // the nine taps of a K chunk are straight-line code with immediate descriptor offsets (a generic tap loop costs the issuing
+        // thread ~100 cycles per MMA -- more than the 64 cycles a 128 x 128 x 16 MMA takes).
+        const uint32_t a_lo0 = ((smem_a >> 4) & 0x3FFFu) | DESC_LO_FLAGS, b_lo0 = ((smem_b >> 4) & 0x3FFFu) | DESC_LO_FLAGS;
+        const uint32_t bar_af0 = smem_u32(&bar_af[0]), bar_ae0 = smem_u32(&bar_ae[0]), bar_bf0 = smem_u32(&bar_bf[0]), bar_be0 = smem_u32(&bar_be[0]);
+        uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0, accumulate = 0;
+        bool ok = true;
+        for (int kc = 0; kc < a.kchunks && ok; kc++) {
+            if (!(ok = warp_mbar_wait(bar_af0 + ac * 8, a_phase, abort_flag))) break;
+            tc_fence_after();
+            if (kc == 0 && lane == 0) t_stamp(trace, 3);
+            const uint32_t chunk_lo = a_lo0 + ac * (TR_A_CHUNK_BYTES >> 4);
+            if (a.taps == 9) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        tc_mma_bf16(tmem_base, make_smem_desc(sa + k * 32, TH * 128), make_smem_desc(sb + k * 32), IDESC, (kc | tap | k) != 0);
-                    tc_commit(smem_u32(&bar_be[bs]));
+                for (int tap = 0; tap < 9; tap++) {
+                    if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
+                        const uint32_t b_lo = b_lo0 + bs * (TR_B_BYTES >> 4);
+                        t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, tap == 0 ? accumulate : 1u);
+                        t_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                        t_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
+                        t_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                        tc_commit_mc(bar_be0 + bs * 8, CMASK);
+                    }
+                    __syncwarp();
                     if (++bs == TR_B_STAGES) { bs = 0; b_phase ^= 1; }
                 }
-                if (ok) tc_commit(smem_u32(&bar_ae[ac]));
-                if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
+            } else {
+                if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_lo = chunk_lo + (uint32_t)(2 * TH + 1) * (128 >> 4);            // centre tap
+                    const uint32_t b_lo = b_lo0 + bs * (TR_B_BYTES >> 4);
+                    t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, accumulate);
+                    t_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                    t_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
+                    t_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                    tc_commit_mc(bar_be0 + bs * 8, CMASK);
+                }
+                __syncwarp();
+                if (++bs == TR_B_STAGES) { bs = 0; b_phase ^= 1; }
             }
-            if (ok) tc_commit(smem_u32(&bar_acc));
+            accumulate = 1;
+            if (ok && elect_one()) tc_commit(bar_ae0 + ac * 8);
+            __syncwarp();
+            if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
         }
+        if (ok && elect_one()) { tc_commit(smem_u32(&bar_acc)); t_stamp(trace, 4); }
+        __syncwarp();
     } else {
         const int lane_group = warp & 3;
         bool ok = mbar_wait(smem_u32(&bar_acc), 0, abort_flag);
         ok = __all_sync(0xFFFFFFFFu, ok);
+        if (warp == 2 && lane == 0) t_stamp(trace, 5);
         if (ok) {
             tc_fence_after();
             const int m = lane_group * 32 + lane;                          // row (oy * 2 + board) * 8 + ox
@@ -207,15 +286,27 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
     __syncthreads();
     tc_fence_after();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    t_cluster_sync();                               // no CTA leaves while a peer's commit may still arrive on its barriers
+    if (threadIdx.x == 0) t_stamp(trace, 6);
     if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
 }
 
 // =================================================================================================
 // wgrad: D[co 128][ci N] (+)= sum over the squares of this CTA's boards of dY[sq][co] * X[sq + tap][ci]
 // =================================================================================================
+struct alignas(64) WgLayer {     // one entry per layer, in device memory: k_wgrad reads its tensor maps straight from here
+    CUtensorMap tm_dy;           // gradient of the layer's convolution output, 1-board boxes
+    CUtensorMap tm_x;            // the layer's input, 1-board boxes
+    float* out;                  // the layer's slot in the flat gradient buffer [cout_pad][ldw]
+    unsigned char pad[56];
+};
+
+static_assert(sizeof(WgLayer) == 320, "WgLayer: two tensor maps and a pointer, padded to a multiple of 64 bytes");
+
 struct WgArgs {
     int taps, m_halves, n_boards, ksplit;
-    float* partial;              // [ksplit][cout_pad][ldw]
+    int layer0;                  // blockIdx.z + layer0 = entry of the layer table
+    float* partial;              // ksplit > 1: [ksplit][cout_pad][ldw] partial sums (one layer per launch); else null: write the layer's `out`
     int ldw;                     // taps * cin_pad
     int cin_pad;
     size_t split_stride;         // cout_pad * ldw
@@ -225,7 +316,10 @@ struct WgArgs {
 
 template <int NB>                // 64-channel boxes of X: N = NB * 64 input channels
 __global__ void __launch_bounds__(TR_THREADS, 1)
-k_wgrad(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x, const WgArgs a) {
+k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
+    const WgLayer* wl = layers + a.layer0 + blockIdx.z;
+    const CUtensorMap* tm_dy = &wl->tm_dy;
+    const CUtensorMap* tm_x = &wl->tm_x;
     constexpr int N = NB * 64;
     constexpr int STAGE = (2 + NB) * WG_BOX;
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -268,32 +362,37 @@ k_wgrad(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUten
                 const uint32_t full = smem_u32(&bar_full[stage]);
                 const uint32_t sa = smem_base + stage * STAGE;
                 mbar_expect_tx(full, STAGE);
-                tma_load_4d(sa, &tm_dy, full, mh * 128, 1, 1, b);
-                tma_load_4d(sa + WG_BOX, &tm_dy, full, mh * 128 + 64, 1, 1, b);
+                tma_load_4d(sa, tm_dy, full, mh * 128, 1, 1, b);
+                tma_load_4d(sa + WG_BOX, tm_dy, full, mh * 128 + 64, 1, 1, b);
 #pragma unroll
-                for (int j = 0; j < NB; j++) tma_load_4d(sa + (2 + j) * WG_BOX, &tm_x, full, j * 64, kx, ky, b);
+                for (int j = 0; j < NB; j++) tma_load_4d(sa + (2 + j) * WG_BOX, tm_x, full, j * 64, kx, ky, b);
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            bool ok = true;
-            for (int b = b_lo; b < b_hi; b++) {
-                if (!(ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag))) break;
-                tc_fence_after();
-                const uint32_t sa = smem_base + stage * STAGE;
-                const uint32_t sb = sa + 2 * WG_BOX;
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    tc_mma_bf16(tmem_base, make_smem_desc_mn(sa + k * 2048, a.lbo, a.sbo), make_smem_desc_mn(sb + k * 2048, a.lbo, a.sbo), IDESC,
-                                (b != b_lo) || k != 0);
-                tc_commit(smem_u32(&bar_empty[stage]));
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        // warp-convergent loop, one elected lane issues; descriptors as (lo, hi) halves advanced with 32-bit adds (see k_tconv)
+        const uint32_t lo_flags = ((a.lbo >> 4) & 0x3FFFu) << 16, hi = ((a.sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+        const uint32_t s_lo0 = ((smem_base >> 4) & 0x3FFFu) | lo_flags;
+        const uint32_t bar_f0 = smem_u32(&bar_full[0]), bar_e0 = smem_u32(&bar_empty[0]);
+        uint32_t stage = 0, phase = 0, accumulate = 0;
+        bool ok = true;
+        for (int b = b_lo; b < b_hi; b++) {
+            if (!(ok = warp_mbar_wait(bar_f0 + stage * 8, phase, abort_flag))) break;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_lo = s_lo0 + stage * (STAGE >> 4), b_lo2 = a_lo + ((2 * WG_BOX) >> 4);
+                t_mma_split(tmem_base, a_lo, hi, b_lo2, hi, IDESC, accumulate);
+                t_mma_split(tmem_base, a_lo + 128, hi, b_lo2 + 128, hi, IDESC, 1u);
+                t_mma_split(tmem_base, a_lo + 256, hi, b_lo2 + 256, hi, IDESC, 1u);
+                t_mma_split(tmem_base, a_lo + 384, hi, b_lo2 + 384, hi, IDESC, 1u);
+                tc_commit(bar_e0 + stage * 8);
             }
-            if (ok) tc_commit(smem_u32(&bar_acc));
+            __syncwarp();
+            accumulate = 1;
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (ok && elect_one()) tc_commit(smem_u32(&bar_acc));
+        __syncwarp();
     } else {
         const int lane_group = warp & 3;
         bool ok = mbar_wait(smem_u32(&bar_acc), 0, abort_flag);
@@ -302,7 +401,7 @@ k_wgrad(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUten
             tc_fence_after();
             const int co = mh * 128 + lane_group * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
-            float* dst = a.partial + (size_t)ks * a.split_stride + (size_t)co * a.ldw + (size_t)tap * a.cin_pad;
+            float* dst = (a.partial ? a.partial + (size_t)ks * a.split_stride : wl->out) + (size_t)co * a.ldw + (size_t)tap * a.cin_pad;
 #pragma unroll 1
             for (int c0 = 0; c0 < N; c0 += 32) {
                 uint32_t v[32];
@@ -366,7 +465,8 @@ __global__ void k_gather_input(const uint64_t* states, long long n_records, int3
 // BatchNorm (training mode), 256 channels
 // =================================================================================================
 constexpr int BN_SLICES = 8;                 // blocks own 32 channels ...
-constexpr int BN_GROUPS = 18;                // ... of one group of boards: 144 blocks, all resident at once (the kernels carry a grid barrier)
+constexpr int BN_GROUPS = 64;                // ... of one group of boards: 512 blocks of 256 threads and ~1 KB of shared memory, all resident at
+                                             // once on any B200 (the kernels carry a grid barrier); few boards per thread = few dependent round trips
 
 struct GridBar { unsigned int count, gen; };
 
@@ -393,17 +493,28 @@ __device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int my_gen, 
     __syncthreads();
 }
 
-// per-channel sums of a [64 squares][32 channels] register tile spread over 256 threads (thread = (square, 8 channels)): fixed order
-__device__ __forceinline__ void bn_block_sums(float (*red)[64][33], const float* s1, const float* s2, float* part, int grp, int slice) {
-    const int t = threadIdx.x, cq = t & 3, pos = t >> 2;
+// per-channel sums of a [64 squares][32 channels] register tile spread over 256 threads (thread = (square, 8 channels)): shuffles over the
+// 8 squares a warp holds, then one thread per channel adds the 8 warps' values -- a fixed order
+__device__ __forceinline__ void bn_block_sums(float (*red)[8][33], float* s1, float* s2, float* part, int grp, int slice) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, cq = t & 3;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { red[0][pos][cq * 8 + j] = s1[j]; red[1][pos][cq * 8 + j] = s2[j]; }
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            s1[j] += __shfl_xor_sync(0xFFFFFFFFu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xFFFFFFFFu, s2[j], o);
+        }
+    }
+    if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { red[0][warp][cq * 8 + j] = s1[j]; red[1][warp][cq * 8 + j] = s2[j]; }
+    }
     __syncthreads();
     if (t < 64) {
         const int which = t >> 5, c = t & 31;
         float a = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < 64; i++) a += red[which][i][c];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a += red[which][i][c];
         part[(grp * 2 + which) * 256 + slice * 32 + c] = a;
     }
 }
@@ -413,7 +524,7 @@ struct BnFwd {
     const float* gamma; const float* beta;
     float* running_mean; float* running_var;
     float* mean; float* invstd;          // saved for the backward pass
-    float* part;                         // [BN_GROUPS][2][256]
+    float* part;                         // [groups][2][256]
     GridBar* bar;
     int n;
     float momentum, eps;
@@ -424,7 +535,7 @@ struct BnFwd {
 __global__ void __launch_bounds__(256) k_bn_fwd(BnFwd p) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[2][64][33];
+    __shared__ float red[2][8][33];
     __shared__ float sc_sh[32], sh_sh[32];
     __shared__ unsigned int gen_sh;
     const int slice = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
@@ -504,7 +615,7 @@ struct BnBwd {
 __global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[2][64][33];
+    __shared__ float red[2][8][33];
     __shared__ float ca_sh[32], cb_sh[32], cc_sh[32];
     __shared__ unsigned int gen_sh;
     const int slice = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
@@ -920,6 +1031,8 @@ struct TLayer {
     bf16* wf = nullptr; bf16* wd = nullptr;
     CUtensorMap tm_wf, tm_wd;
     bf16* y = nullptr; bf16* o = nullptr;        // pre-BatchNorm convolution output, layer output
+    bf16* dy = nullptr;                          // gradient of the convolution output (kept per layer: every tower wgrad runs in ONE launch at the end)
+    CUtensorMap tm_dy2, tm_dy1;
     CUtensorMap tm_o2, tm_o1;                    // layer output as the next layer's operand: 2-board boxes (forward), 1-board boxes (wgrad)
     float* bn = nullptr;                         // running_mean, running_var, mean, invstd: 4 x 256
 };
@@ -934,8 +1047,10 @@ struct Trainer {
     float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
     TLayer L[T_LAYERS];
     bf16* x_in = nullptr; CUtensorMap tm_in2, tm_in1;
-    bf16 *dy = nullptr, *dl = nullptr, *gbuf[2] = {nullptr, nullptr}, *gm1 = nullptr, *skip[2] = {nullptr, nullptr};
-    CUtensorMap tm_dy2, tm_dy1, tm_dl2, tm_dl1;
+    bf16 *dl = nullptr, *gbuf[2] = {nullptr, nullptr}, *gm1 = nullptr, *skip[2] = {nullptr, nullptr};
+    CUtensorMap tm_dl2, tm_dl1;
+    WgLayer* wg_layers = nullptr;                // [T_LAYERS] device table of k_wgrad
+    unsigned long long* trace = nullptr;         // SZB_TRAIN_TRACE=1: stamps of the forward convolution of layer 20
     float* logits = nullptr;
     float* partial = nullptr; size_t partial_floats = 0;
     float* bn_part = nullptr; GridBar* bar = nullptr;
@@ -1000,11 +1115,11 @@ static int t_halo_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, i
     if (r != CUDA_SUCCESS) return fail(ctx, SZB_ERR_CUDA, "cuTensorMapEncodeTiled(training halo activations) failed: %d", (int)r);
     return 0;
 }
-// weight pack [rows][k]: box = 64 k x 128 rows
+// weight pack [rows][k]: box = 64 k x 32 rows (a quarter of k_tconv's 128-row tile: one CTA's share of the multicast)
 static int t_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int rows) {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, 128 / TR_CLUSTER};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = t_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1118,18 +1233,21 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         if (l < T_BN) {
             L.gamma = tr->index.at(t_layer_bn_name(l) + ".weight");
             L.beta = tr->index.at(t_layer_bn_name(l) + ".bias");
-            if ((rc = t_alloc(ctx, tr, &L.y, act)) || (rc = t_alloc(ctx, tr, &L.o, act)) || (rc = t_alloc(ctx, tr, &L.bn, 4 * 256))) return rc;
-            if ((rc = t_halo_map(ctx, &L.tm_o2, L.o, TC, cap)) || (rc = t_act_map(ctx, &L.tm_o1, L.o, TC, cap, 1))) return rc;
+            if ((rc = t_alloc(ctx, tr, &L.y, act)) || (rc = t_alloc(ctx, tr, &L.o, act)) || (rc = t_alloc(ctx, tr, &L.dy, act)) ||
+                (rc = t_alloc(ctx, tr, &L.bn, 4 * 256)))
+                return rc;
+            if ((rc = t_halo_map(ctx, &L.tm_o2, L.o, TC, cap)) || (rc = t_act_map(ctx, &L.tm_o1, L.o, TC, cap, 1)) ||
+                (rc = t_halo_map(ctx, &L.tm_dy2, L.dy, TC, cap)) || (rc = t_act_map(ctx, &L.tm_dy1, L.dy, TC, cap, 1)))
+                return rc;
             tr->buffers.push_back({t_layer_bn_name(l) + ".running_mean", 256, L.bn});
             tr->buffers.push_back({t_layer_bn_name(l) + ".running_var", 256, L.bn + 256});
         }
     }
-    if ((rc = t_alloc(ctx, tr, &tr->dy, act)) || (rc = t_alloc(ctx, tr, &tr->gbuf[0], act)) || (rc = t_alloc(ctx, tr, &tr->gbuf[1], act)) ||
+    if ((rc = t_alloc(ctx, tr, &tr->gbuf[0], act)) || (rc = t_alloc(ctx, tr, &tr->gbuf[1], act)) ||
         (rc = t_alloc(ctx, tr, &tr->gm1, act)) || (rc = t_alloc(ctx, tr, &tr->skip[0], act)) || (rc = t_alloc(ctx, tr, &tr->skip[1], act)) ||
         (rc = t_alloc(ctx, tr, &tr->dl, (size_t)cap * TPIX * DL_C)))
         return rc;
-    if ((rc = t_halo_map(ctx, &tr->tm_dy2, tr->dy, TC, cap)) || (rc = t_act_map(ctx, &tr->tm_dy1, tr->dy, TC, cap, 1)) ||
-        (rc = t_halo_map(ctx, &tr->tm_dl2, tr->dl, DL_C, cap)) || (rc = t_act_map(ctx, &tr->tm_dl1, tr->dl, DL_C, cap, 1)))
+    if ((rc = t_halo_map(ctx, &tr->tm_dl2, tr->dl, DL_C, cap)) || (rc = t_act_map(ctx, &tr->tm_dl1, tr->dl, DL_C, cap, 1)))
         return rc;
     tr->partial_floats = (size_t)WG_MAX_SPLIT * 256 * 256;                      // 1x1 layers: up to 64 splits of 256 x 256
     if (tr->partial_floats < (size_t)8 * 256 * 2304) tr->partial_floats = (size_t)8 * 256 * 2304;
@@ -1153,6 +1271,9 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
     }
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
+    if (const char* e = getenv("SZB_TRAIN_TRACE")) {
+        if (atoi(e) && (rc = t_alloc(ctx, tr, &tr->trace, 8))) return rc;
+    }
     tr->buffers.push_back({"v_norm.running_mean", 1, tr->v_running});
     tr->buffers.push_back({"v_norm.running_var", 1, tr->v_running + 1});
     std::vector<PackDesc> pd(T_LAYERS);
@@ -1161,6 +1282,15 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         pd[l] = PackDesc{tr->w + tr->params[L.param].off, L.wf, L.wd, L.cout_pad, L.taps, L.cin_pad};
     }
     SZB_CUDA(ctx, cudaMemcpyAsync(tr->pack_descs, pd.data(), sizeof(PackDesc) * T_LAYERS, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<WgLayer> wl(T_LAYERS);
+    for (int l = 0; l < T_LAYERS; l++) {
+        memset(&wl[l], 0, sizeof(WgLayer));
+        wl[l].tm_dy = l == L_P2 ? tr->tm_dl1 : tr->L[l].tm_dy1;
+        wl[l].tm_x = l == 0 ? tr->tm_in1 : l == L_P1 ? tr->L[38].tm_o1 : l == L_P2 ? tr->L[L_P1].tm_o1 : tr->L[l - 1].tm_o1;
+        wl[l].out = tr->g + tr->params[tr->L[l].param].off;
+    }
+    if ((rc = t_alloc(ctx, tr, &tr->wg_layers, (size_t)T_LAYERS))) return rc;
+    SZB_CUDA(ctx, cudaMemcpyAsync(tr->wg_layers, wl.data(), sizeof(WgLayer) * T_LAYERS, cudaMemcpyHostToDevice, ctx->stream));
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (!tr->attr_set) {
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
@@ -1249,10 +1379,11 @@ static int t_transfer(szb_ctx* ctx, int kind, int32_t n_tensors, const char* con
 }
 
 static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUtensorMap& tm_w, int taps, int kchunks, int n_out, int n, bf16* out, int mode,
-                  const float* bias) {
+                  const float* bias, unsigned long long* trace = nullptr) {
     TConvArgs a{};
+    a.trace = trace;
     a.taps = taps; a.kchunks = kchunks; a.n_boards = n; a.out = out; a.ldc = TC; a.logits = tr->logits; a.bias = bias; a.error = tr->error;
-    const dim3 grid((n + 1) / 2, n_out / 128);
+    const dim3 grid((unsigned)((((n + 1) / 2 + TR_CLUSTER - 1) / TR_CLUSTER) * TR_CLUSTER), n_out / 128);      // whole clusters: surplus CTAs compute on zero fill, store nothing
     if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv<0>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
     else SZB_CUDA(ctx, launch_kernel(k_tconv<1>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
     ctx->launches++;
@@ -1268,25 +1399,30 @@ static int t_ksplit(int n, int tiles_x) {
     return k;
 }
 
-// dW of layer l: A = gradient of the convolution output (tm_a: 1-board boxes), X = the layer's input (tm_x)
-static int t_wgrad(szb_ctx* ctx, Trainer* tr, int l, const CUtensorMap& tm_a, const CUtensorMap& tm_x, int n) {
-    const TLayer& L = tr->L[l];
+// dW of `count` layers from `l0` on, all of one shape.  One layer: split over the batch into partial sums that k_reduce_partials adds in
+// a fixed order (the GPU is filled by taps x halves x splits).  Several layers (the 38 tower convolutions, at the end of the backward
+// pass): one CTA per (layer, tap, half) sums over the whole batch and writes the gradient itself -- no partials, no second kernel.
+static int t_wgrad(szb_ctx* ctx, Trainer* tr, int l0, int count, int n) {
+    const TLayer& L = tr->L[l0];
     const TParam& p = tr->params[L.param];
     WgArgs a{};
-    a.taps = L.taps; a.m_halves = L.cout_pad / 128; a.n_boards = n;
-    a.ksplit = t_ksplit(n, L.taps * a.m_halves);
-    a.partial = tr->partial; a.ldw = L.taps * L.cin_pad; a.cin_pad = L.cin_pad; a.split_stride = (size_t)L.cout_pad * a.ldw; a.error = tr->error;
+    a.taps = L.taps; a.m_halves = L.cout_pad / 128; a.n_boards = n; a.layer0 = l0;
+    a.ksplit = count > 1 ? 1 : t_ksplit(n, L.taps * a.m_halves);
+    a.partial = a.ksplit > 1 ? tr->partial : nullptr;
+    a.ldw = L.taps * L.cin_pad; a.cin_pad = L.cin_pad; a.split_stride = (size_t)L.cout_pad * a.ldw; a.error = tr->error;
     a.lbo = tr->cfg.probe_lbo ? (uint32_t)tr->cfg.probe_lbo : WG_BOX;
     a.sbo = tr->cfg.probe_sbo ? (uint32_t)tr->cfg.probe_sbo : 1024;
     if ((size_t)a.ksplit * a.split_stride > tr->partial_floats) return fail(ctx, SZB_ERR_INTERNAL, "wgrad scratch too small");
-    const dim3 grid(L.taps * a.m_halves, a.ksplit);
-    if (L.cin_pad == 256) SZB_CUDA(ctx, launch_kernel(k_wgrad<4>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 6 * WG_BOX + 1024), ctx->stream, tr->pdl, tm_a, tm_x, a));
-    else SZB_CUDA(ctx, launch_kernel(k_wgrad<2>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 4 * WG_BOX + 1024), ctx->stream, tr->pdl, tm_a, tm_x, a));
-    const size_t cnt = a.split_stride;
-    SZB_CUDA(ctx, launch_kernel(k_reduce_partials, dim3((unsigned)((cnt / 4 + 255) / 256)), dim3(256), 0, ctx->stream, tr->pdl, (const float*)tr->partial,
-                                a.split_stride, a.ksplit, tr->g + p.off, cnt));
-    ctx->launches += 2;
-    SZB_CUDA(ctx, cudaGetLastError());
+    const dim3 grid(L.taps * a.m_halves, a.ksplit, count);
+    if (L.cin_pad == 256) SZB_CUDA(ctx, launch_kernel(k_wgrad<4>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 6 * WG_BOX + 1024), ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
+    else SZB_CUDA(ctx, launch_kernel(k_wgrad<2>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 4 * WG_BOX + 1024), ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
+    ctx->launches++;
+    if (a.ksplit > 1) {
+        const size_t cnt = a.split_stride;
+        SZB_CUDA(ctx, launch_kernel(k_reduce_partials, dim3((unsigned)((cnt / 4 + 255) / 256)), dim3(256), 0, ctx->stream, tr->pdl, (const float*)tr->partial,
+                                    a.split_stride, a.ksplit, tr->g + p.off, cnt));
+        ctx->launches++;
+    }
     return 0;
 }
 
@@ -1299,15 +1435,16 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
     // an odd batch leaves a phantom board in the last 2-board tile: GEMM rows are independent, its rows are computed and never stored
     k_gather_input<<<(unsigned)(((size_t)n * 64 * 16 + 255) / 256), 256, 0, st>>>(tr->rec_states, (long long)tr->rec_n, tr->rows, n, tr->x_in, tr->error);
     ctx->launches++;
+    const int bn_groups = n / 2 < BN_GROUPS ? (n / 2 > 0 ? n / 2 : 1) : BN_GROUPS;
     // ---------------- forward ----------------
     for (int l = 0; l < T_BN; l++) {
         TLayer& L = tr->L[l];
         const CUtensorMap& tm_a = l == 0 ? tr->tm_in2 : l == L_P1 ? tr->L[38].tm_o2 : tr->L[l - 1].tm_o2;
-        if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr))) return rc;
+        if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr, l == 20 ? tr->trace : nullptr))) return rc;
         const bf16* res = (l >= 2 && l <= 38 && ((l - 1) & 1)) ? tr->L[l - 2].o : nullptr;
         BnFwd bp{L.y, res, L.o, tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768,
                  tr->bn_part, tr->bar, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
-        SZB_CUDA(ctx, launch_kernel(k_bn_fwd, dim3(BN_SLICES, BN_GROUPS), dim3(256), 0, st, tr->pdl, bp));
+        SZB_CUDA(ctx, launch_kernel(k_bn_fwd, dim3(BN_SLICES, bn_groups), dim3(256), 0, st, tr->pdl, bp));
         ctx->launches++;
     }
     if ((rc = t_conv(ctx, tr, tr->L[L_P1].tm_o2, tr->L[L_P2].tm_wf, 1, 4, 128, n, nullptr, 1, t_slot(tr, tr->w, "conv_p2.bias")))) return rc;
@@ -1335,7 +1472,7 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
                                                                        t_slot(tr, tr->g, "fc_v2.bias"));
         ctx->launches += 5;
         // conv_p2: weight gradient, then the gradient of its input (conv_p1's output after BN + ReLU)
-        if ((rc = t_wgrad(ctx, tr, L_P2, tr->tm_dl1, tr->L[L_P1].tm_o1, n))) return rc;
+        if ((rc = t_wgrad(ctx, tr, L_P2, 1, n))) return rc;
         int cur = 0;                                            // gbuf[cur] holds the gradient arriving at the layer being processed
         if ((rc = t_conv(ctx, tr, tr->tm_dl2, tr->L[L_P2].tm_wd, 1, DL_C / 64, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
         int sk = 0;                                             // skip[sk] holds the skip-path gradient for the next residual join
@@ -1344,18 +1481,20 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
             const bool join = l == 0 || (l <= 38 && ((l - 1) & 1));          // layers whose output feeds a residual add as well (or two heads)
             const bf16* skip_in = join ? tr->skip[sk] : nullptr;
             bf16* gm = join ? tr->skip[sk ^ 1] : tr->gm1;
-            BnBwd bp{tr->gbuf[cur], skip_in, L.o, L.y, gm, tr->dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768,
+            BnBwd bp{tr->gbuf[cur], skip_in, L.o, L.y, gm, L.dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768,
                      tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off, tr->bn_part, tr->bar, n};
-            SZB_CUDA(ctx, launch_kernel(k_bn_bwd, dim3(BN_SLICES, BN_GROUPS), dim3(256), 0, st, tr->pdl, bp));
+            SZB_CUDA(ctx, launch_kernel(k_bn_bwd, dim3(BN_SLICES, bn_groups), dim3(256), 0, st, tr->pdl, bp));
             ctx->launches++;
             if (join) sk ^= 1;
-            const CUtensorMap& tm_x = l == 0 ? tr->tm_in1 : l == L_P1 ? tr->L[38].tm_o1 : tr->L[l - 1].tm_o1;
-            if ((rc = t_wgrad(ctx, tr, l, tr->tm_dy1, tm_x, n))) return rc;
+            if (l == 0 || l == L_P1) {
+                if ((rc = t_wgrad(ctx, tr, l, 1, n))) return rc;
+            }
             if (l > 0) {
                 cur ^= 1;
-                if ((rc = t_conv(ctx, tr, tr->tm_dy2, L.tm_wd, L.taps, 4, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
+                if ((rc = t_conv(ctx, tr, L.tm_dy2, L.tm_wd, L.taps, 4, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
             }
         }
+        if ((rc = t_wgrad(ctx, tr, 1, 38, n))) return rc;         // every tower convolution's weight gradient
         if (!(flags & SZB_TRAIN_NO_UPDATE)) {
             const szb_train_config& c = tr->cfg;
             k_hyper<<<1, 1, 0, st>>>(tr->d_step, c.lr, c.lr_gamma, c.lr_step, c.beta1, c.beta2, tr->hyper);
@@ -1417,6 +1556,13 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
         SZB_CUDA(ctx, cudaMemcpyAsync(losses_out, tr->losses, 8, cudaMemcpyDefault, st));
         SZB_CUDA(ctx, cudaMemcpyAsync(&err, tr->error, 4, cudaMemcpyDeviceToHost, st));
         SZB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (tr->trace) {
+            unsigned long long t[8];
+            SZB_CUDA(ctx, cudaMemcpy(t, tr->trace, sizeof(t), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[szb train trace] layer-20 forward convolution, CTA (0,0), us since entry: prologue %.2f, dependency wait %.2f, first chunk landed %.2f, "
+                            "last MMA issued %.2f, accumulator ready %.2f, exit %.2f\n", (t[1] - t[0]) * 1e-3, (t[2] - t[0]) * 1e-3, (t[3] - t[0]) * 1e-3,
+                    (t[4] - t[0]) * 1e-3, (t[5] - t[0]) * 1e-3, (t[6] - t[0]) * 1e-3);
+        }
         if (err) {
             cudaMemsetAsync(tr->error, 0, 4, st);
             return err == 2 ? fail(ctx, SZB_ERR_ARG, "szb_train_step: a row index is outside the %lld records", (long long)tr->rec_n)
