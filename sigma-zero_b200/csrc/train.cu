@@ -477,7 +477,9 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 // Every block of the grid arrives before any leaves.  Sense reversing (the last block clears the count and bumps the generation), so the
 // same two words serve every launch, and a replayed CUDA graph too.  `my_gen` is the generation read before arriving.
-__device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int my_gen, unsigned int nblocks) {
+// The grid must fit on the device at once (the host sizes it with the occupancy API); a wait that outlasts TC_TIMEOUT_CYCLES raises the
+// error flag and returns instead of spinning forever.
+__device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int my_gen, unsigned int nblocks, int32_t* error) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -486,7 +488,10 @@ __device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int my_gen, 
             __threadfence();
             atomicAdd(&bar->gen, 1u);
         } else {
-            while (ld_acquire_u32(&bar->gen) == my_gen) {}
+            const long long t0 = clock64();
+            while (ld_acquire_u32(&bar->gen) == my_gen) {
+                if (clock64() - t0 > TC_TIMEOUT_CYCLES) { atomicExch(error, 3); break; }
+            }
         }
         __threadfence();
     }
@@ -526,13 +531,14 @@ struct BnFwd {
     float* mean; float* invstd;          // saved for the backward pass
     float* part;                         // [groups][2][256]
     GridBar* bar;
+    int32_t* error;
     int n;
     float momentum, eps;
 };
 
 // Training-mode BatchNorm + ReLU (+ residual) in ONE launch: batch statistics of the block's 32 channels over its boards, grid barrier,
 // every block folds the 18 partials of its channels (fixed order) into scale / shift, then normalises the same boards.
-__global__ void __launch_bounds__(256) k_bn_fwd(BnFwd p) {
+__global__ void __launch_bounds__(256, 4) k_bn_fwd(BnFwd p) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[2][8][33];
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(256) k_bn_fwd(BnFwd p) {
         for (int j = 0; j < 8; j++) { const float f = __bfloat162float(vb[j]); s1[j] += f; s2[j] += f * f; }
     }
     bn_block_sums(red, s1, s2, p.part, grp, slice);
-    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y);
+    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y, p.error);
     if (t < 32) {
         const int c = slice * 32 + t;
         double S1 = 0, S2 = 0;
@@ -607,12 +613,13 @@ struct BnBwd {
     float* g_gamma; float* g_beta;       // gradient slots of the flat gradient buffer
     float* part;
     GridBar* bar;
+    int32_t* error;
     int n;
 };
 
 // ReLU + residual-join + BatchNorm backward in ONE launch: g = (d_in [+ skip]) * [out > 0]; per-channel sums of g and g * xhat; grid
 // barrier; dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); d_gamma, d_beta by the first board group.
-__global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
+__global__ void __launch_bounds__(256, 4) k_bn_bwd(BnBwd p) {
     pdl_trigger();
     pdl_wait();
     __shared__ float red[2][8][33];
@@ -627,7 +634,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
     float mean[8], invstd[8], s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { mean[j] = p.mean[c0 + j]; invstd[j] = p.invstd[c0 + j]; s1[j] = s2[j] = 0.f; }
-#pragma unroll 2
+#pragma unroll 1
     for (int b = b_lo; b < b_hi; b++) {
         const size_t off = (size_t)b * TPIX * TC + coff;
         const uint4 dv = *reinterpret_cast<const uint4*>(p.d_in + off), ov = *reinterpret_cast<const uint4*>(p.out + off),
@@ -657,7 +664,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
         *reinterpret_cast<uint4*>(p.gm + off) = o;
     }
     bn_block_sums(red, s1, s2, p.part, grp, slice);
-    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y);
+    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y, p.error);
     if (t < 32) {
         const int c = slice * 32 + t;
         double S1 = 0, S2 = 0;
@@ -672,7 +679,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
     float ca[8], cb[8], cc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { ca[j] = ca_sh[cq * 8 + j]; cb[j] = cb_sh[cq * 8 + j]; cc[j] = cc_sh[cq * 8 + j]; }
-#pragma unroll 4
+#pragma unroll 1
     for (int b = b_lo; b < b_hi; b++) {
         const size_t off = (size_t)b * TPIX * TC + coff;
         const uint4 gv = *reinterpret_cast<const uint4*>(p.gm + off), yv = *reinterpret_cast<const uint4*>(p.y + off);   // gm: this thread's own stores
@@ -1073,6 +1080,7 @@ struct Trainer {
     uint64_t steps_queued = 0;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;     // (boards, flags) -> the captured step
     bool use_graph = true;
+    int bn_groups_max = 18;
     bool pdl = true;                             // programmatic dependent launch along the convolution / BatchNorm chain (SZB_TRAIN_NO_PDL=1: off)
     std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
@@ -1269,6 +1277,17 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         const long long s0 = cfg->step0;
         SZB_CUDA(ctx, cudaMemcpyAsync(tr->d_step, &s0, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
+    {
+        int occ_f = 0, occ_b = 0, sms = 0;
+        SZB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_bn_fwd, 256, 0));
+        SZB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bn_bwd, 256, 0));
+        SZB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        const int occ = occ_f < occ_b ? occ_f : occ_b;
+        // three quarters of what fits: blocks of the neighbouring kernels (programmatic dependent launch) may hold some thread slots
+        tr->bn_groups_max = occ * sms * 3 / 4 / BN_SLICES;
+        if (tr->bn_groups_max < 1) return fail(ctx, SZB_ERR_CUDA, "BatchNorm kernels do not fit on this device");
+        if (tr->bn_groups_max > BN_GROUPS) tr->bn_groups_max = BN_GROUPS;
+    }
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_TRACE")) {
@@ -1435,7 +1454,8 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
     // an odd batch leaves a phantom board in the last 2-board tile: GEMM rows are independent, its rows are computed and never stored
     k_gather_input<<<(unsigned)(((size_t)n * 64 * 16 + 255) / 256), 256, 0, st>>>(tr->rec_states, (long long)tr->rec_n, tr->rows, n, tr->x_in, tr->error);
     ctx->launches++;
-    const int bn_groups = n / 2 < BN_GROUPS ? (n / 2 > 0 ? n / 2 : 1) : BN_GROUPS;
+    int bn_groups = n / 2 < BN_GROUPS ? (n / 2 > 0 ? n / 2 : 1) : BN_GROUPS;
+    if (bn_groups > tr->bn_groups_max) bn_groups = tr->bn_groups_max;          // the BatchNorm kernels' grid barrier needs every block resident
     // ---------------- forward ----------------
     for (int l = 0; l < T_BN; l++) {
         TLayer& L = tr->L[l];
@@ -1443,7 +1463,7 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
         if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr, l == 20 ? tr->trace : nullptr))) return rc;
         const bf16* res = (l >= 2 && l <= 38 && ((l - 1) & 1)) ? tr->L[l - 2].o : nullptr;
         BnFwd bp{L.y, res, L.o, tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768,
-                 tr->bn_part, tr->bar, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
+                 tr->bn_part, tr->bar, tr->error, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
         SZB_CUDA(ctx, launch_kernel(k_bn_fwd, dim3(BN_SLICES, bn_groups), dim3(256), 0, st, tr->pdl, bp));
         ctx->launches++;
     }
@@ -1482,7 +1502,7 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
             const bf16* skip_in = join ? tr->skip[sk] : nullptr;
             bf16* gm = join ? tr->skip[sk ^ 1] : tr->gm1;
             BnBwd bp{tr->gbuf[cur], skip_in, L.o, L.y, gm, L.dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768,
-                     tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off, tr->bn_part, tr->bar, n};
+                     tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off, tr->bn_part, tr->bar, tr->error, n};
             SZB_CUDA(ctx, launch_kernel(k_bn_bwd, dim3(BN_SLICES, bn_groups), dim3(256), 0, st, tr->pdl, bp));
             ctx->launches++;
             if (join) sk ^= 1;
@@ -1565,8 +1585,9 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
         }
         if (err) {
             cudaMemsetAsync(tr->error, 0, 4, st);
-            return err == 2 ? fail(ctx, SZB_ERR_ARG, "szb_train_step: a row index is outside the %lld records", (long long)tr->rec_n)
-                            : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
+            return err == 2   ? fail(ctx, SZB_ERR_ARG, "szb_train_step: a row index is outside the %lld records", (long long)tr->rec_n)
+                   : err == 3 ? fail(ctx, SZB_ERR_INTERNAL, "a BatchNorm kernel's grid barrier timed out")
+                              : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
         }
     }
     return 0;

@@ -239,6 +239,31 @@ def test_deterministic_resumable_and_graph_free_path_identical(setup):
     assert not torch.equal(a["conv1.weight"], model.state_dict()["conv1.weight"].flatten())
 
 
+def test_reference_batch_size(setup):
+    """batch 128 (train_RL.py:175) and an odd 255: the BatchNorm kernels run their widest grids (every block must be resident for the grid
+    barrier), steps are queued without reading losses back; the losses fall and two runs agree bit for bit"""
+    from sigma_zero_b200 import _lib
+    from sigma_zero_b200.trainer import Trainer
+    eng, dev = setup
+    rec = _records(512, seed=11)
+    rng = np.random.default_rng(12)
+    for batch in (128, 255):
+        batches = [rng.permutation(512)[:batch].astype(np.int32) for _ in range(12)]
+        outs = []
+        for _ in range(2):
+            tr = Trainer(eng, _model(6), batch_size=batch)
+            tr.set_records(rec)
+            first = tr.step(batches[0])
+            for rows in batches[1:-1]:
+                tr.step(rows, want_losses=False)
+            last = tr.step(batches[-1])
+            outs.append((first, last, tr.get_tensors(_lib.TRAIN_PARAMS, ["conv1.weight", "fc_v2.weight", "resnet_blocks.9.bn1.running_var"])))
+            tr.close()
+        (f0, l0, w0), (f1, l1, w1) = outs
+        assert f0 == f1 and l0 == l1 and all(torch.equal(w0[k], w1[k]) for k in w0)
+        assert np.isfinite([*f0, *l0]).all() and l0[1] < f0[1] - 0.3, (f0, l0)
+
+
 def test_train_on_records_product_path(setup):
     """train_RL.train_on_records on a CUDA device runs the library's trainer: weights change in the torch module, the optimiser and
     scheduler objects carry the state on (interchangeable with the torch trainer's checkpoints), the inference network of the same
