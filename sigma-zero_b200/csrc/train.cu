@@ -81,9 +81,32 @@ struct TConvArgs {
     int ldc;
     float* logits;               // MODE 1: [board][4672] plane-major (torch.flatten of conv_p2's output), + bias
     const float* bias;
+    // MODE 0, optional: per-tile column sums [tile][2][ldc] of what this launch stores (after bf16 rounding), for the BatchNorm that follows:
+    //   forward  (bn_o == null): sum(y), sum(y^2)                      -> batch statistics (k_bn_fwd)
+    //   backward (bn_o != null): the accumulator is the gradient arriving at the OUTPUT of the BatchNorm below; the epilogue applies the
+    //            residual join and the ReLU mask, g = (acc [+ bn_skip]) * [bn_o > 0], stores g, and sums g, g * xhat (k_bn_bwd)
+    float* stat_part;
+    const bf16* bn_skip; const bf16* bn_o; const bf16* bn_y;
+    const float* bn_mean; const float* bn_invstd;
     int32_t* error;
     unsigned long long* trace;   // measurement aid (SZB_TRAIN_TRACE): %globaltimer stamps of CTA (0, 0), or null
 };
+
+// Column sums over the 32 lanes of a warp of 32 per-lane values: lane L returns the sum over all lanes of v[L].  Halving exchange
+// (16 + 8 + 4 + 2 + 1 shuffles, no dynamic register indexing); the order of the additions is fixed.
+__device__ __forceinline__ float warp_col_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, s);
+        }
+    }
+    return v[0];
+}
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
@@ -140,6 +163,7 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
     __shared__ __align__(8) uint64_t bar_af[TR_A_CHUNKS], bar_ae[TR_A_CHUNKS], bar_bf[TR_B_STAGES], bar_be[TR_B_STAGES], bar_acc;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int abort_sh;
+    __shared__ float st_sh[2][4][128], mi_sh[2][128];                  // fused BatchNorm sums of the four epilogue warps; mean / invstd
 
     const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_b = smem_a + TR_A_CHUNKS * TR_A_CHUNK_BYTES;
@@ -247,11 +271,15 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
         __syncwarp();
     } else {
         const int lane_group = warp & 3;
+        const int e = (warp - 2) * 32 + lane;                              // 0..127 over the four epilogue warps
+        const bool stats = MODE == 0 && a.stat_part != nullptr, bwd = MODE == 0 && a.bn_o != nullptr;
+        if (bwd) { mi_sh[0][e] = a.bn_mean[nh * 128 + e]; mi_sh[1][e] = a.bn_invstd[nh * 128 + e]; }
         bool ok = mbar_wait(smem_u32(&bar_acc), 0, abort_flag);
         ok = __all_sync(0xFFFFFFFFu, ok);
         if (warp == 2 && lane == 0) t_stamp(trace, 5);
         if (ok) {
             tc_fence_after();
+            if (bwd) asm volatile("bar.sync 1, 128;" ::: "memory");
             const int m = lane_group * 32 + lane;                          // row (oy * 2 + board) * 8 + ox
             const int board = tile * 2 + ((m >> 3) & 1), sq = (m >> 4) * 8 + (m & 7);
             const bool live = board < a.n_boards;
@@ -263,21 +291,74 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
                 tmem_ld_32x32b_x16(taddr + c0, v);
                 tmem_ld_32x32b_x16(taddr + c0 + 16, v + 16);
                 tmem_ld_wait();
-                if (!live) continue;
                 if (MODE == 0) {
+                    const size_t off = pix * a.ldc + nh * 128 + c0;
+                    float f[32], xh[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) f[j] = live ? __uint_as_float(v[j]) : 0.f;
+                    if (bwd) {
+                        if (live) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint4 ov = *reinterpret_cast<const uint4*>(a.bn_o + off + q * 8), yv = *reinterpret_cast<const uint4*>(a.bn_y + off + q * 8);
+                                const bf16* ob = reinterpret_cast<const bf16*>(&ov);
+                                const bf16* yb = reinterpret_cast<const bf16*>(&yv);
+                                if (a.bn_skip) {
+                                    const uint4 sv = *reinterpret_cast<const uint4*>(a.bn_skip + off + q * 8);
+                                    const bf16* sb = reinterpret_cast<const bf16*>(&sv);
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) f[q * 8 + j] += __bfloat162float(sb[j]);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    if (!(__bfloat162float(ob[j]) > 0.f)) f[q * 8 + j] = 0.f;
+                                    xh[q * 8 + j] = (__bfloat162float(yb[j]) - mi_sh[0][c0 + q * 8 + j]) * mi_sh[1][c0 + q * 8 + j];
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) xh[j] = 0.f;
+                        }
+                    }
                     uint4 o[4];
-                    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(o);
+                    __nv_bfloat162* ob2 = reinterpret_cast<__nv_bfloat162*>(o);
 #pragma unroll
-                    for (int j = 0; j < 16; j++) ob[j] = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                    uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.ldc + nh * 128 + c0);
+                    for (int j = 0; j < 16; j++) ob2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                    if (live) {
+                        uint4* op = reinterpret_cast<uint4*>(a.out + off);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) op[j] = o[j];
-                } else {
+                        for (int j = 0; j < 4; j++) op[j] = o[j];
+                    }
+                    if (stats) {
+                        // sums of the ROUNDED values: exactly what the BatchNorm kernel will read back
+                        float s2[32];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float2 r = __bfloat1622float2(ob2[j]);
+                            f[2 * j] = r.x;
+                            f[2 * j + 1] = r.y;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j++) s2[j] = bwd ? f[j] * xh[j] : f[j] * f[j];
+                        const float c1 = warp_col_sum32(f, lane), c2 = warp_col_sum32(s2, lane);
+                        st_sh[0][lane_group][c0 + lane] = c1;
+                        st_sh[1][lane_group][c0 + lane] = c2;
+                    }
+                } else if (live) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int c = nh * 128 + c0 + j;
                         if (c < 73) a.logits[(size_t)board * T_ACTIONS + c * 64 + sq] = __uint_as_float(v[j]) + a.bias[c];
                     }
+                }
+            }
+            if (stats) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tile * 2 < a.n_boards) {
+#pragma unroll
+                    for (int which = 0; which < 2; which++)
+                        a.stat_part[((size_t)tile * 2 + which) * a.ldc + nh * 128 + e] =
+                            ((st_sh[which][0][e] + st_sh[which][1][e]) + st_sh[which][2][e]) + st_sh[which][3][e];
                 }
             }
         }
@@ -465,62 +546,25 @@ __global__ void k_gather_input(const uint64_t* states, long long n_records, int3
 // BatchNorm (training mode), 256 channels
 // =================================================================================================
 constexpr int BN_SLICES = 8;                 // blocks own 32 channels ...
-constexpr int BN_GROUPS = 64;                // ... of one group of boards: 512 blocks of 256 threads and ~1 KB of shared memory, all resident at
-                                             // once on any B200 (the kernels carry a grid barrier); few boards per thread = few dependent round trips
+constexpr int BN_GROUPS = 64;                // ... of one group of boards (few boards per thread = few dependent round trips)
 
-struct GridBar { unsigned int count, gen; };
-
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// Every block of the grid arrives before any leaves.  Sense reversing (the last block clears the count and bumps the generation), so the
-// same two words serve every launch, and a replayed CUDA graph too.  `my_gen` is the generation read before arriving.
-// The grid must fit on the device at once (the host sizes it with the occupancy API); a wait that outlasts TC_TIMEOUT_CYCLES raises the
-// error flag and returns instead of spinning forever.
-__device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int my_gen, unsigned int nblocks, int32_t* error) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&bar->count, 1u) == nblocks - 1) {
-            bar->count = 0;
-            __threadfence();
-            atomicAdd(&bar->gen, 1u);
-        } else {
-            const long long t0 = clock64();
-            while (ld_acquire_u32(&bar->gen) == my_gen) {
-                if (clock64() - t0 > TC_TIMEOUT_CYCLES) { atomicExch(error, 3); break; }
-            }
-        }
-        __threadfence();
+// Every block first folds the per-tile column sums the convolution's epilogue left (k_tconv: stat_part [tile][2][256]) for its 32
+// channels -- 8 strided partial sums, then one thread per channel adds those in a fixed order, in double.  Returns (sum 0, sum 1) to
+// threads 0..31 (channel slice * 32 + t).
+__device__ __forceinline__ void bn_fold_tile_sums(const float* part, int n_tiles, int slice, double (*red)[8][32], double& S1, double& S2) {
+    const int t = threadIdx.x, c = t & 31, pr = t >> 5;
+    double a1 = 0, a2 = 0;
+    for (int tile = pr; tile < n_tiles; tile += 8) {
+        a1 += (double)part[((size_t)tile * 2) * 256 + slice * 32 + c];
+        a2 += (double)part[((size_t)tile * 2 + 1) * 256 + slice * 32 + c];
     }
+    red[0][pr][c] = a1;
+    red[1][pr][c] = a2;
     __syncthreads();
-}
-
-// per-channel sums of a [64 squares][32 channels] register tile spread over 256 threads (thread = (square, 8 channels)): shuffles over the
-// 8 squares a warp holds, then one thread per channel adds the 8 warps' values -- a fixed order
-__device__ __forceinline__ void bn_block_sums(float (*red)[8][33], float* s1, float* s2, float* part, int grp, int slice) {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, cq = t & 3;
+    S1 = S2 = 0;
+    if (t < 32) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-            s1[j] += __shfl_xor_sync(0xFFFFFFFFu, s1[j], o);
-            s2[j] += __shfl_xor_sync(0xFFFFFFFFu, s2[j], o);
-        }
-    }
-    if (lane < 4) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) { red[0][warp][cq * 8 + j] = s1[j]; red[1][warp][cq * 8 + j] = s2[j]; }
-    }
-    __syncthreads();
-    if (t < 64) {
-        const int which = t >> 5, c = t & 31;
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) a += red[which][i][c];
-        part[(grp * 2 + which) * 256 + slice * 32 + c] = a;
+        for (int i = 0; i < 8; i++) { S1 += red[0][i][t]; S2 += red[1][i][t]; }
     }
 }
 
@@ -529,42 +573,24 @@ struct BnFwd {
     const float* gamma; const float* beta;
     float* running_mean; float* running_var;
     float* mean; float* invstd;          // saved for the backward pass
-    float* part;                         // [groups][2][256]
-    GridBar* bar;
-    int32_t* error;
-    int n;
+    const float* part;                   // [tiles][2][256]: sum(y), sum(y^2) per tile, from the convolution's epilogue
+    int n_tiles, n;
     float momentum, eps;
 };
 
-// Training-mode BatchNorm + ReLU (+ residual) in ONE launch: batch statistics of the block's 32 channels over its boards, grid barrier,
-// every block folds the 18 partials of its channels (fixed order) into scale / shift, then normalises the same boards.
-__global__ void __launch_bounds__(256, 4) k_bn_fwd(BnFwd p) {
+// Training-mode BatchNorm + ReLU (+ residual): batch statistics from the convolution's per-tile sums, then normalise this block's boards.
+__global__ void __launch_bounds__(256) k_bn_fwd(BnFwd p) {
+    __shared__ double red[2][8][32];
+    __shared__ float sc_sh[32], sh_sh[32];
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[2][8][33];
-    __shared__ float sc_sh[32], sh_sh[32];
-    __shared__ unsigned int gen_sh;
     const int slice = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
     const int t = threadIdx.x, cq = t & 3, pos = t >> 2;
     const int b_lo = (int)((long long)grp * p.n / G), b_hi = (int)((long long)(grp + 1) * p.n / G);
-    if (t == 0) gen_sh = ld_acquire_u32(&p.bar->gen);
-    const size_t coff = (size_t)halo_pix(pos) * TC + slice * 32 + cq * 8;
-    float s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) s1[j] = s2[j] = 0.f;
-#pragma unroll 4
-    for (int b = b_lo; b < b_hi; b++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(p.y + (size_t)b * TPIX * TC + coff);
-        const bf16* vb = reinterpret_cast<const bf16*>(&v);
-#pragma unroll
-        for (int j = 0; j < 8; j++) { const float f = __bfloat162float(vb[j]); s1[j] += f; s2[j] += f * f; }
-    }
-    bn_block_sums(red, s1, s2, p.part, grp, slice);
-    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y, p.error);
+    double S1, S2;
+    bn_fold_tile_sums(p.part, p.n_tiles, slice, red, S1, S2);
     if (t < 32) {
         const int c = slice * 32 + t;
-        double S1 = 0, S2 = 0;
-        for (int g = 0; g < G; g++) { S1 += (double)__ldcg(&p.part[(g * 2) * 256 + c]); S2 += (double)__ldcg(&p.part[(g * 2 + 1) * 256 + c]); }
         const double cnt = (double)p.n * 64.0, mean = S1 / cnt;
         double var = S2 / cnt - mean * mean;
         if (var < 0) var = 0;
@@ -580,10 +606,11 @@ __global__ void __launch_bounds__(256, 4) k_bn_fwd(BnFwd p) {
         }
     }
     __syncthreads();
+    const size_t coff = (size_t)halo_pix(pos) * TC + slice * 32 + cq * 8;
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { sc[j] = sc_sh[cq * 8 + j]; sh[j] = sh_sh[cq * 8 + j]; }
-#pragma unroll 4
+#pragma unroll 2
     for (int b = b_lo; b < b_hi; b++) {
         const size_t off = (size_t)b * TPIX * TC + coff;
         const uint4 v = *reinterpret_cast<const uint4*>(p.y + off);
@@ -606,69 +633,28 @@ __global__ void __launch_bounds__(256, 4) k_bn_fwd(BnFwd p) {
 }
 
 struct BnBwd {
-    const bf16* d_in; const bf16* skip; const bf16* out; const bf16* y;
-    bf16* gm;                            // (d_in [+ skip]) * [out > 0]: the gradient arriving at the BatchNorm output (kept: it is the skip-path gradient below)
+    const bf16* gm;                      // (d_out [+ skip]) * [out > 0], written by the dgrad convolution's epilogue
+    const bf16* y;
     bf16* dy;                            // gradient of the convolution output
     const float* gamma; const float* mean; const float* invstd;
     float* g_gamma; float* g_beta;       // gradient slots of the flat gradient buffer
-    float* part;
-    GridBar* bar;
-    int32_t* error;
-    int n;
+    const float* part;                   // [tiles][2][256]: sum(g), sum(g * xhat) per tile
+    int n_tiles, n;
 };
 
-// ReLU + residual-join + BatchNorm backward in ONE launch: g = (d_in [+ skip]) * [out > 0]; per-channel sums of g and g * xhat; grid
-// barrier; dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); d_gamma, d_beta by the first board group.
-__global__ void __launch_bounds__(256, 4) k_bn_bwd(BnBwd p) {
+// BatchNorm backward: dy = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)); d_gamma, d_beta by the first board group.
+__global__ void __launch_bounds__(256) k_bn_bwd(BnBwd p) {
+    __shared__ double red[2][8][32];
+    __shared__ float ca_sh[32], cb_sh[32], cc_sh[32];
     pdl_trigger();
     pdl_wait();
-    __shared__ float red[2][8][33];
-    __shared__ float ca_sh[32], cb_sh[32], cc_sh[32];
-    __shared__ unsigned int gen_sh;
     const int slice = blockIdx.x, grp = blockIdx.y, G = gridDim.y;
     const int t = threadIdx.x, cq = t & 3, pos = t >> 2;
     const int b_lo = (int)((long long)grp * p.n / G), b_hi = (int)((long long)(grp + 1) * p.n / G);
-    if (t == 0) gen_sh = ld_acquire_u32(&p.bar->gen);
-    const int c0 = slice * 32 + cq * 8;
-    const size_t coff = (size_t)halo_pix(pos) * TC + c0;
-    float mean[8], invstd[8], s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { mean[j] = p.mean[c0 + j]; invstd[j] = p.invstd[c0 + j]; s1[j] = s2[j] = 0.f; }
-#pragma unroll 1
-    for (int b = b_lo; b < b_hi; b++) {
-        const size_t off = (size_t)b * TPIX * TC + coff;
-        const uint4 dv = *reinterpret_cast<const uint4*>(p.d_in + off), ov = *reinterpret_cast<const uint4*>(p.out + off),
-                    yv = *reinterpret_cast<const uint4*>(p.y + off);
-        const bf16* db = reinterpret_cast<const bf16*>(&dv);
-        const bf16* obf = reinterpret_cast<const bf16*>(&ov);
-        const bf16* yb = reinterpret_cast<const bf16*>(&yv);
-        float g[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) g[j] = __bfloat162float(db[j]);
-        if (p.skip) {
-            const uint4 sv = *reinterpret_cast<const uint4*>(p.skip + off);
-            const bf16* sb = reinterpret_cast<const bf16*>(&sv);
-#pragma unroll
-            for (int j = 0; j < 8; j++) g[j] += __bfloat162float(sb[j]);
-        }
-        uint4 o;
-        bf16* gb = reinterpret_cast<bf16*>(&o);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (!(__bfloat162float(obf[j]) > 0.f)) g[j] = 0.f;
-            gb[j] = __float2bfloat16(g[j]);
-            const float gr = __bfloat162float(gb[j]);
-            s1[j] += gr;
-            s2[j] += gr * ((__bfloat162float(yb[j]) - mean[j]) * invstd[j]);
-        }
-        *reinterpret_cast<uint4*>(p.gm + off) = o;
-    }
-    bn_block_sums(red, s1, s2, p.part, grp, slice);
-    grid_barrier(p.bar, gen_sh, gridDim.x * gridDim.y, p.error);
+    double S1, S2;
+    bn_fold_tile_sums(p.part, p.n_tiles, slice, red, S1, S2);
     if (t < 32) {
         const int c = slice * 32 + t;
-        double S1 = 0, S2 = 0;
-        for (int g = 0; g < G; g++) { S1 += (double)__ldcg(&p.part[(g * 2) * 256 + c]); S2 += (double)__ldcg(&p.part[(g * 2 + 1) * 256 + c]); }
         const double cnt = (double)p.n * 64.0;
         ca_sh[t] = p.gamma[c] * p.invstd[c];
         cb_sh[t] = (float)(S1 / cnt);
@@ -676,13 +662,18 @@ __global__ void __launch_bounds__(256, 4) k_bn_bwd(BnBwd p) {
         if (grp == 0) { p.g_beta[c] = (float)S1; p.g_gamma[c] = (float)S2; }
     }
     __syncthreads();
-    float ca[8], cb[8], cc[8];
+    const int c0 = slice * 32 + cq * 8;
+    const size_t coff = (size_t)halo_pix(pos) * TC + c0;
+    float mean[8], invstd[8], ca[8], cb[8], cc[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { ca[j] = ca_sh[cq * 8 + j]; cb[j] = cb_sh[cq * 8 + j]; cc[j] = cc_sh[cq * 8 + j]; }
-#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+        mean[j] = p.mean[c0 + j]; invstd[j] = p.invstd[c0 + j];
+        ca[j] = ca_sh[cq * 8 + j]; cb[j] = cb_sh[cq * 8 + j]; cc[j] = cc_sh[cq * 8 + j];
+    }
+#pragma unroll 2
     for (int b = b_lo; b < b_hi; b++) {
         const size_t off = (size_t)b * TPIX * TC + coff;
-        const uint4 gv = *reinterpret_cast<const uint4*>(p.gm + off), yv = *reinterpret_cast<const uint4*>(p.y + off);   // gm: this thread's own stores
+        const uint4 gv = *reinterpret_cast<const uint4*>(p.gm + off), yv = *reinterpret_cast<const uint4*>(p.y + off);
         const bf16* gb = reinterpret_cast<const bf16*>(&gv);
         const bf16* yb = reinterpret_cast<const bf16*>(&yv);
         float f[8];
@@ -1054,13 +1045,13 @@ struct Trainer {
     float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
     TLayer L[T_LAYERS];
     bf16* x_in = nullptr; CUtensorMap tm_in2, tm_in1;
-    bf16 *dl = nullptr, *gbuf[2] = {nullptr, nullptr}, *gm1 = nullptr, *skip[2] = {nullptr, nullptr};
+    bf16 *dl = nullptr, *gm1 = nullptr, *skip[2] = {nullptr, nullptr};
     CUtensorMap tm_dl2, tm_dl1;
     WgLayer* wg_layers = nullptr;                // [T_LAYERS] device table of k_wgrad
     unsigned long long* trace = nullptr;         // SZB_TRAIN_TRACE=1: stamps of the forward convolution of layer 20
     float* logits = nullptr;
     float* partial = nullptr; size_t partial_floats = 0;
-    float* bn_part = nullptr; GridBar* bar = nullptr;
+    float* bn_part = nullptr;                    // [tiles][2][256] per-tile sums from the convolution epilogues
     // value head
     float *yv = nullptr, *vr = nullptr, *dh1 = nullptr, *h1r = nullptr, *du = nullptr, *gr = nullptr, *dyv = nullptr, *value = nullptr, *se = nullptr, *ce = nullptr;
     float *vpart = nullptr, *db_part = nullptr, *v_running = nullptr;
@@ -1080,7 +1071,6 @@ struct Trainer {
     uint64_t steps_queued = 0;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;     // (boards, flags) -> the captured step
     bool use_graph = true;
-    int bn_groups_max = 18;
     bool pdl = true;                             // programmatic dependent launch along the convolution / BatchNorm chain (SZB_TRAIN_NO_PDL=1: off)
     std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
@@ -1251,8 +1241,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
             tr->buffers.push_back({t_layer_bn_name(l) + ".running_var", 256, L.bn + 256});
         }
     }
-    if ((rc = t_alloc(ctx, tr, &tr->gbuf[0], act)) || (rc = t_alloc(ctx, tr, &tr->gbuf[1], act)) ||
-        (rc = t_alloc(ctx, tr, &tr->gm1, act)) || (rc = t_alloc(ctx, tr, &tr->skip[0], act)) || (rc = t_alloc(ctx, tr, &tr->skip[1], act)) ||
+    if (        (rc = t_alloc(ctx, tr, &tr->gm1, act)) || (rc = t_alloc(ctx, tr, &tr->skip[0], act)) || (rc = t_alloc(ctx, tr, &tr->skip[1], act)) ||
         (rc = t_alloc(ctx, tr, &tr->dl, (size_t)cap * TPIX * DL_C)))
         return rc;
     if ((rc = t_halo_map(ctx, &tr->tm_dl2, tr->dl, DL_C, cap)) || (rc = t_act_map(ctx, &tr->tm_dl1, tr->dl, DL_C, cap, 1)))
@@ -1260,7 +1249,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
     tr->partial_floats = (size_t)WG_MAX_SPLIT * 256 * 256;                      // 1x1 layers: up to 64 splits of 256 x 256
     if (tr->partial_floats < (size_t)8 * 256 * 2304) tr->partial_floats = (size_t)8 * 256 * 2304;
     if ((rc = t_alloc(ctx, tr, &tr->partial, tr->partial_floats)) || (rc = t_alloc(ctx, tr, &tr->logits, (size_t)cap * T_ACTIONS)) ||
-        (rc = t_alloc(ctx, tr, &tr->bn_part, (size_t)BN_GROUPS * 512)) || (rc = t_alloc(ctx, tr, &tr->bar, 1)) ||
+        (rc = t_alloc(ctx, tr, &tr->bn_part, (size_t)(cap / 2) * 512)) ||
         (rc = t_alloc(ctx, tr, &tr->yv, (size_t)cap * 64)) || (rc = t_alloc(ctx, tr, &tr->vr, (size_t)cap * 64)) ||
         (rc = t_alloc(ctx, tr, &tr->dh1, (size_t)cap * 256)) || (rc = t_alloc(ctx, tr, &tr->h1r, (size_t)cap * 256)) ||
         (rc = t_alloc(ctx, tr, &tr->du, (size_t)cap)) || (rc = t_alloc(ctx, tr, &tr->gr, (size_t)cap * 64)) ||
@@ -1276,17 +1265,6 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
     {
         const long long s0 = cfg->step0;
         SZB_CUDA(ctx, cudaMemcpyAsync(tr->d_step, &s0, 8, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    {
-        int occ_f = 0, occ_b = 0, sms = 0;
-        SZB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_bn_fwd, 256, 0));
-        SZB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_bn_bwd, 256, 0));
-        SZB_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        const int occ = occ_f < occ_b ? occ_f : occ_b;
-        // three quarters of what fits: blocks of the neighbouring kernels (programmatic dependent launch) may hold some thread slots
-        tr->bn_groups_max = occ * sms * 3 / 4 / BN_SLICES;
-        if (tr->bn_groups_max < 1) return fail(ctx, SZB_ERR_CUDA, "BatchNorm kernels do not fit on this device");
-        if (tr->bn_groups_max > BN_GROUPS) tr->bn_groups_max = BN_GROUPS;
     }
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
@@ -1397,10 +1375,18 @@ static int t_transfer(szb_ctx* ctx, int kind, int32_t n_tensors, const char* con
     return rc;
 }
 
+struct TConvFuse {               // what the epilogue adds for the BatchNorm that follows (see TConvArgs)
+    bool stats = false;
+    const bf16* skip = nullptr; const bf16* o = nullptr; const bf16* y = nullptr;
+    const float* mean = nullptr; const float* invstd = nullptr;
+};
+
 static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUtensorMap& tm_w, int taps, int kchunks, int n_out, int n, bf16* out, int mode,
-                  const float* bias, unsigned long long* trace = nullptr) {
+                  const float* bias, unsigned long long* trace = nullptr, const TConvFuse& fuse = TConvFuse()) {
     TConvArgs a{};
     a.trace = trace;
+    a.stat_part = fuse.stats ? tr->bn_part : nullptr;
+    a.bn_skip = fuse.skip; a.bn_o = fuse.o; a.bn_y = fuse.y; a.bn_mean = fuse.mean; a.bn_invstd = fuse.invstd;
     a.taps = taps; a.kchunks = kchunks; a.n_boards = n; a.out = out; a.ldc = TC; a.logits = tr->logits; a.bias = bias; a.error = tr->error;
     const dim3 grid((unsigned)((((n + 1) / 2 + TR_CLUSTER - 1) / TR_CLUSTER) * TR_CLUSTER), n_out / 128);      // whole clusters: surplus CTAs compute on zero fill, store nothing
     if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv<0>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
@@ -1454,16 +1440,18 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
     // an odd batch leaves a phantom board in the last 2-board tile: GEMM rows are independent, its rows are computed and never stored
     k_gather_input<<<(unsigned)(((size_t)n * 64 * 16 + 255) / 256), 256, 0, st>>>(tr->rec_states, (long long)tr->rec_n, tr->rows, n, tr->x_in, tr->error);
     ctx->launches++;
-    int bn_groups = n / 2 < BN_GROUPS ? (n / 2 > 0 ? n / 2 : 1) : BN_GROUPS;
-    if (bn_groups > tr->bn_groups_max) bn_groups = tr->bn_groups_max;          // the BatchNorm kernels' grid barrier needs every block resident
+    const int bn_groups = n / 2 < BN_GROUPS ? (n / 2 > 0 ? n / 2 : 1) : BN_GROUPS;
+    const int n_tiles = (n + 1) / 2;
+    TConvFuse fwd_stats;
+    fwd_stats.stats = true;
     // ---------------- forward ----------------
     for (int l = 0; l < T_BN; l++) {
         TLayer& L = tr->L[l];
         const CUtensorMap& tm_a = l == 0 ? tr->tm_in2 : l == L_P1 ? tr->L[38].tm_o2 : tr->L[l - 1].tm_o2;
-        if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr, l == 20 ? tr->trace : nullptr))) return rc;
+        if ((rc = t_conv(ctx, tr, tm_a, L.tm_wf, L.taps, L.cin_pad / 64, 256, n, L.y, 0, nullptr, l == 20 ? tr->trace : nullptr, fwd_stats))) return rc;
         const bf16* res = (l >= 2 && l <= 38 && ((l - 1) & 1)) ? tr->L[l - 2].o : nullptr;
         BnFwd bp{L.y, res, L.o, tr->w + tr->params[L.gamma].off, tr->w + tr->params[L.beta].off, L.bn, L.bn + 256, L.bn + 512, L.bn + 768,
-                 tr->bn_part, tr->bar, tr->error, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
+                 tr->bn_part, n_tiles, n, tr->cfg.bn_momentum, tr->cfg.bn_eps};
         SZB_CUDA(ctx, launch_kernel(k_bn_fwd, dim3(BN_SLICES, bn_groups), dim3(256), 0, st, tr->pdl, bp));
         ctx->launches++;
     }
@@ -1493,25 +1481,38 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
         ctx->launches += 5;
         // conv_p2: weight gradient, then the gradient of its input (conv_p1's output after BN + ReLU)
         if ((rc = t_wgrad(ctx, tr, L_P2, 1, n))) return rc;
-        int cur = 0;                                            // gbuf[cur] holds the gradient arriving at the layer being processed
-        if ((rc = t_conv(ctx, tr, tr->tm_dl2, tr->L[L_P2].tm_wd, 1, DL_C / 64, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
+        // Every dgrad convolution's epilogue finishes the layer BELOW it: residual join, ReLU mask, the masked gradient `gm` and the two
+        // per-tile sums its BatchNorm backward needs.  below(l) = the layer whose output convolution l reads.
         int sk = 0;                                             // skip[sk] holds the skip-path gradient for the next residual join
+        bf16* gm_next = nullptr;                                // where the running dgrad left gm for the layer being processed
+        auto fuse_for = [&](int lb, bf16** gm_out) {
+            const TLayer& B = tr->L[lb];
+            const bool join = lb == 0 || (lb <= 38 && ((lb - 1) & 1));   // layers whose output feeds a residual add as well (or both heads)
+            TConvFuse f;
+            f.stats = true;
+            f.skip = join ? tr->skip[sk] : nullptr;
+            f.o = B.o; f.y = B.y; f.mean = B.bn + 512; f.invstd = B.bn + 768;
+            *gm_out = join ? tr->skip[sk ^ 1] : tr->gm1;
+            if (join) sk ^= 1;
+            return f;
+        };
+        {
+            const TConvFuse f = fuse_for(L_P1, &gm_next);
+            if ((rc = t_conv(ctx, tr, tr->tm_dl2, tr->L[L_P2].tm_wd, 1, DL_C / 64, 256, n, gm_next, 0, nullptr, nullptr, f))) return rc;
+        }
         for (int l = L_P1; l >= 0; l--) {
             TLayer& L = tr->L[l];
-            const bool join = l == 0 || (l <= 38 && ((l - 1) & 1));          // layers whose output feeds a residual add as well (or two heads)
-            const bf16* skip_in = join ? tr->skip[sk] : nullptr;
-            bf16* gm = join ? tr->skip[sk ^ 1] : tr->gm1;
-            BnBwd bp{tr->gbuf[cur], skip_in, L.o, L.y, gm, L.dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768,
-                     tr->g + tr->params[L.gamma].off, tr->g + tr->params[L.beta].off, tr->bn_part, tr->bar, tr->error, n};
+            BnBwd bp{gm_next, L.y, L.dy, tr->w + tr->params[L.gamma].off, L.bn + 512, L.bn + 768, tr->g + tr->params[L.gamma].off,
+                     tr->g + tr->params[L.beta].off, tr->bn_part, n_tiles, n};
             SZB_CUDA(ctx, launch_kernel(k_bn_bwd, dim3(BN_SLICES, bn_groups), dim3(256), 0, st, tr->pdl, bp));
             ctx->launches++;
-            if (join) sk ^= 1;
             if (l == 0 || l == L_P1) {
                 if ((rc = t_wgrad(ctx, tr, l, 1, n))) return rc;
             }
             if (l > 0) {
-                cur ^= 1;
-                if ((rc = t_conv(ctx, tr, L.tm_dy2, L.tm_wd, L.taps, 4, 256, n, tr->gbuf[cur], 0, nullptr))) return rc;
+                const int lb = l == L_P1 ? 38 : l - 1;
+                const TConvFuse f = fuse_for(lb, &gm_next);
+                if ((rc = t_conv(ctx, tr, L.tm_dy2, L.tm_wd, L.taps, 4, 256, n, gm_next, 0, nullptr, nullptr, f))) return rc;
             }
         }
         if ((rc = t_wgrad(ctx, tr, 1, 38, n))) return rc;         // every tower convolution's weight gradient
