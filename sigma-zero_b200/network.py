@@ -5,8 +5,9 @@ hand-written sm_100a kernels of libszb200 (szb_net_forward), not on torch ops, a
 
 `precision` selects the kernel family: "bf16" = tcgen05/TMEM implicit-GEMM tower, "fp32" = SIMT parity path.
 
-In model.train() mode the same modules are evaluated by torch with autograd (batch-statistics BatchNorm), which is what
-the reference's fine-tuning step does (train_RL.py:77-154; SURVEY.md 8f rank 1, a "next" row outside the hot path)."""
+In model.train() mode the same modules are evaluated by torch with autograd (batch-statistics BatchNorm): the reference's own
+fine-tuning code path (train_RL.py:77-154), kept as the oracle of the CUDA trainer (trainer.py / csrc/train.cu, which is what
+train_RL.train_on_records runs on a GPU) and for CPU-only use."""
 import torch
 import torch.nn as nn
 

@@ -1,14 +1,17 @@
 """Self-play fan-out of the reference's train_RL.py (args + launcher, train_RL.py:156-244) and, as a "next" row
-(SURVEY.md 8f rank 1), its fine-tuning step on the self-play records (train_RL.py:77-154) in torch.
+(SURVEY.md 8f rank 1), its fine-tuning step on the self-play records (train_RL.py:77-154): on the GPU library's own trainer
+(trainer.py -> szb_train_*, csrc/train.cu) whenever the training device is a GPU, in torch otherwise.
 
 The reference spawns `num_process` CPU workers that each play `num_games // num_process` games one after another
 and merges their pickled dicts.  Here every rank (one process per GPU, torch.distributed over NCCL) plays its
 shard of the games concurrently on its GPU; the only collective is the broadcast of the flat fp32 weight buffer
 from the trainer rank at the start of an iteration.  `num_selfPlay_iterations` -- which the reference's args
 carry but never read -- is defined as the number of self-play games per outer iteration.
-Training (train_on_records / rl_iteration below) is outside the self-play hot path: it runs the reference's own torch
-recipe -- loss = MSE(v, z) + CE(logits, pi) (:103-113), Adam lr 1e-4 wd 1e-4 (:187), StepLR(500, 0.95) (:199) -- on the
-packed record format of records.py; the weights it produces reach the CUDA engine through runtime.sync_weights."""
+Training (train_on_records / rl_iteration below) follows the reference's recipe -- loss = MSE(v, z) + CE(logits, pi) (:103-113),
+Adam lr 1e-4 wd 1e-4 (:187), StepLR(500, 0.95) (:199) -- on the packed record format of records.py.  The CUDA trainer is deterministic,
+so the ranks of a job, which all train on the same gathered records, keep identical weights; the trained flat weight buffer is folded
+into the inference network on the device (Engine.load_flat_device), torch objects (module, optimiser, scheduler) carry the state
+between iterations and into checkpoints."""
 import os
 
 import torch
