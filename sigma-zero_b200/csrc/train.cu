@@ -46,7 +46,8 @@ constexpr int DL_C = 128;                    // channels of the logits-gradient 
 constexpr int TR_THREADS = 192;              // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
 constexpr int TR_A_CHUNKS = 3;
 constexpr int TR_A_CHUNK_BYTES = 2 * TPIX * 128;      // two boards with their halo x 64 channels: 25600 = 25 * 1024
-constexpr int TR_B_STAGES = 6;
+constexpr int TR_B_STAGES = 6;                        // (10 stages with 2 activation chunks measured the same: the loop is not latency bound)
+constexpr bool TR_DUAL_ACC = false;                   // A/B aid: even / odd K steps accumulate into two TMEM tiles (two independent MMA chains); measured: no change
 constexpr int TR_CLUSTER = 4;                         // CTAs (neighbouring tiles) that share every weight tile through TMA multicast
 constexpr int TR_B_BYTES = 128 * 64 * 2;              // 128 output channels x 64 k
 constexpr int TR_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TR_B_STAGES * TR_B_BYTES + 1024;
@@ -146,6 +147,115 @@ __device__ __forceinline__ void t_stamp(unsigned long long* tr, int k) {
     if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tr[k] = t; }
 }
 
+// Epilogue of the training convolutions (the four epilogue warps of a CTA; `tile` = index of this CTA's two boards): TMEM -> registers ->
+// [backward: + skip, ReLU mask] -> bf16 rows / fp32 logits, and the fused BatchNorm sums (see TConvArgs).
+template <int MODE, bool DUAL = false>
+__device__ __forceinline__ void tconv_epilogue(const TConvArgs& a, uint32_t tmem_base, int tile, int nh, int warp, int lane, uint32_t bar_acc_addr,
+                                               volatile int* abort_flag, float (*st_sh)[4][128], float (*mi_sh)[128], unsigned long long* trace) {
+    const int lane_group = warp & 3;
+    const int e = (warp - 2) * 32 + lane;                              // 0..127 over the four epilogue warps
+    const bool stats = MODE == 0 && a.stat_part != nullptr, bwd = MODE == 0 && a.bn_o != nullptr;
+    if (bwd) { mi_sh[0][e] = a.bn_mean[nh * 128 + e]; mi_sh[1][e] = a.bn_invstd[nh * 128 + e]; }
+    bool ok = mbar_wait(bar_acc_addr, 0, abort_flag);
+    ok = __all_sync(0xFFFFFFFFu, ok);
+    if (warp == 2 && lane == 0) t_stamp(trace, 5);
+    if (ok) {
+        tc_fence_after();
+        if (bwd) asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int m = lane_group * 32 + lane;                          // row (oy * 2 + board) * 8 + ox
+        const int board = tile * 2 + ((m >> 3) & 1), sq = (m >> 4) * 8 + (m & 7);
+        const bool live = board < a.n_boards;
+        const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+        const size_t pix = (size_t)board * TPIX + halo_pix(sq);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x16(taddr + c0, v);
+            tmem_ld_32x32b_x16(taddr + c0 + 16, v + 16);
+            if (DUAL) {
+                // two interleaved accumulation chains (even / odd K steps): their sum is the convolution
+                uint32_t w[32];
+                tmem_ld_32x32b_x16(taddr + 128 + c0, w);
+                tmem_ld_32x32b_x16(taddr + 128 + c0 + 16, w + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            } else {
+                tmem_ld_wait();
+            }
+            if (MODE == 0) {
+                const size_t off = pix * a.ldc + nh * 128 + c0;
+                float f[32], xh[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) f[j] = live ? __uint_as_float(v[j]) : 0.f;
+                if (bwd) {
+                    if (live) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint4 ov = *reinterpret_cast<const uint4*>(a.bn_o + off + q * 8), yv = *reinterpret_cast<const uint4*>(a.bn_y + off + q * 8);
+                            const bf16* ob = reinterpret_cast<const bf16*>(&ov);
+                            const bf16* yb = reinterpret_cast<const bf16*>(&yv);
+                            if (a.bn_skip) {
+                                const uint4 sv = *reinterpret_cast<const uint4*>(a.bn_skip + off + q * 8);
+                                const bf16* sb = reinterpret_cast<const bf16*>(&sv);
+#pragma unroll
+                                for (int j = 0; j < 8; j++) f[q * 8 + j] += __bfloat162float(sb[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                if (!(__bfloat162float(ob[j]) > 0.f)) f[q * 8 + j] = 0.f;
+                                xh[q * 8 + j] = (__bfloat162float(yb[j]) - mi_sh[0][c0 + q * 8 + j]) * mi_sh[1][c0 + q * 8 + j];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) xh[j] = 0.f;
+                    }
+                }
+                uint4 o[4];
+                __nv_bfloat162* ob2 = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+                for (int j = 0; j < 16; j++) ob2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                if (live) {
+                    uint4* op = reinterpret_cast<uint4*>(a.out + off);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) op[j] = o[j];
+                }
+                if (stats) {
+                    // sums of the ROUNDED values: exactly what the BatchNorm kernel will read back
+                    float s2[32];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float2 r = __bfloat1622float2(ob2[j]);
+                        f[2 * j] = r.x;
+                        f[2 * j + 1] = r.y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) s2[j] = bwd ? f[j] * xh[j] : f[j] * f[j];
+                    const float c1 = warp_col_sum32(f, lane), c2 = warp_col_sum32(s2, lane);
+                    st_sh[0][lane_group][c0 + lane] = c1;
+                    st_sh[1][lane_group][c0 + lane] = c2;
+                }
+            } else if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int c = nh * 128 + c0 + j;
+                    if (c < 73) a.logits[(size_t)board * T_ACTIONS + c * 64 + sq] = __uint_as_float(v[j]) + a.bias[c];
+                }
+            }
+        }
+        if (stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tile * 2 < a.n_boards) {
+#pragma unroll
+                for (int which = 0; which < 2; which++)
+                    a.stat_part[((size_t)tile * 2 + which) * a.ldc + nh * 128 + e] =
+                        ((st_sh[which][0][e] + st_sh[which][1][e]) + st_sh[which][2][e]) + st_sh[which][3][e];
+            }
+        }
+    }
+}
+
 // Shared memory: a ring of TR_A_CHUNKS activation chunks and a ring of TR_B_STAGES weight tiles.  An activation chunk is one 64-channel
 // slice of the tile's two boards INCLUDING the halo, 200 rows of 128 bytes in the order [y][board][x] (one TMA box through a tensor map
 // with dims (c, x, board, y)); all nine taps read it in place: the A descriptor of tap (ky, kx) starts (ky * 20 + kx) rows into the chunk
@@ -181,7 +291,7 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(TR_DUAL_ACC ? 256 : 128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -238,10 +348,11 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
                     if (elect_one()) {
                         const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
                         const uint32_t b_lo = b_lo0 + bs * (TR_B_BYTES >> 4);
-                        t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, tap == 0 ? accumulate : 1u);
-                        t_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                        const uint32_t d1 = tmem_base + (TR_DUAL_ACC ? 128u : 0u), first = tap == 0 ? accumulate : 1u;
+                        t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, first);
+                        t_mma_split(d1, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, TR_DUAL_ACC ? first : 1u);
                         t_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
-                        t_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                        t_mma_split(d1, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
                         tc_commit_mc(bar_be0 + bs * 8, CMASK);
                     }
                     __syncwarp();
@@ -253,10 +364,11 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
                 if (elect_one()) {
                     const uint32_t a_lo = chunk_lo + (uint32_t)(2 * TH + 1) * (128 >> 4);            // centre tap
                     const uint32_t b_lo = b_lo0 + bs * (TR_B_BYTES >> 4);
+                    const uint32_t d1 = tmem_base + (TR_DUAL_ACC ? 128u : 0u);
                     t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, accumulate);
-                    t_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                    t_mma_split(d1, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, TR_DUAL_ACC ? accumulate : 1u);
                     t_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
-                    t_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                    t_mma_split(d1, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
                     tc_commit_mc(bar_be0 + bs * 8, CMASK);
                 }
                 __syncwarp();
@@ -270,104 +382,174 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
         if (ok && elect_one()) { tc_commit(smem_u32(&bar_acc)); t_stamp(trace, 4); }
         __syncwarp();
     } else {
-        const int lane_group = warp & 3;
-        const int e = (warp - 2) * 32 + lane;                              // 0..127 over the four epilogue warps
-        const bool stats = MODE == 0 && a.stat_part != nullptr, bwd = MODE == 0 && a.bn_o != nullptr;
-        if (bwd) { mi_sh[0][e] = a.bn_mean[nh * 128 + e]; mi_sh[1][e] = a.bn_invstd[nh * 128 + e]; }
-        bool ok = mbar_wait(smem_u32(&bar_acc), 0, abort_flag);
-        ok = __all_sync(0xFFFFFFFFu, ok);
-        if (warp == 2 && lane == 0) t_stamp(trace, 5);
-        if (ok) {
-            tc_fence_after();
-            if (bwd) asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int m = lane_group * 32 + lane;                          // row (oy * 2 + board) * 8 + ox
-            const int board = tile * 2 + ((m >> 3) & 1), sq = (m >> 4) * 8 + (m & 7);
-            const bool live = board < a.n_boards;
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
-            const size_t pix = (size_t)board * TPIX + halo_pix(sq);
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x16(taddr + c0, v);
-                tmem_ld_32x32b_x16(taddr + c0 + 16, v + 16);
-                tmem_ld_wait();
-                if (MODE == 0) {
-                    const size_t off = pix * a.ldc + nh * 128 + c0;
-                    float f[32], xh[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) f[j] = live ? __uint_as_float(v[j]) : 0.f;
-                    if (bwd) {
-                        if (live) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const uint4 ov = *reinterpret_cast<const uint4*>(a.bn_o + off + q * 8), yv = *reinterpret_cast<const uint4*>(a.bn_y + off + q * 8);
-                                const bf16* ob = reinterpret_cast<const bf16*>(&ov);
-                                const bf16* yb = reinterpret_cast<const bf16*>(&yv);
-                                if (a.bn_skip) {
-                                    const uint4 sv = *reinterpret_cast<const uint4*>(a.bn_skip + off + q * 8);
-                                    const bf16* sb = reinterpret_cast<const bf16*>(&sv);
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) f[q * 8 + j] += __bfloat162float(sb[j]);
-                                }
-#pragma unroll
-                                for (int j = 0; j < 8; j++) {
-                                    if (!(__bfloat162float(ob[j]) > 0.f)) f[q * 8 + j] = 0.f;
-                                    xh[q * 8 + j] = (__bfloat162float(yb[j]) - mi_sh[0][c0 + q * 8 + j]) * mi_sh[1][c0 + q * 8 + j];
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) xh[j] = 0.f;
-                        }
-                    }
-                    uint4 o[4];
-                    __nv_bfloat162* ob2 = reinterpret_cast<__nv_bfloat162*>(o);
-#pragma unroll
-                    for (int j = 0; j < 16; j++) ob2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                    if (live) {
-                        uint4* op = reinterpret_cast<uint4*>(a.out + off);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) op[j] = o[j];
-                    }
-                    if (stats) {
-                        // sums of the ROUNDED values: exactly what the BatchNorm kernel will read back
-                        float s2[32];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const float2 r = __bfloat1622float2(ob2[j]);
-                            f[2 * j] = r.x;
-                            f[2 * j + 1] = r.y;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; j++) s2[j] = bwd ? f[j] * xh[j] : f[j] * f[j];
-                        const float c1 = warp_col_sum32(f, lane), c2 = warp_col_sum32(s2, lane);
-                        st_sh[0][lane_group][c0 + lane] = c1;
-                        st_sh[1][lane_group][c0 + lane] = c2;
-                    }
-                } else if (live) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int c = nh * 128 + c0 + j;
-                        if (c < 73) a.logits[(size_t)board * T_ACTIONS + c * 64 + sq] = __uint_as_float(v[j]) + a.bias[c];
-                    }
-                }
-            }
-            if (stats) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (tile * 2 < a.n_boards) {
-#pragma unroll
-                    for (int which = 0; which < 2; which++)
-                        a.stat_part[((size_t)tile * 2 + which) * a.ldc + nh * 128 + e] =
-                            ((st_sh[which][0][e] + st_sh[which][1][e]) + st_sh[which][2][e]) + st_sh[which][3][e];
-                }
-            }
-        }
+        tconv_epilogue<MODE, TR_DUAL_ACC>(a, tmem_base, tile, nh, warp, lane, smem_u32(&bar_acc), abort_flag, st_sh, mi_sh, trace);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TR_DUAL_ACC ? 256 : 128) : "memory");
     t_cluster_sync();                               // no CTA leaves while a peer's commit may still arrive on its barriers
+    if (threadIdx.x == 0) t_stamp(trace, 6);
+    if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// The same convolution as a CTA PAIR (cta_group::2): M 256 (four boards, 128 rows per CTA) x N 128 x K 16 per MMA, issued by the leader for
+// both SMs.  Each CTA stages its own activation chunk and HALF of every weight tile (64 rows); per 64-cycle MMA an SM then reads 4 KB of A
+// and 2 KB of B from shared memory instead of 4 + 4 KB.  A/B aid (SZB_TRAIN_CONV=2): it measured no faster than k_tconv (9.4 vs 8.6 us main
+// loop at 128 boards), which rules shared-memory operand bandwidth out as the bound of the 64-cycle MMAs.  Barriers live on the
+// leader for "data landed" (both CTAs' TMA bytes are counted there) and in both CTAs for "stage free" / "accumulator ready" (the leader's
+// commits are multicast) -- the protocol of k_tower_tc2 (net.cu).
+constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in the pair's even CTA
+constexpr int TP_B_STAGES = 8;
+constexpr int TP_B_BYTES = 64 * 64 * 2;               // this CTA's half of a 128-channel x 64-k weight tile
+constexpr int TP_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TP_B_STAGES * TP_B_BYTES + 1024;
+
+__device__ __forceinline__ void tp_tma_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar & T2_PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tp_tma_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar & T2_PEER_MASK), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tp_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tp_mma_split(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TR_THREADS, 1)
+k_tconv_pair(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TConvArgs a) {
+    constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);      // M 256, N 128
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_af[TR_A_CHUNKS], bar_ae[TR_A_CHUNKS], bar_bf[TP_B_STAGES], bar_be[TP_B_STAGES], bar_acc;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ int abort_sh;
+    __shared__ float st_sh[2][4][128], mi_sh[2][128];
+
+    const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = smem_a + TR_A_CHUNKS * TR_A_CHUNK_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = t_cluster_rank();
+    const int tile = blockIdx.x, nh = blockIdx.y;          // tile = this CTA's two boards; the pair = tiles (2p, 2p + 1)
+    volatile int* abort_flag = &abort_sh;
+    unsigned long long* trace = (blockIdx.x == 0 && blockIdx.y == 0) ? a.trace : nullptr;
+    if (threadIdx.x == 0) t_stamp(trace, 0);
+
+    if (threadIdx.x == 0) {
+        abort_sh = 0;
+        for (int s = 0; s < TR_A_CHUNKS; s++) { mbar_init(smem_u32(&bar_af[s]), 1); mbar_init(smem_u32(&bar_ae[s]), 1); }
+        for (int s = 0; s < TP_B_STAGES; s++) { mbar_init(smem_u32(&bar_bf[s]), 1); mbar_init(smem_u32(&bar_be[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    t_cluster_sync();                               // both CTAs' barriers and TMEM exist from here on
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    if (threadIdx.x == 0) t_stamp(trace, 1);
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x == 0) t_stamp(trace, 2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ac = 0, bs = 0;
+            uint32_t a_phase = 0, b_phase = 0;
+            bool ok = true;
+            for (int kc = 0; kc < a.kchunks && ok; kc++) {
+                if (!(ok = mbar_wait(smem_u32(&bar_ae[ac]), a_phase ^ 1, abort_flag))) break;
+                const uint32_t af = smem_u32(&bar_af[ac]);
+                if (rank == 0) mbar_expect_tx(af, 2u * TR_A_CHUNK_BYTES);      // both CTAs' bytes land on the leader's barrier
+                tp_tma_4d(smem_a + ac * TR_A_CHUNK_BYTES, &tm_a, af, kc * 64, 0, tile * 2, 0);
+                if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
+                for (int tap = 0; tap < a.taps; tap++) {
+                    if (!(ok = mbar_wait(smem_u32(&bar_be[bs]), b_phase ^ 1, abort_flag))) break;
+                    const uint32_t bf = smem_u32(&bar_bf[bs]);
+                    if (rank == 0) mbar_expect_tx(bf, 2u * TP_B_BYTES);
+                    const int k = (tap * a.kchunks + kc) * 64, row = nh * 128 + (int)rank * 64;
+                    tp_tma_2d(smem_b + bs * TP_B_BYTES, &tm_w, bf, k, row);                        // the weight map's box is 32 rows
+                    tp_tma_2d(smem_b + bs * TP_B_BYTES + TP_B_BYTES / 2, &tm_w, bf, k, row + 32);
+                    if (++bs == TP_B_STAGES) { bs = 0; b_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            const uint32_t a_lo0 = ((smem_a >> 4) & 0x3FFFu) | DESC_LO_FLAGS, b_lo0 = ((smem_b >> 4) & 0x3FFFu) | DESC_LO_FLAGS;
+            const uint32_t bar_af0 = smem_u32(&bar_af[0]), bar_ae0 = smem_u32(&bar_ae[0]), bar_bf0 = smem_u32(&bar_bf[0]), bar_be0 = smem_u32(&bar_be[0]);
+            uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0, accumulate = 0;
+            bool ok = true;
+            for (int kc = 0; kc < a.kchunks && ok; kc++) {
+                if (!(ok = warp_mbar_wait(bar_af0 + ac * 8, a_phase, abort_flag))) break;
+                tc_fence_after();
+                if (kc == 0 && lane == 0) t_stamp(trace, 3);
+                const uint32_t chunk_lo = a_lo0 + ac * (TR_A_CHUNK_BYTES >> 4);
+                if (a.taps == 9) {
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) {
+                        if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
+                            const uint32_t b_lo = b_lo0 + bs * (TP_B_BYTES >> 4);
+                            tp_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, tap == 0 ? accumulate : 1u);
+                            tp_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                            tp_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
+                            tp_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                            tp_commit(bar_be0 + bs * 8);
+                        }
+                        __syncwarp();
+                        if (++bs == TP_B_STAGES) { bs = 0; b_phase ^= 1; }
+                    }
+                } else {
+                    if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = chunk_lo + (uint32_t)(2 * TH + 1) * (128 >> 4);
+                        const uint32_t b_lo = b_lo0 + bs * (TP_B_BYTES >> 4);
+                        tp_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, accumulate);
+                        tp_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                        tp_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
+                        tp_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                        tp_commit(bar_be0 + bs * 8);
+                    }
+                    __syncwarp();
+                    if (++bs == TP_B_STAGES) { bs = 0; b_phase ^= 1; }
+                }
+                accumulate = 1;
+                if (ok && elect_one()) tp_commit(bar_ae0 + ac * 8);
+                __syncwarp();
+                if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
+            }
+            if (ok && elect_one()) { tp_commit(smem_u32(&bar_acc)); t_stamp(trace, 4); }
+            __syncwarp();
+        }
+    } else {
+        tconv_epilogue<MODE>(a, tmem_base, tile, nh, warp, lane, smem_u32(&bar_acc), abort_flag, st_sh, mi_sh, trace);
+    }
+    tc_fence_before();
+    t_cluster_sync();
+    tc_fence_after();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
     if (threadIdx.x == 0) t_stamp(trace, 6);
     if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
 }
@@ -1071,6 +1253,7 @@ struct Trainer {
     uint64_t steps_queued = 0;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;     // (boards, flags) -> the captured step
     bool use_graph = true;
+    bool conv_pair = false;                      // SZB_TRAIN_CONV=2: convolutions as CTA pairs (k_tconv_pair; measured 4 % slower than k_tconv at 128 boards)
     bool pdl = true;                             // programmatic dependent launch along the convolution / BatchNorm chain (SZB_TRAIN_NO_PDL=1: off)
     std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
@@ -1268,6 +1451,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
     }
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
+    if (const char* e = getenv("SZB_TRAIN_CONV")) tr->conv_pair = atoi(e) == 2;
     if (const char* e = getenv("SZB_TRAIN_TRACE")) {
         if (atoi(e) && (rc = t_alloc(ctx, tr, &tr->trace, 8))) return rc;
     }
@@ -1292,6 +1476,8 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
     if (!tr->attr_set) {
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 6 * WG_BOX + 1024));
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 4 * WG_BOX + 1024));
         tr->attr_set = true;
@@ -1388,6 +1574,13 @@ static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUte
     a.stat_part = fuse.stats ? tr->bn_part : nullptr;
     a.bn_skip = fuse.skip; a.bn_o = fuse.o; a.bn_y = fuse.y; a.bn_mean = fuse.mean; a.bn_invstd = fuse.invstd;
     a.taps = taps; a.kchunks = kchunks; a.n_boards = n; a.out = out; a.ldc = TC; a.logits = tr->logits; a.bias = bias; a.error = tr->error;
+    if (tr->conv_pair) {
+        const dim3 grid2((unsigned)(((n + 3) / 4) * 2), n_out / 128);                       // whole pairs: a surplus CTA computes on zero fill, stores nothing
+        if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv_pair<0>, grid2, dim3(TR_THREADS), TP_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+        else SZB_CUDA(ctx, launch_kernel(k_tconv_pair<1>, grid2, dim3(TR_THREADS), TP_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+        ctx->launches++;
+        return 0;
+    }
     const dim3 grid((unsigned)((((n + 1) / 2 + TR_CLUSTER - 1) / TR_CLUSTER) * TR_CLUSTER), n_out / 128);      // whole clusters: surplus CTAs compute on zero fill, store nothing
     if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv<0>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
     else SZB_CUDA(ctx, launch_kernel(k_tconv<1>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
