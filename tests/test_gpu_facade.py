@@ -319,9 +319,15 @@ def test_train_rl_main_loop_and_resume(tmp_path):
         assert (tmp_path / "saves" / ("RL_960_%d.pt" % epoch)).exists() and (tmp_path / "saves" / ("RL_960_opt_%d.pt" % epoch)).exists()
     saved = torch.load(str(tmp_path / "saves" / "RL_960_2.pt"), map_location="cpu")
     assert all(torch.equal(v.cpu(), saved[k]) for k, v in model.state_dict().items())
+    # the CUDA trainer's state travels in torch's formats: 3 batches per epoch -> Adam step 6, StepLR counter 6
+    opt2 = torch.load(str(tmp_path / "saves" / "RL_960_opt_2.pt"), map_location="cpu")
+    assert len(opt2["state"]) == 129 and float(opt2["state"][0]["step"]) == 6 and opt2["state"][0]["exp_avg"].shape == saved["conv1.weight"].shape
+    assert torch.load(str(tmp_path / "saves" / "RL_960_sched_2.pt"), map_location="cpu")["last_epoch"] == 6
     # resume: epoch 3 starts from the weights of epoch 2
     logs.clear()
     model2, hist2 = main(dict(args, start_epoch=3, num_epochs=4), model=policyNN({}), num_games=4, out_dir=str(tmp_path),
                          max_plies=2, passes_per_epoch=1, train_device="cuda", log=logs.append)
     assert [h["epoch"] for h in hist2] == [3] and not any("No saved weights" in str(l) for l in logs)
     assert (tmp_path / "saves" / "RL_960_3.pt").exists()
+    opt3 = torch.load(str(tmp_path / "saves" / "RL_960_opt_3.pt"), map_location="cpu")
+    assert float(opt3["state"][0]["step"]) == 6 + len(hist2[0]["losses"])          # the step counter continued from the checkpoint
