@@ -271,6 +271,10 @@ int szb_train_records(szb_ctx *ctx, int64_t n, const uint64_t *states, const int
 /* one optimiser step on the batch of record rows `rows` [n] (2 <= n <= cfg.batch); losses_out (may be null: no synchronisation)
  * receives {mse, cross entropy} of the batch BEFORE the update, as the reference prints them */
 int szb_train_step(szb_ctx *ctx, int32_t n, const int32_t *rows, int32_t flags, float *losses_out);
+/* {mse, cross entropy} of steps [first, first + count) since szb_train_create (every szb_train_step counts), from a device ring of
+ * the last 65,536 steps: a loop can queue steps with losses_out = null and read the history in bulk.  Synchronises; reports a
+ * kernel-side failure of any step run since the last check. */
+int szb_train_loss_history(szb_ctx *ctx, int64_t first, int32_t count, float *out);
 /* optimiser step counter: read (set = 0) or overwrite (set = 1) */
 int szb_train_state(szb_ctx *ctx, int64_t *step_inout, int32_t set);
 

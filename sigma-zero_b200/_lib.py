@@ -98,6 +98,7 @@ SIGNATURES = {
     "szb_train_get": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "szb_train_records": (ctypes.c_int, [_vp, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "szb_train_step": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp]),
+    "szb_train_loss_history": (ctypes.c_int, [_vp, ctypes.c_int64, _i32, _vp]),
     "szb_train_state": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int64), _i32]),
 }
 

@@ -1111,12 +1111,18 @@ __global__ void __launch_bounds__(256) k_policy_loss(LossArgs a) {
 }
 
 // losses[0] = mean squared error, losses[1] = mean cross entropy (sequential sums: deterministic)
-__global__ void k_loss_reduce(const float* se, const float* ce, int n, float* losses) {
+// ... and appended to a ring of the last LOSS_HIST steps' losses, so that a training loop can queue steps without a host round trip each
+// and read the history back in bulk (szb_train_loss_history)
+constexpr int LOSS_HIST = 1 << 16;
+__global__ void k_loss_reduce(const float* se, const float* ce, int n, float* losses, float* hist, unsigned long long* hist_count) {
     if (threadIdx.x == 0) {
         double a = 0, c = 0;
         for (int i = 0; i < n; i++) { a += se[i]; c += ce[i]; }
         losses[0] = (float)(a / n);
         losses[1] = (float)(c / n);
+        const unsigned long long k = (*hist_count)++ % LOSS_HIST;
+        hist[2 * k] = losses[0];
+        hist[2 * k + 1] = losses[1];
     }
 }
 
@@ -1239,6 +1245,8 @@ struct Trainer {
     float *vpart = nullptr, *db_part = nullptr, *v_running = nullptr;
     VStat* vstat = nullptr;
     float* losses = nullptr;
+    float* loss_hist = nullptr; unsigned long long* hist_count = nullptr;      // device ring of per-step losses and its step counter
+    int64_t steps_run = 0;                                                     // host mirror of *hist_count
     PackDesc* pack_descs = nullptr;
     int32_t* error = nullptr;
     int32_t* rows = nullptr;
@@ -1441,7 +1449,8 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         (rc = t_alloc(ctx, tr, &tr->vpart, (size_t)cap * 256)) || (rc = t_alloc(ctx, tr, &tr->db_part, (size_t)cap * DL_C)) ||
         (rc = t_alloc(ctx, tr, &tr->v_running, 4)) || (rc = t_alloc(ctx, tr, &tr->vstat, 1)) || (rc = t_alloc(ctx, tr, &tr->losses, 2)) ||
         (rc = t_alloc(ctx, tr, &tr->error, 1)) || (rc = t_alloc(ctx, tr, &tr->rows, (size_t)cap)) ||
-        (rc = t_alloc(ctx, tr, &tr->pack_descs, (size_t)T_LAYERS)) || (rc = t_alloc(ctx, tr, &tr->d_step, 1)) || (rc = t_alloc(ctx, tr, &tr->hyper, 2)))
+        (rc = t_alloc(ctx, tr, &tr->pack_descs, (size_t)T_LAYERS)) || (rc = t_alloc(ctx, tr, &tr->d_step, 1)) || (rc = t_alloc(ctx, tr, &tr->hyper, 2)) ||
+        (rc = t_alloc(ctx, tr, &tr->loss_hist, (size_t)2 * LOSS_HIST)) || (rc = t_alloc(ctx, tr, &tr->hist_count, 1)))
         return rc;
     SZB_CUDA(ctx, cudaMallocHost((void**)&tr->rows_host, (size_t)ROWS_RING * cap * 4));
     for (int i = 0; i < ROWS_RING; i++) SZB_CUDA(ctx, cudaEventCreateWithFlags(&tr->rows_ev[i], cudaEventDisableTiming));
@@ -1658,7 +1667,7 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
     k_vhead<<<n, 256, 0, st>>>(vh);
     LossArgs la{tr->logits, tr->rows, tr->rec_off, tr->rec_index, tr->rec_prob, tr->dl, tr->ce, tr->db_part, n};
     k_policy_loss<<<n, 256, 0, st>>>(la);
-    k_loss_reduce<<<1, 32, 0, st>>>(tr->se, tr->ce, n, tr->losses);
+    k_loss_reduce<<<1, 32, 0, st>>>(tr->se, tr->ce, n, tr->losses, tr->loss_hist, tr->hist_count);
     ctx->launches += 5;
     SZB_CUDA(ctx, cudaGetLastError());
     if (!(flags & SZB_TRAIN_FORWARD_ONLY)) {
@@ -1765,6 +1774,7 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
     }
     if (!done && (rc = t_step_launches(ctx, tr, n, flags))) return rc;
     if (!(flags & (SZB_TRAIN_NO_UPDATE | SZB_TRAIN_FORWARD_ONLY))) tr->step++;
+    tr->steps_run++;
     if (losses_out) {
         int32_t err = 0;
         SZB_CUDA(ctx, cudaMemcpyAsync(losses_out, tr->losses, 8, cudaMemcpyDefault, st));
@@ -1856,6 +1866,32 @@ int szb_train_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, 
     if (!ctx) return SZB_ERR_ARG;
     cudaSetDevice(ctx->device);
     return t_step(ctx, n, rows, flags, losses_out);
+}
+
+int szb_train_loss_history(szb_ctx* ctx, int64_t first, int32_t count, float* out) {
+    if (!ctx) return SZB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    Trainer* tr = ctx->trainer;
+    if (!tr) return fail(ctx, SZB_ERR_STATE, "no trainer");
+    if (count < 0 || first < 0 || first + count > tr->steps_run || (count && !out))
+        return fail(ctx, SZB_ERR_ARG, "szb_train_loss_history: steps [%lld, %lld) of %lld run", (long long)first, (long long)(first + count), (long long)tr->steps_run);
+    if (tr->steps_run - first > LOSS_HIST) return fail(ctx, SZB_ERR_ARG, "szb_train_loss_history: only the last %d steps are kept", LOSS_HIST);
+    int32_t err = 0;
+    SZB_CUDA(ctx, cudaMemcpyAsync(&err, tr->error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int32_t done = 0; done < count;) {
+        const int64_t k = (first + done) % LOSS_HIST;
+        const int32_t run = (int32_t)((LOSS_HIST - k) < (count - done) ? (LOSS_HIST - k) : (count - done));
+        SZB_CUDA(ctx, cudaMemcpyAsync(out + 2 * (size_t)done, tr->loss_hist + 2 * k, (size_t)run * 8, cudaMemcpyDefault, ctx->stream));
+        done += run;
+    }
+    SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        cudaMemsetAsync(tr->error, 0, 4, ctx->stream);
+        return err == 2   ? fail(ctx, SZB_ERR_ARG, "a step's row index was outside the %lld records", (long long)tr->rec_n)
+               : err == 3 ? fail(ctx, SZB_ERR_INTERNAL, "a BatchNorm kernel's grid barrier timed out")
+                          : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
+    }
+    return 0;
 }
 
 int szb_train_state(szb_ctx* ctx, int64_t* step_inout, int32_t set) {

@@ -164,10 +164,19 @@ def train_on_records_cuda(model, rec, epochs=1, batch_size=64, optimiser=None, l
                 tr.step_count = step0                        # StepLR's counter is the one the learning rate follows
         tr.set_records(rec)
         history = []
-        for rows in _batches(len(rec["z"]), batch_size, epochs, seed):
-            history.append(tr.step(rows))
-            if log is not None:
+        if log is not None:
+            for rows in _batches(len(rec["z"]), batch_size, epochs, seed):
+                history.append(tr.step(rows))
                 log({"MSE Loss": history[-1][0], "CE Loss": history[-1][1]}, len(history))
+        else:
+            # nobody watches the losses step by step: queue the steps (the host runs ahead of the GPU) and read the history in bulk
+            first = tr.steps_run
+            for rows in _batches(len(rec["z"]), batch_size, epochs, seed):
+                tr.step(rows, want_losses=False)
+                if tr.steps_run - first == 32768:
+                    history += tr.loss_history(first)
+                    first = tr.steps_run
+            history += tr.loss_history(first)
         flat = tr.write_back(model, steps_taken=len(history))
         if optimiser is not None:
             optimiser.load_state_dict(tr.optimiser_state(model))

@@ -37,6 +37,7 @@ class Trainer:
         self.numels = [int(sd[k].numel()) for k in self.keys]
         self.device = torch.device("cuda", engine.device)
         self.n_records = 0
+        self.steps_run = 0
         self.set_tensors(_lib.TRAIN_PARAMS, {k: sd[k] for k in self.keys})
 
     def close(self):
@@ -106,7 +107,16 @@ class Trainer:
         losses = (ctypes.c_float * 2)()
         self.engine._check(self.lib.szb_train_step(self.engine._h, len(rows), rows.ctypes.data_as(ctypes.c_void_p), int(flags),
                                                    ctypes.cast(losses, ctypes.c_void_p) if want_losses else None))
+        self.steps_run += 1
         return (float(losses[0]), float(losses[1])) if want_losses else None
+
+    def loss_history(self, first=0, count=None):
+        """[(mse, ce)] of steps [first, first + count) since the trainer was created (the library keeps the last 65,536): lets a loop
+        queue its steps with want_losses=False -- no host round trip per step -- and collect the losses in bulk"""
+        count = self.steps_run - first if count is None else count
+        out = np.empty((count, 2), dtype=np.float32)
+        self.engine._check(self.lib.szb_train_loss_history(self.engine._h, int(first), int(count), out.ctypes.data_as(ctypes.c_void_p)))
+        return [(float(a), float(b)) for a, b in out]
 
     # ---- back to torch -----------------------------------------------------------------------
     def flat_weights(self):

@@ -257,6 +257,9 @@ def test_reference_batch_size(setup):
             for rows in batches[1:-1]:
                 tr.step(rows, want_losses=False)
             last = tr.step(batches[-1])
+            hist = tr.loss_history()                        # the device-side ring: what a loop that never synchronises reads at the end
+            assert len(hist) == 12 and hist[0] == first and hist[-1] == last and np.isfinite(hist).all()
+            assert tr.loss_history(3, 2) == hist[3:5]
             outs.append((first, last, tr.get_tensors(_lib.TRAIN_PARAMS, ["conv1.weight", "fc_v2.weight", "resnet_blocks.9.bn1.running_var"])))
             tr.close()
         (f0, l0, w0), (f1, l1, w1) = outs
