@@ -1266,6 +1266,7 @@ struct Trainer {
     std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
     bool loaded = false, attr_set = false;
+    std::vector<bool> have_param, have_buffer;   // set at least once through szb_train_set(SZB_TRAIN_PARAMS)
     std::vector<void*> allocs;
 };
 
@@ -1458,6 +1459,8 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         const long long s0 = cfg->step0;
         SZB_CUDA(ctx, cudaMemcpyAsync(tr->d_step, &s0, 8, cudaMemcpyHostToDevice, ctx->stream));
     }
+    tr->have_param.assign(tr->params.size(), false);
+    tr->have_buffer.assign(tr->buffers.size(), false);
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_CONV")) tr->conv_pair = atoi(e) == 2;
@@ -1530,6 +1533,7 @@ static int t_transfer(szb_ctx* ctx, int kind, int32_t n_tensors, const char* con
             for (auto& b : tr->buffers) if (b.name == name) bf = &b;
             if (!bf || kind != 0) { rc = fail(ctx, SZB_ERR_ARG, "unknown tensor '%s' (kind %d)", name.c_str(), kind); break; }
             if (numel[i] != bf->numel) { rc = fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", name.c_str(), (long long)numel[i], (long long)bf->numel); break; }
+            if (to_trainer) tr->have_buffer[(size_t)(bf - tr->buffers.data())] = true;
             cudaError_t e = to_trainer ? cudaMemcpyAsync(bf->ptr, data[i], (size_t)bf->numel * 4, cudaMemcpyDefault, ctx->stream)
                                        : cudaMemcpyAsync(data[i], bf->ptr, (size_t)bf->numel * 4, cudaMemcpyDefault, ctx->stream);
             if (e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaMemcpyAsync(buffer)");
@@ -1538,6 +1542,7 @@ static int t_transfer(szb_ctx* ctx, int kind, int32_t n_tensors, const char* con
         const TParam& p = tr->params[it->second];
         if (numel[i] != p.numel) { rc = fail(ctx, SZB_ERR_ARG, "'%s' has %lld elements, expected %lld", name.c_str(), (long long)numel[i], (long long)p.numel); break; }
         float* slot = t_kind_base(tr, kind) + p.off;
+        if (to_trainer && kind == 0) tr->have_param[(size_t)it->second] = true;
         if (p.kind == 0) {
             cudaError_t e = to_trainer ? cudaMemcpyAsync(slot, data[i], (size_t)p.numel * 4, cudaMemcpyDefault, ctx->stream)
                                        : cudaMemcpyAsync(data[i], slot, (size_t)p.numel * 4, cudaMemcpyDefault, ctx->stream);
@@ -1566,7 +1571,12 @@ static int t_transfer(szb_ctx* ctx, int kind, int32_t n_tensors, const char* con
     if (scratch) cudaFree(scratch);
     if (!rc && e != cudaSuccess) rc = cuda_fail(ctx, e, "cudaStreamSynchronize");
     if (!rc && (e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(ctx, e, "szb_train_get/set");
-    if (!rc && to_trainer && kind == 0) { tr->loaded = true; rc = t_pack(ctx, tr); }
+    if (!rc && to_trainer && kind == 0) {
+        tr->loaded = true;
+        for (bool b : tr->have_param) tr->loaded = tr->loaded && b;
+        for (bool b : tr->have_buffer) tr->loaded = tr->loaded && b;
+        rc = t_pack(ctx, tr);
+    }
     return rc;
 }
 
@@ -1732,7 +1742,14 @@ static int t_step_launches(szb_ctx* ctx, Trainer* tr, int n, int flags) {
 
 static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, float* losses_out) {
     Trainer* tr = ctx->trainer;
-    if (!tr || !tr->loaded) return fail(ctx, SZB_ERR_STATE, "trainer has no weights: szb_train_create + szb_train_set(kind 0) first");
+    if (!tr) return fail(ctx, SZB_ERR_STATE, "no trainer: szb_train_create first");
+    if (!tr->loaded) {
+        for (size_t i = 0; i < tr->params.size(); i++)
+            if (!tr->have_param[i]) return fail(ctx, SZB_ERR_STATE, "trainer weights incomplete: '%s' was never set (szb_train_set, SZB_TRAIN_PARAMS)", tr->params[i].name.c_str());
+        for (size_t i = 0; i < tr->buffers.size(); i++)
+            if (!tr->have_buffer[i]) return fail(ctx, SZB_ERR_STATE, "trainer weights incomplete: '%s' was never set (szb_train_set, SZB_TRAIN_PARAMS)", tr->buffers[i].name.c_str());
+        return fail(ctx, SZB_ERR_STATE, "trainer has no weights: szb_train_set(SZB_TRAIN_PARAMS) first");
+    }
     if (!tr->rec_states) return fail(ctx, SZB_ERR_STATE, "no records: szb_train_records first");
     if (n < 2 || n > tr->cfg.batch || !rows) return fail(ctx, SZB_ERR_ARG, "szb_train_step: 2 <= n <= %d boards (BatchNorm needs more than one)", tr->cfg.batch);
     cudaStream_t st = ctx->stream;
@@ -1837,6 +1854,9 @@ int szb_train_records(szb_ctx* ctx, int64_t n, const uint64_t* states, const int
     if (!tr) return fail(ctx, SZB_ERR_STATE, "no trainer: call szb_train_create first");
     if (n < 1 || !states || !pi_off || !pi_index || !pi_prob || !z) return fail(ctx, SZB_ERR_ARG, "szb_train_records: bad arguments");
     cudaStreamSynchronize(ctx->stream);
+    // the captured steps carry the old buffers' addresses as kernel parameters: drop them, the next step captures afresh
+    for (auto& kv : tr->graphs) cudaGraphExecDestroy(kv.second);
+    tr->graphs.clear();
     void* old[5] = {tr->rec_states, tr->rec_off, tr->rec_index, tr->rec_prob, tr->rec_z};
     for (void* p : old) if (p) cudaFree(p);
     tr->rec_states = nullptr; tr->rec_off = nullptr; tr->rec_index = nullptr; tr->rec_prob = nullptr; tr->rec_z = nullptr;

@@ -321,5 +321,27 @@ def test_bad_calls_are_refused(setup):
             tr.get_tensors(0, ["no.such.tensor"], shapes={"no.such.tensor": (1,)})
         mse, ce = tr.step(np.arange(8, dtype=np.int32))                     # and the trainer still works afterwards
         assert np.isfinite([mse, ce]).all()
+        # replacing the records invalidates the captured steps (they carry the old buffers' addresses): the same rows of NEW records
+        # must give what a fresh trainer in the same state gives
+        from sigma_zero_b200 import _lib
+        rec2 = _records(24, seed=13)
+        tr.set_records(rec2)
+        got = tr.step(np.arange(8, dtype=np.int32), flags=_lib.TRAIN_FORWARD_ONLY)
+        m = _model(5)
+        tr.write_back(m)
     finally:
         tr.close()
+    tr = Trainer(eng, m, batch_size=8)
+    try:
+        tr.set_records(rec2)
+        assert tr.step(np.arange(8, dtype=np.int32), flags=_lib.TRAIN_FORWARD_ONLY) == got
+    finally:
+        tr.close()
+    # a trainer that was given only part of the state_dict refuses to step and names a missing tensor
+    import ctypes
+    cfg = _lib.TrainConfig(8, 1e-4, 0.9, 0.999, 1e-8, 1e-4, 500, 0.95, 0.1, 1e-5, 0, 0, 0)
+    eng._check(eng.lib.szb_train_create(eng._h, ctypes.byref(cfg)))
+    rows = np.arange(4, dtype=np.int32)
+    rc = eng.lib.szb_train_step(eng._h, 4, rows.ctypes.data_as(ctypes.c_void_p), 0, None)
+    assert rc == -5 and b"never set" in eng.lib.szb_last_error(eng._h)
+    eng.lib.szb_train_destroy(eng._h)
