@@ -17,8 +17,9 @@ then a move sampled from the visit counts and pushed (szb_selfplay_ply; referenc
             on the device inside the timed region (the kernel stamps %globaltimer at its first CTA's start and its last CTA's end;
             the two cohorts' launches overlap on two streams, which CUDA events cannot bracket), against the measured sustained
             bf16 peak of MEASURED_PEAKS.json;
-  extras  : (same JSON line) config c3 (4096 Chess960 games) as a rate, and a bounded config-c4 iteration (500 games sharded over
-            the ranks, strong scaling) next to the weak-scaling headline;
+  extras  : (same JSON line) config c3 (4096 Chess960 games) as a rate, a bounded config-c4 iteration (500 games sharded over
+            the ranks, strong scaling) next to the weak-scaling headline, and the fine-tuning step of the same loop on the
+            library's trainer (f1_trainer: positions/s at batch 128, torch eager on the same GPU beside it);
   cpu_baseline / --impl reference: the restated reference search (oracle/ref_path.py: the reference's Python
             control flow + torch CPU fp32 network, batch 1, all host threads) on a bounded sample of the workload.
 
@@ -752,7 +753,7 @@ def main():
     ap.add_argument("--leaves-per-tree", type=int, default=1,
                     help="--workload c4 only: opt-in multi-leaf search with virtual loss (not the reference's algorithm; reported separately)")
     ap.add_argument("--max-plies", type=int, default=None, help="--workload c4: cut games after this many plies (default: play every game out)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the c3 rate and the bounded c4 iteration that ride on the default (c2) line")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3 rate, the bounded c4 iteration and the trainer step that ride on the default (c2) line")
     ap.add_argument("--extras-c4-plies", type=int, default=24, help="plies per game of the bounded c4 iteration in `extras`")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
