@@ -43,14 +43,17 @@ constexpr int T_ACTIONS = 4672;
 constexpr int T_PLANES = 119;
 constexpr int DL_C = 128;                    // channels of the logits-gradient buffer (73 policy planes padded)
 
-constexpr int TR_THREADS = 192;              // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
-constexpr int TR_A_CHUNKS = 3;
+constexpr int TR_THREADS = 192;              // k_wgrad: warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int TC_CONV_THREADS = 320;         // k_tconv / k_tconv_pair: eight epilogue warps (two per TMEM lane group, 64 columns each)
+constexpr int TR_A_CHUNKS = 2;
 constexpr int TR_A_CHUNK_BYTES = 2 * TPIX * 128;      // two boards with their halo x 64 channels: 25600 = 25 * 1024
-constexpr int TR_B_STAGES = 6;                        // (10 stages with 2 activation chunks measured the same: the loop is not latency bound)
+constexpr int TR_TPS = 3;                             // taps per weight stage of a 3x3 layer
+constexpr int TR_B_STAGES = 3;
 constexpr bool TR_DUAL_ACC = false;                   // A/B aid: even / odd K steps accumulate into two TMEM tiles (two independent MMA chains); measured: no change
 constexpr int TR_CLUSTER = 4;                         // CTAs (neighbouring tiles) that share every weight tile through TMA multicast
 constexpr int TR_B_BYTES = 128 * 64 * 2;              // 128 output channels x 64 k
-constexpr int TR_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TR_B_STAGES * TR_B_BYTES + 1024;
+constexpr int TR_B_STAGE_BYTES = TR_TPS * TR_B_BYTES;
+constexpr int TR_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TR_B_STAGES * TR_B_STAGE_BYTES + 1024;
 
 constexpr int WG_STAGES = 4;
 constexpr int WG_BOX = 64 * 64 * 2;          // one board (64 squares) x 64 channels
@@ -152,23 +155,24 @@ __device__ __forceinline__ void t_stamp(unsigned long long* tr, int k) {
 template <int MODE, bool DUAL = false>
 __device__ __forceinline__ void tconv_epilogue(const TConvArgs& a, uint32_t tmem_base, int tile, int nh, int warp, int lane, uint32_t bar_acc_addr,
                                                volatile int* abort_flag, float (*st_sh)[4][128], float (*mi_sh)[128], unsigned long long* trace) {
-    const int lane_group = warp & 3;
-    const int e = (warp - 2) * 32 + lane;                              // 0..127 over the four epilogue warps
+    const int lane_group = warp & 3;                                   // TMEM lanes this warp may read
+    const int col0 = ((warp - 2) >> 2) * 64;                           // ... and its half of the 128 columns
+    const int e = (warp - 2) * 32 + lane;                              // 0..255 over the eight epilogue warps
     const bool stats = MODE == 0 && a.stat_part != nullptr, bwd = MODE == 0 && a.bn_o != nullptr;
-    if (bwd) { mi_sh[0][e] = a.bn_mean[nh * 128 + e]; mi_sh[1][e] = a.bn_invstd[nh * 128 + e]; }
+    if (bwd) mi_sh[e >> 7][e & 127] = (e < 128 ? a.bn_mean : a.bn_invstd)[nh * 128 + (e & 127)];
     bool ok = mbar_wait(bar_acc_addr, 0, abort_flag);
     ok = __all_sync(0xFFFFFFFFu, ok);
     if (warp == 2 && lane == 0) t_stamp(trace, 5);
     if (ok) {
         tc_fence_after();
-        if (bwd) asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (bwd) asm volatile("bar.sync 1, 256;" ::: "memory");
         const int m = lane_group * 32 + lane;                          // row (oy * 2 + board) * 8 + ox
         const int board = tile * 2 + ((m >> 3) & 1), sq = (m >> 4) * 8 + (m & 7);
         const bool live = board < a.n_boards;
         const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
         const size_t pix = (size_t)board * TPIX + halo_pix(sq);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = col0; c0 < col0 + 64; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32b_x16(taddr + c0, v);
             tmem_ld_32x32b_x16(taddr + c0 + 16, v + 16);
@@ -245,12 +249,10 @@ __device__ __forceinline__ void tconv_epilogue(const TConvArgs& a, uint32_t tmem
             }
         }
         if (stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tile * 2 < a.n_boards) {
-#pragma unroll
-                for (int which = 0; which < 2; which++)
-                    a.stat_part[((size_t)tile * 2 + which) * a.ldc + nh * 128 + e] =
-                        ((st_sh[which][0][e] + st_sh[which][1][e]) + st_sh[which][2][e]) + st_sh[which][3][e];
+                const int which = e >> 7, c = e & 127;
+                a.stat_part[((size_t)tile * 2 + which) * a.ldc + nh * 128 + c] = ((st_sh[which][0][c] + st_sh[which][1][c]) + st_sh[which][2][c]) + st_sh[which][3][c];
             }
         }
     }
@@ -266,7 +268,7 @@ __device__ __forceinline__ void tconv_epilogue(const TConvArgs& a, uint32_t tmem
 // on every CTA's barrier).  The kernel is bound by L2 -> SM traffic (measured: 6.8 TB/s with one L2 read per CTA and tile); multicast cuts
 // the weight reads four-fold.
 template <int MODE>
-__global__ void __cluster_dims__(TR_CLUSTER, 1, 1) __launch_bounds__(TR_THREADS, 1)
+__global__ void __cluster_dims__(TR_CLUSTER, 1, 1) __launch_bounds__(TC_CONV_THREADS, 1)
 k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TConvArgs a) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -317,12 +319,15 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
                 mbar_expect_tx(af, TR_A_CHUNK_BYTES);
                 tma_load_4d(smem_a + ac * TR_A_CHUNK_BYTES, &tm_a, af, kc * 64, 0, tile * 2, 0);
                 if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
-                for (int tap = 0; tap < a.taps; tap++) {
+                // weight stages: TR_TPS consecutive taps of this K chunk per stage (3x3 layers), one tile for a 1x1 layer
+                const int per = a.taps == 9 ? TR_TPS : 1;
+                for (int tap0 = 0; tap0 < a.taps; tap0 += per) {
                     if (!(ok = mbar_wait(smem_u32(&bar_be[bs]), b_phase ^ 1, abort_flag))) break;
                     const uint32_t bf = smem_u32(&bar_bf[bs]);
-                    mbar_expect_tx(bf, TR_B_BYTES);                  // four quarters, one from each CTA of the cluster
-                    tma_load_2d_mc(smem_b + bs * TR_B_BYTES + crank * (TR_B_BYTES / TR_CLUSTER), &tm_w, bf, (tap * a.kchunks + kc) * 64,
-                                   nh * 128 + (int)crank * (128 / TR_CLUSTER), CMASK);
+                    mbar_expect_tx(bf, (uint32_t)per * TR_B_BYTES);          // four quarters of every tile, one from each CTA of the cluster
+                    for (int u = 0; u < per; u++)
+                        tma_load_2d_mc(smem_b + bs * TR_B_STAGE_BYTES + u * TR_B_BYTES + crank * (TR_B_BYTES / TR_CLUSTER), &tm_w, bf,
+                                       ((tap0 + u) * a.kchunks + kc) * 64, nh * 128 + (int)crank * (128 / TR_CLUSTER), CMASK);
                     if (++bs == TR_B_STAGES) { bs = 0; b_phase ^= 1; }
                 }
             }
@@ -341,18 +346,25 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
             if (kc == 0 && lane == 0) t_stamp(trace, 3);
             const uint32_t chunk_lo = a_lo0 + ac * (TR_A_CHUNK_BYTES >> 4);
             if (a.taps == 9) {
+                // One wait / elect / commit per TR_TPS taps: the issuing warp's own instruction stream costs ~450 cycles per stage whatever the
+                // stage holds (scripts/mma_rate_probe.cu) -- more than the 256 cycles four 128 x 128 x 16 MMAs take, less than the 768 of twelve.
 #pragma unroll
-                for (int tap = 0; tap < 9; tap++) {
+                for (int s0 = 0; s0 < 9; s0 += TR_TPS) {
                     if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
-                        const uint32_t b_lo = b_lo0 + bs * (TR_B_BYTES >> 4);
-                        const uint32_t d1 = tmem_base + (TR_DUAL_ACC ? 128u : 0u), first = tap == 0 ? accumulate : 1u;
-                        t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, first);
-                        t_mma_split(d1, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, TR_DUAL_ACC ? first : 1u);
-                        t_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
-                        t_mma_split(d1, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                        const uint32_t d1 = tmem_base + (TR_DUAL_ACC ? 128u : 0u);
+#pragma unroll
+                        for (int u = 0; u < TR_TPS; u++) {
+                            const int tap = s0 + u;
+                            const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
+                            const uint32_t b_lo = b_lo0 + bs * (TR_B_STAGE_BYTES >> 4) + u * (TR_B_BYTES >> 4);
+                            const uint32_t first = tap == 0 ? accumulate : 1u;
+                            t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, first);
+                            t_mma_split(d1, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, TR_DUAL_ACC ? first : 1u);
+                            t_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
+                            t_mma_split(d1, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                        }
                         tc_commit_mc(bar_be0 + bs * 8, CMASK);
                     }
                     __syncwarp();
@@ -363,7 +375,7 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_lo = chunk_lo + (uint32_t)(2 * TH + 1) * (128 >> 4);            // centre tap
-                    const uint32_t b_lo = b_lo0 + bs * (TR_B_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + bs * (TR_B_STAGE_BYTES >> 4);
                     const uint32_t d1 = tmem_base + (TR_DUAL_ACC ? 128u : 0u);
                     t_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, accumulate);
                     t_mma_split(d1, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, TR_DUAL_ACC ? accumulate : 1u);
@@ -402,9 +414,10 @@ k_tconv(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtens
 // leader for "data landed" (both CTAs' TMA bytes are counted there) and in both CTAs for "stage free" / "accumulator ready" (the leader's
 // commits are multicast) -- the protocol of k_tower_tc2 (net.cu).
 constexpr uint32_t T2_PEER_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in the pair's even CTA
-constexpr int TP_B_STAGES = 8;
+constexpr int TP_B_STAGES = 6;
 constexpr int TP_B_BYTES = 64 * 64 * 2;               // this CTA's half of a 128-channel x 64-k weight tile
-constexpr int TP_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TP_B_STAGES * TP_B_BYTES + 1024;
+constexpr int TP_B_STAGE_BYTES = TR_TPS * TP_B_BYTES;
+constexpr int TP_SMEM = TR_A_CHUNKS * TR_A_CHUNK_BYTES + TP_B_STAGES * TP_B_STAGE_BYTES + 1024;
 
 __device__ __forceinline__ void tp_tma_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -431,7 +444,7 @@ __device__ __forceinline__ void tp_mma_split(uint32_t tmem_d, uint32_t a_lo, uin
 }
 
 template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TR_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_CONV_THREADS, 1)
 k_tconv_pair(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const TConvArgs a) {
     constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);      // M 256, N 128
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -481,13 +494,13 @@ k_tconv_pair(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 if (rank == 0) mbar_expect_tx(af, 2u * TR_A_CHUNK_BYTES);      // both CTAs' bytes land on the leader's barrier
                 tp_tma_4d(smem_a + ac * TR_A_CHUNK_BYTES, &tm_a, af, kc * 64, 0, tile * 2, 0);
                 if (++ac == TR_A_CHUNKS) { ac = 0; a_phase ^= 1; }
-                for (int tap = 0; tap < a.taps; tap++) {
+                const int per = a.taps == 9 ? TR_TPS : 1;
+                for (int tap0 = 0; tap0 < a.taps; tap0 += per) {
                     if (!(ok = mbar_wait(smem_u32(&bar_be[bs]), b_phase ^ 1, abort_flag))) break;
                     const uint32_t bf = smem_u32(&bar_bf[bs]);
-                    if (rank == 0) mbar_expect_tx(bf, 2u * TP_B_BYTES);
-                    const int k = (tap * a.kchunks + kc) * 64, row = nh * 128 + (int)rank * 64;
-                    tp_tma_2d(smem_b + bs * TP_B_BYTES, &tm_w, bf, k, row);                        // the weight map's box is 32 rows
-                    tp_tma_2d(smem_b + bs * TP_B_BYTES + TP_B_BYTES / 2, &tm_w, bf, k, row + 32);
+                    if (rank == 0) mbar_expect_tx(bf, 2u * (uint32_t)per * TP_B_BYTES);
+                    for (int u = 0; u < per; u++)
+                        tp_tma_2d(smem_b + bs * TP_B_STAGE_BYTES + u * TP_B_BYTES, &tm_w, bf, ((tap0 + u) * a.kchunks + kc) * 64, nh * 128 + (int)rank * 64);
                     if (++bs == TP_B_STAGES) { bs = 0; b_phase ^= 1; }
                 }
             }
@@ -505,16 +518,20 @@ k_tconv_pair(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 const uint32_t chunk_lo = a_lo0 + ac * (TR_A_CHUNK_BYTES >> 4);
                 if (a.taps == 9) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; tap++) {
+                    for (int s0 = 0; s0 < 9; s0 += TR_TPS) {
                         if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
-                            const uint32_t b_lo = b_lo0 + bs * (TP_B_BYTES >> 4);
-                            tp_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, tap == 0 ? accumulate : 1u);
-                            tp_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
-                            tp_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
-                            tp_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+#pragma unroll
+                            for (int u = 0; u < TR_TPS; u++) {
+                                const int tap = s0 + u;
+                                const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * TH + tap % 3) * (128 >> 4);
+                                const uint32_t b_lo = b_lo0 + bs * (TP_B_STAGE_BYTES >> 4) + u * (TP_B_BYTES >> 4);
+                                tp_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, tap == 0 ? accumulate : 1u);
+                                tp_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
+                                tp_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
+                                tp_mma_split(tmem_base, a_lo + 6, DESC_HI_K1280, b_lo + 6, DESC_HI_K1024, IDESC, 1u);
+                            }
                             tp_commit(bar_be0 + bs * 8);
                         }
                         __syncwarp();
@@ -525,7 +542,7 @@ k_tconv_pair(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t a_lo = chunk_lo + (uint32_t)(2 * TH + 1) * (128 >> 4);
-                        const uint32_t b_lo = b_lo0 + bs * (TP_B_BYTES >> 4);
+                        const uint32_t b_lo = b_lo0 + bs * (TP_B_STAGE_BYTES >> 4);
                         tp_mma_split(tmem_base, a_lo, DESC_HI_K1280, b_lo, DESC_HI_K1024, IDESC, accumulate);
                         tp_mma_split(tmem_base, a_lo + 2, DESC_HI_K1280, b_lo + 2, DESC_HI_K1024, IDESC, 1u);
                         tp_mma_split(tmem_base, a_lo + 4, DESC_HI_K1280, b_lo + 4, DESC_HI_K1024, IDESC, 1u);
@@ -1215,7 +1232,7 @@ struct TLayer {
     int taps = 9, cin_pad = 256, cout_pad = 256;
     int param = -1, gamma = -1, beta = -1;       // indices into Trainer::params
     bf16* wf = nullptr; bf16* wd = nullptr;
-    CUtensorMap tm_wf, tm_wd;
+    CUtensorMap tm_wf[2], tm_wd[2];              // box rows: [0] 32 (k_tconv: a quarter tile per CTA of the cluster), [1] 64 (k_tconv_pair: half a tile)
     bf16* y = nullptr; bf16* o = nullptr;        // pre-BatchNorm convolution output, layer output
     bf16* dy = nullptr;                          // gradient of the convolution output (kept per layer: every tower wgrad runs in ONE launch at the end)
     CUtensorMap tm_dy2, tm_dy1;
@@ -1261,7 +1278,7 @@ struct Trainer {
     uint64_t steps_queued = 0;
     std::map<std::pair<int, int>, cudaGraphExec_t> graphs;     // (boards, flags) -> the captured step
     bool use_graph = true;
-    bool conv_pair = false;                      // SZB_TRAIN_CONV=2: convolutions as CTA pairs (k_tconv_pair; measured 4 % slower than k_tconv at 128 boards)
+    bool conv_pair = true;                       // convolutions as CTA pairs (k_tconv_pair); SZB_TRAIN_CONV=1: the single-CTA kernel with multicast weights
     bool pdl = true;                             // programmatic dependent launch along the convolution / BatchNorm chain (SZB_TRAIN_NO_PDL=1: off)
     std::map<std::pair<int, int>, uint64_t> launches_per_step;
     int last_n = 0;
@@ -1306,10 +1323,10 @@ static int t_halo_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int channels, i
     return 0;
 }
 // weight pack [rows][k]: box = 64 k x 32 rows (a quarter of k_tconv's 128-row tile: one CTA's share of the multicast)
-static int t_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int rows) {
+static int t_w_map(szb_ctx* ctx, CUtensorMap* tm, void* base, int k_total, int rows, int box_rows) {
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-    cuuint32_t box[2] = {64, 128 / TR_CLUSTER};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = t_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1415,10 +1432,14 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         L.param = tr->index.at(t_layer_conv_name(l) + ".weight");
         const size_t wn = (size_t)L.cout_pad * L.taps * L.cin_pad;
         if ((rc = t_alloc(ctx, tr, &L.wf, wn))) return rc;
-        if ((rc = t_w_map(ctx, &L.tm_wf, L.wf, L.taps * L.cin_pad, L.cout_pad))) return rc;
+        if ((rc = t_w_map(ctx, &L.tm_wf[0], L.wf, L.taps * L.cin_pad, L.cout_pad, 128 / TR_CLUSTER)) ||
+            (rc = t_w_map(ctx, &L.tm_wf[1], L.wf, L.taps * L.cin_pad, L.cout_pad, 64)))
+            return rc;
         if (l != 0) {
             if ((rc = t_alloc(ctx, tr, &L.wd, wn))) return rc;
-            if ((rc = t_w_map(ctx, &L.tm_wd, L.wd, L.taps * L.cout_pad, L.cin_pad))) return rc;
+            if ((rc = t_w_map(ctx, &L.tm_wd[0], L.wd, L.taps * L.cout_pad, L.cin_pad, 128 / TR_CLUSTER)) ||
+                (rc = t_w_map(ctx, &L.tm_wd[1], L.wd, L.taps * L.cout_pad, L.cin_pad, 64)))
+                return rc;
         }
         if (l < T_BN) {
             L.gamma = tr->index.at(t_layer_bn_name(l) + ".weight");
@@ -1463,7 +1484,7 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
     tr->have_buffer.assign(tr->buffers.size(), false);
     if (const char* e = getenv("SZB_TRAIN_NO_GRAPH")) tr->use_graph = atoi(e) == 0;
     if (const char* e = getenv("SZB_TRAIN_NO_PDL")) tr->pdl = atoi(e) == 0;
-    if (const char* e = getenv("SZB_TRAIN_CONV")) tr->conv_pair = atoi(e) == 2;
+    if (const char* e = getenv("SZB_TRAIN_CONV")) tr->conv_pair = atoi(e) != 1;
     if (const char* e = getenv("SZB_TRAIN_TRACE")) {
         if (atoi(e) && (rc = t_alloc(ctx, tr, &tr->trace, 8))) return rc;
     }
@@ -1586,8 +1607,9 @@ struct TConvFuse {               // what the epilogue adds for the BatchNorm tha
     const float* mean = nullptr; const float* invstd = nullptr;
 };
 
-static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUtensorMap& tm_w, int taps, int kchunks, int n_out, int n, bf16* out, int mode,
+static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUtensorMap* tm_w2, int taps, int kchunks, int n_out, int n, bf16* out, int mode,
                   const float* bias, unsigned long long* trace = nullptr, const TConvFuse& fuse = TConvFuse()) {
+    const CUtensorMap& tm_w = tm_w2[tr->conv_pair ? 1 : 0];
     TConvArgs a{};
     a.trace = trace;
     a.stat_part = fuse.stats ? tr->bn_part : nullptr;
@@ -1595,14 +1617,14 @@ static int t_conv(szb_ctx* ctx, Trainer* tr, const CUtensorMap& tm_a, const CUte
     a.taps = taps; a.kchunks = kchunks; a.n_boards = n; a.out = out; a.ldc = TC; a.logits = tr->logits; a.bias = bias; a.error = tr->error;
     if (tr->conv_pair) {
         const dim3 grid2((unsigned)(((n + 3) / 4) * 2), n_out / 128);                       // whole pairs: a surplus CTA computes on zero fill, stores nothing
-        if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv_pair<0>, grid2, dim3(TR_THREADS), TP_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
-        else SZB_CUDA(ctx, launch_kernel(k_tconv_pair<1>, grid2, dim3(TR_THREADS), TP_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+        if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv_pair<0>, grid2, dim3(TC_CONV_THREADS), TP_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+        else SZB_CUDA(ctx, launch_kernel(k_tconv_pair<1>, grid2, dim3(TC_CONV_THREADS), TP_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
         ctx->launches++;
         return 0;
     }
     const dim3 grid((unsigned)((((n + 1) / 2 + TR_CLUSTER - 1) / TR_CLUSTER) * TR_CLUSTER), n_out / 128);      // whole clusters: surplus CTAs compute on zero fill, store nothing
-    if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv<0>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
-    else SZB_CUDA(ctx, launch_kernel(k_tconv<1>, grid, dim3(TR_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+    if (mode == 0) SZB_CUDA(ctx, launch_kernel(k_tconv<0>, grid, dim3(TC_CONV_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
+    else SZB_CUDA(ctx, launch_kernel(k_tconv<1>, grid, dim3(TC_CONV_THREADS), TR_SMEM, ctx->stream, tr->pdl, tm_a, tm_w, a));
     ctx->launches++;
     SZB_CUDA(ctx, cudaGetLastError());
     return 0;
