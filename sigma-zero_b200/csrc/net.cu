@@ -86,6 +86,7 @@ struct Net {
     int final_x = 0, final_y = 0;        // activation buffers holding the tower output / the policy-head hidden layer
     int tower_mode = 2;                  // 0: single-CTA kernel per layer, 1: pair kernel per layer, 2: pair kernel, one launch
     int tower_nsplit = 0;                // 0: automatic (launch_tower), else forced 1 / 2 / 4 / 8
+    int tower_tps1 = 1;                  // taps per weight stage of large-batch launches (SZB_TOWER_TPS=2: three 32 KiB stages)
     int last_nsplit = 1;                 // what the last multi-layer launch used (trace aid)
     int chunk = 512;                     // boards per tower launch of a large evaluation (net_forward_chunked); 0 = unlimited
     int tower_pairs = 74;                // CTA pairs of an exclusive launch (SZB_TOWER_PAIRS)
@@ -362,6 +363,8 @@ constexpr int T2_A_CHUNK_BYTES = T2_A_ROWS * 128;         // 25600 = 25 * 1024
 constexpr int T2_A_SBO = HALO * 128;                      // 1280: one halo row of one board
 constexpr int T2_B_STAGES = 7;
 constexpr int T2_B_BYTES = 128 * TC_BLOCK_K * 2;          // this CTA's half (128 output channels) of a 64-wide weight tile
+constexpr int T2_BIG_STAGES = 3;                          // tps1 == 2: the same ring seen as three stages of two tiles
+constexpr int T2_BIG_BYTES = 2 * T2_B_BYTES;
 constexpr int T2_SMEM = T2_A_CHUNKS * T2_A_CHUNK_BYTES + T2_B_STAGES * T2_B_BYTES + 1024;
 constexpr int MAX_TOWER_LAYERS = 41;                      // stem + 38 tower convolutions + policy 1x1 + policy output (256 -> 73)
 constexpr int POLICY_LAYER = MAX_TOWER_LAYERS - 1;
@@ -412,6 +415,8 @@ struct TowerArgs {
     int in_delta;        // the input planes of board b are row b + in_delta of the NHWC input buffer (rows written by k_tree_step)
     int layer_begin, layer_end;
     int nsplit;          // 1, 2, 4 or 8: a (layer, tile) is cut into nsplit work items of N / nsplit output channels each (small batches)
+    int tps1;            // nsplit == 1 launches: taps per weight stage, 1 (seven 16 KiB stages) or 2 (three 32 KiB stages: half as many waits /
+                         // commits on the MMA-issuing warp per MMA; SZB_TOWER_TPS=2, scripts/mma_rate_probe.cu)
     int n_main;          // work items of the layers cut nsplit ways; the items after them are whole tiles of the LAST layer (fused heads
                          // need all 73 planes of a board in one accumulator)
     int n_items;
@@ -553,6 +558,35 @@ __device__ __forceinline__ bool mma_chunk_3x3(uint32_t d_tmem, uint32_t chunk_lo
     return true;
 }
 
+// the same for whole 128-row tiles, two taps per 32 KiB stage (2 + 2 + 2 + 2 + 1): large-batch launches with TowerArgs::tps1 == 2
+__device__ __forceinline__ bool mma_chunk_3x3_big(uint32_t d_tmem, uint32_t chunk_lo, uint32_t b_lo0, uint32_t bar_bf0, uint32_t bar_be0, uint32_t& bs,
+                                                  uint32_t& b_phase, uint32_t idesc, uint32_t accumulate, volatile int* abort_flag) {
+#pragma unroll
+    for (int s0 = 0; s0 < 9; s0 += 2) {
+        if (!warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag)) return false;
+        tc_fence_after();
+        const uint32_t b_base = b_lo0 + bs * (T2_BIG_BYTES >> 4);
+        if (elect_one()) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int tap = s0 + u;
+                if (tap < 9) {
+                    const uint32_t a_lo = chunk_lo + (uint32_t)((tap / 3) * 2 * HALO + tap % 3) * (128 >> 4);
+                    const uint32_t b_lo = b_base + u * (T2_B_BYTES >> 4);
+                    tc2_mma_bf16_split(d_tmem, a_lo, T2_A_HI, b_lo, T2_B_HI, idesc, tap == 0 ? accumulate : 1u);
+                    tc2_mma_bf16_split(d_tmem, a_lo + 2, T2_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
+                    tc2_mma_bf16_split(d_tmem, a_lo + 4, T2_A_HI, b_lo + 4, T2_B_HI, idesc, 1u);
+                    tc2_mma_bf16_split(d_tmem, a_lo + 6, T2_A_HI, b_lo + 6, T2_B_HI, idesc, 1u);
+                }
+            }
+            tc2_commit(bar_be0 + bs * 8);
+        }
+        __syncwarp();
+        if (++bs == T2_BIG_STAGES) { bs = 0; b_phase ^= 1; }
+    }
+    return true;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ TowerArgs a) {
     constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);      // M = 256, N per layer
@@ -647,6 +681,22 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     __syncwarp();
                     if (++ac == T2_A_CHUNKS) { ac = 0; a_phase ^= 1; }
                     int kcol = kc * TC_BLOCK_K;                                           // weight column of (tap 0, kc); taps are C_in apart
+                    if (a.tps1 == 2) {
+                        // two taps per stage, three 32 KiB stages (a 1x1 layer: one tile per stage)
+                        for (int tap = 0; tap < L.taps; tap += 2) {
+                            const int cnt = min(2, L.taps - tap);
+                            if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
+                            if (elect_one()) {
+                                const uint32_t b_full = bar_bf0 + bs * 8;
+                                if (rank == 0) mbar_expect_tx(b_full, b_tx * (uint32_t)cnt);
+                                for (int u = 0; u < cnt; u++)
+                                    tma2_load_2d(smem_b + bs * T2_BIG_BYTES + u * T2_B_BYTES, tm_w, b_full, kcol + (tap + u) * L.kchunks * TC_BLOCK_K, wrow);
+                            }
+                            __syncwarp();
+                            if (++bs == T2_BIG_STAGES) { bs = 0; b_phase ^= 1; }
+                        }
+                        continue;
+                    }
                     for (int tap = 0; tap < L.taps; tap++, kcol += L.kchunks * TC_BLOCK_K) {
                         if (!(ok = warp_mbar_wait(bar_be0 + bs * 8, b_phase ^ 1, abort_flag))) break;
                         if (elect_one()) {
@@ -732,6 +782,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
             uint32_t ac = 0, bs = 0, a_phase = 0, b_phase = 0;
             int local = 0;
             bool ok = true;
+            const bool big = a.nsplit == 1 && a.tps1 == 2;
             for (int item = pair; item < n_items && ok; item += n_pairs, local++) {
                 const TowerItem it = tower_item(a, item);
                 const TowerLayer L = a.L[it.l];
@@ -751,7 +802,8 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                     const uint32_t chunk_lo = a_lo0 + ac * (T2_A_CHUNK_BYTES >> 4);
                     if (L.taps == 9) {
                         // a weight stage holds nsplit consecutive taps of 128 / nsplit rows per CTA (see the producer)
-                        ok = it.ns == 1   ? mma_chunk_3x3<1>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                        ok = big          ? mma_chunk_3x3_big(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
+                             : it.ns == 1 ? mma_chunk_3x3<1>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
                              : it.ns == 2 ? mma_chunk_3x3<2>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
                              : it.ns == 8 ? mma_chunk_3x3<8>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag)
                                              : mma_chunk_3x3<4>(d_tmem, chunk_lo, b_lo0, bar_bf0, bar_be0, bs, b_phase, idesc, accumulate, abort_flag);
@@ -760,7 +812,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                         if (!(ok = warp_mbar_wait(bar_bf0 + bs * 8, b_phase, abort_flag))) break;
                         tc_fence_after();
                         const uint32_t a_lo = chunk_lo + (uint32_t)(2 * HALO + 1) * (128 >> 4);
-                        const uint32_t b_lo = b_lo0 + bs * (T2_B_BYTES >> 4);
+                        const uint32_t b_lo = b_lo0 + bs * ((big ? T2_BIG_BYTES : T2_B_BYTES) >> 4);
                         if (elect_one()) {
                             tc2_mma_bf16_split(d_tmem, a_lo, T2_A_HI, b_lo, T2_B_HI, idesc, accumulate);
                             tc2_mma_bf16_split(d_tmem, a_lo + 2, T2_A_HI, b_lo + 2, T2_B_HI, idesc, 1u);
@@ -769,7 +821,7 @@ k_tower_tc2(const __grid_constant__ TowerMaps maps, const __grid_constant__ Towe
                             tc2_commit(bar_be0 + bs * 8);
                         }
                         __syncwarp();
-                        if (++bs == T2_B_STAGES) { bs = 0; b_phase ^= 1; }
+                        if (++bs == (uint32_t)(big ? T2_BIG_STAGES : T2_B_STAGES)) { bs = 0; b_phase ^= 1; }
                     }
                     accumulate = 1;
                     if (ok && elect_one()) tc2_commit(bar_ae0 + ac * 8);                              // chunk free once its last tap's MMAs retire
@@ -1922,6 +1974,7 @@ static int net_setup_tower(szb_ctx* ctx, Net* net) {
     if (const char* e = getenv("SZB_TOWER_CLUSTER_SIZE")) net->cluster_force = atoi(e);
     const char* ck = getenv("SZB_TOWER_CHUNK");              // measurement aid: boards per tower launch (0 = whole batch)
     if (ck && ck[0]) net->chunk = std::max(0, atoi(ck)) & ~3;
+    if (const char* e = getenv("SZB_TOWER_TPS")) net->tower_tps1 = atoi(e) == 2 ? 2 : 1;
     const char* ns = getenv("SZB_TOWER_NSPLIT");             // measurement aid: force the N split of small batches (1, 2, 4); default automatic
     if (ns && (ns[0] == '1' || ns[0] == '2' || ns[0] == '4' || ns[0] == '8')) net->tower_nsplit = ns[0] - '0';
     ctx->net_tower_mode = net->tower_mode;
@@ -2024,6 +2077,7 @@ static int launch_tower(szb_ctx* ctx, Net* net, int b0, int n, int layer_begin, 
     const bool exclusive = net->tower_exclusive && (n + 3) / 4 > net->tower_pairs;      // large launches only
     const int pairs = std::min(exclusive ? net->tower_pairs : net->num_sms / 2, net->pairs_resident);
     a.nsplit = 1;
+    a.tps1 = net->tower_tps1;
     if (layer_end - layer_begin > 1) {
         if (net->tower_nsplit) a.nsplit = net->tower_nsplit;
         else if (a.n_pair_tiles * 8 <= pairs) a.nsplit = 8;
