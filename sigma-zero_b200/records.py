@@ -1,4 +1,5 @@
-"""Training-data record format for self-play output (format only -- the trainer is out of scope).
+"""Training-data record format for self-play output: what sim.selfplay_records writes and what the library's trainer
+(trainer.py -> szb_train_records) reads.
 
 The reference stores one uncompressed bool[119,8,8] tensor and one {Move: probability} dict per position
 (sim.py:56,71-72) and train_RL.chessDataset / collatefn (:14-49) expect bit-packed states.  Here a batch of game
