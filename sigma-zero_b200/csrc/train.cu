@@ -6,11 +6,15 @@
 //
 // Mixed precision: fp32 master weights, Adam moments and BatchNorm arithmetic; bf16 operands on the tensor cores with fp32 accumulation
 // in TMEM; activations and activation gradients are stored as bf16.  Three tcgen05 GEMM shapes do all the heavy work of a step:
-//   forward   Y[pos][co]  = sum_{tap,ci} X[pos+tap][ci] * W[co][tap][ci]          k_tconv   (A: shifted TMA boxes of X, K-major)
-//   dgrad     dX[pos][ci] = sum_{tap,co} dY[pos+tap][co] * W[co][8-tap][ci]       k_tconv   (same kernel, transposed/flipped weight pack)
-//   wgrad     dW[co][tap][ci] = sum_pos dY[pos][co] * X[pos+tap][ci]              k_wgrad   (both operands MN-major: the K dimension is the
-//                                                                                           board square, exactly as the tensors lie in HBM)
-// wgrad is split over the batch (K) into `ksplit` partial sums that a second kernel adds in a fixed order: a step is deterministic.
+//   forward   Y[pos][co]  = sum_{tap,ci} X[pos+tap][ci] * W[co][tap][ci]          k_tconv_pair  (A: a halo chunk of X resident in shared memory,
+//                                                                                               every tap a shifted descriptor; cta_group::2)
+//   dgrad     dX[pos][ci] = sum_{tap,co} dY[pos+tap][co] * W[co][8-tap][ci]       k_tconv_pair  (same kernel, transposed / tap-mirrored weights)
+//   wgrad     dW[co][tap][ci] = sum_pos dY[pos][co] * X[pos+tap][ci]              k_wgrad       (both operands MN-major: the K dimension is the
+//                                                                                               board square, exactly as the tensors lie in HBM)
+// The convolution epilogues also produce the sums the BatchNorm kernels need (forward statistics; backward: residual join, ReLU mask,
+// gradient sums).  The 38 tower layers' weight gradients run as one launch after the backward chain; the three odd-shaped layers split the
+// batch into partial sums that a second kernel adds in a fixed order.  No value atomics anywhere: a step is deterministic.  The whole step
+// is captured as one CUDA graph per (batch size, flags).
 // Activations live in HBM as NHWC bf16 with a one-square zero halo, [B][10][10][C], like the inference tower (net.cu).
 //
 // Everything here is reached through szb_train_* (include/szb200.h); there is no CPU path.
@@ -1828,9 +1832,8 @@ static int t_step(szb_ctx* ctx, int32_t n, const int32_t* rows, int32_t flags, f
         }
         if (err) {
             cudaMemsetAsync(tr->error, 0, 4, st);
-            return err == 2   ? fail(ctx, SZB_ERR_ARG, "szb_train_step: a row index is outside the %lld records", (long long)tr->rec_n)
-                   : err == 3 ? fail(ctx, SZB_ERR_INTERNAL, "a BatchNorm kernel's grid barrier timed out")
-                              : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
+            return err == 2 ? fail(ctx, SZB_ERR_ARG, "szb_train_step: a row index is outside the %lld records", (long long)tr->rec_n)
+                            : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
         }
     }
     return 0;
@@ -1929,9 +1932,8 @@ int szb_train_loss_history(szb_ctx* ctx, int64_t first, int32_t count, float* ou
     SZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (err) {
         cudaMemsetAsync(tr->error, 0, 4, ctx->stream);
-        return err == 2   ? fail(ctx, SZB_ERR_ARG, "a step's row index was outside the %lld records", (long long)tr->rec_n)
-               : err == 3 ? fail(ctx, SZB_ERR_INTERNAL, "a BatchNorm kernel's grid barrier timed out")
-                          : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
+        return err == 2 ? fail(ctx, SZB_ERR_ARG, "a step's row index was outside the %lld records", (long long)tr->rec_n)
+                        : fail(ctx, SZB_ERR_INTERNAL, "a training kernel's pipeline timed out");
     }
     return 0;
 }
