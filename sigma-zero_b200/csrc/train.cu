@@ -121,6 +121,11 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+                 : "memory");
+}
 // MMA completion -> one arrival on the barrier at this offset in every CTA of the mask
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
@@ -598,8 +603,11 @@ struct WgArgs {
     uint32_t lbo, sbo;           // descriptor strides (probe aid; 8192 / 1024)
 };
 
-template <int NB>                // 64-channel boxes of X: N = NB * 64 input channels
-__global__ void __launch_bounds__(TR_THREADS, 1)
+// CS = 2: the two CTAs that compute the two halves of the output channels of one (layer, tap, batch split) form a cluster and share the
+// input tile X -- each loads half of its 64-channel boxes and multicasts them into both shared memories (a third less L2 -> SM traffic,
+// which is what bounds this kernel); a stage is refilled when both CTAs' MMAs have released it.
+template <int NB, int CS>        // NB: 64-channel boxes of X (N = NB * 64 input channels); CS: cluster size (1 when there is one half only)
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(TR_THREADS, 1)
 k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
     const WgLayer* wl = layers + a.layer0 + blockIdx.z;
     const CUtensorMap* tm_dy = &wl->tm_dy;
@@ -622,7 +630,7 @@ k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
 
     if (threadIdx.x == 0) {
         abort_sh = 0;
-        for (int s = 0; s < WG_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        for (int s = 0; s < WG_STAGES; s++) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), CS); }
         mbar_init(smem_u32(&bar_acc), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -632,8 +640,11 @@ k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) t_cluster_sync();                  // the peer's barriers exist before a multicast or a commit can reach them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
+    const uint32_t crank = CS > 1 ? t_cluster_rank() : 0u;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1);
     pdl_trigger();
     pdl_wait();
 
@@ -649,7 +660,10 @@ k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
                 tma_load_4d(sa, tm_dy, full, mh * 128, 1, 1, b);
                 tma_load_4d(sa + WG_BOX, tm_dy, full, mh * 128 + 64, 1, 1, b);
 #pragma unroll
-                for (int j = 0; j < NB; j++) tma_load_4d(sa + (2 + j) * WG_BOX, tm_x, full, j * 64, kx, ky, b);
+                for (int j = 0; j < NB; j++) {
+                    if (CS == 1) tma_load_4d(sa + (2 + j) * WG_BOX, tm_x, full, j * 64, kx, ky, b);
+                    else if ((uint32_t)(j % CS) == crank) tma_load_4d_mc(sa + (2 + j) * WG_BOX, tm_x, full, j * 64, kx, ky, b, CMASK);
+                }
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -669,7 +683,7 @@ k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
                 t_mma_split(tmem_base, a_lo + 128, hi, b_lo2 + 128, hi, IDESC, 1u);
                 t_mma_split(tmem_base, a_lo + 256, hi, b_lo2 + 256, hi, IDESC, 1u);
                 t_mma_split(tmem_base, a_lo + 384, hi, b_lo2 + 384, hi, IDESC, 1u);
-                tc_commit(bar_e0 + stage * 8);
+                if (CS > 1) tc_commit_mc(bar_e0 + stage * 8, CMASK); else tc_commit(bar_e0 + stage * 8);
             }
             __syncwarp();
             accumulate = 1;
@@ -702,6 +716,7 @@ k_wgrad(const WgLayer* __restrict__ layers, const WgArgs a) {
     __syncthreads();
     tc_fence_after();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    if (CS > 1) t_cluster_sync();                  // no CTA leaves while the peer's commit may still arrive on its barriers
     if (threadIdx.x == 0 && abort_sh) atomicExch(a.error, 1);
 }
 
@@ -1515,8 +1530,9 @@ static int t_create(szb_ctx* ctx, const szb_train_config* cfg) {
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM));
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_pair<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
         SZB_CUDA(ctx, cudaFuncSetAttribute(k_tconv_pair<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
-        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 6 * WG_BOX + 1024));
-        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 4 * WG_BOX + 1024));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 6 * WG_BOX + 1024));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 6 * WG_BOX + 1024));
+        SZB_CUDA(ctx, cudaFuncSetAttribute(k_wgrad<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_STAGES * 4 * WG_BOX + 1024));
         tr->attr_set = true;
     }
     return 0;
@@ -1657,8 +1673,10 @@ static int t_wgrad(szb_ctx* ctx, Trainer* tr, int l0, int count, int n) {
     a.sbo = tr->cfg.probe_sbo ? (uint32_t)tr->cfg.probe_sbo : 1024;
     if ((size_t)a.ksplit * a.split_stride > tr->partial_floats) return fail(ctx, SZB_ERR_INTERNAL, "wgrad scratch too small");
     const dim3 grid(L.taps * a.m_halves, a.ksplit, count);
-    if (L.cin_pad == 256) SZB_CUDA(ctx, launch_kernel(k_wgrad<4>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 6 * WG_BOX + 1024), ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
-    else SZB_CUDA(ctx, launch_kernel(k_wgrad<2>, grid, dim3(TR_THREADS), (size_t)(WG_STAGES * 4 * WG_BOX + 1024), ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
+    const size_t smem4 = (size_t)(WG_STAGES * 6 * WG_BOX + 1024), smem2 = (size_t)(WG_STAGES * 4 * WG_BOX + 1024);
+    if (L.cin_pad == 256 && a.m_halves == 2) SZB_CUDA(ctx, launch_kernel(k_wgrad<4, 2>, grid, dim3(TR_THREADS), smem4, ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
+    else if (L.cin_pad == 256) SZB_CUDA(ctx, launch_kernel(k_wgrad<4, 1>, grid, dim3(TR_THREADS), smem4, ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
+    else SZB_CUDA(ctx, launch_kernel(k_wgrad<2, 2>, grid, dim3(TR_THREADS), smem2, ctx->stream, tr->pdl, (const WgLayer*)tr->wg_layers, a));
     ctx->launches++;
     if (a.ksplit > 1) {
         const size_t cnt = a.split_stride;
