@@ -1,6 +1,7 @@
 /*
  * szb200.h -- C ABI of libszb200.so: the B200-native replacement for the self-play hot path of
- * DidItWork/Sigma-Zero (batched AlphaZero MCTS over many concurrent chess / Chess960 games).
+ * DidItWork/Sigma-Zero (batched AlphaZero MCTS over many concurrent chess / Chess960 games) and, at the
+ * end of this header, for the fine-tuning step of the same loop (szb_train_*, train_RL.py:77-154).
  *
  * The reference has no FFI of its own: its boundary for this path is a Python call surface
  * (SURVEY.md 8b).  Each entry point below names the reference call it replaces (file:line into the
